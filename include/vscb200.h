@@ -1,0 +1,155 @@
+/* vscb200 -- C ABI of the B200-native VSC22 hot path (libvscb200.so).
+ *
+ * Plain C: opaque handles, raw pointers, sizes, an explicit CUDA stream (passed as void*, it is a
+ * cudaStream_t / CUstream; NULL = legacy default stream).  Every function returns an int status
+ * (0 = ok); no exception crosses this boundary; vscb200_last_error() gives the message of the last
+ * failure on the calling thread.  No CUDA call is made at library-load time (the reference forks
+ * DataLoader workers before CUDA init -- vsc/baseline/inference.py:1-17).
+ *
+ * Two seams of the reference are served:
+ *
+ *  (B) the `faiss` calls of vsc/index.py, vsc/exhaustive_search.py,
+ *      vsc/baseline/score_normalization.py and M/infer/infer_matching.py   -> vscb200_index_*
+ *  (A) the TorchScript encoder call `model(frames)` of D/infer/src/extractor.py:25,
+ *      D/infer/extract_query_feats.py:148,160 and M/infer/infer_matching.py:127 -> vscb200_vit_*
+ *
+ * `_host` variants take HOST buffers and perform the host<->device copies themselves: they are what
+ * the numpy-facing faiss-compatible module binds (the reference passes numpy arrays to faiss).
+ */
+#ifndef VSCB200_H_
+#define VSCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSCB200_OK 0
+#define VSCB200_ERR_INVALID 1 /* bad argument / shape / state */
+#define VSCB200_ERR_CUDA 2    /* a CUDA runtime/driver call failed */
+#define VSCB200_ERR_NOMEM 3
+
+#define VSCB200_METRIC_INNER_PRODUCT 0 /* faiss.METRIC_INNER_PRODUCT */
+#define VSCB200_METRIC_L2 1            /* faiss.METRIC_L2 (squared L2) */
+
+const char* vscb200_last_error(void);
+int vscb200_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t vscb200_launch_count(void);
+/* faiss.get_num_gpus() -- vsc/index.py:169, exhaustive_search.py:28,229; 0 when no CUDA device */
+int vscb200_device_count(void);
+int vscb200_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * (B) flat similarity index.  Replaces faiss.index_factory(d,"Flat",metric) / IndexFlat
+ *     (vsc/index.py:81; exhaustive_search.py:26,70,102) and its methods.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vscb200_index vscb200_index;
+
+/* faiss.index_factory(d, "Flat", metric) -- vsc/index.py:81 */
+int vscb200_index_create(int d, int metric, vscb200_index** out);
+void vscb200_index_destroy(vscb200_index* ix);
+/* index.add(x) -- vsc/index.py:94.  x: [n, d] float32, C-contiguous. Rows get ids ntotal..ntotal+n-1. */
+int vscb200_index_add(vscb200_index* ix, const float* x_dev, int64_t n, void* stream);
+int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n);
+/* index.reset() -- exhaustive_search.py:39 */
+int vscb200_index_reset(vscb200_index* ix);
+/* index.ntotal / index.d / index.metric_type */
+int64_t vscb200_index_ntotal(const vscb200_index* ix);
+int vscb200_index_dim(const vscb200_index* ix);
+int vscb200_index_metric(const vscb200_index* ix);
+/* Restrict searches to bank rows [row0, row0+rows) and report ids offset by id_offset: bank
+ * sharding over ranks.  Default: whole bank, offset 0. */
+int vscb200_index_set_id_offset(vscb200_index* ix, int64_t id_offset);
+
+/* index.search(x, k) -> (D, I) -- vsc/index.py:174, score_normalization.py:95,141,
+ * exhaustive_search.py:62, infer_matching.py:232.  D: [nq,k] float32 best-first, I: [nq,k] int64;
+ * ties -> lower id; k > ntotal pads with (-FLT_MAX | +FLT_MAX, -1).  1 <= k <= 2048. */
+int vscb200_index_search(vscb200_index* ix, const float* q_dev, int64_t nq, int k, float* D_dev, int64_t* I_dev,
+                         void* stream);
+int vscb200_index_search_host(vscb200_index* ix, const float* q_host, int64_t nq, int k, float* D_host,
+                              int64_t* I_host);
+
+/* index.range_search(x, thresh) -> (lims, D, I) -- exhaustive_search.py:74,126,246,
+ * infer_matching.py:235.  Strict '>' (IP) / '<' (L2).  lims: [nq+1] uint64 (host); D/I are allocated
+ * by the library in HOST memory (ascending id inside each row) and released with vscb200_free. */
+int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int64_t nq, float thresh,
+                                    uint64_t* lims_host, float** D_host, int64_t** I_host);
+void vscb200_free(void* p);
+
+/* Dense score block S[nq, ntotal] (float32, device) -- the per-pair similarity matrices of
+ * vsc/baseline/localization.py:32-35 and BASELINE config 5. */
+int vscb200_index_scores(vscb200_index* ix, const float* q_dev, int64_t nq, float* S_dev, int64_t ldS,
+                         void* stream);
+
+/* Fused score normalisation prologue (vsc/baseline/score_normalization.py:71-103):
+ * out[n, d] = [ l2norm(drop(x, drop_dim)) , last ] where last is `fill` (1.0 for references, :99-101)
+ * or, when bias_dev != NULL, bias_dev[row] (queries, :96-97).  x: [n, d] -> out: [n, d]. */
+int vscb200_sn_transform(const float* x_dev, int64_t n, int d, int drop_dim, int l2_normalize, float fill,
+                         const float* bias_dev, float* out_dev, void* stream);
+/* column variance argmin of a [n, d] matrix (score_normalization.py:72), result to *dim_host */
+int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, void* stream);
+/* bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96) */
+int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (A) ViT frame encoder.  Replaces the TorchScript module called at D/infer/src/extractor.py:25
+ *     (architecture: D/train/train_vid_score/video/clip.py:85-163 + backbones/vit.py:42-58 tail,
+ *     or timm ViT + sscd.py:30-40,86 head).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vscb200_vit vscb200_vit;
+
+#define VSCB200_ACT_QUICK_GELU 0 /* clip.py:22-25 */
+#define VSCB200_ACT_GELU 1       /* timm Mlp (erf) */
+#define VSCB200_TAIL_TOKENS 0          /* [n, T, W]  (clip.py:158; caller slices [:,0]) */
+#define VSCB200_TAIL_GEM_LINEAR 1      /* backbones/vit.py:42-58 */
+#define VSCB200_TAIL_GEM_CONV_LINEAR 2 /* sscd.py:30-40 + :86 */
+
+typedef struct vscb200_vit_spec {
+  int img, patch, width, layers, heads;
+  int patch_bias; /* timm: 1, CLIP: 0 (clip.py:105) */
+  int pre_norm;   /* CLIP ln_pre (clip.py:152) */
+  int act;
+  int tail;
+  int out_dim;
+  int gem_hidden;
+  float ln_eps;
+  float gem_p;
+} vscb200_vit_spec;
+
+int vscb200_vit_create(const vscb200_vit_spec* spec, int max_frames, vscb200_vit** out);
+void vscb200_vit_destroy(vscb200_vit* m);
+/* Upload one named fp32 parameter (device pointer); names as in oracle/vit_ref.py / encoder.py:
+ * patch_w patch_b cls pos ln_pre_w ln_pre_b l<i>.{ln1_w,ln1_b,qkv_w,qkv_b,proj_w,proj_b,ln2_w,ln2_b,
+ * fc1_w,fc1_b,fc2_w,fc2_b} ln_post_w ln_post_b gem_conv_w gem_conv_b head_w head_b */
+int vscb200_vit_set_param(vscb200_vit* m, const char* name, const float* w_dev, int64_t count, void* stream);
+/* model(frames): frames [n,3,img,img] float32 NCHW contiguous (device) -> out (device) [n,out_dim] or
+ * [n,T,W]. Any n >= 1 (internally chunked by max_frames). */
+int vscb200_vit_forward(vscb200_vit* m, const float* frames_dev, int64_t n, float* out_dev, void* stream);
+/* same with pinned/pageable HOST buffers (copies inside) */
+int vscb200_vit_forward_host(vscb200_vit* m, const float* frames_host, int64_t n, float* out_host);
+int64_t vscb200_vit_out_elems_per_frame(const vscb200_vit* m);
+
+/* ------------------------------------------------------------------------------------------------
+ * Building blocks exported for unit tests and micro-benchmarks.
+ * ---------------------------------------------------------------------------------------------- */
+#define VSCB200_EPI_BF16 0          /* C_bf16 = act(A*W^T + bias)            */
+#define VSCB200_EPI_F32 1           /* C_f32  = act(A*W^T + bias)            */
+#define VSCB200_EPI_RESIDUAL_F32 2  /* C_f32 += A*W^T + bias   (in place)    */
+/* C[M,N] = A[M,K](bf16) * W[N,K]^T(bf16) (+bias f32[N]) ; tcgen05 + TMA + TMEM persistent kernel.
+ * K % 8 == 0, N % 8 == 0; act: -1 none, VSCB200_ACT_*. */
+int vscb200_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* C, int64_t M, int N, int K,
+                      int64_t lda, int64_t ldw, int64_t ldc, int epilogue, int act, void* stream);
+int vscb200_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width,
+                      float eps, int out_bf16, void* stream);
+/* qkv: [n*T, 3W] bf16 (q|k|v, heads contiguous 64-wide) -> out [n*T, W] bf16; head_dim 64 */
+int vscb200_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int T, int heads, int head_dim,
+                      void* stream);
+int vscb200_cast_f32_bf16(const float* x, void* y_bf16, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSCB200_H_ */

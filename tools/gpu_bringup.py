@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""GPU bring-up diagnostics: each stage runs in its own process (a trapped kernel poisons the CUDA
+context) under a timeout.  `python tools/gpu_bringup.py` runs all stages; `... <stage>` runs one."""
+import ctypes as C
+import os
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+STAGES = ["gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def gemm(A, W, bias=None, epi=0, act=-1, C_out=None):
+    import torch
+    from vsc22_submission_b200 import _lib
+    M, K = A.shape
+    N = W.shape[0]
+    if C_out is None:
+        C_out = torch.empty((M, N), dtype=torch.bfloat16 if epi == 0 else torch.float32, device=A.device)
+    _lib.check(_lib.lib().vscb200_gemm_bf16(_p(A), _p(W), _p(bias) if bias is not None else None, _p(C_out), M, N, K,
+                                            A.stride(0), W.stride(0), C_out.stride(0), epi, act,
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream)), "gemm")
+    return C_out
+
+
+def report(name, got, ref, tol):
+    import torch
+    err = (got.float() - ref.float()).abs()
+    scale = ref.float().abs().max().item() + 1e-9
+    mx = err.max().item()
+    ok = mx <= tol * scale
+    print(f"  {name}: max_abs_err {mx:.3e} (ref max {scale:.3e}) -> {'OK' if ok else 'FAIL'}")
+    if not ok:
+        bad = (err > tol * scale)
+        rows = bad.any(1).nonzero().flatten()
+        cols = bad.any(0).nonzero().flatten()
+        print(f"    bad rows: {rows.numel()} first {rows[:8].tolist()} last {rows[-4:].tolist()}; "
+              f"bad cols: {cols.numel()} first {cols[:8].tolist()} last {cols[-4:].tolist()}")
+        print("    got[0,:8]", got[0, :8].float().tolist())
+        print("    ref[0,:8]", ref[0, :8].float().tolist())
+    return ok
+
+
+def stage_gemm_small():
+    import torch
+    torch.manual_seed(0)
+    ok = True
+    for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 128, 128), (256, 256, 256), (128, 64, 64)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = torch.randn(N, K, device="cuda").bfloat16()
+        out = gemm(A, W, epi=1)
+        torch.cuda.synchronize()
+        ok &= report(f"gemm f32 M{M} N{N} K{K}", out, A.float() @ W.float().T, 1e-3)
+    return ok
+
+
+def stage_gemm_shapes():
+    import torch
+    torch.manual_seed(1)
+    ok = True
+    for (M, N, K) in [(1000, 768, 768), (197 * 8, 2304, 768), (333, 3072, 768), (4096, 768, 3072), (85, 128, 128),
+                      (50432, 768, 768)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        out = gemm(A, W, epi=1)
+        torch.cuda.synchronize()
+        ok &= report(f"gemm f32 M{M} N{N} K{K}", out, A.float() @ W.float().T, 2e-3)
+    # timing of the big shapes
+    for (M, N, K) in [(50432, 2304, 768), (50432, 768, 768), (50432, 3072, 768), (50432, 768, 3072)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        out = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+        for _ in range(3):
+            gemm(A, W, epi=0, C_out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gemm(A, W, epi=0, C_out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"  gemm bf16 M{M} N{N} K{K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+        t0 = time.time()
+        ref = None
+        for _ in range(3):
+            ref = A @ W.T
+        e0.record()
+        for _ in range(10):
+            ref = A @ W.T
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"     cuBLAS (torch.matmul) same shape: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    return ok
+
+
+def stage_gemm_epilogues():
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(2)
+    ok = True
+    M, N, K = 600, 512, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = A.float() @ W.float().T + b
+    ok &= report("bias bf16", gemm(A, W, b, epi=0), ref, 1e-2)
+    ok &= report("bias f32", gemm(A, W, b, epi=1), ref, 2e-3)
+    ok &= report("quick_gelu bf16", gemm(A, W, b, epi=0, act=0), ref * torch.sigmoid(1.702 * ref), 1e-2)
+    ok &= report("gelu bf16", gemm(A, W, b, epi=0, act=1), F.gelu(ref), 1e-2)
+    res = torch.randn(M, N, device="cuda")
+    out = res.clone()
+    gemm(A, W, b, epi=2, C_out=out)
+    ok &= report("residual f32", out, res + ref, 2e-3)
+    torch.cuda.synchronize()
+    return ok
+
+
+def stage_layernorm():
+    import torch
+    import torch.nn.functional as F
+    from vsc22_submission_b200 import _lib
+    ok = True
+    for W in (128, 768, 1024):
+        x = torch.randn(1000, W, device="cuda") * 3 + 1
+        g, b = torch.randn(W, device="cuda"), torch.randn(W, device="cuda")
+        for out_bf16 in (0, 1):
+            y = torch.empty((1000, W), dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda")
+            _lib.check(_lib.lib().vscb200_layernorm(_p(x), _p(g), _p(b), _p(y), 1000, W, 1e-5, out_bf16, None))
+            torch.cuda.synchronize()
+            ok &= report(f"layernorm W{W} bf16={out_bf16}", y, F.layer_norm(x, (W,), g, b, 1e-5), 1e-2 if out_bf16 else 1e-5)
+    return ok
+
+
+def stage_attention():
+    import torch
+    from vsc22_submission_b200 import _lib
+    ok = True
+    torch.manual_seed(3)
+    for (n, T, H) in [(2, 17, 2), (3, 197, 12), (2, 145, 12), (1, 257, 16), (2, 64, 1), (1, 577, 2)]:
+        W = H * 64
+        qkv = (torch.randn(n * T, 3 * W, device="cuda")).bfloat16()
+        out = torch.empty((n * T, W), dtype=torch.bfloat16, device="cuda")
+        _lib.check(_lib.lib().vscb200_attention(_p(qkv), _p(out), n, T, H, 64, None))
+        torch.cuda.synchronize()
+        q, k, v = (qkv.float().reshape(n, T, 3, H, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        att = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
+        ref = (att @ v).permute(0, 2, 1, 3).reshape(n * T, W)
+        ok &= report(f"attention n{n} T{T} H{H}", out, ref, 2e-2)
+    return ok
+
+
+def stage_index():
+    import numpy as np
+    from oracle import faiss_np
+    from vsc22_submission_b200 import faiss_compat
+    ok = True
+    rng = np.random.default_rng(0)
+    for (nb, nq, d, k, metric) in [(5, 3, 3, 2, 1), (1000, 37, 64, 10, 0), (5000, 100, 512, 100, 0), (3000, 50, 128, 1024, 0),
+                                   (777, 33, 20, 5, 1)]:
+        xb = rng.standard_normal((nb, d)).astype(np.float32)
+        xq = rng.standard_normal((nq, d)).astype(np.float32)
+        a, b = faiss_compat.IndexFlat(d, metric), faiss_np.IndexFlat(d, metric)
+        a.add(xb[: nb // 2]); a.add(xb[nb // 2:]); b.add(xb)
+        D, I = a.search(xq, k)
+        Do, Io = b.search(xq, k)
+        same = (I == Io).mean()
+        derr = np.abs(D - Do)[Io >= 0].max()
+        print(f"  search nb{nb} nq{nq} d{d} k{k} metric{metric}: idx match {same:.4f}, max |dD| {derr:.2e}")
+        ok &= same > 0.999 and derr < 1e-3
+        thr = float(np.median(Do[:, min(k, nb) // 2]))
+        lims, Dr, Ir = a.range_search(xq, thr)
+        lo, Dro, Iro = b.range_search(xq, thr)
+        print(f"  range thr {thr:.3f}: total {lims[-1]} vs oracle {lo[-1]}; lims equal {np.array_equal(lims, lo)}; "
+              f"ids equal {np.array_equal(Ir, Iro) if len(Ir) == len(Iro) else False}")
+        ok &= abs(int(lims[-1]) - int(lo[-1])) <= 2
+    return ok
+
+
+def stage_vit_small():
+    import numpy as np
+    import torch
+    from oracle import vit_ref
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VitSpec
+    ok = True
+    for tail, kw in (("gem_linear", {}), ("tokens", {}),
+                     ("gem_conv_linear", dict(patch_bias=True, pre_norm=False, act="gelu", ln_eps=1e-6, gem_hidden=256))):
+        ospec = vit_ref.VitSpec(img=64, patch=16, width=128, layers=2, heads=2, tail=tail, out_dim=64, **kw)
+        w = vit_ref.init_weights(ospec, seed=0)
+        frames = torch.randn(6, 3, 64, 64, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+        ref = vit_ref.forward(ospec, w, frames)
+        spec = VitSpec(img=64, patch=16, width=128, layers=2, heads=2, tail=tail, out_dim=64, **kw)
+        enc = B200ViTEncoder(spec, w, max_frames=4).cuda().eval()
+        out = enc(frames.cuda()).cpu()
+        rel = (out - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)
+        print(f"  vit small tail={tail}: rel L2 per frame {rel.tolist()}")
+        ok &= bool(rel.max() < 3e-2)
+    return ok
+
+
+def stage_vit_b16():
+    import torch
+    from oracle import vit_ref
+    from vsc22_submission_b200 import _lib
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_B16_224_GEM
+    ospec = vit_ref.CLIP_B16_224
+    w = vit_ref.init_weights(ospec, seed=0)
+    frames = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+    t0 = time.time()
+    ref = vit_ref.forward(ospec, w, frames)
+    print(f"  oracle 4 frames: {time.time() - t0:.2f} s")
+    enc = B200ViTEncoder(VIT_B16_224_GEM, w, max_frames=256).cuda().eval()
+    out = enc(frames.cuda()).cpu()
+    rel = (out - ref).norm(dim=1) / ref.norm(dim=1)
+    cos = torch.nn.functional.cosine_similarity(out, ref)
+    print(f"  ViT-B/16 rel L2 {rel.tolist()} cos {cos.tolist()}")
+    x = torch.randn(256, 3, 224, 224, device="cuda").clamp(-1, 1)
+    for _ in range(2):
+        enc(x)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        enc(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    fl = VIT_B16_224_GEM.flops_per_frame() * 256
+    print(f"  ViT-B/16 batch 256: {ms:.2f} ms/step {256 / ms * 1e3:.0f} frames/s {fl / ms / 1e9:.1f} TFLOP/s "
+          f"({(_lib.launch_count() - n0) // 5} launches/step)")
+    return bool(rel.max() < 3e-2)
+
+
+def main():
+    if len(sys.argv) > 1:
+        name = sys.argv[1]
+        ok = globals()["stage_" + name]()
+        print(f"STAGE {name}: {'PASS' if ok else 'FAIL'}")
+        sys.exit(0 if ok else 1)
+    results = {}
+    for name in STAGES:
+        print(f"=== {name}", flush=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=420, capture_output=True, text=True)
+            print(r.stdout[-6000:])
+            if r.returncode != 0:
+                print(r.stderr[-3000:])
+            results[name] = r.returncode == 0
+        except subprocess.TimeoutExpired as e:
+            print("TIMEOUT", (e.stdout or b"")[-2000:])
+            results[name] = False
+    print("SUMMARY", results)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,282 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T (+bias, act, residual)
+//
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, 4-stage ring)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM)
+//   warp 2      TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-11  epilogue       (tcgen05.ld -> bias / QuickGELU / GELU / residual -> 128-bit global stores)
+//
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
+// static persistent tile schedule (tile = blockIdx.x + i*gridDim.x, N-blocks fastest so that
+// concurrently resident CTAs share A tiles through L2 while W stays L2 resident).
+//
+// This is the dense-projection engine of the ViT encoder (reference: every nn.Linear /
+// nn.MultiheadAttention projection of D/train/train_vid_score/video/clip.py:33-39,45-49 and the
+// conv patch-embed :105,143 as an im2row GEMM), replacing the cuBLAS calls of torch 1.11.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace vscb200 {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+
+struct GemmParams {
+  const float* bias;
+  void* C;
+  int64_t M;
+  int N, K;
+  int64_t ldc;
+  int epilogue;
+  int act;
+  int tiles_m, tiles_n;
+  // patch-embed epilogue (VSCB_EPI_PATCH_F32): GEMM row m = frame*P + patch  ->  token row m + m/P + 1
+  // (slot 0 of every frame is the class token), plus the positional embedding pos[(m % P) + 1, :].
+  const float* pos;
+  int patch_P;
+};
+
+constexpr int VSCB_EPI_PATCH_F32 = 3;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == VSCB200_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  if (act == VSCB200_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
+          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_desc_k_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t b_desc = make_desc_k_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128B swizzle row: +2 in the (addr>>4) field
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;           // column half of the tile
+    constexpr int kChunks = BN / 2 / 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * kBM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int col0 = half * (BN / 2) + c * 32;
+        const int gcol = n_blk * BN + col0;
+        uint32_t v[32];
+        __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, v);
+        tmem_ld_wait();
+        if (gcol >= p.N) continue;   // warp-uniform
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (gcol + j < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          }
+        }
+        if (p.act >= 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+        }
+        if (!row_ok) {
+          // nothing to store for rows past M (TMA zero-filled them)
+        } else if (p.epilogue == VSCB200_EPI_BF16) {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + gcol;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (gcol + j < p.N) {
+              uint4 o;
+              o.x = pack_bf16x2(f[j], f[j + 1]);
+              o.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              o.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              o.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(out + j) = o;
+            }
+          }
+        } else if (p.epilogue == VSCB_EPI_PATCH_F32) {
+          const int64_t orow = row + row / p.patch_P + 1;
+          float* out = reinterpret_cast<float*>(p.C) + orow * p.ldc + gcol;
+          const float* pe = p.pos + (row % p.patch_P + 1) * p.N + gcol;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (gcol + j < p.N) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(pe + j));
+              *reinterpret_cast<float4*>(out + j) = make_float4(f[j] + q.x, f[j + 1] + q.y, f[j + 2] + q.z, f[j + 3] + q.w);
+            }
+          }
+        } else {
+          float* out = reinterpret_cast<float*>(p.C) + row * p.ldc + gcol;
+          const bool residual = p.epilogue == VSCB200_EPI_RESIDUAL_F32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (gcol + j < p.N) {
+              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (residual) {
+                const float4 r = *reinterpret_cast<const float4*>(out + j);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              *reinterpret_cast<float4*>(out + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes));
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();
+  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
+              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P) {
+  VSCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+  VSCB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
+  VSCB_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N/ldc must be multiples of 8");
+  VSCB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  VSCB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue");
+  VSCB_REQUIRE(epilogue != VSCB_EPI_PATCH_F32 || (pos != nullptr && patch_P > 0), "gemm: patch epilogue needs pos/P");
+  const int BN = (N >= 256 || N > 128) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, kBM, kBK, true);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, BN, kBK, true);
+  if (rc) return rc;
+  GemmParams p;
+  p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epilogue = epilogue; p.act = act;
+  p.pos = pos; p.patch_P = patch_P;
+  p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
+  p.tiles_n = (N + BN - 1) / BN;
+  return BN == 256 ? launch_gemm<256>(tmA, tmB, p, stream) : launch_gemm<128>(tmA, tmB, p, stream);
+}
+
+}  // namespace vscb200
+
+extern "C" int vscb200_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
+                                 int64_t lda, int64_t ldw, int64_t ldc, int epilogue, int act, void* stream) {
+  if (epilogue < 0 || epilogue > 2) {
+    vscb200::set_last_error("vscb200_gemm_bf16: epilogue must be VSCB200_EPI_{BF16,F32,RESIDUAL_F32}");
+    return VSCB200_ERR_INVALID;
+  }
+  return vscb200::gemm_bf16(A, W, bias, C, M, N, K, lda, ldw, ldc, epilogue, act, static_cast<cudaStream_t>(stream),
+                            nullptr, 0);
+}

@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: error codes, CUDA checks,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/vscb200.h"
+
+namespace vscb200 {
+
+void set_last_error(const std::string& msg);
+extern std::atomic<int64_t> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define VSCB_CUDA_OK(expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::vscb200::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                std::to_string(__LINE__) + ")");                                  \
+      return VSCB200_ERR_CUDA;                                                                    \
+    }                                                                                             \
+  } while (0)
+
+#define VSCB_REQUIRE(cond, msg)                                                                   \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      ::vscb200::set_last_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return VSCB200_ERR_INVALID;                                                                 \
+    }                                                                                             \
+  } while (0)
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes` elements with `ld` elements between rows;
+// box = [box_rows, box_cols]; 128B swizzle when box_cols*elem_bytes == 128, else none.
+int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
+                 uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
+
+int device_sm_count();
+
+}  // namespace vscb200

@@ -1,0 +1,351 @@
+// Flat similarity index (C ABI of seam B): owns the device copy of the descriptor bank, a score
+// workspace and staging buffers; search = dense score block (tensor-core or SIMT) + row select.
+// Reference: faiss IndexFlat behind vsc/index.py:74-177, vsc/exhaustive_search.py:52-92,206-292,
+// vsc/baseline/score_normalization.py:87-98, M/infer/infer_matching.py:217-247.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "host_util.h"
+#include "kernels.h"
+
+using namespace vscb200;
+
+namespace vscb200 {
+// sim_tc.cu: fp32-equivalent tensor-core scoring (split-bf16 tcgen05); returns VSCB200_OK and sets
+// *handled = false when the shape is not supported.
+int scores_tc(const float* Q, const float* R, float* S, int64_t nq, int64_t nr, int d, int64_t ldS, bool l2,
+              const float* qn, const float* rn, cudaStream_t stream, bool* handled);
+}  // namespace vscb200
+
+struct vscb200_index {
+  int d = 0, metric = 0;
+  int64_t ntotal = 0;        // rows resident on the device
+  int64_t capacity = 0;
+  float* bank = nullptr;     // [capacity, d]
+  float* rnorm = nullptr;    // [capacity] squared norms (L2 metric only)
+  std::vector<float> pending;   // host rows appended by add_host, uploaded lazily in one copy
+  int64_t id_offset = 0;
+  float* ws = nullptr;       // score workspace
+  size_t ws_bytes = 0;
+  // staging for the host-buffer API
+  float* q_stage = nullptr; size_t q_stage_bytes = 0;
+  float* D_stage = nullptr; size_t D_stage_bytes = 0;
+  int64_t* I_stage = nullptr; size_t I_stage_bytes = 0;
+  float* qnorm = nullptr; size_t qnorm_bytes = 0;
+  unsigned long long* counts = nullptr; size_t counts_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  int force_simt = 0;
+};
+
+namespace {
+
+size_t ws_budget_bytes() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("VSCB200_WS_MB");
+    v = (e ? static_cast<size_t>(atoll(e)) : 2048) << 20;
+    if (v < (1u << 20)) v = 1u << 20;
+  }
+  return v;
+}
+
+template <typename Tp>
+int grow(Tp** p, size_t* have, size_t need) {
+  if (*have >= need) return VSCB200_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  size_t want = std::max(need, static_cast<size_t>(256));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), want);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("cudaMalloc(") + std::to_string(want) + ") failed: " + cudaGetErrorString(e));
+    return VSCB200_ERR_NOMEM;
+  }
+  *have = want;
+  return VSCB200_OK;
+}
+
+int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
+  if (rows <= ix->capacity) return VSCB200_OK;
+  int64_t cap = std::max<int64_t>(rows, ix->capacity + ix->capacity / 2);
+  cap = std::max<int64_t>(cap, 1024);
+  float* nb = nullptr;
+  cudaError_t e = cudaMalloc(&nb, static_cast<size_t>(cap) * ix->d * sizeof(float));
+  if (e != cudaSuccess) {
+    set_last_error(std::string("index: cudaMalloc bank failed: ") + cudaGetErrorString(e));
+    return VSCB200_ERR_NOMEM;
+  }
+  if (ix->ntotal) {
+    VSCB_CUDA_OK(cudaMemcpyAsync(nb, ix->bank, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+  }
+  float* nn = nullptr;
+  if (ix->metric == VSCB200_METRIC_L2) {
+    VSCB_CUDA_OK(cudaMalloc(&nn, static_cast<size_t>(cap) * sizeof(float)));
+    if (ix->ntotal)
+      VSCB_CUDA_OK(cudaMemcpyAsync(nn, ix->rnorm, static_cast<size_t>(ix->ntotal) * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, s));
+  }
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  if (ix->bank) cudaFree(ix->bank);
+  if (ix->rnorm) cudaFree(ix->rnorm);
+  ix->bank = nb;
+  ix->rnorm = nn;
+  ix->capacity = cap;
+  return VSCB200_OK;
+}
+
+int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kind, cudaStream_t s) {
+  if (n == 0) return VSCB200_OK;
+  int rc = ensure_capacity(ix, ix->ntotal + n, s);
+  if (rc) return rc;
+  float* dst = ix->bank + ix->ntotal * ix->d;
+  VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
+  if (ix->metric == VSCB200_METRIC_L2) {
+    rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);
+    if (rc) return rc;
+  }
+  ix->ntotal += n;
+  return VSCB200_OK;
+}
+
+int flush_pending(vscb200_index* ix, cudaStream_t s) {
+  if (ix->pending.empty()) return VSCB200_OK;
+  const int64_t n = static_cast<int64_t>(ix->pending.size()) / ix->d;
+  int rc = append_rows(ix, ix->pending.data(), n, cudaMemcpyHostToDevice, s);
+  if (rc) return rc;
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));   // the host vector is released next
+  std::vector<float>().swap(ix->pending);
+  return VSCB200_OK;
+}
+
+int64_t block_rows(const vscb200_index* ix, int64_t nq) {
+  const size_t per_row = static_cast<size_t>(std::max<int64_t>(ix->ntotal, 1)) * sizeof(float);
+  int64_t rows = static_cast<int64_t>(ws_budget_bytes() / per_row);
+  rows = std::max<int64_t>(rows, 1);
+  rows = std::min<int64_t>(rows, 65535 * 64);
+  return std::min(rows, std::max<int64_t>(nq, 1));
+}
+
+// S[0:nq, 0:ntotal] for one query block
+int score_block(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t ldS, cudaStream_t s) {
+  const bool l2 = ix->metric == VSCB200_METRIC_L2;
+  const float* qn = nullptr;
+  if (l2) {
+    int rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float));
+    if (rc) return rc;
+    rc = row_sqnorm(q, nq, ix->d, ix->qnorm, s);
+    if (rc) return rc;
+    qn = ix->qnorm;
+  }
+  if (!ix->force_simt) {
+    bool handled = false;
+    int rc = scores_tc(q, ix->bank, S, nq, ix->ntotal, ix->d, ldS, l2, qn, ix->rnorm, s, &handled);
+    if (rc) return rc;
+    if (handled) return VSCB200_OK;
+  }
+  return scores_simt(q, ix->bank, S, nq, ix->ntotal, ix->d, ldS, l2, qn, ix->rnorm, s);
+}
+
+int own_stream(vscb200_index* ix, cudaStream_t* s) {
+  if (!ix->own_stream) VSCB_CUDA_OK(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+  *s = ix->own_stream;
+  return VSCB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vscb200_index_create(int d, int metric, vscb200_index** out) {
+  VSCB_REQUIRE(out != nullptr, "index_create: null out");
+  VSCB_REQUIRE(d > 0, "index_create: d must be positive");
+  VSCB_REQUIRE(metric == VSCB200_METRIC_INNER_PRODUCT || metric == VSCB200_METRIC_L2,
+               "index_create: metric must be METRIC_INNER_PRODUCT or METRIC_L2");
+  vscb200_index* ix = new vscb200_index();
+  ix->d = d;
+  ix->metric = metric;
+  const char* e = getenv("VSCB200_FORCE_SIMT");
+  ix->force_simt = (e && atoi(e)) ? 1 : 0;
+  *out = ix;
+  return VSCB200_OK;
+}
+
+void vscb200_index_destroy(vscb200_index* ix) {
+  if (!ix) return;
+  cudaFree(ix->bank); cudaFree(ix->rnorm); cudaFree(ix->ws); cudaFree(ix->q_stage); cudaFree(ix->D_stage);
+  cudaFree(ix->I_stage); cudaFree(ix->qnorm); cudaFree(ix->counts);
+  if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+  delete ix;
+}
+
+int vscb200_index_add(vscb200_index* ix, const float* x_dev, int64_t n, void* stream) {
+  VSCB_REQUIRE(ix && (n == 0 || x_dev), "index_add: null argument");
+  VSCB_REQUIRE(n >= 0, "index_add: negative row count");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = flush_pending(ix, s);
+  if (rc) return rc;
+  return append_rows(ix, x_dev, n, cudaMemcpyDeviceToDevice, s);
+}
+
+int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n) {
+  VSCB_REQUIRE(ix && (n == 0 || x_host), "index_add_host: null argument");
+  VSCB_REQUIRE(n >= 0, "index_add_host: negative row count");
+  // The reference adds one video (~30 rows) at a time (vsc/index.py:87-94): rows are staged on the
+  // host and uploaded in ONE copy at the next search.
+  ix->pending.insert(ix->pending.end(), x_host, x_host + n * ix->d);
+  return VSCB200_OK;
+}
+
+int vscb200_index_reset(vscb200_index* ix) {
+  VSCB_REQUIRE(ix, "index_reset: null index");
+  ix->ntotal = 0;
+  std::vector<float>().swap(ix->pending);
+  return VSCB200_OK;
+}
+
+int64_t vscb200_index_ntotal(const vscb200_index* ix) {
+  return ix ? ix->ntotal + static_cast<int64_t>(ix->pending.size()) / ix->d : 0;
+}
+int vscb200_index_dim(const vscb200_index* ix) { return ix ? ix->d : 0; }
+int vscb200_index_metric(const vscb200_index* ix) { return ix ? ix->metric : 0; }
+int vscb200_index_set_id_offset(vscb200_index* ix, int64_t id_offset) {
+  VSCB_REQUIRE(ix, "index_set_id_offset: null index");
+  ix->id_offset = id_offset;
+  return VSCB200_OK;
+}
+
+int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, float* D, int64_t* I, void* stream) {
+  VSCB_REQUIRE(ix && (nq == 0 || (q && D && I)), "index_search: null argument");
+  VSCB_REQUIRE(nq >= 0, "index_search: negative query count");
+  VSCB_REQUIRE(k >= 1 && k <= 2048, "index_search: k must be in [1, 2048]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = flush_pending(ix, s);
+  if (rc) return rc;
+  const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
+  const int64_t blk = block_rows(ix, nq);
+  const int64_t ldS = (ix->ntotal + 3) & ~3ll;
+  rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float));
+  if (rc) return rc;
+  for (int64_t q0 = 0; q0 < nq; q0 += blk) {
+    const int64_t nb = std::min(blk, nq - q0);
+    if (ix->ntotal > 0) {
+      rc = score_block(ix, q + q0 * ix->d, nb, ix->ws, ldS, s);
+      if (rc) return rc;
+    }
+    rc = topk_rows(ix->ws, ldS, nb, ix->ntotal, k, keep_max, D + q0 * k, I + q0 * k, ix->id_offset, s);
+    if (rc) return rc;
+  }
+  return VSCB200_OK;
+}
+
+int vscb200_index_search_host(vscb200_index* ix, const float* q_host, int64_t nq, int k, float* D_host,
+                              int64_t* I_host) {
+  VSCB_REQUIRE(ix && (nq == 0 || (q_host && D_host && I_host)), "index_search_host: null argument");
+  if (nq == 0) return VSCB200_OK;
+  cudaStream_t s;
+  int rc = own_stream(ix, &s);
+  if (rc) return rc;
+  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(nq) * ix->d * sizeof(float)))) return rc;
+  if ((rc = grow(&ix->D_stage, &ix->D_stage_bytes, static_cast<size_t>(nq) * k * sizeof(float)))) return rc;
+  if ((rc = grow(&ix->I_stage, &ix->I_stage_bytes, static_cast<size_t>(nq) * k * sizeof(int64_t)))) return rc;
+  VSCB_CUDA_OK(cudaMemcpyAsync(ix->q_stage, q_host, static_cast<size_t>(nq) * ix->d * sizeof(float),
+                               cudaMemcpyHostToDevice, s));
+  rc = vscb200_index_search(ix, ix->q_stage, nq, k, ix->D_stage, ix->I_stage, s);
+  if (rc) return rc;
+  VSCB_CUDA_OK(cudaMemcpyAsync(D_host, ix->D_stage, static_cast<size_t>(nq) * k * sizeof(float),
+                               cudaMemcpyDeviceToHost, s));
+  VSCB_CUDA_OK(cudaMemcpyAsync(I_host, ix->I_stage, static_cast<size_t>(nq) * k * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, s));
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  return VSCB200_OK;
+}
+
+int vscb200_index_scores(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t ldS, void* stream) {
+  VSCB_REQUIRE(ix && (nq == 0 || (q && S)), "index_scores: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = flush_pending(ix, s);
+  if (rc) return rc;
+  VSCB_REQUIRE(ldS >= ix->ntotal, "index_scores: ldS < ntotal");
+  if (nq == 0 || ix->ntotal == 0) return VSCB200_OK;
+  for (int64_t q0 = 0; q0 < nq; q0 += 65535ll * 64) {
+    const int64_t nb = std::min<int64_t>(65535ll * 64, nq - q0);
+    rc = score_block(ix, q + q0 * ix->d, nb, S + q0 * ldS, ldS, s);
+    if (rc) return rc;
+  }
+  return VSCB200_OK;
+}
+
+int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int64_t nq, float thresh,
+                                    uint64_t* lims_host, float** D_out, int64_t** I_out) {
+  VSCB_REQUIRE(ix && lims_host && D_out && I_out && (nq == 0 || q_host), "index_range_search_host: null argument");
+  *D_out = nullptr;
+  *I_out = nullptr;
+  lims_host[0] = 0;
+  cudaStream_t s;
+  int rc = own_stream(ix, &s);
+  if (rc) return rc;
+  if ((rc = flush_pending(ix, s))) return rc;
+  const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
+  const int64_t blk = block_rows(ix, nq);
+  const int64_t ldS = (ix->ntotal + 3) & ~3ll;
+  if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float)))) return rc;
+  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * ix->d * sizeof(float)))) return rc;
+  if ((rc = grow(&ix->counts, &ix->counts_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * sizeof(unsigned long long)))) return rc;
+  std::vector<unsigned long long> cnt(static_cast<size_t>(std::max<int64_t>(blk, 1)));
+  size_t total = 0, cap = 0;
+  float* Dh = nullptr;
+  int64_t* Ih = nullptr;
+  float* Dd = nullptr; size_t Dd_bytes = 0;
+  int64_t* Id = nullptr; size_t Id_bytes = 0;
+  auto fail = [&](int code) {
+    free(Dh); free(Ih); cudaFree(Dd); cudaFree(Id);
+    return code;
+  };
+  for (int64_t q0 = 0; q0 < nq; q0 += blk) {
+    const int64_t nb = std::min(blk, nq - q0);
+    if (cudaMemcpyAsync(ix->q_stage, q_host + q0 * ix->d, static_cast<size_t>(nb) * ix->d * sizeof(float),
+                        cudaMemcpyHostToDevice, s) != cudaSuccess) { set_last_error("range_search: H2D failed"); return fail(VSCB200_ERR_CUDA); }
+    if (ix->ntotal > 0 && (rc = score_block(ix, ix->q_stage, nb, ix->ws, ldS, s))) return fail(rc);
+    if ((rc = range_count(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, s))) return fail(rc);
+    if (cudaMemcpyAsync(cnt.data(), ix->counts, static_cast<size_t>(nb) * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { set_last_error(std::string("range_search: count failed: ") + cudaGetErrorString(cudaGetLastError())); return fail(VSCB200_ERR_CUDA); }
+    // exclusive scan on the host (block of <= a few thousand rows), offsets back to the device
+    size_t blk_total = 0;
+    for (int64_t i = 0; i < nb; ++i) {
+      const unsigned long long c = cnt[i];
+      cnt[i] = blk_total;
+      blk_total += c;
+      lims_host[q0 + i + 1] = total + blk_total;
+    }
+    if (blk_total == 0) continue;
+    if (total + blk_total > cap) {
+      cap = std::max(total + blk_total, cap * 2);
+      float* nD = static_cast<float*>(realloc(Dh, cap * sizeof(float)));
+      int64_t* nI = static_cast<int64_t*>(realloc(Ih, cap * sizeof(int64_t)));
+      if (!nD || !nI) { Dh = nD ? nD : Dh; Ih = nI ? nI : Ih; set_last_error("range_search: host realloc failed"); return fail(VSCB200_ERR_NOMEM); }
+      Dh = nD; Ih = nI;
+    }
+    if ((rc = grow(&Dd, &Dd_bytes, blk_total * sizeof(float)))) return fail(rc);
+    if ((rc = grow(&Id, &Id_bytes, blk_total * sizeof(int64_t)))) return fail(rc);
+    if (cudaMemcpyAsync(ix->counts, cnt.data(), static_cast<size_t>(nb) * sizeof(unsigned long long),
+                        cudaMemcpyHostToDevice, s) != cudaSuccess) { set_last_error("range_search: H2D offsets failed"); return fail(VSCB200_ERR_CUDA); }
+    if ((rc = range_fill(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, Dd, Id, ix->id_offset, s))) return fail(rc);
+    if (cudaMemcpyAsync(Dh + total, Dd, blk_total * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(Ih + total, Id, blk_total * sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) { set_last_error(std::string("range_search: fill failed: ") + cudaGetErrorString(cudaGetLastError())); return fail(VSCB200_ERR_CUDA); }
+    total += blk_total;
+  }
+  cudaFree(Dd);
+  cudaFree(Id);
+  if (!Dh) { Dh = static_cast<float*>(malloc(sizeof(float))); Ih = static_cast<int64_t*>(malloc(sizeof(int64_t))); }
+  *D_out = Dh;
+  *I_out = Ih;
+  return VSCB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Internal (C++) launch entry points shared between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vscb200 {
+
+constexpr int VSCB_EPI_PATCH_F32_ID = 3;
+
+int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
+              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P);
+int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream);
+int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,
+              int out_bf16, cudaStream_t stream);
+int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream);
+int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream);
+int cls_rows(const float* cls, const float* pos, float* x, int64_t n, int T, int W, cudaStream_t stream);
+int gem_head(const float* y, const float* gamma, const float* beta, const float* head_w, const float* head_b,
+             float* out, int64_t n, int T, int C, int out_dim, float eps, float p, bool fuse_ln,
+             cudaStream_t stream);
+
+}  // namespace vscb200
+
+namespace vscb200 {
+int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr, int d, int64_t ldS, bool l2,
+                const float* qn, const float* rn, cudaStream_t stream);
+int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
+int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
+                 float* out, cudaStream_t stream);
+int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
+              int64_t id_offset, cudaStream_t stream);
+int range_count(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
+                unsigned long long* counts, cudaStream_t stream);
+int range_fill(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
+               const unsigned long long* offsets, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
+}  // namespace vscb200

@@ -1,0 +1,229 @@
+// Dense similarity block S[nq, nr] = Q . R^T (inner product) or squared L2, fp32, plus the score
+// normalisation prologue kernels.  Reference: faiss IndexFlat scoring behind vsc/index.py:174,
+// vsc/exhaustive_search.py:62,74, score_normalization.py:71-103; per-pair sim matrices of
+// vsc/baseline/localization.py:32-35.
+//
+// scores_simt: exact-fp32 FFMA tile kernel (64x64 tile, 4x4 per thread) -- the shape-generic path
+// (any d, including the d=3 vectors of the reference's tests).  The tcgen05 split-bf16 kernel in
+// sim_tc.cu takes over for d % 8 == 0.
+#include "host_util.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vscb200 {
+
+constexpr int kST = 64;    // tile edge
+constexpr int kSK = 16;    // k step
+
+template <bool kL2>
+__global__ void __launch_bounds__(256)
+scores_simt_kernel(const float* __restrict__ Q, const float* __restrict__ R, float* __restrict__ S, int64_t nq,
+                   int64_t nr, int d, int64_t ldS, const float* __restrict__ qn, const float* __restrict__ rn) {
+  __shared__ float sQ[kSK][kST + 4];
+  __shared__ float sR[kSK][kST + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t q0 = static_cast<int64_t>(blockIdx.y) * kST, r0 = static_cast<int64_t>(blockIdx.x) * kST;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += kSK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      const int rr = idx >> 4, kk = idx & 15;
+      const bool kin = k0 + kk < d;
+      sQ[kk][rr] = (kin && q0 + rr < nq) ? Q[(q0 + rr) * d + k0 + kk] : 0.f;
+      sR[kk][rr] = (kin && r0 + rr < nr) ? R[(r0 + rr) * d + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&sQ[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sR[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t q = q0 + ty * 4 + i;
+    if (q >= nq) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = r0 + tx * 4 + j;
+      if (r >= nr) continue;
+      float v = acc[i][j];
+      if (kL2) v = fmaxf(qn[q] + rn[r] - 2.0f * v, 0.f);
+      S[q * ldS + r] = v;
+    }
+  }
+}
+
+int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr, int d, int64_t ldS, bool l2,
+                const float* qn, const float* rn, cudaStream_t stream) {
+  if (nq == 0 || nr == 0) return VSCB200_OK;
+  dim3 grid(static_cast<unsigned>((nr + kST - 1) / kST), static_cast<unsigned>((nq + kST - 1) / kST));
+  VSCB_REQUIRE(grid.y <= 65535, "scores: too many query rows in one block");
+  if (l2)
+    scores_simt_kernel<true><<<grid, 256, 0, stream>>>(Q, R, S, nq, nr, d, ldS, qn, rn);
+  else
+    scores_simt_kernel<false><<<grid, 256, 0, stream>>>(Q, R, S, nq, nr, d, ldS, qn, rn);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+// ------------------------------------------------------------------ squared row norms (warp per row)
+__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = x[row * d + c];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream) {
+  if (n == 0) return VSCB200_OK;
+  row_sqnorm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, out);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+// ------------------------------------------------------------------ score-normalisation prologue
+// out[row] = [ l2norm(x[row] without column drop_dim) , last ]   (score_normalization.py:73-83,96-101)
+// sklearn.normalize semantics: zero rows stay zero.  Norm accumulated in fp32 like sklearn (float32 in).
+__global__ void sn_transform_kernel(const float* __restrict__ x, int64_t n, int d, int drop_dim, int l2_normalize,
+                                    float fill, const float* __restrict__ bias, float* __restrict__ out) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    if (c == drop_dim) continue;
+    const float v = xr[c];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float denom = 1.0f;
+  if (l2_normalize) {
+    denom = sqrtf(s);
+    if (denom == 0.f) denom = 1.0f;
+  }
+  // output layout: kept columns in order, then the extra dimension.  With drop_dim < 0 nothing is
+  // dropped and the output has d+1 columns.
+  const int dout = (drop_dim >= 0 && drop_dim < d) ? d : d + 1;
+  float* orow = out + row * dout;
+  for (int c = lane; c < d; c += 32) {
+    if (c == drop_dim) continue;
+    const int oc = (drop_dim >= 0 && c > drop_dim) ? c - 1 : c;
+    orow[oc] = xr[c] / denom;
+  }
+  if (lane == 0) orow[dout - 1] = bias ? bias[row] : fill;
+}
+
+int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
+                 float* out, cudaStream_t stream) {
+  if (n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(drop_dim < d, "sn_transform: drop_dim out of range");
+  sn_transform_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, drop_dim, l2_normalize,
+                                                                                      fill, bias, out);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+// bias[row] = -beta * mean(D[row, :nk])
+__global__ void sn_bias_kernel(const float* __restrict__ D, int64_t nq, int k, int nk, float beta,
+                               float* __restrict__ bias) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  float s = 0.f;
+  for (int j = 0; j < nk; ++j) s += D[row * k + j];
+  bias[row] = -beta * (s / nk);
+}
+
+// column sums and sums of squares in double (var.argmin, score_normalization.py:72)
+__global__ void col_moments_kernel(const float* __restrict__ x, int64_t n, int d, double* __restrict__ sums) {
+  // grid.x = column blocks of 32, grid.y = row slabs; block = 32 x 8
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+  double s = 0.0, s2 = 0.0;
+  if (c < d) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const double v = x[r * d + c];
+      s += v;
+      s2 += v * v;
+    }
+    atomicAdd(&sums[c], s);
+    atomicAdd(&sums[d + c], s2);
+  }
+}
+
+}  // namespace vscb200
+
+extern "C" {
+int vscb200_sn_transform(const float* x_dev, int64_t n, int d, int drop_dim, int l2_normalize, float fill,
+                         const float* bias_dev, float* out_dev, void* stream) {
+  return vscb200::sn_transform(x_dev, n, d, drop_dim, l2_normalize, fill, bias_dev, out_dev,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(nk >= 1 && nk <= k, "sn_bias: need 1 <= nk <= k");
+  if (nq == 0) return VSCB200_OK;
+  sn_bias_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      D_dev, nq, k, nk, beta, bias_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, void* stream_v) {
+  using namespace vscb200;
+  VSCB_REQUIRE(n > 0 && d > 0 && dim_host, "low_var_dim: empty input");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  double* sums = nullptr;
+  VSCB_CUDA_OK(cudaMalloc(&sums, sizeof(double) * 2 * d));
+  VSCB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream));
+  dim3 grid((d + 31) / 32, static_cast<unsigned>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048)));
+  col_moments_kernel<<<grid, dim3(32, 8), 0, stream>>>(x_dev, n, d, sums);
+  count_launch();
+  std::string err;
+  double* h = static_cast<double*>(malloc(sizeof(double) * 2 * d));
+  cudaError_t e = cudaMemcpyAsync(h, sums, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(sums);
+  if (e != cudaSuccess) {
+    free(h);
+    set_last_error(std::string("low_var_dim: ") + cudaGetErrorString(e));
+    return VSCB200_ERR_CUDA;
+  }
+  int best = 0;
+  double best_var = 0;
+  for (int c = 0; c < d; ++c) {
+    const double mean = h[c] / n;
+    const double var = h[d + c] / n - mean * mean;
+    if (c == 0 || var < best_var) { best = c; best_var = var; }
+  }
+  free(h);
+  *dim_host = best;
+  return VSCB200_OK;
+}
+}
