@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the VSC22 hot path on B200 (contract in the task statement).
+
+Primary line (BASELINE.json configs[1]): ViT-B/16@224 bf16 frame encoder, 10 000 synthetic frames per
+step per GPU, metric ``frame-descriptors/sec``; a step = one pass over the 10k-frame job in batches of
+256 through the encoder plan.  Secondary object ``"sim"`` (configs[2]): 10k x 40k x 512 score
+normalisation + top-10, metric ``sim-pairs/sec``.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload both|encoder|sim]
+
+N > 1: launched by torchrun, one rank per GPU; frames shard over ranks for encoding (no data-path
+collective, weak scaling) and the reference bank shards for similarity (one all-gather of partial
+top-k).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, MAX over
+ranks.  ``--impl reference`` times the CPU port of the reference's path (oracle/, numpy/torch on the
+host cores) on a bounded sample of the same workload; /root/reference itself does not exist on the
+GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_FRAMES = 10_000          # configs[1]: 10k synthetic frames
+BATCH = 256                # encoder plan max_frames
+SIM_NQ, SIM_NR, SIM_NZ, SIM_D, SIM_K = 10_000, 40_000, 40_000, 512, 10   # configs[2]
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.1 <= ts <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def barrier_sync(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, world):
+    import torch
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+def bench_encoder(args, world, rank, peaks):
+    import numpy as np
+    import torch
+
+    from vsc22_submission_b200 import _lib
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_B16_224_GEM, random_weights
+    spec = VIT_B16_224_GEM
+    dev = torch.device("cuda", torch.cuda.current_device())
+    enc = B200ViTEncoder(spec, random_weights(spec, seed=0), max_frames=BATCH).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    frames = torch.empty((N_FRAMES, 3, spec.img, spec.img), dtype=torch.float32, device=dev)
+    for i in range(0, N_FRAMES, 1000):     # 6.0 GB resident in HBM: >> L2, nothing is cached between steps
+        frames[i:i + 1000] = torch.randn((min(1000, N_FRAMES - i), 3, spec.img, spec.img), generator=g, device=dev).clamp_(-1, 1)
+    out = None
+    for _ in range(args.warmup):
+        out = enc(frames)
+    barrier_sync(world)
+    _lib.prof_collect()
+    _lib.prof_enable(True)
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    time.sleep(0.3)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        out = enc(frames)
+    e1.record()
+    barrier_sync(world)
+    t_wall1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = _lib.launch_count() - n0
+    _lib.prof_enable(False)
+    prof = _lib.prof_collect()
+    clk = clocks.stop(t_wall0, t_wall1)
+    ms_per_step = ms / args.steps
+    value = N_FRAMES * world / (ms_per_step / 1e3)
+
+    # ---- e2e: host (pinned) frames in, host descriptors out, copies inside the timed region
+    e2e_frames = N_FRAMES
+    host = None
+    while host is None and e2e_frames >= BATCH:
+        try:
+            host = torch.empty((e2e_frames, 3, spec.img, spec.img), dtype=torch.float32, pin_memory=True)
+        except RuntimeError:
+            e2e_frames //= 2
+    for i in range(0, e2e_frames, 1000):
+        host[i:i + 1000].copy_(frames[i:i + 1000])
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    for _ in range(min(args.warmup, 2)):
+        enc.forward_host(host_np[:4 * BATCH], dev)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_host = enc.forward_host(host_np, dev)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world) / args.steps
+    barrier_sync(world)
+    e2e = {"value": e2e_frames * world / (e2e_ms / 1e3), "unit": "frame-descriptors/sec",
+           "h2d_bytes_per_step": int(e2e_frames * 3 * spec.img * spec.img * 4 * world),
+           "d2h_bytes_per_step": int(e2e_frames * spec.out_dim * 4 * world), "ms_per_step": e2e_ms,
+           "frames_per_step": e2e_frames * world, "api": "B200ViTEncoder.forward_host (vscb200_vit_forward_host)"}
+    dev_vs_host = float(np.abs(out_host[:64] - out[:64].cpu().numpy()).max())
+
+    gm = prof["gemm"]
+    roof_peak = peaks["bf16_tflops_sustained"]
+    gemm_tflops = gm["work"] / (gm["ms"] / 1e3) / 1e12 if gm["ms"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all projections + patch embed)",
+                "achieved": gemm_tflops, "peak": roof_peak, "unit": "TFLOP/s", "frac": gemm_tflops / roof_peak,
+                "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": None, "launches": gm["launches"],
+                "share_of_step": gm["ms"] / ms if ms > 0 else None,
+                "whole_step_tflops": value / world * spec.flops_per_frame() / 1e12,
+                "whole_step_frac": value / world * spec.flops_per_frame() / 1e12 / roof_peak,
+                "kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}}
+    return {"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "roofline": roofline, "dev_vs_host_maxabs": dev_vs_host, "enc": enc, "frames": frames, "out": out}
+
+
+def cpu_baseline_encoder(frames_cpu_fn, seconds_budget=20.0):
+    """The oracle port of the reference ViT forward (torch fp32, all host cores) on a bounded sample."""
+    import torch
+
+    from oracle import vit_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = vit_ref.CLIP_B16_224
+    w = vit_ref.init_weights(spec, seed=0)
+    x = frames_cpu_fn(8)
+    vit_ref.forward(spec, w, x)          # warm-up batch
+    n, t0 = 0, time.perf_counter()
+    while n < 64 or (time.perf_counter() - t0 < seconds_budget and n < 512):
+        vit_ref.forward(spec, w, x)
+        n += 8
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frame-descriptors/sec", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} frames of the same 224x224 workload in batches of 8, fp32, oracle/vit_ref.py "
+                      f"(restated CLIPModel.forward + gem tail), {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------ similarity
+def make_sim_data(device, rank=0):
+    import torch
+    def unit(n, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        x = torch.randn((n, SIM_D), generator=g, device=device)
+        return x / x.norm(dim=1, keepdim=True)
+    return unit(SIM_NQ, 2), unit(SIM_NR, 3), unit(SIM_NZ, 4)
+
+
+def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
+    """score_normalize(beta=1.2, nk=1) + top-10 with Q, R, Z resident in HBM.  With world > 1 the noise
+    bank and the reference bank are sharded by rows; partial top-k are all-gathered and merged."""
+    import torch
+
+    from vsc22_submission_b200 import search
+    lvd = search.low_var_dim(Z_shard) if world == 1 else _global_low_var_dim(Z_shard)
+    z_t = search.sn_transform(Z_shard, lvd, True, fill=0.0)
+    q_0 = search.sn_transform(Q, lvd, True, fill=0.0)
+    zi = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
+    zi.add(z_t)
+    Dz, _ = zi.search(q_0, 1)
+    if world > 1:
+        Dz = _merge_topk(Dz, torch.zeros_like(Dz, dtype=torch.int64), 1)[0]
+    bias = search.bias_from_topk(Dz, 1.2, 1)
+    q_t = search.sn_transform(Q, lvd, True, bias=bias)
+    r_t = search.sn_transform(R_shard, lvd, True, fill=1.0)
+    ri = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
+    ri.set_id_offset(row0_r)
+    ri.add(r_t)
+    D, I = ri.search(q_t, SIM_K)
+    if world > 1:
+        D, I = _merge_topk(D, I, SIM_K)
+    return D, I
+
+
+def _merge_topk(D, I, k):
+    """One all-gather of the [nq, k] partial results per rank, then a k-way merge."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
+    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
+    dist.all_gather_into_tensor(Dg, D.contiguous())
+    dist.all_gather_into_tensor(Ig, I.contiguous())
+    Dc = Dg.permute(1, 0, 2).reshape(D.shape[0], -1)
+    Ic = Ig.permute(1, 0, 2).reshape(I.shape[0], -1)
+    top, pos = torch.topk(Dc, k, dim=1)
+    return top, torch.gather(Ic, 1, pos)
+
+
+def _global_low_var_dim(Z_shard):
+    import torch
+    import torch.distributed as dist
+    z = Z_shard.double()
+    mom = torch.stack([z.sum(0), (z * z).sum(0), torch.full((z.shape[1],), float(z.shape[0]), dtype=torch.float64, device=z.device)])
+    dist.all_reduce(mom)
+    mean = mom[0] / mom[2]
+    return int((mom[1] / mom[2] - mean * mean).argmin().item())
+
+
+def bench_sim(args, world, rank, peaks):
+    import numpy as np
+    import torch
+
+    from vsc22_submission_b200 import _lib
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Q, R, Z = make_sim_data(dev)
+    def shard(x):
+        per = (x.shape[0] + world - 1) // world
+        return x[rank * per:(rank + 1) * per].contiguous(), rank * per
+    R_s, row0 = shard(R)
+    Z_s, _ = shard(Z)
+    for _ in range(args.warmup):
+        D, I = sim_step_device(Q, R_s, Z_s, world, rank, row0)
+    barrier_sync(world)
+    _lib.prof_collect()
+    _lib.prof_enable(True)
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2: flushed between steps
+    total = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier_sync(world)
+        e0.record()
+        D, I = sim_step_device(Q, R_s, Z_s, world, rank, row0)
+        e1.record()
+        torch.cuda.synchronize()
+        total += e0.elapsed_time(e1)
+    barrier_sync(world)
+    ms = max_over_ranks(total, world) / args.steps
+    launches = _lib.launch_count() - n0
+    _lib.prof_enable(False)
+    prof = _lib.prof_collect()
+    pairs = SIM_NQ * (SIM_NR + SIM_NZ)
+    value = pairs / (ms / 1e3)
+    # e2e through the numpy-facing API (host arrays in, host results out)
+    e2e = None
+    if world == 1:
+        from vsc22_submission_b200 import faiss_compat as faiss
+        Qh, Rh, Zh = (x.cpu().numpy() for x in (Q, R, Z))
+        def host_step():
+            lvd = int(np.asarray(Zh).var(axis=0).argmin())
+            def tr(x):
+                x = np.delete(x, lvd, axis=1)
+                return x / np.linalg.norm(x, axis=1, keepdims=True)
+            zi = faiss.IndexFlat(SIM_D - 1, faiss.METRIC_INNER_PRODUCT)
+            zi.add(tr(Zh))
+            qn = tr(Qh)
+            Dz, _ = zi.search(qn, 1)
+            qh = np.concatenate([qn, -1.2 * Dz[:, :1].mean(axis=1, keepdims=True)], axis=1)
+            rn = tr(Rh)
+            rh = np.concatenate([rn, np.ones_like(rn[:, :1])], axis=1)
+            ri = faiss.IndexFlat(SIM_D, faiss.METRIC_INNER_PRODUCT)
+            ri.add(rh)
+            return ri.search(qh, SIM_K)
+        host_step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            Dh, Ih = host_step()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e = {"value": pairs / (e2e_ms / 1e3), "unit": "sim-pairs/sec", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int((SIM_NQ * 2 + SIM_NR + SIM_NZ) * SIM_D * 4),
+               "d2h_bytes_per_step": int(SIM_NQ * (SIM_K * 12 + 12)),
+               "api": "faiss_compat.IndexFlat.add/search on numpy arrays (the reference's score_normalize + search steps)",
+               "idx_agree_with_device_path": float((Ih == I.cpu().numpy()).mean())}
+    flops = 2.0 * SIM_D * pairs
+    bytes_alg = (SIM_NQ + SIM_NR + SIM_NZ) * SIM_D * 4 + SIM_NQ * SIM_K * 12
+    sc = prof["scores"]
+    roof = {"bound": "tensor", "kernel": "similarity scores kernel (both banks)",
+            "achieved": (sc["work"] / (sc["ms"] / 1e3) / 1e12) if sc["ms"] > 0 else 0.0, "peak": peaks["bf16_tflops"],
+            "unit": "TFLOP/s", "peak_source": f"{peaks['source']} bf16_tflops (burst)", "traffic": None,
+            "whole_step_tensor_frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
+            "whole_step_hbm_frac": bytes_alg / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+            "kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    return {"metric": "sim-pairs/sec", "value": value, "unit": "sim-pairs/sec", "ms_per_step": ms, "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roof, "dtype": "f32",
+            "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
+                                   "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
+                       "k": SIM_K, "l2_flush": "256 MiB write between steps",
+                       "sharding": "bank rows over ranks + all-gather of partial top-k" if world > 1 else "single GPU"}}
+
+
+def cpu_baseline_sim():
+    import numpy as np
+
+    from oracle import faiss_np, score_norm_np
+    faiss_np.set_accumulate("f32")     # plain sgemm, what faiss-CPU IndexFlat executes
+    rng = np.random.default_rng(2)
+    nq = 1000                          # bounded sample: 1k of the 10k queries against the full banks
+    unit = lambda n: (lambda x: x / np.linalg.norm(x, axis=1, keepdims=True))(rng.standard_normal((n, SIM_D)).astype(np.float32))
+    Q, R, Z = unit(nq), unit(SIM_NR), unit(SIM_NZ)
+    t0 = time.perf_counter()
+    q2, r2, _ = score_norm_np.score_normalize(Q, R, Z, beta=1.2, nk=1)
+    ix = faiss_np.IndexFlat(SIM_D, faiss_np.METRIC_INNER_PRODUCT)
+    ix.add(r2)
+    ix.search(q2, SIM_K)
+    dt = time.perf_counter() - t0
+    faiss_np.set_accumulate("f64")
+    return {"value": nq * (SIM_NR + SIM_NZ) / dt, "unit": "sim-pairs/sec", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{nq} of the 10k queries against the full 40k+40k banks, numpy sgemm + argsort "
+                      f"(oracle/score_norm_np.py + oracle/faiss_np.py), {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    g = torch.Generator().manual_seed(1)
+    sample_fn = lambda n: torch.randn((n, 3, 224, 224), generator=g).clamp_(-1, 1)
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline_encoder(sample_fn, seconds_budget=15.0)
+        vals.append(base["value"])
+    value = sum(vals) / len(vals)
+    base["value"] = value
+    sim = cpu_baseline_sim() if args.workload in ("both", "sim") else None
+    line = {"impl": "reference", "metric": "frame-descriptors/sec", "value": value, "unit": "frame-descriptors/sec",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: ViT-B/16 224x224 frame encoder (CLIPModel(224,16,768,12,12) + gem/Linear "
+                                   "tail), CPU port on host cores, bounded sample", "batch": 8},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "frame-descriptors/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if sim:
+        line["sim"] = {"metric": "sim-pairs/sec", "value": sim["value"], "unit": "sim-pairs/sec", "cpu_baseline": sim}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="both", choices=["both", "encoder", "sim"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    world, rank, local = dist_setup(args.gpus)
+    peaks = load_peaks()
+    line = {"metric": "frame-descriptors/sec", "unit": "frame-descriptors/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic"}
+    enc_res = None
+    if args.workload in ("both", "encoder"):
+        enc_res = bench_encoder(args, world, rank, peaks)
+        line.update(value=enc_res["value"], ms_per_step=enc_res["ms_per_step"], e2e=enc_res["e2e"],
+                    gpu_launches=enc_res["gpu_launches"], clocks=enc_res["clocks"], roofline=enc_res["roofline"])
+        line["config"] = {"workload": "configs[1]: ViT-B/16 224x224 bf16 frame encoder, 10k synthetic frames per GPU per step",
+                          "arch": "CLIPModel(224,16,768,12,12) + gem(p=3)/Linear(768->512) tail, random init (seed 0)",
+                          "frames_per_step_per_gpu": N_FRAMES, "batch": BATCH, "tokens": 197,
+                          "flops_per_frame": enc_res["enc"].spec.flops_per_frame(),
+                          "cache": "6.0 GB of input frames per step, far larger than the 126 MB L2 (no flush needed)",
+                          "parallelism": f"dp{world} (frames sharded over ranks, no data-path collective)",
+                          "dev_vs_host_api_maxabs": enc_res["dev_vs_host_maxabs"]}
+    if args.workload in ("both", "sim"):
+        if enc_res is not None:
+            enc_res["enc"], enc_res["frames"] = None, None
+            torch.cuda.empty_cache()
+        sim = bench_sim(args, world, rank, peaks)
+        if enc_res is None:
+            line.update(metric="sim-pairs/sec", unit="sim-pairs/sec", value=sim["value"], ms_per_step=sim["ms_per_step"],
+                        e2e=sim["e2e"], gpu_launches=sim["gpu_launches"], roofline=sim["roofline"], dtype="f32",
+                        config=sim["config"])
+        else:
+            line["sim"] = sim
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        g = torch.Generator().manual_seed(1)
+        if args.workload in ("both", "encoder"):
+            line["cpu_baseline"] = cpu_baseline_encoder(lambda n: torch.randn((n, 3, 224, 224), generator=g).clamp_(-1, 1))
+            # parity beside the timing: first frames of the job vs the oracle on the same weights
+            from oracle import vit_ref
+            from vsc22_submission_b200.encoder import VIT_B16_224_GEM, random_weights
+            w = random_weights(VIT_B16_224_GEM, seed=0)
+            gd = torch.Generator(device="cuda").manual_seed(1)
+            x = torch.randn((1000, 3, 224, 224), generator=gd, device="cuda").clamp_(-1, 1)[:4].cpu()
+            ref = vit_ref.forward(vit_ref.CLIP_B16_224, w, x)
+            got = enc_res["out"][:4].cpu()
+            rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+            line["parity"] = {"encoder_rel_l2_max_vs_fp32_oracle": rel, "frames": 4, "tolerance": 2e-2}
+        if args.workload in ("both", "sim"):
+            cb = cpu_baseline_sim()
+            if "sim" in line:
+                line["sim"]["cpu_baseline"] = cb
+            else:
+                line["cpu_baseline"] = cb
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if enc_res:
+            line.pop("enc", None)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

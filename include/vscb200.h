@@ -41,6 +41,11 @@ int64_t vscb200_launch_count(void);
 /* faiss.get_num_gpus() -- vsc/index.py:169, exhaustive_search.py:28,229; 0 when no CUDA device */
 int vscb200_device_count(void);
 int vscb200_set_device(int device);
+/* Per-kernel device timing with CUDA events on the launching stream (bench.py's live roofline).
+ * kinds: 0 gemm, 1 attention, 2 layernorm, 3 other encoder kernels, 4 similarity scores, 5 select.
+ * work = algorithmic FLOPs (gemm/attention/scores) or bytes (others). */
+int vscb200_prof_enable(int on);
+int vscb200_prof_collect(double* ms_by_kind, int64_t* launches_by_kind, double* work_by_kind, int nkinds);
 
 /* ------------------------------------------------------------------------------------------------
  * (B) flat similarity index.  Replaces faiss.index_factory(d,"Flat",metric) / IndexFlat

@@ -1,0 +1,160 @@
+"""Parity of the CUDA ViT encoder (through the C ABI / nn.Module seam) with the oracle and with the
+golden vectors produced by the reference's own CLIPModel class."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# bf16 tensor-core operands with fp32 accumulation/residual/LN/softmax: per-descriptor relative L2
+# error vs the fp32 oracle.  (The reference itself ran these matmuls in TF32 on A100, torch 1.11
+# default; BASELINE config 2 names bf16.)  The north-star 1e-3 figure is met by the similarity path;
+# for the encoder the bf16 figure below is the contract, measured and reported by bench.py.
+BF16_REL_TOL = 2e-2
+
+
+def _rel(out, ref):
+    out, ref = out.reshape(len(out), -1), ref.reshape(len(ref), -1)
+    return np.linalg.norm(out - ref, axis=1) / np.linalg.norm(ref, axis=1)
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def test_gemm_against_fp32(torch):
+    from vsc22_submission_b200 import _lib
+    torch.manual_seed(0)
+    for (M, N, K, epi) in [(128, 128, 64, 1), (1000, 768, 768, 1), (1576, 2304, 768, 0), (333, 3072, 768, 0),
+                           (4096, 768, 3072, 1), (85, 64, 128, 1)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        out = torch.empty((M, N), dtype=torch.bfloat16 if epi == 0 else torch.float32, device="cuda")
+        _lib.check(_lib.lib().vscb200_gemm_bf16(_p(A), _p(W), _p(b), _p(out), M, N, K, K, K, N, epi, -1, None))
+        torch.cuda.synchronize()
+        ref = A.float() @ W.float().T + b
+        tol = 1e-2 if epi == 0 else 1e-4
+        assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item(), (M, N, K, epi)
+
+
+def test_gemm_epilogues(torch):
+    import torch.nn.functional as F
+    from vsc22_submission_b200 import _lib
+    torch.manual_seed(2)
+    M, N, K = 600, 512, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = A.float() @ W.float().T + b
+
+    def run(epi, act, out):
+        _lib.check(_lib.lib().vscb200_gemm_bf16(_p(A), _p(W), _p(b), _p(out), M, N, K, K, K, N, epi, act, None))
+        torch.cuda.synchronize()
+        return out.float()
+
+    o = run(0, 0, torch.empty((M, N), dtype=torch.bfloat16, device="cuda"))
+    assert (o - ref * torch.sigmoid(1.702 * ref)).abs().max() < 1e-2 * ref.abs().max()
+    o = run(0, 1, torch.empty((M, N), dtype=torch.bfloat16, device="cuda"))
+    assert (o - F.gelu(ref)).abs().max() < 1e-2 * ref.abs().max()
+    res = torch.randn(M, N, device="cuda")
+    o = run(2, -1, res.clone())
+    assert (o - (res + ref)).abs().max() < 1e-4 * ref.abs().max()
+
+
+def test_attention_against_fp32(torch):
+    from vsc22_submission_b200 import _lib
+    torch.manual_seed(3)
+    for (n, T, H) in [(2, 17, 2), (3, 197, 12), (2, 145, 12), (1, 257, 16), (2, 64, 1), (1, 577, 2)]:
+        W = H * 64
+        qkv = torch.randn(n * T, 3 * W, device="cuda").bfloat16()
+        out = torch.empty((n * T, W), dtype=torch.bfloat16, device="cuda")
+        _lib.check(_lib.lib().vscb200_attention(_p(qkv), _p(out), n, T, H, 64, None))
+        torch.cuda.synchronize()
+        q, k, v = (qkv.float().reshape(n, T, 3, H, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1) @ v).permute(0, 2, 1, 3).reshape(n * T, W)
+        assert (out.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item(), (n, T, H)
+
+
+def test_layernorm_against_fp32(torch):
+    import torch.nn.functional as F
+    from vsc22_submission_b200 import _lib
+    for W in (128, 768, 1024):
+        x = torch.randn(999, W, device="cuda") * 3 + 1
+        g, b = torch.randn(W, device="cuda"), torch.randn(W, device="cuda")
+        y = torch.empty_like(x)
+        _lib.check(_lib.lib().vscb200_layernorm(_p(x), _p(g), _p(b), _p(y), 999, W, 1e-5, 0, None))
+        torch.cuda.synchronize()
+        assert (y - F.layer_norm(x, (W,), g, b, 1e-5)).abs().max().item() < 2e-5
+
+
+def test_encoder_matches_reference_class_golden(torch, golden_dir):
+    """tokens / descriptors of the reference's own CLIPModel (+ gem/Linear tail) on seeded weights."""
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VitSpec
+    g = np.load(os.path.join(golden_dir, "vit_clip_small.npz"))
+    img, patch, width, layers, heads, out_dim = (int(v) for v in g["spec"])
+    w = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w.")}
+    frames = torch.from_numpy(g["frames"]).cuda()
+    enc = B200ViTEncoder(VitSpec(img, patch, width, layers, heads, tail="gem_linear", out_dim=out_dim), w, max_frames=3)
+    enc = enc.cuda().eval()
+    desc = enc(frames).cpu().numpy()           # 5 frames, max_frames 3 -> exercises chunking
+    assert _rel(desc, g["desc"]).max() < BF16_REL_TOL
+    enc_t = B200ViTEncoder(VitSpec(img, patch, width, layers, heads, tail="tokens"),
+                           {k: v for k, v in w.items() if not k.startswith("head")}, max_frames=8).cuda().eval()
+    tok = enc_t(frames).cpu().numpy()
+    assert tok.shape == g["tokens"].shape
+    assert _rel(tok, g["tokens"]).max() < BF16_REL_TOL
+    # host-buffer entry point gives the same answer
+    host = enc.forward_host(g["frames"])
+    np.testing.assert_allclose(host, desc, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("flavour", ["clip_gem", "timm_sscd"])
+def test_encoder_matches_oracle(torch, flavour):
+    from oracle import vit_ref
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VitSpec
+    kw = dict(img=96, patch=16, width=192, layers=3, heads=3, out_dim=128)
+    if flavour == "timm_sscd":
+        kw.update(patch=32, patch_bias=True, pre_norm=False, act="gelu", ln_eps=1e-6, tail="gem_conv_linear", gem_hidden=256)
+    else:
+        kw.update(tail="gem_linear")
+    ospec = vit_ref.VitSpec(**kw)
+    w = vit_ref.init_weights(ospec, seed=4)
+    frames = torch.randn(7, 3, 96, 96, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+    ref = vit_ref.forward(ospec, w, frames).numpy()
+    enc = B200ViTEncoder(VitSpec(**kw), w, max_frames=4).cuda().eval()
+    out = enc(frames.cuda()).cpu().numpy()
+    assert out.shape == ref.shape
+    assert _rel(out, ref).max() < BF16_REL_TOL
+    # ragged n, idempotence, frame independence
+    out1 = enc(frames[:1].cuda()).cpu().numpy()
+    np.testing.assert_allclose(out1[0], out[0], rtol=0, atol=1e-5)
+    assert enc(frames[:0].cuda()).shape == (0, kw["out_dim"])
+
+
+def test_encoder_vit_b16_full_config(torch):
+    """BASELINE config 2 architecture (ViT-B/16@224, T=197, W=768, L=12) on a few frames vs the oracle."""
+    from oracle import vit_ref
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_B16_224_GEM
+    w = vit_ref.init_weights(vit_ref.CLIP_B16_224, seed=0)
+    frames = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(1)).clamp(-1, 1)
+    ref = vit_ref.forward(vit_ref.CLIP_B16_224, w, frames).numpy()
+    enc = B200ViTEncoder(VIT_B16_224_GEM, w, max_frames=64).cuda().eval()
+    out = enc(frames.cuda()).cpu().numpy()
+    rel = _rel(out, ref)
+    cos = (out * ref).sum(1) / np.linalg.norm(out, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < BF16_REL_TOL and cos.min() > 0.9995, (rel, cos)
+    # a 130-frame batch (2 chunks + ragged tail) equals per-frame results
+    big = frames.repeat(44, 1, 1, 1)[:130].cuda()
+    outb = enc(big).cpu().numpy()
+    np.testing.assert_allclose(outb[:3], out, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(outb[129], out[129 % 3], rtol=0, atol=1e-5)

@@ -38,6 +38,8 @@ SIGNATURES = {
     "vscb200_launch_count": (_i64, []),
     "vscb200_device_count": (_i, []),
     "vscb200_set_device": (_i, [_i]),
+    "vscb200_prof_enable": (_i, [_i]),
+    "vscb200_prof_collect": (_i, [_p, _p, _p, _i]),
     "vscb200_index_create": (_i, [_i, _i, C.POINTER(_p)]),
     "vscb200_index_destroy": (None, [_p]),
     "vscb200_index_add": (_i, [_p, _p, _i64, _p]),
@@ -94,3 +96,18 @@ def check(rc: int, what: str = ""):
 
 def launch_count() -> int:
     return int(lib().vscb200_launch_count())
+
+
+PROF_KINDS = ("gemm", "attention", "layernorm", "vit_other", "scores", "select")
+
+
+def prof_enable(on: bool):
+    lib().vscb200_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """-> {kind: {"ms": device ms, "launches": n, "work": algorithmic flops or bytes}} since the last call."""
+    n = len(PROF_KINDS)
+    ms, ln, wk = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)()
+    check(lib().vscb200_prof_collect(ms, ln, wk, n), "prof_collect")
+    return {k: {"ms": ms[i], "launches": int(ln[i]), "work": wk[i]} for i, k in enumerate(PROF_KINDS)}

@@ -195,6 +195,7 @@ int attention(const void* qkv, void* out, int n_frames, int T, int heads, int he
   VSCB_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((T + kAttQTile - 1) / kAttQTile, heads, n_frames);
   const float scale_log2e = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
+  ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * head_dim);
   attention_kernel<<<grid, kAttThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                         reinterpret_cast<__nv_bfloat16*>(out), T, Tpad, heads,
                                                         scale_log2e);

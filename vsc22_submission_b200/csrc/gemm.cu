@@ -239,6 +239,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                     Cfg::kSmemBytes));
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();
+  ProfScope prof(kProfGemm, stream, 2.0 * static_cast<double>(p.M) * p.N * p.K);
   gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());

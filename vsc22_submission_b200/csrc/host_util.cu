@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace vscb200 {
 
@@ -59,9 +60,70 @@ int device_sm_count() {
   return sms;
 }
 
+// ---------------------------------------------------------------- event profiler
+struct ProfRec { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; double work = 0; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;       // records of the current collection window
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+ProfScope::ProfScope(int kind, cudaStream_t stream, double work) : slot_(-1), stream_(stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.a = get_event();
+  r.b = get_event();
+  r.kind = kind;
+  r.work = work;
+  cudaEventRecord(r.a, stream);
+  g_prof.push_back(r);
+  slot_ = static_cast<int>(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot_ < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[slot_].b, stream_);
+}
+
 }  // namespace vscb200
 
 extern "C" {
+int vscb200_prof_enable(int on) {
+  vscb200::g_prof_on.store(on ? 1 : 0);
+  return VSCB200_OK;
+}
+// Sum the device time (ms), launch count and algorithmic work of the records of `kind` collected
+// since the last call, then drop ALL records.  Synchronises on the recorded events.
+int vscb200_prof_collect(double* ms_by_kind, int64_t* launches_by_kind, double* work_by_kind, int nkinds) {
+  using namespace vscb200;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int k = 0; k < nkinds; ++k) { ms_by_kind[k] = 0; launches_by_kind[k] = 0; work_by_kind[k] = 0; }
+  for (ProfRec& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess &&
+        r.kind < nkinds) {
+      ms_by_kind[r.kind] += ms;
+      launches_by_kind[r.kind] += 1;
+      work_by_kind[r.kind] += r.work;
+    }
+    g_event_pool.push_back(r.a);
+    g_event_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  cudaGetLastError();
+  return VSCB200_OK;
+}
 const char* vscb200_last_error(void) { return vscb200::g_last_error.c_str(); }
 int vscb200_version(void) { return 100; }
 int64_t vscb200_launch_count(void) { return vscb200::g_launch_count.load(); }

@@ -42,4 +42,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
 
 int device_sm_count();
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's live roofline
+// numbers).  Disabled by default: zero cost beyond one relaxed atomic load per launch.
+enum ProfKind { kProfGemm = 0, kProfAttention = 1, kProfLayerNorm = 2, kProfVitOther = 3, kProfScores = 4,
+                kProfSelect = 5, kProfKinds = 6 };
+struct ProfScope {
+  ProfScope(int kind, cudaStream_t stream, double work);
+  ~ProfScope();
+  int slot_;
+  cudaStream_t stream_;
+};
+
 }  // namespace vscb200

@@ -133,6 +133,7 @@ int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool ke
   if (nq == 0) return VSCB200_OK;
   int kpad = 2;
   while (kpad < k) kpad <<= 1;
+  ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * n * 4);
   topk_select_kernel<<<static_cast<unsigned>(nq), kSelThreads, kpad * sizeof(unsigned long long), stream>>>(
       S, ldS, n, k, kpad, keep_max ? 1 : 0, D, I, id_offset);
   count_launch();

@@ -70,6 +70,7 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
   if (nq == 0 || nr == 0) return VSCB200_OK;
   dim3 grid(static_cast<unsigned>((nr + kST - 1) / kST), static_cast<unsigned>((nq + kST - 1) / kST));
   VSCB_REQUIRE(grid.y <= 65535, "scores: too many query rows in one block");
+  ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * d);
   if (l2)
     scores_simt_kernel<true><<<grid, 256, 0, stream>>>(Q, R, S, nq, nr, d, ldS, qn, rn);
   else

@@ -71,6 +71,7 @@ int layernorm(const float* x, const float* gamma, const float* beta, void* y, in
   if (rows == 0) return VSCB200_OK;
   const int rows_per_block = 8;
   const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * width * (out_bf16 ? 6 : 8));
   if (out_bf16)
     layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps);
   else
@@ -131,6 +132,7 @@ int im2row(const float* frames, void* patches, int64_t n, int img, int patch, in
   const int P = (img / patch) * (img / patch);
   const int64_t total = n * P * (Kp / 2);
   if (total == 0) return VSCB200_OK;
+  ProfScope prof(kProfVitOther, stream, static_cast<double>(total) * 2 * 6);
   im2row_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       frames, reinterpret_cast<__nv_bfloat16*>(patches), n, img, patch, Kp);
   count_launch();
@@ -262,6 +264,7 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
   if (n == 0) return VSCB200_OK;
   VSCB_REQUIRE(!fuse_ln || (C % 4 == 0 && C <= 128 * kLnMaxVec), "gem_head: fused LN needs width % 4 == 0 and <= 1024");
   const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  ProfScope prof(kProfVitOther, stream, static_cast<double>(n) * T * C * 4);
   if (fuse_ln)
     gem_head_kernel<true><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, head_w, head_b,
                                                                                    out, T, C, out_dim, eps, p);

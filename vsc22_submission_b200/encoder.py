@@ -88,6 +88,38 @@ def param_names(spec: VitSpec):
     return names
 
 
+def random_weights(spec: VitSpec, seed: int = 0, device="cpu") -> Dict[str, torch.Tensor]:
+    """Seeded random-init weights of the given architecture (there are no shipped checkpoints:
+    D/checkpoints/.gitkeep).  Distributions follow the reference's init (clip.py:107-124: class/pos
+    ~ W^-0.5 N(0,1), Linear ~ N(0, 0.02)); LayerNorm affine is perturbed around (1, 0)."""
+    g = torch.Generator().manual_seed(seed)
+    W, T = spec.width, spec.tokens
+
+    def n(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    shapes = {"patch_w": ((W, 3, spec.patch, spec.patch), (3 * spec.patch ** 2) ** -0.5), "patch_b": ((W,), 0.02),
+              "cls": ((W,), W ** -0.5), "pos": ((T, W), W ** -0.5), "head_b": ((spec.out_dim,), 0.02),
+              "gem_conv_w": ((spec.gem_hidden, W), W ** -0.5), "gem_conv_b": ((spec.gem_hidden,), 0.2)}
+    w = {}
+    for name in param_names(spec):
+        f = name.split(".")[-1]
+        if name in shapes:
+            w[name] = n(*shapes[name][0], std=shapes[name][1])
+        elif name == "head_w":
+            cin = spec.gem_hidden if spec.tail == "gem_conv_linear" else W
+            w[name] = n(spec.out_dim, cin, std=cin ** -0.5)
+        elif f.startswith("ln") and f.endswith("_w"):
+            w[name] = 1.0 + n(W, std=0.1)
+        elif f.startswith("ln") and f.endswith("_b"):
+            w[name] = n(W, std=0.1)
+        else:
+            rows = {"qkv": 3 * W, "proj": W, "fc1": 4 * W, "fc2": W}[f[:-2]]
+            cols = 4 * W if f == "fc2_w" else W
+            w[name] = n(rows, cols) if f.endswith("_w") else n(rows)
+    return {k: v.to(device) for k, v in w.items()}
+
+
 class B200ViTEncoder(nn.Module):
     """Frame encoder backed by a vscb200_vit plan.  Weights are held as fp32 buffers (so ``.to()`` /
     ``.cuda()`` / ``state_dict()`` behave) and packed to bf16 inside the plan on first use per device."""

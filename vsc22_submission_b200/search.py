@@ -1,0 +1,226 @@
+"""Device-resident similarity search and score normalisation (host side of seam B, one level above
+``faiss_compat``): the reference's ``score_normalize`` family and kNN, with descriptors living in HBM.
+
+Mirrors, with the same names / argument meaning / error behaviour:
+
+* ``score_normalize`` / ``query_score_normalize`` / ``ref_score_normalize``
+  -- VSC22-Descriptor-Track-1st/infer/vsc/baseline/score_normalization.py:33-104, 107-148, 150-192
+  (operating on lists of ``VideoFeature``-like objects: ``.video_id``, ``.feature``; returned with
+  ``dataclasses.replace`` exactly as the reference does)
+* ``DeviceIndex`` -- faiss ``IndexFlat`` with torch CUDA tensors in and out (no host copies)
+
+All arithmetic is in libvscb200.so; torch is used for device memory and streams only.  The reference
+loops ``index.search`` once per query VIDEO (score_normalization.py:93-98 -- 8 295 bank scans at test
+scale); here all query rows go through ONE batched search.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+METRIC_INNER_PRODUCT = _lib.METRIC_INNER_PRODUCT
+METRIC_L2 = _lib.METRIC_L2
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32_cuda(x: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (no CPU fallback)")
+    return x.contiguous().float()
+
+
+class DeviceIndex:
+    """Flat exact index over device-resident descriptors (faiss.IndexFlat semantics, tensors in/out)."""
+
+    def __init__(self, d: int, metric: int = METRIC_INNER_PRODUCT, device: Optional[torch.device] = None):
+        self.d, self.metric_type = int(d), int(metric)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._ptr = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vscb200_index_create(self.d, self.metric_type, C.byref(self._ptr)), "index_create")
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                _lib.lib().vscb200_index_destroy(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+    @property
+    def ntotal(self) -> int:
+        return int(_lib.lib().vscb200_index_ntotal(self._ptr))
+
+    def set_id_offset(self, offset: int):
+        """Global id of this shard's first row (bank sharding over ranks)."""
+        _lib.check(_lib.lib().vscb200_index_set_id_offset(self._ptr, int(offset)), "index_set_id_offset")
+
+    def add(self, x: torch.Tensor):
+        x = _f32_cuda(x, "DeviceIndex.add")
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise AssertionError(f"add: expected [n, {self.d}], got {tuple(x.shape)}")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vscb200_index_add(self._ptr, _p(x), x.shape[0], _stream(self.device)), "index.add")
+
+    def reset(self):
+        _lib.check(_lib.lib().vscb200_index_reset(self._ptr), "index.reset")
+
+    def search(self, q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = _f32_cuda(q, "DeviceIndex.search")
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise AssertionError(f"search: expected [n, {self.d}], got {tuple(q.shape)}")
+        nq = q.shape[0]
+        D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        if nq:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().vscb200_index_search(self._ptr, _p(q), nq, int(k), _p(D), _p(I),
+                                                           _stream(self.device)), "index.search")
+        return D, I
+
+    def scores(self, q: torch.Tensor) -> torch.Tensor:
+        """Dense [nq, ntotal] score matrix (localization.py:32-35 form)."""
+        q = _f32_cuda(q, "DeviceIndex.scores")
+        S = torch.empty((q.shape[0], self.ntotal), dtype=torch.float32, device=self.device)
+        if S.numel():
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().vscb200_index_scores(self._ptr, _p(q), q.shape[0], _p(S), S.stride(0),
+                                                           _stream(self.device)), "index.scores")
+        return S
+
+
+# ------------------------------------------------------------------------------------------------
+# score normalisation on device tensors
+# ------------------------------------------------------------------------------------------------
+def low_var_dim(noise: torch.Tensor) -> int:
+    """``sn_features.var(axis=0).argmin()`` (score_normalization.py:72)."""
+    noise = _f32_cuda(noise, "low_var_dim")
+    out = C.c_int(0)
+    with torch.cuda.device(noise.device):
+        _lib.check(_lib.lib().vscb200_low_var_dim(_p(noise), noise.shape[0], noise.shape[1], C.byref(out),
+                                                  _stream(noise.device)), "low_var_dim")
+    return int(out.value)
+
+
+def sn_transform(x: torch.Tensor, drop_dim: int, l2_normalize: bool, fill: float = 0.0,
+                 bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[l2norm(delete(x, drop_dim)), last] in one pass (score_normalization.py:73-83, 96-101).
+    drop_dim < 0: nothing dropped, output gains a column."""
+    x = _f32_cuda(x, "sn_transform")
+    n, d = x.shape
+    dout = d if 0 <= drop_dim < d else d + 1
+    out = torch.empty((n, dout), dtype=torch.float32, device=x.device)
+    if n:
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().vscb200_sn_transform(_p(x), n, d, int(drop_dim), int(bool(l2_normalize)), float(fill),
+                                                       _p(bias), _p(out), _stream(x.device)), "sn_transform")
+    return out
+
+
+def bias_from_topk(D: torch.Tensor, beta: float, nk: int) -> torch.Tensor:
+    """bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96)."""
+    D = _f32_cuda(D, "bias_from_topk")
+    bias = torch.empty((D.shape[0],), dtype=torch.float32, device=D.device)
+    if D.shape[0]:
+        with torch.cuda.device(D.device):
+            _lib.check(_lib.lib().vscb200_sn_bias(_p(D), D.shape[0], D.shape[1], int(nk), float(beta), _p(bias),
+                                                  _stream(D.device)), "sn_bias")
+    return bias
+
+
+def noise_bias(q_t: torch.Tensor, z_t: torch.Tensor, beta: float, nk: int) -> torch.Tensor:
+    """bias[row] = -beta * mean(top-nk inner products of q_t[row] against the noise bank z_t)."""
+    ix = DeviceIndex(z_t.shape[1], METRIC_INNER_PRODUCT, z_t.device)
+    ix.add(z_t)
+    D, _ = ix.search(q_t, nk)
+    return bias_from_topk(D, beta, nk)
+
+
+def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch.Tensor, l2_normalize=True,
+                            replace_dim=True, beta=1.0, nk=1, low_var_dim_: Optional[int] = None,
+                            gated_rows: Optional[torch.Tensor] = None):
+    """Array form of score_normalize: -> (q' , r' or None, low_var_dim)."""
+    lvd = -1
+    if replace_dim:
+        lvd = low_var_dim(z) if low_var_dim_ is None else int(low_var_dim_)
+    # the noise search ignores the appended column (0 on both sides)
+    z_t = sn_transform(z, lvd, l2_normalize, fill=0.0)
+    q_0 = sn_transform(q, lvd, l2_normalize, fill=0.0)
+    bias = noise_bias(q_0, z_t, beta, nk)
+    if gated_rows is not None:
+        bias = torch.where(gated_rows.to(bias.device), torch.full_like(bias, -100.0), bias)
+    q_t = sn_transform(q, lvd, l2_normalize, bias=bias)
+    r_t = sn_transform(r, lvd, l2_normalize, fill=1.0) if r is not None else None
+    return q_t, r_t, lvd
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's function signatures (lists of VideoFeature-like objects, numpy features)
+# ------------------------------------------------------------------------------------------------
+def _cat(features: Sequence, device) -> torch.Tensor:
+    arr = np.concatenate([np.asarray(f.feature, dtype=np.float32) for f in features], axis=0)
+    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=False)
+
+
+def _split(features: Sequence, arr: np.ndarray) -> List:
+    out, i = [], 0
+    for f in features:
+        n = f.feature.shape[0]
+        out.append(dataclasses.replace(f, feature=arr[i:i + n]))
+        i += n
+    return out
+
+
+def _check_disjoint(refs, score_norm_refs):
+    if {f.video_id for f in refs}.intersection({f.video_id for f in score_norm_refs}):
+        raise Exception(
+            "Normalizing on the dataset we're evaluating on is against VSC rules. "
+            "An independent dataset is needed."
+        )
+
+
+def score_normalize(queries, refs, score_norm_refs, l2_normalize: bool = True, replace_dim: bool = True,
+                    beta: float = 1.0, nk: int = 1, device="cuda"):
+    """score_normalization.py:33-104."""
+    _check_disjoint(refs, score_norm_refs)
+    dev = torch.device(device)
+    q_t, r_t, _ = score_normalize_tensors(_cat(queries, dev), _cat(refs, dev), _cat(score_norm_refs, dev),
+                                          l2_normalize, replace_dim, beta, nk)
+    return _split(queries, q_t.cpu().numpy()), _split(refs, r_t.cpu().numpy())
+
+
+def query_score_normalize(queries, score_norm_refs, video_scores: dict, score_threshold: float = 0.001,
+                          low_var_dim: int = 0, l2_normalize: bool = True, replace_dim: bool = True,
+                          beta: float = 1.0, nk: int = 1, device="cuda"):
+    """score_normalization.py:107-148 (video-score gate: bias = -100 below the threshold, :142-143)."""
+    dev = torch.device(device)
+    gated = np.concatenate([np.full(q.feature.shape[0], video_scores[q.video_id] < score_threshold) for q in queries])
+    q_t, _, _ = score_normalize_tensors(_cat(queries, dev), None, _cat(score_norm_refs, dev), l2_normalize,
+                                        replace_dim, beta, nk, low_var_dim_=low_var_dim,
+                                        gated_rows=torch.from_numpy(gated))
+    return _split(queries, q_t.cpu().numpy())
+
+
+def ref_score_normalize(refs, score_norm_refs, l2_normalize: bool = True, replace_dim: bool = True,
+                        beta: float = 1.0, nk: int = 1, device="cuda"):
+    """score_normalization.py:150-192."""
+    _check_disjoint(refs, score_norm_refs)
+    dev = torch.device(device)
+    lvd = -1
+    if replace_dim:
+        lvd = low_var_dim(_cat(score_norm_refs, dev))
+    r_t = sn_transform(_cat(refs, dev), lvd, l2_normalize, fill=1.0)
+    return _split(refs, r_t.cpu().numpy())
