@@ -145,3 +145,36 @@ def test_full_size_properties(faiss):
     ok, frac = tie_aware_equal(I[sel], D[sel], Io, Do)
     assert ok and frac > 0.995
     assert np.abs(D[sel] - Do).max() < 1e-5
+
+
+def test_simt_and_tensor_core_paths_agree(faiss, monkeypatch):
+    """The exact-fp32 SIMT kernel (VSCB200_FORCE_SIMT=1) and the split-bf16 tcgen05 kernel give the
+    same neighbours and scores to fp32 rounding."""
+    rng = np.random.default_rng(11)
+    xb = rng.standard_normal((5000, 96)).astype(np.float32)
+    xq = rng.standard_normal((130, 96)).astype(np.float32)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("VSCB200_FORCE_SIMT", mode)
+        ix = faiss.IndexFlat(96, faiss.METRIC_INNER_PRODUCT)
+        ix.add(xb)
+        res[mode] = ix.search(xq, 20)
+    (D0, I0), (D1, I1) = res["0"], res["1"]
+    assert np.abs(D0 - D1).max() < 2e-5
+    ok, frac = tie_aware_equal(I0, D0, I1, D1, gap=2e-6)
+    assert ok and frac > 0.999
+
+
+def test_dense_scores_fp32_equivalent(faiss):
+    import torch
+    from vsc22_submission_b200 import search
+    g = torch.Generator(device="cuda").manual_seed(0)
+    unit = lambda n, d: torch.nn.functional.normalize(torch.randn((n, d), generator=g, device="cuda"))
+    for (nq, nr, d) in [(700, 3001, 512), (65, 130, 24)]:
+        Q, R = unit(nq, d), unit(nr, d)
+        ix = search.DeviceIndex(d)
+        ix.add(R)
+        S = ix.scores(Q)
+        ref = Q.double() @ R.double().T
+        assert S.shape == (nq, nr)
+        assert (S.double() - ref).abs().max().item() < 5e-7       # |scores| <= 1

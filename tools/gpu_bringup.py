@@ -10,7 +10,7 @@ import time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-STAGES = ["gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]
+STAGES = ["sim_precision", "gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]
 
 
 def _p(t):
@@ -181,6 +181,61 @@ def stage_index():
         print(f"  range thr {thr:.3f}: total {lims[-1]} vs oracle {lo[-1]}; lims equal {np.array_equal(lims, lo)}; "
               f"ids equal {np.array_equal(Ir, Iro) if len(Ir) == len(Iro) else False}")
         ok &= abs(int(lims[-1]) - int(lo[-1])) <= 2
+    return ok
+
+
+def stage_sim_precision():
+    """fp32-equivalence of the split-bf16 tensor-core scores: error vs a float64 reference."""
+    import numpy as np
+    import torch
+    from vsc22_submission_b200 import search
+    g = torch.Generator(device="cuda").manual_seed(0)
+    unit = lambda n, d: torch.nn.functional.normalize(torch.randn((n, d), generator=g, device="cuda"))
+    ok = True
+    for (nq, nr, d) in [(1000, 5000, 512), (300, 3000, 64), (256, 2048, 2048)]:
+        Q, R = unit(nq, d), unit(nr, d)
+        ix = search.DeviceIndex(d)
+        ix.add(R)
+        S = ix.scores(Q)
+        ref = Q.double() @ R.double().T
+        sgemm = (Q @ R.T)
+        err = (S.double() - ref)
+        err32 = (sgemm.double() - ref)
+        print(f"  scores nq{nq} nr{nr} d{d}: tc max|err| {err.abs().max().item():.3e} mean signed {err.mean().item():+.3e} "
+              f"rms {err.pow(2).mean().sqrt().item():.3e} | torch fp32 matmul max {err32.abs().max().item():.3e} "
+              f"rms {err32.pow(2).mean().sqrt().item():.3e} | corr(err, ref) {torch.corrcoef(torch.stack([err.flatten(), ref.flatten()]))[0,1].item():+.3f}")
+        ok &= err.abs().max().item() < 1e-6
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            S = ix.scores(Q)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"     scores kernel path: {e0.elapsed_time(e1) / 5:.3f} ms")
+    Q, R = unit(10000, 512), unit(40000, 512)
+    ix = search.DeviceIndex(512)
+    ix.add(R)
+    for k in (10, 1):
+        ix.search(Q, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            D, I = ix.search(Q, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"  search 10k x 40k x 512 k={k}: {ms:.3f} ms  {1e4 * 4e4 / ms / 1e6:.1f} Gpairs/s")
+    D, I = ix.search(Q[:40], 10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        D, I = ix.search(Q[:40], 10)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"  streaming 40 x 40k x 512 k=10: {ms:.3f} ms -> bank stream {4e4 * 2048 / ms / 1e6:.1f} GB/s")
     return ok
 
 

@@ -3,7 +3,8 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, 4-stage ring)
 //   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-11  epilogue       (tcgen05.ld -> bias / QuickGELU / GELU / residual -> 128-bit global stores)
+//   warps 4-11  epilogue       (tcgen05.ld -> smem transpose -> bias / QuickGELU / GELU / residual ->
+//                               coalesced 128-bit global accesses, 4 full 128 B row segments per instruction)
 //
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
 // static persistent tile schedule (tile = blockIdx.x + i*gridDim.x, N-blocks fastest so that
@@ -45,7 +46,9 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 256 /*barriers*/ + 1024 /*align slack*/;
+  static constexpr int kStageBytes = kEpiWarps * 32 * 32 * 4;   // per-warp epilogue transpose tiles
+  static constexpr int kSmemBytes =
+      kStages * (kABytes + kBBytes) + 256 /*barriers*/ + kStageBytes + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -69,6 +72,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float4* stage_all = reinterpret_cast<float4*>(smem + kStages * (Cfg::kABytes + Cfg::kBBytes) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,6 +148,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;           // column half of the tile
+    float4* stage = stage_all + ew * 256;   // 32 rows x 8 float4
     constexpr int kChunks = BN / 2 / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -151,8 +156,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * kBM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int64_t row_base = static_cast<int64_t>(m_blk) * kBM + quad * 32;
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = half * (BN / 2) + c * 32;
@@ -162,63 +166,49 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, v);
         tmem_ld_wait();
         if (gcol >= p.N) continue;   // warp-uniform
-        float f[32];
+        // Transpose through this warp's 4 KB staging tile so that every global access of the warp
+        // covers whole 128-byte row segments (row-per-thread TMEM layout -> 4 rows x 128 B per
+        // instruction).  16-byte chunks are XOR-swizzled by the row: conflict-free both ways.
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+        for (int q = 0; q < 8; ++q)
+          stage[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                           __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        const int q = lane & 7;
+        const int gc = gcol + q * 4;
+        const bool col_ok = gc < p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (gcol + j < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int64_t grow = row_base + r;
+          float4 o = stage[r * 8 + (q ^ (r & 7))];
+          o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+          if (p.act >= 0) {
+            o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+            o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
           }
-        }
-        if (p.act >= 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-        }
-        if (!row_ok) {
-          // nothing to store for rows past M (TMA zero-filled them)
-        } else if (p.epilogue == VSCB200_EPI_BF16) {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + gcol;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (gcol + j < p.N) {
-              uint4 o;
-              o.x = pack_bf16x2(f[j], f[j + 1]);
-              o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(out + j) = o;
-            }
-          }
-        } else if (p.epilogue == VSCB_EPI_PATCH_F32) {
-          const int64_t orow = row + row / p.patch_P + 1;
-          float* out = reinterpret_cast<float*>(p.C) + orow * p.ldc + gcol;
-          const float* pe = p.pos + (row % p.patch_P + 1) * p.N + gcol;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (gcol + j < p.N) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(pe + j));
-              *reinterpret_cast<float4*>(out + j) = make_float4(f[j] + q.x, f[j + 1] + q.y, f[j + 2] + q.z, f[j + 3] + q.w);
-            }
-          }
-        } else {
-          float* out = reinterpret_cast<float*>(p.C) + row * p.ldc + gcol;
-          const bool residual = p.epilogue == VSCB200_EPI_RESIDUAL_F32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (gcol + j < p.N) {
-              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if (residual) {
-                const float4 r = *reinterpret_cast<const float4*>(out + j);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          if (grow < p.M && col_ok) {
+            if (p.epilogue == VSCB200_EPI_BF16) {
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + grow * p.ldc + gc) =
+                  make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+            } else if (p.epilogue == VSCB_EPI_PATCH_F32) {
+              const int64_t orow = grow + grow / p.patch_P + 1;
+              const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (grow % p.patch_P + 1) * p.N + gc));
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + gc) =
+                  make_float4(o.x + pe.x, o.y + pe.y, o.z + pe.z, o.w + pe.w);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + grow * p.ldc + gc);
+              if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) {
+                const float4 rr = *dst;
+                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
               }
-              *reinterpret_cast<float4*>(out + j) = o;
+              *dst = o;
             }
           }
         }
+        __syncwarp();                 // the staging tile is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();

@@ -14,10 +14,10 @@
 using namespace vscb200;
 
 namespace vscb200 {
-// sim_tc.cu: fp32-equivalent tensor-core scoring (split-bf16 tcgen05); returns VSCB200_OK and sets
-// *handled = false when the shape is not supported.
-int scores_tc(const float* Q, const float* R, float* S, int64_t nq, int64_t nr, int d, int64_t ldS, bool l2,
-              const float* qn, const float* rn, cudaStream_t stream, bool* handled);
+// sim_tc.cu: fp32-equivalent tensor-core scoring (split-bf16 tcgen05) on pre-split operand planes
+int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, cudaStream_t stream);
+int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
+                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream);
 }  // namespace vscb200
 
 struct vscb200_index {
@@ -26,6 +26,10 @@ struct vscb200_index {
   int64_t capacity = 0;
   float* bank = nullptr;     // [capacity, d]
   float* rnorm = nullptr;    // [capacity] squared norms (L2 metric only)
+  int dp = 0;                // d rounded up to 8: row length of the bf16 operand planes
+  uint16_t* bank_hi = nullptr;   // [capacity, dp] bf16(x)
+  uint16_t* bank_lo = nullptr;   // [capacity, dp] bf16(x - hi)
+  uint16_t* q_planes = nullptr; size_t q_planes_bytes = 0;   // hi | lo planes of the current query block
   std::vector<float> pending;   // host rows appended by add_host, uploaded lazily in one copy
   int64_t id_offset = 0;
   float* ws = nullptr;       // score workspace
@@ -89,11 +93,26 @@ int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
       VSCB_CUDA_OK(cudaMemcpyAsync(nn, ix->rnorm, static_cast<size_t>(ix->ntotal) * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
   }
+  uint16_t *nh = nullptr, *nl = nullptr;
+  if (!ix->force_simt) {
+    const size_t pb = static_cast<size_t>(cap) * ix->dp * sizeof(uint16_t);
+    VSCB_CUDA_OK(cudaMalloc(&nh, pb));
+    VSCB_CUDA_OK(cudaMalloc(&nl, pb));
+    if (ix->ntotal) {
+      const size_t ob = static_cast<size_t>(ix->ntotal) * ix->dp * sizeof(uint16_t);
+      VSCB_CUDA_OK(cudaMemcpyAsync(nh, ix->bank_hi, ob, cudaMemcpyDeviceToDevice, s));
+      VSCB_CUDA_OK(cudaMemcpyAsync(nl, ix->bank_lo, ob, cudaMemcpyDeviceToDevice, s));
+    }
+  }
   VSCB_CUDA_OK(cudaStreamSynchronize(s));
   if (ix->bank) cudaFree(ix->bank);
   if (ix->rnorm) cudaFree(ix->rnorm);
+  if (ix->bank_hi) cudaFree(ix->bank_hi);
+  if (ix->bank_lo) cudaFree(ix->bank_lo);
   ix->bank = nb;
   ix->rnorm = nn;
+  ix->bank_hi = nh;
+  ix->bank_lo = nl;
   ix->capacity = cap;
   return VSCB200_OK;
 }
@@ -106,6 +125,10 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
   VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
   if (ix->metric == VSCB200_METRIC_L2) {
     rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);
+    if (rc) return rc;
+  }
+  if (!ix->force_simt) {
+    rc = split_planes(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->bank_lo + ix->ntotal * ix->dp, n, ix->d, ix->dp, s);
     if (rc) return rc;
   }
   ix->ntotal += n;
@@ -142,10 +165,12 @@ int score_block(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t
     qn = ix->qnorm;
   }
   if (!ix->force_simt) {
-    bool handled = false;
-    int rc = scores_tc(q, ix->bank, S, nq, ix->ntotal, ix->d, ldS, l2, qn, ix->rnorm, s, &handled);
+    const size_t plane = static_cast<size_t>(nq) * ix->dp;
+    int rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t));
     if (rc) return rc;
-    if (handled) return VSCB200_OK;
+    if ((rc = split_planes(q, ix->q_planes, ix->q_planes + plane, nq, ix->d, ix->dp, s))) return rc;
+    return scores_tc_planes(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, S, nq, ix->ntotal, ix->dp,
+                            ldS, l2, qn, ix->rnorm, s);
   }
   return scores_simt(q, ix->bank, S, nq, ix->ntotal, ix->d, ldS, l2, qn, ix->rnorm, s);
 }
@@ -167,6 +192,7 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
                "index_create: metric must be METRIC_INNER_PRODUCT or METRIC_L2");
   vscb200_index* ix = new vscb200_index();
   ix->d = d;
+  ix->dp = (d + 7) & ~7;
   ix->metric = metric;
   const char* e = getenv("VSCB200_FORCE_SIMT");
   ix->force_simt = (e && atoi(e)) ? 1 : 0;
@@ -178,6 +204,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   if (!ix) return;
   cudaFree(ix->bank); cudaFree(ix->rnorm); cudaFree(ix->ws); cudaFree(ix->q_stage); cudaFree(ix->D_stage);
   cudaFree(ix->I_stage); cudaFree(ix->qnorm); cudaFree(ix->counts);
+  cudaFree(ix->bank_hi); cudaFree(ix->bank_lo); cudaFree(ix->q_planes);
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
 }

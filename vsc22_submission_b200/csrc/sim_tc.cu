@@ -1,12 +1,263 @@
-// Tensor-core similarity scoring (fp32-equivalent split-bf16 tcgen05 path).  Placeholder: reports
-// "not handled" so that index.cu uses the exact SIMT kernel until this path lands.
+// Tensor-core similarity scoring, fp32-equivalent: S[nq, nr] = Q . R^T on tcgen05 with a 2-way bf16
+// split of both operands (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)) and three MMAs per K step:
+//     S = Qh.Rh + Ql.Rh + Qh.Rl        (the dropped lo.lo term is <= 2^-18 |q.r| per product)
+// accumulated in fp32 in TMEM.  The K loop is cut into kSeg independent accumulator segments that are
+// summed in the epilogue, which shortens every tensor-core accumulation chain (fewer roundings of the
+// running sum).  Operand planes are produced once per bank row at add() time and once per query block;
+// hi+lo is 4 bytes per element, i.e. the HBM traffic of the fp32 bank.
+//
+// Same pipeline skeleton as gemm.cu: TMA producer warp / single-thread MMA issuer / TMEM allocator /
+// 8 epilogue warps, 3-stage smem ring of {Qh, Ql, Rh, Rl} 128x64 tiles (64 KB per stage), persistent
+// over 128x128 output tiles.  Epilogue: segment sum -> optional squared-L2 transform -> coalesced fp32
+// stores of the dense score block (consumed by select.cu: top-k, range search, dense sim matrices).
+//
+// Reference: faiss IndexFlat scoring (cuBLAS SGEMM on GPU / sgemm on CPU) behind vsc/index.py:174,
+// vsc/exhaustive_search.py:62,74, vsc/baseline/score_normalization.py:95.
 #include "host_util.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace vscb200 {
-int scores_tc(const float*, const float*, float*, int64_t, int64_t, int, int64_t, bool, const float*, const float*,
-              cudaStream_t, bool* handled) {
-  *handled = false;
+
+constexpr int kTM = 128, kTN = 128, kTK = 64;
+constexpr int kTStages = 3;
+constexpr int kTSeg = 2;
+constexpr int kTEpiWarps = 8;
+constexpr int kTThreads = 128 + 32 * kTEpiWarps;
+constexpr int kTTile = kTM * kTK * 2;                 // one 128x64 bf16 tile: 16 KB
+constexpr int kTStageBytes = 4 * kTTile;              // Qh, Ql, Rh, Rl
+constexpr int kTTmemCols = 2 * kTSeg * kTN;           // 2 buffers x kSeg segments x 128 columns = 512
+constexpr int kTSmem = kTStages * kTStageBytes + 256 + kTEpiWarps * 4096 + 1024;
+
+struct SimParams {
+  float* S;
+  int64_t ldS;
+  int64_t nq, nr;
+  int K;            // padded feature dim (multiple of 8)
+  int l2;
+  int vec4;         // S rows are 16-byte aligned (ldS % 4 == 0): 128-bit stores
+  const float* qn;
+  const float* rn;
+  int tiles_m, tiles_n;
+};
+
+__global__ void __launch_bounds__(kTThreads, 1)
+sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
+            const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl, SimParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTStages * kTStageBytes);
+  uint64_t* empty_bar = full_bar + kTStages;
+  uint64_t* tfull_bar = empty_bar + kTStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float4* stage_all = reinterpret_cast<float4*>(smem + kTStages * kTStageBytes + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQh); prefetch_tmap(&tmQl); prefetch_tmap(&tmRh); prefetch_tmap(&tmRl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kTEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kblocks = (p.K + kTK - 1) / kTK;
+  const int nseg = kblocks < kTSeg ? kblocks : kTSeg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kTStageBytes);
+          uint8_t* st = smem + stage * kTStageBytes;
+          tma_load_2d(st, &tmQh, &full_bar[stage], kb * kTK, m_blk * kTM, kEvictLast);
+          tma_load_2d(st + kTTile, &tmQl, &full_bar[stage], kb * kTK, m_blk * kTM, kEvictLast);
+          tma_load_2d(st + 2 * kTTile, &tmRh, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
+          tma_load_2d(st + 3 * kTTile, &tmRl, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
+          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kTM, kTN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        int seg = 0, seg_end = kblocks / nseg;        // segment s covers [s*kblocks/nseg, (s+1)*kblocks/nseg)
+        bool fresh = true;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          if (kb == seg_end) {
+            ++seg;
+            seg_end = (seg + 1) * kblocks / nseg;
+            fresh = true;
+          }
+          const uint32_t d_tmem = tmem_base + (acc * kTSeg + seg) * kTN;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * kTStageBytes);
+          const uint64_t qh = make_desc_k_sw128(st), ql = make_desc_k_sw128(st + kTTile);
+          const uint64_t rh = make_desc_k_sw128(st + 2 * kTTile), rl = make_desc_k_sw128(st + 3 * kTTile);
+#pragma unroll
+          for (int k = 0; k < kTK / 16; ++k) {
+            umma_bf16_ss(d_tmem, qh + 2 * k, rh + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
+            umma_bf16_ss(d_tmem, ql + 2 * k, rh + 2 * k, idesc, 1u);
+            umma_bf16_ss(d_tmem, qh + 2 * k, rl + 2 * k, idesc, 1u);
+          }
+          fresh = false;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4, quad = warp & 3, half = ew >> 2;
+    float4* stage = stage_all + ew * 256;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row_base = static_cast<int64_t>(m_blk) * kTM + quad * 32;
+#pragma unroll 1
+      for (int c = 0; c < kTN / 2 / 32; ++c) {
+        const int col0 = half * (kTN / 2) + c * 32;
+        const int64_t gcol = static_cast<int64_t>(n_blk) * kTN + col0;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kTSeg * kTN + col0;
+        uint32_t v[32];
+        float f[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (nseg > 1) {
+          tmem_ld_32x32(taddr + kTN, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
+        }
+        if (gcol >= p.nr) continue;   // warp-uniform
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        __syncwarp();
+        const int q = lane & 7;
+        const int64_t gc = gcol + q * 4;
+        float4 rn4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.l2) {
+          rn4.x = gc < p.nr ? p.rn[gc] : 0.f;
+          rn4.y = gc + 1 < p.nr ? p.rn[gc + 1] : 0.f;
+          rn4.z = gc + 2 < p.nr ? p.rn[gc + 2] : 0.f;
+          rn4.w = gc + 3 < p.nr ? p.rn[gc + 3] : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int64_t grow = row_base + r;
+          float4 o = stage[r * 8 + (q ^ (r & 7))];
+          if (grow < p.nq && gc < p.nr) {
+            if (p.l2) {
+              const float qn = p.qn[grow];
+              o.x = fmaxf(qn + rn4.x - 2.0f * o.x, 0.f);
+              o.y = fmaxf(qn + rn4.y - 2.0f * o.y, 0.f);
+              o.z = fmaxf(qn + rn4.z - 2.0f * o.z, 0.f);
+              o.w = fmaxf(qn + rn4.w - 2.0f * o.w, 0.f);
+            }
+            float* dst = p.S + grow * p.ldS + gc;
+            if (p.vec4 && gc + 3 < p.nr) {
+              *reinterpret_cast<float4*>(dst) = o;          // ldS % 4 == 0 and gc % 4 == 0: 16-byte aligned
+            } else {
+              dst[0] = o.x;
+              if (gc + 1 < p.nr) dst[1] = o.y;
+              if (gc + 2 < p.nr) dst[2] = o.z;
+              if (gc + 3 < p.nr) dst[3] = o.w;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<kTTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------ operand planes
+// x [n, d] fp32 -> hi, lo [n, dp] bf16 (dp = d rounded up to 8, zero padded)
+__global__ void split_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int64_t n, int d, int dp) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * dp) return;
+  const int64_t r = i / dp;
+  const int c = static_cast<int>(i % dp);
+  const float v = c < d ? x[r * d + c] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, cudaStream_t stream) {
+  const int64_t total = n * dp;
+  if (total == 0) return VSCB200_OK;
+  split_planes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), n, d, dp);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
+
+int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
+                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream) {
+  if (nq == 0 || nr == 0) return VSCB200_OK;
+  VSCB_REQUIRE(dp % 8 == 0, "scores_tc: dp must be a multiple of 8");
+  CUtensorMap tQh, tQl, tRh, tRl;
+  int rc;
+  if ((rc = make_tmap_2d(&tQh, Qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nq, dp, dp, kTM, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tQl, Ql, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nq, dp, dp, kTM, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRh, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nr, dp, dp, kTN, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRl, Rl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nr, dp, dp, kTN, kTK, true))) return rc;
+  SimParams p;
+  p.S = S; p.ldS = ldS; p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0;
+  p.vec4 = (ldS % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) ? 1 : 0;
+  p.qn = qn; p.rn = rn;
+  p.tiles_m = static_cast<int>((nq + kTM - 1) / kTM);
+  const int64_t tn = (nr + kTN - 1) / kTN;
+  VSCB_REQUIRE(static_cast<int64_t>(p.tiles_m) * tn < (1ll << 31), "scores_tc: too many tiles");
+  p.tiles_n = static_cast<int>(tn);
+  VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+  const int64_t num_tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  const int grid = static_cast<int>(num_tiles < device_sm_count() ? num_tiles : device_sm_count());
+  ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * dp);
+  sim3_kernel<<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
 }  // namespace vscb200
