@@ -13,6 +13,8 @@
 // This is the dense-projection engine of the ViT encoder (reference: every nn.Linear /
 // nn.MultiheadAttention projection of D/train/train_vid_score/video/clip.py:33-39,45-49 and the
 // conv patch-embed :105,143 as an im2row GEMM), replacing the cuBLAS calls of torch 1.11.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -57,7 +59,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN>
+// kCluster == 2: CTA pairs along M share every W tile -- each CTA fetches half of it (BN/2 rows) and
+// TMA-multicasts it into both CTAs' shared memory, halving the L2->SM operand traffic per CTA
+// (A 16 KB + W/2 16 KB per 64-wide K block instead of 48 KB).  A stage is released to both producers by a
+// multicast tcgen05.commit, so the pair advances through the K loop in lockstep.
+template <int BN, int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -84,7 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kCluster);   // one tcgen05.commit per CTA of the pair
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -95,23 +101,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();    // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // Tile schedule.  kCluster == 1: tile = blockIdx.x + i*gridDim.x.  kCluster == 2: the pair walks
+  // "pair tiles" (two consecutive M blocks x one N block); rank r takes M block 2*pm + r.
+  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+  const int sched_m = kCluster > 1 ? (p.tiles_m + 1) / 2 : p.tiles_m;
+  const int num_tiles = sched_m * p.tiles_n;
+  const int sched_first = kCluster > 1 ? static_cast<int>(blockIdx.x / kCluster) : static_cast<int>(blockIdx.x);
+  const int sched_step = kCluster > 1 ? static_cast<int>(gridDim.x / kCluster) : static_cast<int>(gridDim.x);
   const int kblocks = (p.K + kBK - 1) / kBK;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
+        const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
           tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
+          if (kCluster > 1) {
+            constexpr int kHalf = Cfg::kBBytes / 2;      // BN/2 rows of the W tile, multicast to both CTAs
+            tma_load_2d_mcast(sB + stage * Cfg::kBBytes + crank * kHalf, &tmB, &full_bar[stage], kb * kBK,
+                              n_blk * BN + static_cast<int>(crank) * (BN / 2), static_cast<uint16_t>(0x3), kEvictLast);
+          } else {
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -123,7 +142,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -137,7 +156,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // +32 bytes per K=16 step inside the 128B swizzle row: +2 in the (addr>>4) field
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
@@ -152,8 +172,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kChunks = BN / 2 / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+    for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
+      const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int64_t row_base = static_cast<int64_t>(m_blk) * kBM + quad * 32;
@@ -219,18 +239,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();    // no CTA exits while its peer may still multicast into it
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN>
+template <int BN, int kCluster>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  const int grid = num_tiles < device_sm_count() ? num_tiles : device_sm_count();
+  const int sched_tiles = ((p.tiles_m + kCluster - 1) / kCluster) * p.tiles_n;     // (pair) tiles
+  const int max_groups = device_sm_count() / kCluster;
+  const int groups = sched_tiles < max_groups ? sched_tiles : max_groups;
   ProfScope prof(kProfGemm, stream, 2.0 * static_cast<double>(p.M) * p.N * p.K);
-  gemm_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * kCluster);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster>, tmA, tmB, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -247,17 +281,25 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
   VSCB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue");
   VSCB_REQUIRE(epilogue != VSCB_EPI_PATCH_F32 || (pos != nullptr && patch_P > 0), "gemm: patch epilogue needs pos/P");
   const int BN = (N >= 256 || N > 128) ? 256 : 128;
+  const int tiles_m_all = static_cast<int>((M + kBM - 1) / kBM);
+  static const int force_cluster = [] { const char* e = getenv("VSCB200_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
+  const int tiles_n_all = (N + BN - 1) / BN;
+  const bool pair = force_cluster ? (force_cluster == 2 && tiles_m_all >= 2)
+                                  : (BN == 256 && tiles_m_all >= 2 &&
+                                     static_cast<int64_t>(tiles_m_all) * tiles_n_all >= 2 * device_sm_count());
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, kBM, kBK, true);
   if (rc) return rc;
-  rc = make_tmap_2d(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, BN, kBK, true);
+  // in pair mode each CTA's TMA box is its half of the W tile (BN/2 rows)
+  rc = make_tmap_2d(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, pair ? BN / 2 : BN, kBK, true);
   if (rc) return rc;
   GemmParams p;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epilogue = epilogue; p.act = act;
   p.pos = pos; p.patch_P = patch_P;
   p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
   p.tiles_n = (N + BN - 1) / BN;
-  return BN == 256 ? launch_gemm<256>(tmA, tmB, p, stream) : launch_gemm<128>(tmA, tmB, p, stream);
+  if (pair) return BN == 256 ? launch_gemm<256, 2>(tmA, tmB, p, stream) : launch_gemm<128, 2>(tmA, tmB, p, stream);
+  return BN == 256 ? launch_gemm<256, 1>(tmA, tmB, p, stream) : launch_gemm<128, 1>(tmA, tmB, p, stream);
 }
 
 }  // namespace vscb200

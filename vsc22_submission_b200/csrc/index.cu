@@ -40,6 +40,8 @@ struct vscb200_index {
   int64_t* I_stage = nullptr; size_t I_stage_bytes = 0;
   float* qnorm = nullptr; size_t qnorm_bytes = 0;
   unsigned long long* counts = nullptr; size_t counts_bytes = 0;
+  float* Dtmp = nullptr; size_t Dtmp_bytes = 0;       // survivors of the tensor-core pass (k + slack per row)
+  int64_t* Itmp = nullptr; size_t Itmp_bytes = 0;
   cudaStream_t own_stream = nullptr;
   int force_simt = 0;
 };
@@ -87,7 +89,7 @@ int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
                                  cudaMemcpyDeviceToDevice, s));
   }
   float* nn = nullptr;
-  if (ix->metric == VSCB200_METRIC_L2) {
+  {
     VSCB_CUDA_OK(cudaMalloc(&nn, static_cast<size_t>(cap) * sizeof(float)));
     if (ix->ntotal)
       VSCB_CUDA_OK(cudaMemcpyAsync(nn, ix->rnorm, static_cast<size_t>(ix->ntotal) * sizeof(float),
@@ -123,10 +125,8 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
   if (rc) return rc;
   float* dst = ix->bank + ix->ntotal * ix->d;
   VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
-  if (ix->metric == VSCB200_METRIC_L2) {
-    rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);
-    if (rc) return rc;
-  }
+  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);   // L2 transform + range-search error margins
+  if (rc) return rc;
   if (!ix->force_simt) {
     rc = split_planes(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->bank_lo + ix->ntotal * ix->dp, n, ix->d, ix->dp, s);
     if (rc) return rc;
@@ -157,7 +157,7 @@ int64_t block_rows(const vscb200_index* ix, int64_t nq) {
 int score_block(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t ldS, cudaStream_t s) {
   const bool l2 = ix->metric == VSCB200_METRIC_L2;
   const float* qn = nullptr;
-  if (l2) {
+  {
     int rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float));
     if (rc) return rc;
     rc = row_sqnorm(q, nq, ix->d, ix->qnorm, s);
@@ -204,7 +204,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   if (!ix) return;
   cudaFree(ix->bank); cudaFree(ix->rnorm); cudaFree(ix->ws); cudaFree(ix->q_stage); cudaFree(ix->D_stage);
   cudaFree(ix->I_stage); cudaFree(ix->qnorm); cudaFree(ix->counts);
-  cudaFree(ix->bank_hi); cudaFree(ix->bank_lo); cudaFree(ix->q_planes);
+  cudaFree(ix->bank_hi); cudaFree(ix->bank_lo); cudaFree(ix->q_planes); cudaFree(ix->Dtmp); cudaFree(ix->Itmp);
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
 }
@@ -257,14 +257,28 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   const int64_t ldS = (ix->ntotal + 3) & ~3ll;
   rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float));
   if (rc) return rc;
+  // Tensor-core scores are fp32-equivalent to ~1e-6: keep k + slack survivors, rescore them exactly.
+  const int kRescoreSlack = 8;
+  const bool rescore = !ix->force_simt && ix->ntotal > 0;
+  const int kin = rescore ? static_cast<int>(std::min<int64_t>(std::min<int64_t>(ix->ntotal, 2048), k + kRescoreSlack)) : k;
+  if (rescore) {
+    if ((rc = grow(&ix->Dtmp, &ix->Dtmp_bytes, static_cast<size_t>(blk) * kin * sizeof(float)))) return rc;
+    if ((rc = grow(&ix->Itmp, &ix->Itmp_bytes, static_cast<size_t>(blk) * kin * sizeof(int64_t)))) return rc;
+  }
   for (int64_t q0 = 0; q0 < nq; q0 += blk) {
     const int64_t nb = std::min(blk, nq - q0);
     if (ix->ntotal > 0) {
       rc = score_block(ix, q + q0 * ix->d, nb, ix->ws, ldS, s);
       if (rc) return rc;
     }
-    rc = topk_rows(ix->ws, ldS, nb, ix->ntotal, k, keep_max, D + q0 * k, I + q0 * k, ix->id_offset, s);
-    if (rc) return rc;
+    if (rescore) {
+      if ((rc = topk_rows(ix->ws, ldS, nb, ix->ntotal, kin, keep_max, ix->Dtmp, ix->Itmp, 0, s))) return rc;
+      if ((rc = rescore_sort(q + q0 * ix->d, ix->bank, ix->d, !keep_max, ix->Itmp, kin, nb, k, D + q0 * k, I + q0 * k,
+                             ix->id_offset, s))) return rc;
+    } else {
+      rc = topk_rows(ix->ws, ldS, nb, ix->ntotal, k, keep_max, D + q0 * k, I + q0 * k, ix->id_offset, s);
+      if (rc) return rc;
+    }
   }
   return VSCB200_OK;
 }
@@ -337,7 +351,10 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
     if (cudaMemcpyAsync(ix->q_stage, q_host + q0 * ix->d, static_cast<size_t>(nb) * ix->d * sizeof(float),
                         cudaMemcpyHostToDevice, s) != cudaSuccess) { set_last_error("range_search: H2D failed"); return fail(VSCB200_ERR_CUDA); }
     if (ix->ntotal > 0 && (rc = score_block(ix, ix->q_stage, nb, ix->ws, ldS, s))) return fail(rc);
-    if ((rc = range_count(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, s))) return fail(rc);
+    const bool exact = !ix->force_simt && ix->ntotal > 0;
+    const float* Qx = exact ? ix->q_stage : nullptr;
+    if ((rc = range_count(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, s, Qx, ix->bank, ix->d, ix->qnorm,
+                          ix->rnorm))) return fail(rc);
     if (cudaMemcpyAsync(cnt.data(), ix->counts, static_cast<size_t>(nb) * sizeof(unsigned long long),
                         cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) { set_last_error(std::string("range_search: count failed: ") + cudaGetErrorString(cudaGetLastError())); return fail(VSCB200_ERR_CUDA); }
@@ -361,7 +378,8 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
     if ((rc = grow(&Id, &Id_bytes, blk_total * sizeof(int64_t)))) return fail(rc);
     if (cudaMemcpyAsync(ix->counts, cnt.data(), static_cast<size_t>(nb) * sizeof(unsigned long long),
                         cudaMemcpyHostToDevice, s) != cudaSuccess) { set_last_error("range_search: H2D offsets failed"); return fail(VSCB200_ERR_CUDA); }
-    if ((rc = range_fill(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, Dd, Id, ix->id_offset, s))) return fail(rc);
+    if ((rc = range_fill(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, Dd, Id, ix->id_offset, s, Qx, ix->bank,
+                         ix->d, ix->qnorm, ix->rnorm))) return fail(rc);
     if (cudaMemcpyAsync(Dh + total, Dd, blk_total * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaMemcpyAsync(Ih + total, Id, blk_total * sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) { set_last_error(std::string("range_search: fill failed: ") + cudaGetErrorString(cudaGetLastError())); return fail(VSCB200_ERR_CUDA); }

@@ -29,8 +29,13 @@ int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normaliz
                  float* out, cudaStream_t stream);
 int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
               int64_t id_offset, cudaStream_t stream);
+int rescore_sort(const float* Q, const float* bank, int d, bool l2, const int64_t* Iin, int kin, int64_t nq, int k,
+                 float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
+// Q != nullptr: S holds tensor-core scores; borderline pairs and reported distances are recomputed in fp32
 int range_count(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
-                unsigned long long* counts, cudaStream_t stream);
+                unsigned long long* counts, cudaStream_t stream, const float* Q, const float* bank, int d,
+                const float* qn, const float* rn);
 int range_fill(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
-               const unsigned long long* offsets, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
+               const unsigned long long* offsets, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream,
+               const float* Q, const float* bank, int d, const float* qn, const float* rn);
 }  // namespace vscb200

@@ -141,18 +141,136 @@ int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool ke
   return VSCB200_OK;
 }
 
+// ------------------------------------------------------------------ exact rescoring of the survivors
+// The tensor-core score block is fp32-equivalent only to ~1e-6 (2-way bf16 split).  search() therefore
+// selects k' = k + kRescoreSlack survivors per row on those scores, recomputes their scores here in plain
+// fp32 from the original fp32 descriptors (the arithmetic faiss IndexFlat performs), re-sorts and keeps k:
+// reported scores are fp32 dot products and the order can only differ from an fp32 brute force where two
+// scores agree to fp32 rounding.
+constexpr int kRescoreThreads = 128;
+
+__global__ void __launch_bounds__(kRescoreThreads)
+rescore_sort_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2,
+                    const int64_t* __restrict__ Iin, int kin, int kpad, int k, float* __restrict__ D,
+                    int64_t* __restrict__ I, int64_t id_offset) {
+  extern __shared__ unsigned long long rs_smem[];        // [kpad] composite keys, then [d] floats
+  unsigned long long* cand = rs_smem;
+  float* sq = reinterpret_cast<float*>(rs_smem + kpad);
+  float* sval = sq + d;                                   // [kin] exact scores
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row = blockIdx.x;
+  const bool keep_max = !l2;
+  for (int c = tid; c < d; c += kRescoreThreads) sq[c] = Q[row * d + c];
+  for (int i = tid; i < kpad; i += kRescoreThreads) cand[i] = 0ull;
+  __syncthreads();
+  for (int c = warp; c < kin; c += kRescoreThreads / 32) {
+    const int64_t id = Iin[row * kin + c];
+    if (id < 0) continue;                                  // padding (k > ntotal)
+    const float* r = bank + id * d;
+    float acc = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      if (l2) {
+        const float df = sq[j] - r[j];
+        acc = fmaf(df, df, acc);
+      } else {
+        acc = fmaf(sq[j], r[j], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      sval[c] = acc;
+      // key 0 is reserved for empty slots: okey() of a finite float is never 0
+      cand[c] = (static_cast<unsigned long long>(okey(acc, keep_max)) << 32) |
+                static_cast<uint32_t>(~static_cast<uint32_t>(id));
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (kpad >> 1); i += kRescoreThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = cand[lo], b = cand[hi];
+        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += kRescoreThreads) {
+    const unsigned long long c = cand[j];
+    if (c != 0ull) {
+      const uint32_t key = static_cast<uint32_t>(c >> 32);
+      const uint32_t ok = keep_max ? key : ~key;
+      const uint32_t u = (ok & 0x80000000u) ? (ok ^ 0x80000000u) : ~ok;     // inverse of okey()
+      D[row * k + j] = __uint_as_float(u);
+      I[row * k + j] = id_offset + static_cast<int64_t>(~static_cast<uint32_t>(c & 0xFFFFFFFFull));
+    } else {
+      D[row * k + j] = keep_max ? -FLT_MAX : FLT_MAX;
+      I[row * k + j] = -1;
+    }
+  }
+}
+
+int rescore_sort(const float* Q, const float* bank, int d, bool l2, const int64_t* Iin, int kin, int64_t nq, int k,
+                 float* D, int64_t* I, int64_t id_offset, cudaStream_t stream) {
+  if (nq == 0) return VSCB200_OK;
+  int kpad = 2;
+  while (kpad < kin) kpad <<= 1;
+  const size_t smem = kpad * sizeof(unsigned long long) + (static_cast<size_t>(d) + kin) * sizeof(float);
+  VSCB_REQUIRE(smem <= 200 * 1024, "rescore: descriptor dimension too large");
+  VSCB_CUDA_OK(cudaFuncSetAttribute(rescore_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * kin * d * 4);
+  rescore_sort_kernel<<<static_cast<unsigned>(nq), kRescoreThreads, smem, stream>>>(Q, bank, d, l2 ? 1 : 0, Iin, kin, kpad, k,
+                                                                                    D, I, id_offset);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
 // ------------------------------------------------------------------ range search
+// S holds tensor-core scores (fp32-equivalent to ~1e-6 relative to |q||r|).  Pairs whose score lies
+// within that error of the threshold are decided on an exact fp32 recomputation, and every reported
+// distance is the exact fp32 value, so the CSR result equals an fp32 brute force.  `exact == 0`
+// (S already exact, SIMT path) skips both.
 constexpr int kRangeThreads = 256;
 
-__global__ void __launch_bounds__(kRangeThreads)
-range_count_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, float thr, int keep_max,
-                   unsigned long long* __restrict__ counts) {
-  const float* row = S + static_cast<int64_t>(blockIdx.x) * ldS;
-  unsigned int c = 0;
-  for (int64_t i = threadIdx.x; i < n; i += kRangeThreads) {
-    const float v = row[i];
-    c += keep_max ? (v > thr) : (v < thr);
+struct RangeArgs {
+  const float* S; int64_t ldS; int64_t n; float thr; int keep_max;
+  int exact; const float* Q; const float* bank; int d; const float* qn; const float* rn;
+};
+
+__device__ __forceinline__ float exact_pair(const float* __restrict__ q, const float* __restrict__ r, int d, bool l2) {
+  float acc = 0.f;
+  for (int j = 0; j < d; ++j) {
+    if (l2) { const float df = q[j] - r[j]; acc = fmaf(df, df, acc); }
+    else acc = fmaf(q[j], r[j], acc);
   }
+  return acc;
+}
+
+__device__ __forceinline__ bool range_hit(const RangeArgs& a, const float* sq, float qn, int64_t i, float v) {
+  if (a.exact) {
+    const float margin = 1.5e-5f * sqrtf(qn * a.rn[i]) * (a.keep_max ? 1.f : 2.f);
+    if (fabsf(v - a.thr) <= margin) v = exact_pair(sq, a.bank + i * a.d, a.d, !a.keep_max);
+  }
+  return a.keep_max ? (v > a.thr) : (v < a.thr);
+}
+
+__global__ void __launch_bounds__(kRangeThreads)
+range_count_kernel(RangeArgs a, unsigned long long* __restrict__ counts) {
+  extern __shared__ float rg_q[];
+  const int64_t row_id = blockIdx.x;
+  const float* row = a.S + row_id * a.ldS;
+  float qn = 0.f;
+  if (a.exact) {
+    for (int c = threadIdx.x; c < a.d; c += kRangeThreads) rg_q[c] = a.Q[row_id * a.d + c];
+    qn = a.qn[row_id];
+    __syncthreads();
+  }
+  unsigned int c = 0;
+  for (int64_t i = threadIdx.x; i < a.n; i += kRangeThreads) c += range_hit(a, rg_q, qn, i, row[i]) ? 1u : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   __shared__ unsigned int wsum[kRangeThreads / 32];
@@ -167,20 +285,28 @@ range_count_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, float th
 
 // offsets[row] = exclusive prefix of counts (element offsets inside this block's output)
 __global__ void __launch_bounds__(kRangeThreads)
-range_fill_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, float thr, int keep_max,
-                  const unsigned long long* __restrict__ offsets, float* __restrict__ D, int64_t* __restrict__ I,
-                  int64_t id_offset) {
+range_fill_kernel(RangeArgs a, const unsigned long long* __restrict__ offsets, float* __restrict__ D,
+                  int64_t* __restrict__ I, int64_t id_offset) {
+  extern __shared__ float rg_q[];
   __shared__ unsigned int wtot[kRangeThreads / 32];
-  const float* row = S + static_cast<int64_t>(blockIdx.x) * ldS;
-  unsigned long long pos = offsets[blockIdx.x];
+  const int64_t row_id = blockIdx.x;
+  const float* row = a.S + row_id * a.ldS;
+  const unsigned long long pos0 = offsets[blockIdx.x];
+  unsigned long long pos = pos0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < n; base += kRangeThreads) {
+  float qn = 0.f;
+  if (a.exact) {
+    for (int c = threadIdx.x; c < a.d; c += kRangeThreads) rg_q[c] = a.Q[row_id * a.d + c];
+    qn = a.qn[row_id];
+    __syncthreads();
+  }
+  for (int64_t base = 0; base < a.n; base += kRangeThreads) {
     const int64_t i = base + threadIdx.x;
     float v = 0.f;
     bool hit = false;
-    if (i < n) {
+    if (i < a.n) {
       v = row[i];
-      hit = keep_max ? (v > thr) : (v < thr);
+      hit = range_hit(a, rg_q, qn, i, v);
     }
     const unsigned int bal = __ballot_sync(0xffffffffu, hit);
     if (lane == 0) wtot[warp] = __popc(bal);
@@ -195,27 +321,54 @@ range_fill_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, float thr
     if (hit) {
       const unsigned long long o = pos + before + __popc(bal & ((1u << lane) - 1u));
       D[o] = v;
-      I[o] = id_offset + i;
+      I[o] = a.exact ? i : id_offset + i;
     }
     pos += total;
     __syncthreads();
   }
+  if (a.exact) {
+    // second phase: exact fp32 value of every hit of this row, one warp per hit (coalesced row reads)
+    __threadfence_block();
+    __syncthreads();
+    const unsigned long long cnt = pos - pos0;
+    for (unsigned long long j = warp; j < cnt; j += kRangeThreads / 32) {
+      const int64_t id = I[pos0 + j];
+      const float* r = a.bank + id * a.d;
+      float acc = 0.f;
+      for (int c = lane; c < a.d; c += 32) {
+        if (!a.keep_max) { const float df = rg_q[c] - r[c]; acc = fmaf(df, df, acc); }
+        else acc = fmaf(rg_q[c], r[c], acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        D[pos0 + j] = acc;
+        I[pos0 + j] = id_offset + id;
+      }
+    }
+  }
 }
 
 int range_count(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
-                unsigned long long* counts, cudaStream_t stream) {
+                unsigned long long* counts, cudaStream_t stream, const float* Q, const float* bank, int d,
+                const float* qn, const float* rn) {
   if (nq == 0) return VSCB200_OK;
-  range_count_kernel<<<static_cast<unsigned>(nq), kRangeThreads, 0, stream>>>(S, ldS, n, thr, keep_max ? 1 : 0, counts);
+  RangeArgs a{S, ldS, n, thr, keep_max ? 1 : 0, Q != nullptr ? 1 : 0, Q, bank, d, qn, rn};
+  const size_t smem = a.exact ? static_cast<size_t>(d) * sizeof(float) : 0;
+  VSCB_REQUIRE(smem <= 40 * 1024, "range_search: descriptor dimension too large");
+  range_count_kernel<<<static_cast<unsigned>(nq), kRangeThreads, smem, stream>>>(a, counts);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
 
 int range_fill(const float* S, int64_t ldS, int64_t nq, int64_t n, float thr, bool keep_max,
-               const unsigned long long* offsets, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream) {
+               const unsigned long long* offsets, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream,
+               const float* Q, const float* bank, int d, const float* qn, const float* rn) {
   if (nq == 0) return VSCB200_OK;
-  range_fill_kernel<<<static_cast<unsigned>(nq), kRangeThreads, 0, stream>>>(S, ldS, n, thr, keep_max ? 1 : 0, offsets,
-                                                                             D, I, id_offset);
+  RangeArgs a{S, ldS, n, thr, keep_max ? 1 : 0, Q != nullptr ? 1 : 0, Q, bank, d, qn, rn};
+  const size_t smem = a.exact ? static_cast<size_t>(d) * sizeof(float) : 0;
+  range_fill_kernel<<<static_cast<unsigned>(nq), kRangeThreads, smem, stream>>>(a, offsets, D, I, id_offset);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
