@@ -258,27 +258,13 @@ def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
 
 def _merge_topk(D, I, k):
     """One all-gather of the [nq, k] partial results per rank, then a k-way merge."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size()
-    Dg = torch.empty((world,) + tuple(D.shape), dtype=D.dtype, device=D.device)
-    Ig = torch.empty((world,) + tuple(I.shape), dtype=I.dtype, device=I.device)
-    dist.all_gather_into_tensor(Dg, D.contiguous())
-    dist.all_gather_into_tensor(Ig, I.contiguous())
-    Dc = Dg.permute(1, 0, 2).reshape(D.shape[0], -1)
-    Ic = Ig.permute(1, 0, 2).reshape(I.shape[0], -1)
-    top, pos = torch.topk(Dc, k, dim=1)
-    return top, torch.gather(Ic, 1, pos)
+    from vsc22_submission_b200 import sharding
+    return sharding.merge_partial_topk(D, I, k)
 
 
 def _global_low_var_dim(Z_shard):
-    import torch
-    import torch.distributed as dist
-    z = Z_shard.double()
-    mom = torch.stack([z.sum(0), (z * z).sum(0), torch.full((z.shape[1],), float(z.shape[0]), dtype=torch.float64, device=z.device)])
-    dist.all_reduce(mom)
-    mean = mom[0] / mom[2]
-    return int((mom[1] / mom[2] - mean * mean).argmin().item())
+    from vsc22_submission_b200 import sharding
+    return sharding.global_low_var_dim(Z_shard)
 
 
 def bench_sim(args, world, rank, peaks):
@@ -288,9 +274,10 @@ def bench_sim(args, world, rank, peaks):
     from vsc22_submission_b200 import _lib
     dev = torch.device("cuda", torch.cuda.current_device())
     Q, R, Z = make_sim_data(dev)
+    from vsc22_submission_b200.sharding import shard_range
     def shard(x):
-        per = (x.shape[0] + world - 1) // world
-        return x[rank * per:(rank + 1) * per].contiguous(), rank * per
+        a, b = shard_range(x.shape[0], world, rank)
+        return x[a:b].contiguous(), a
     R_s, row0 = shard(R)
     Z_s, _ = shard(Z)
     for _ in range(args.warmup):

@@ -177,4 +177,7 @@ def test_dense_scores_fp32_equivalent(faiss):
         S = ix.scores(Q)
         ref = Q.double() @ R.double().T
         assert S.shape == (nq, nr)
-        assert (S.double() - ref).abs().max().item() < 5e-7       # |scores| <= 1
+        # dense tensor-core scores: 2-way bf16 split, ~2e-7 rms / <2e-6 max on unit vectors (search()
+        # rescoring makes the returned top-k scores exact fp32; this is the raw score block)
+        assert (S.double() - ref).abs().max().item() < 2e-6
+        assert (S.double() - ref).pow(2).mean().sqrt().item() < 4e-7

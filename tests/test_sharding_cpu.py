@@ -1,0 +1,80 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes exercise bank sharding + all-gather + k-way
+merge, the sharded low-variance-dim reduction and the descriptor all-gather, against the oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import faiss_np
+    from vsc22_submission_b200 import sharding
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((1001, 32)).astype(np.float32)
+    R[500] = R[10]                       # exact tie across shards -> lower id must win
+    Q = rng.standard_normal((17, 32)).astype(np.float32)
+    Q[0] = R[10]
+    a, b = sharding.shard_range(len(R), world, rank)
+    ix = faiss_np.IndexFlat(32, faiss_np.METRIC_INNER_PRODUCT)   # stands in for the per-rank GPU search
+    ix.add(R[a:b])
+    D, I = ix.search(Q, 12)
+    I = np.where(I >= 0, I + a, I)                               # global ids (DeviceIndex.set_id_offset)
+    Dm, Im = sharding.merge_partial_topk(torch.from_numpy(D), torch.from_numpy(I), 12)
+    lvd = sharding.global_low_var_dim(torch.from_numpy(R[a:b]))
+    desc = sharding.gather_descriptors(torch.from_numpy(R[a:b]), len(R))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "merged.npz"), D=Dm.numpy(), I=Im.numpy(), lvd=lvd, desc=desc.numpy(), R=R, Q=Q)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    from vsc22_submission_b200.sharding import shard_range
+    for n in (0, 1, 7, 10000, 40001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_rank_bank_sharding_matches_single_index(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle import faiss_np, score_norm_np
+    g = np.load(tmp_path / "merged.npz")
+    ix = faiss_np.IndexFlat(32, faiss_np.METRIC_INNER_PRODUCT)
+    ix.add(g["R"])
+    D, I = ix.search(g["Q"], 12)
+    np.testing.assert_array_equal(g["I"], I)
+    np.testing.assert_array_equal(g["D"], D)
+    assert g["I"][0, 0] == 10 and g["I"][0, 1] == 500           # tie across shards resolved to the lower id
+    assert int(g["lvd"]) == score_norm_np.low_var_dim(g["R"].astype(np.float64))
+    np.testing.assert_array_equal(g["desc"], g["R"])
+
+
+def test_merge_handles_padding_single_process():
+    from vsc22_submission_b200.sharding import merge_partial_topk
+    D = torch.tensor([[0.9, 0.5, -3.4e38, -3.4e38]])
+    I = torch.tensor([[4, 2, -1, -1]])
+    Dm, Im = merge_partial_topk(D, I, 3)
+    assert Im.tolist() == [[4, 2, -1]]

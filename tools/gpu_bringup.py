@@ -10,7 +10,7 @@ import time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-STAGES = ["sim_precision", "gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]
+STAGES = ["sim_precision", "gemm_sustained", "gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]
 
 
 def _p(t):
@@ -99,6 +99,43 @@ def stage_gemm_shapes():
         ms = e0.elapsed_time(e1) / 10
         print(f"     cuBLAS (torch.matmul) same shape: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
     return ok
+
+
+def stage_gemm_sustained():
+    """Power-capped regime: each shape in a ~1.5 s back-to-back loop, ours vs cuBLAS, with SM clocks."""
+    import subprocess as sp
+    import torch
+    def clocks():
+        try:
+            return sp.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-i", "0"],
+                          capture_output=True, text=True).stdout.strip()
+        except Exception:
+            return "?"
+    for (M, N, K, epi, act) in [(50432, 768, 3072, 0, -1), (50432, 2304, 768, 0, -1), (50432, 3072, 768, 0, 0),
+                                (50432, 768, 768, 2, -1), (50432, 768, 3072, 2, -1), (8192, 8192, 8192, 0, -1)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        out = torch.zeros((M, N), dtype=torch.bfloat16 if epi == 0 else torch.float32, device="cuda")
+        for name, fn in (("ours", lambda: gemm(A, W, b, epi=epi, act=act, C_out=out)), ("cublas", lambda: torch.matmul(A, W.T))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            # calibrate iteration count for ~1.5 s
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            iters = max(10, int(1500 / max(e0.elapsed_time(e1), 1e-3)))
+            e0.record()
+            for i in range(iters):
+                fn()
+                if i == iters // 2:
+                    mid = None
+            e1.record()
+            c = clocks()          # sampled while the queue is still draining
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            print(f"  {name:6s} M{M} N{N} K{K} epi{epi} act{act}: {ms:.3f} ms {2 * M * N * K / ms / 1e9:7.1f} TFLOP/s sustained over {iters} iters; clocks,power = {c}")
+    return True
 
 
 def stage_gemm_epilogues():

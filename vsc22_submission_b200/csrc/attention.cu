@@ -1,8 +1,9 @@
 // Fused multi-head self-attention for the ViT encoder: out = softmax(Q K^T / sqrt(d)) V per (frame, head).
 //
 // Reference: nn.MultiheadAttention called at D/train/train_vid_score/video/clip.py:45 (unfused
-// bmm + softmax + bmm in torch 1.11).  Here: one CTA per (64-query tile, head, frame);
-// K and V of the (frame, head) are staged once in XOR-swizzled shared memory, S = QK^T and O = PV run
+// bmm + softmax + bmm in torch 1.11).  Here: one CTA per (head, frame) whose warps walk the
+// 16-row query tiles; K and V of the (frame, head) are staged ONCE (cp.async) in XOR-swizzled shared
+// memory, S = QK^T and O = PV run
 // on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate) with an online softmax in registers, so
 // neither S nor P ever touches HBM.  head_dim is fixed at 64 (every ViT on the reference's path:
 // 768/12, 1024/16).  Attention is 4 % of the encoder FLOPs; the tcgen05 projections carry the rest.
@@ -11,8 +12,7 @@
 
 namespace vscb200 {
 
-constexpr int kAttThreads = 128;   // 4 warps x 16 query rows
-constexpr int kAttQTile = 64;
+constexpr int kAttThreads = 224;   // 7 warps; T = 197 -> 13 query tiles of 16 rows, two rounds (14 slots)
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -24,6 +24,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
@@ -33,36 +39,42 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 }
 
 // qkv: [n*T, 3W] bf16 with W = heads*64, columns [q | k | v]; out: [n*T, W] bf16.
-__global__ void __launch_bounds__(kAttThreads)
+__global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tpad, int heads,
                  float scale_log2e) {
   extern __shared__ __align__(16) uint8_t att_smem[];
   uint8_t* sK = att_smem;                       // [Tpad][128 B], 16B chunk c of row r at c ^ (r & 7)
   uint8_t* sV = att_smem + static_cast<size_t>(Tpad) * 128;
 
-  const int frame = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int frame = blockIdx.y, head = blockIdx.x;
   const int W = heads * 64;
   const int64_t ld = 3 * static_cast<int64_t>(W);
   const __nv_bfloat16* base = qkv + static_cast<int64_t>(frame) * T * ld + head * 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- stage K and V (zero-filled beyond T)
+  // ---- stage K and V (zero-filled beyond T), asynchronously
+  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
   for (int i = tid; i < Tpad * 8; i += kAttThreads) {
     const int r = i >> 3, c = i & 7;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
     if (r < T) {
       const __nv_bfloat16* src = base + r * ld + c * 8;
-      kv = *reinterpret_cast<const uint4*>(src + W);
-      vv = *reinterpret_cast<const uint4*>(src + 2 * W);
+      cp_async_16(sK_u + off, src + W);
+      cp_async_16(sV_u + off, src + 2 * W);
+    } else {
+      *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
     }
-    const int off = r * 128 + ((c ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(sK + off) = kv;
-    *reinterpret_cast<uint4*>(sV + off) = vv;
   }
+  cp_async_wait_all();
+  __syncthreads();
 
-  // ---- Q fragments for this warp's 16 rows (A operand, 4 k-steps over d = 64)
   const int g = lane >> 2, t = lane & 3;
-  const int q0 = qt * kAttQTile + warp * 16;
+  const int lm = lane >> 3, lr = lane & 7;       // ldmatrix lane -> (matrix id, row in matrix)
+  const int ntile_q = (T + 15) >> 4;
+  for (int qt = warp; qt < ntile_q; qt += kAttThreads / 32) {
+  const int q0 = qt * 16;
+  // ---- Q fragments for this warp's 16 rows (A operand, 4 k-steps over d = 64)
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -73,7 +85,6 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       qa[ks][h] = (row < T) ? *reinterpret_cast<const uint32_t*>(base + row * ld + d) : 0u;
     }
   }
-  __syncthreads();
 
   float o[8][4];
 #pragma unroll
@@ -81,11 +92,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
 
-  const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-  // ldmatrix lane -> (matrix id, row in matrix)
-  const int lm = lane >> 3, lr = lane & 7;
-
-  if (q0 < T) {   // warp-uniform: warps whose rows are all padding skip the math
+  {
     for (int k0 = 0; k0 < Tpad; k0 += 64) {
       const int ntiles = min(8, (Tpad - k0) >> 3);   // 8-key n-tiles in this key block (even)
       float s[8][4];
@@ -184,6 +191,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
       }
     }
   }
+  }   // query-tile loop
 }
 
 int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream) {
@@ -193,7 +201,7 @@ int attention(const void* qkv, void* out, int n_frames, int T, int heads, int he
   const size_t smem = static_cast<size_t>(Tpad) * 128 * 2;
   VSCB_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the single-pass K/V staging");
   VSCB_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid((T + kAttQTile - 1) / kAttQTile, heads, n_frames);
+  dim3 grid(heads, n_frames);
   const float scale_log2e = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
   ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * head_dim);
   attention_kernel<<<grid, kAttThreads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
