@@ -41,6 +41,8 @@ int64_t vscb200_launch_count(void);
 /* faiss.get_num_gpus() -- vsc/index.py:169, exhaustive_search.py:28,229; 0 when no CUDA device */
 int vscb200_device_count(void);
 int vscb200_set_device(int device);
+/* return the library's cached device blocks (index workspaces / staging) to the driver */
+int vscb200_trim(void);
 /* Per-kernel device timing with CUDA events on the launching stream (bench.py's live roofline).
  * kinds: 0 gemm, 1 attention, 2 layernorm, 3 other encoder kernels, 4 similarity scores, 5 select.
  * work = algorithmic FLOPs (gemm/attention/scores) or bytes (others). */

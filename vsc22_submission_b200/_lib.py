@@ -38,6 +38,7 @@ SIGNATURES = {
     "vscb200_launch_count": (_i64, []),
     "vscb200_device_count": (_i, []),
     "vscb200_set_device": (_i, [_i]),
+    "vscb200_trim": (_i, []),
     "vscb200_prof_enable": (_i, [_i]),
     "vscb200_prof_collect": (_i, [_p, _p, _p, _i]),
     "vscb200_index_create": (_i, [_i, _i, C.POINTER(_p)]),

@@ -53,8 +53,19 @@ struct GemmCfg {
       kStages * (kABytes + kBBytes) + 256 /*barriers*/ + kStageBytes + 1024 /*align slack*/;
 };
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == VSCB200_ACT_QUICK_GELU) return __fdividef(x, 1.0f + __expf(-1.702f * x));
+  // QuickGELU x*sigmoid(1.702x) = 0.5x*tanh(0.851x) + 0.5x : ONE MUFU op per element (ex2 + rcp would be
+  // two, and the epilogue of the K=768 fc1 GEMM is MUFU-paced).  tanh.approx error 2^-11 << bf16 output ulp.
+  if (act == VSCB200_ACT_QUICK_GELU) {
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(0.851f * x), h);
+  }
   if (act == VSCB200_ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
   return x;
 }
@@ -182,6 +193,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = half * (BN / 2) + c * 32;
         const int gcol = n_blk * BN + col0;
         uint32_t v[32];
+        // Residual tile of this chunk: all 8 loads are issued up front (they depend on addresses only), so
+        // their HBM latency overlaps the TMEM load and the transpose instead of serialising load->add->store.
+        float4 res[8];
+        if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) {
+          const int gcr = gcol + (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int64_t grow = row_base + it * 4 + (lane >> 3);
+            res[it] = (grow < p.M && gcr < p.N)
+                          ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.C) + grow * p.ldc + gcr))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, v);
         tmem_ld_wait();
@@ -219,12 +243,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + gc) =
                   make_float4(o.x + pe.x, o.y + pe.y, o.z + pe.z, o.w + pe.w);
             } else {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + grow * p.ldc + gc);
               if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) {
-                const float4 rr = *dst;
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
               }
-              *dst = o;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + grow * p.ldc + gc) = o;
             }
           }
         }

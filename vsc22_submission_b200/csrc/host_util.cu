@@ -60,6 +60,83 @@ int device_sm_count() {
   return sms;
 }
 
+// ---------------------------------------------------------------- caching allocator
+struct PoolBlock { void* p; size_t bytes; int device; cudaEvent_t ev; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBlock> g_pool_free;
+static std::vector<PoolBlock> g_pool_live;
+
+static size_t pool_round(size_t b) {
+  const size_t g = b < (1u << 20) ? 512 : (2u << 20);
+  return (b + g - 1) / g * g;
+}
+
+int pool_alloc(void** p, size_t bytes, cudaStream_t stream) {
+  bytes = pool_round(bytes ? bytes : 1);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < static_cast<int>(g_pool_free.size()); ++i) {
+      const PoolBlock& b = g_pool_free[i];
+      if (b.device == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 4 + (1u << 20) &&
+          (best < 0 || b.bytes < g_pool_free[best].bytes))
+        best = i;
+    }
+    if (best >= 0) {
+      PoolBlock b = g_pool_free[best];
+      g_pool_free.erase(g_pool_free.begin() + best);
+      if (b.ev) cudaStreamWaitEvent(stream, b.ev, 0);
+      g_pool_live.push_back(b);
+      *p = b.p;
+      return VSCB200_OK;
+    }
+  }
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) {
+    pool_trim();                      // give cached blocks back and retry once
+    e = cudaMalloc(&q, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("cudaMalloc(" + std::to_string(bytes) + ") failed: " + cudaGetErrorString(e));
+    return VSCB200_ERR_NOMEM;
+  }
+  PoolBlock b{q, bytes, dev, nullptr};
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_live.push_back(b);
+  *p = q;
+  return VSCB200_OK;
+}
+
+void pool_free(void* p, cudaStream_t stream) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (size_t i = 0; i < g_pool_live.size(); ++i) {
+    if (g_pool_live[i].p == p) {
+      PoolBlock b = g_pool_live[i];
+      g_pool_live.erase(g_pool_live.begin() + i);
+      if (!b.ev) cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+      if (b.ev) cudaEventRecord(b.ev, stream);
+      g_pool_free.push_back(b);
+      return;
+    }
+  }
+  cudaFree(p);   // not ours
+}
+
+void pool_trim() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (PoolBlock& b : g_pool_free) {
+    if (b.ev) { cudaEventSynchronize(b.ev); cudaEventDestroy(b.ev); }
+    cudaFree(b.p);
+  }
+  g_pool_free.clear();
+  cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- event profiler
 struct ProfRec { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; double work = 0; };
 static std::atomic<int> g_prof_on{0};
@@ -135,6 +212,10 @@ int vscb200_device_count(void) {
     return 0;
   }
   return n;
+}
+int vscb200_trim(void) {
+  vscb200::pool_trim();
+  return VSCB200_OK;
 }
 int vscb200_set_device(int device) {
   VSCB_CUDA_OK(cudaSetDevice(device));

@@ -42,6 +42,15 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
 
 int device_sm_count();
 
+// Caching device allocator for the index's transient buffers (score workspace, staging, operand
+// planes).  The reference builds a fresh faiss index per score_normalize call
+// (score_normalization.py:87); without caching every such call would pay cudaMalloc/cudaFree
+// (milliseconds + device syncs).  Freed blocks keep an event recorded on the freeing stream; a block is
+// handed out again only after the new stream waits on it.  Memory returns to the driver at vscb200_trim().
+int pool_alloc(void** p, size_t bytes, cudaStream_t stream);
+void pool_free(void* p, cudaStream_t stream);
+void pool_trim();
+
 // Optional per-kernel timing with CUDA events on the launching stream (bench.py's live roofline
 // numbers).  Disabled by default: zero cost beyond one relaxed atomic load per launch.
 enum ProfKind { kProfGemm = 0, kProfAttention = 1, kProfLayerNorm = 2, kProfVitOther = 3, kProfScores = 4,

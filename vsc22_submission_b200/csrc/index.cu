@@ -43,6 +43,7 @@ struct vscb200_index {
   float* Dtmp = nullptr; size_t Dtmp_bytes = 0;       // survivors of the tensor-core pass (k + slack per row)
   int64_t* Itmp = nullptr; size_t Itmp_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t last_stream = nullptr;   // stream of the most recent call (orders the final frees)
   int force_simt = 0;
 };
 
@@ -59,17 +60,14 @@ size_t ws_budget_bytes() {
 }
 
 template <typename Tp>
-int grow(Tp** p, size_t* have, size_t need) {
+int grow(Tp** p, size_t* have, size_t need, cudaStream_t s) {
   if (*have >= need) return VSCB200_OK;
-  if (*p) cudaFree(*p);
+  if (*p) pool_free(*p, s);
   *p = nullptr;
   *have = 0;
   size_t want = std::max(need, static_cast<size_t>(256));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), want);
-  if (e != cudaSuccess) {
-    set_last_error(std::string("cudaMalloc(") + std::to_string(want) + ") failed: " + cudaGetErrorString(e));
-    return VSCB200_ERR_NOMEM;
-  }
+  int rc = pool_alloc(reinterpret_cast<void**>(p), want, s);
+  if (rc) return rc;
   *have = want;
   return VSCB200_OK;
 }
@@ -79,18 +77,15 @@ int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
   int64_t cap = std::max<int64_t>(rows, ix->capacity + ix->capacity / 2);
   cap = std::max<int64_t>(cap, 1024);
   float* nb = nullptr;
-  cudaError_t e = cudaMalloc(&nb, static_cast<size_t>(cap) * ix->d * sizeof(float));
-  if (e != cudaSuccess) {
-    set_last_error(std::string("index: cudaMalloc bank failed: ") + cudaGetErrorString(e));
-    return VSCB200_ERR_NOMEM;
-  }
+  int rc0 = pool_alloc(reinterpret_cast<void**>(&nb), static_cast<size_t>(cap) * ix->d * sizeof(float), s);
+  if (rc0) return rc0;
   if (ix->ntotal) {
     VSCB_CUDA_OK(cudaMemcpyAsync(nb, ix->bank, static_cast<size_t>(ix->ntotal) * ix->d * sizeof(float),
                                  cudaMemcpyDeviceToDevice, s));
   }
   float* nn = nullptr;
   {
-    VSCB_CUDA_OK(cudaMalloc(&nn, static_cast<size_t>(cap) * sizeof(float)));
+    if ((rc0 = pool_alloc(reinterpret_cast<void**>(&nn), static_cast<size_t>(cap) * sizeof(float), s))) return rc0;
     if (ix->ntotal)
       VSCB_CUDA_OK(cudaMemcpyAsync(nn, ix->rnorm, static_cast<size_t>(ix->ntotal) * sizeof(float),
                                    cudaMemcpyDeviceToDevice, s));
@@ -98,19 +93,18 @@ int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
   uint16_t *nh = nullptr, *nl = nullptr;
   if (!ix->force_simt) {
     const size_t pb = static_cast<size_t>(cap) * ix->dp * sizeof(uint16_t);
-    VSCB_CUDA_OK(cudaMalloc(&nh, pb));
-    VSCB_CUDA_OK(cudaMalloc(&nl, pb));
+    if ((rc0 = pool_alloc(reinterpret_cast<void**>(&nh), pb, s))) return rc0;
+    if ((rc0 = pool_alloc(reinterpret_cast<void**>(&nl), pb, s))) return rc0;
     if (ix->ntotal) {
       const size_t ob = static_cast<size_t>(ix->ntotal) * ix->dp * sizeof(uint16_t);
       VSCB_CUDA_OK(cudaMemcpyAsync(nh, ix->bank_hi, ob, cudaMemcpyDeviceToDevice, s));
       VSCB_CUDA_OK(cudaMemcpyAsync(nl, ix->bank_lo, ob, cudaMemcpyDeviceToDevice, s));
     }
   }
-  VSCB_CUDA_OK(cudaStreamSynchronize(s));
-  if (ix->bank) cudaFree(ix->bank);
-  if (ix->rnorm) cudaFree(ix->rnorm);
-  if (ix->bank_hi) cudaFree(ix->bank_hi);
-  if (ix->bank_lo) cudaFree(ix->bank_lo);
+  pool_free(ix->bank, s);      // stream-ordered after the copies above
+  pool_free(ix->rnorm, s);
+  pool_free(ix->bank_hi, s);
+  pool_free(ix->bank_lo, s);
   ix->bank = nb;
   ix->rnorm = nn;
   ix->bank_hi = nh;
@@ -136,6 +130,7 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
 }
 
 int flush_pending(vscb200_index* ix, cudaStream_t s) {
+  ix->last_stream = s;
   if (ix->pending.empty()) return VSCB200_OK;
   const int64_t n = static_cast<int64_t>(ix->pending.size()) / ix->d;
   int rc = append_rows(ix, ix->pending.data(), n, cudaMemcpyHostToDevice, s);
@@ -158,7 +153,7 @@ int score_block(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t
   const bool l2 = ix->metric == VSCB200_METRIC_L2;
   const float* qn = nullptr;
   {
-    int rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float));
+    int rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float), s);
     if (rc) return rc;
     rc = row_sqnorm(q, nq, ix->d, ix->qnorm, s);
     if (rc) return rc;
@@ -166,7 +161,7 @@ int score_block(vscb200_index* ix, const float* q, int64_t nq, float* S, int64_t
   }
   if (!ix->force_simt) {
     const size_t plane = static_cast<size_t>(nq) * ix->dp;
-    int rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t));
+    int rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s);
     if (rc) return rc;
     if ((rc = split_planes(q, ix->q_planes, ix->q_planes + plane, nq, ix->d, ix->dp, s))) return rc;
     return scores_tc_planes(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, S, nq, ix->ntotal, ix->dp,
@@ -202,9 +197,15 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
 
 void vscb200_index_destroy(vscb200_index* ix) {
   if (!ix) return;
-  cudaFree(ix->bank); cudaFree(ix->rnorm); cudaFree(ix->ws); cudaFree(ix->q_stage); cudaFree(ix->D_stage);
-  cudaFree(ix->I_stage); cudaFree(ix->qnorm); cudaFree(ix->counts);
-  cudaFree(ix->bank_hi); cudaFree(ix->bank_lo); cudaFree(ix->q_planes); cudaFree(ix->Dtmp); cudaFree(ix->Itmp);
+  // the blocks go back to the library pool, ordered after the last stream this index worked on
+  cudaStream_t s = ix->last_stream;
+  void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
+                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp};
+  if (ix->own_stream && s == ix->own_stream) {
+    cudaStreamSynchronize(s);     // own stream is destroyed below: drain it, then free un-ordered
+    s = nullptr;
+  }
+  for (void* b : blocks) pool_free(b, s);
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
   delete ix;
 }
@@ -255,15 +256,15 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (ix->ntotal + 3) & ~3ll;
-  rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float));
+  rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s);
   if (rc) return rc;
   // Tensor-core scores are fp32-equivalent to ~1e-6: keep k + slack survivors, rescore them exactly.
   const int kRescoreSlack = 8;
   const bool rescore = !ix->force_simt && ix->ntotal > 0;
   const int kin = rescore ? static_cast<int>(std::min<int64_t>(std::min<int64_t>(ix->ntotal, 2048), k + kRescoreSlack)) : k;
   if (rescore) {
-    if ((rc = grow(&ix->Dtmp, &ix->Dtmp_bytes, static_cast<size_t>(blk) * kin * sizeof(float)))) return rc;
-    if ((rc = grow(&ix->Itmp, &ix->Itmp_bytes, static_cast<size_t>(blk) * kin * sizeof(int64_t)))) return rc;
+    if ((rc = grow(&ix->Dtmp, &ix->Dtmp_bytes, static_cast<size_t>(blk) * kin * sizeof(float), s))) return rc;
+    if ((rc = grow(&ix->Itmp, &ix->Itmp_bytes, static_cast<size_t>(blk) * kin * sizeof(int64_t), s))) return rc;
   }
   for (int64_t q0 = 0; q0 < nq; q0 += blk) {
     const int64_t nb = std::min(blk, nq - q0);
@@ -290,9 +291,9 @@ int vscb200_index_search_host(vscb200_index* ix, const float* q_host, int64_t nq
   cudaStream_t s;
   int rc = own_stream(ix, &s);
   if (rc) return rc;
-  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(nq) * ix->d * sizeof(float)))) return rc;
-  if ((rc = grow(&ix->D_stage, &ix->D_stage_bytes, static_cast<size_t>(nq) * k * sizeof(float)))) return rc;
-  if ((rc = grow(&ix->I_stage, &ix->I_stage_bytes, static_cast<size_t>(nq) * k * sizeof(int64_t)))) return rc;
+  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(nq) * ix->d * sizeof(float), s))) return rc;
+  if ((rc = grow(&ix->D_stage, &ix->D_stage_bytes, static_cast<size_t>(nq) * k * sizeof(float), s))) return rc;
+  if ((rc = grow(&ix->I_stage, &ix->I_stage_bytes, static_cast<size_t>(nq) * k * sizeof(int64_t), s))) return rc;
   VSCB_CUDA_OK(cudaMemcpyAsync(ix->q_stage, q_host, static_cast<size_t>(nq) * ix->d * sizeof(float),
                                cudaMemcpyHostToDevice, s));
   rc = vscb200_index_search(ix, ix->q_stage, nq, k, ix->D_stage, ix->I_stage, s);
@@ -333,9 +334,9 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
   const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (ix->ntotal + 3) & ~3ll;
-  if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float)))) return rc;
-  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * ix->d * sizeof(float)))) return rc;
-  if ((rc = grow(&ix->counts, &ix->counts_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * sizeof(unsigned long long)))) return rc;
+  if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s))) return rc;
+  if ((rc = grow(&ix->q_stage, &ix->q_stage_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * ix->d * sizeof(float), s))) return rc;
+  if ((rc = grow(&ix->counts, &ix->counts_bytes, static_cast<size_t>(std::max<int64_t>(blk, 1)) * sizeof(unsigned long long), s))) return rc;
   std::vector<unsigned long long> cnt(static_cast<size_t>(std::max<int64_t>(blk, 1)));
   size_t total = 0, cap = 0;
   float* Dh = nullptr;
@@ -343,7 +344,7 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
   float* Dd = nullptr; size_t Dd_bytes = 0;
   int64_t* Id = nullptr; size_t Id_bytes = 0;
   auto fail = [&](int code) {
-    free(Dh); free(Ih); cudaFree(Dd); cudaFree(Id);
+    free(Dh); free(Ih); pool_free(Dd, s); pool_free(Id, s);
     return code;
   };
   for (int64_t q0 = 0; q0 < nq; q0 += blk) {
@@ -374,8 +375,8 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
       if (!nD || !nI) { Dh = nD ? nD : Dh; Ih = nI ? nI : Ih; set_last_error("range_search: host realloc failed"); return fail(VSCB200_ERR_NOMEM); }
       Dh = nD; Ih = nI;
     }
-    if ((rc = grow(&Dd, &Dd_bytes, blk_total * sizeof(float)))) return fail(rc);
-    if ((rc = grow(&Id, &Id_bytes, blk_total * sizeof(int64_t)))) return fail(rc);
+    if ((rc = grow(&Dd, &Dd_bytes, blk_total * sizeof(float), s))) return fail(rc);
+    if ((rc = grow(&Id, &Id_bytes, blk_total * sizeof(int64_t), s))) return fail(rc);
     if (cudaMemcpyAsync(ix->counts, cnt.data(), static_cast<size_t>(nb) * sizeof(unsigned long long),
                         cudaMemcpyHostToDevice, s) != cudaSuccess) { set_last_error("range_search: H2D offsets failed"); return fail(VSCB200_ERR_CUDA); }
     if ((rc = range_fill(ix->ws, ldS, nb, ix->ntotal, thresh, keep_max, ix->counts, Dd, Id, ix->id_offset, s, Qx, ix->bank,
@@ -385,8 +386,8 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
         cudaStreamSynchronize(s) != cudaSuccess) { set_last_error(std::string("range_search: fill failed: ") + cudaGetErrorString(cudaGetLastError())); return fail(VSCB200_ERR_CUDA); }
     total += blk_total;
   }
-  cudaFree(Dd);
-  cudaFree(Id);
+  pool_free(Dd, s);
+  pool_free(Id, s);
   if (!Dh) { Dh = static_cast<float*>(malloc(sizeof(float))); Ih = static_cast<int64_t*>(malloc(sizeof(int64_t))); }
   *D_out = Dh;
   *I_out = Ih;
