@@ -18,6 +18,12 @@ namespace vscb200 {
 int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, cudaStream_t stream);
 int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
                      int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream);
+int fused_topk_slabs(int64_t nq, int64_t nr);
+int fused_topk_list_len();
+int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp, bool l2,
+                  const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream);
+int merge_rescore(const float* Q, const float* bank, int d, bool l2, const float* cand_d, const int32_t* cand_i,
+                  int ncand, int kmid, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
 }  // namespace vscb200
 
 struct vscb200_index {
@@ -42,6 +48,9 @@ struct vscb200_index {
   unsigned long long* counts = nullptr; size_t counts_bytes = 0;
   float* Dtmp = nullptr; size_t Dtmp_bytes = 0;       // survivors of the tensor-core pass (k + slack per row)
   int64_t* Itmp = nullptr; size_t Itmp_bytes = 0;
+  float* cand_d = nullptr; size_t cand_d_bytes = 0;   // fused top-k epilogue candidates [nq, slabs*2*kFK]
+  int32_t* cand_i = nullptr; size_t cand_i_bytes = 0;
+  int no_fused = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t last_stream = nullptr;   // stream of the most recent call (orders the final frees)
   int force_simt = 0;
@@ -191,6 +200,8 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
   ix->metric = metric;
   const char* e = getenv("VSCB200_FORCE_SIMT");
   ix->force_simt = (e && atoi(e)) ? 1 : 0;
+  const char* nf = getenv("VSCB200_NO_FUSED_TOPK");
+  ix->no_fused = (nf && atoi(nf)) ? 1 : 0;
   *out = ix;
   return VSCB200_OK;
 }
@@ -200,7 +211,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
   void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
-                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp};
+                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i};
   if (ix->own_stream && s == ix->own_stream) {
     cudaStreamSynchronize(s);     // own stream is destroyed below: drain it, then free un-ordered
     s = nullptr;
@@ -254,6 +265,31 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   int rc = flush_pending(ix, s);
   if (rc) return rc;
   const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
+  // Small k on a large bank: top-k fused into the scoring kernel's epilogue (no score block in HBM), then a
+  // per-query merge + exact rescoring of the survivors.
+  const int kFusedSlack = 6;
+  if (!ix->force_simt && !ix->no_fused && k + kFusedSlack <= fused_topk_list_len() && ix->ntotal >= 2048 &&
+      ix->ntotal < (1ll << 31)) {
+    const int fk = fused_topk_list_len();
+    for (int64_t q0 = 0; q0 < nq; q0 += (1 << 20)) {
+      const int64_t nb = std::min<int64_t>(1 << 20, nq - q0);
+      const int slabs = fused_topk_slabs(nb, ix->ntotal);
+      const int ncand = slabs * 2 * fk;
+      if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nb) * ncand * sizeof(float), s))) return rc;
+      if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nb) * ncand * sizeof(int32_t), s))) return rc;
+      if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nb) * sizeof(float), s))) return rc;
+      const float* qb = q + q0 * ix->d;
+      if ((rc = row_sqnorm(qb, nb, ix->d, ix->qnorm, s))) return rc;
+      const size_t plane = static_cast<size_t>(nb) * ix->dp;
+      if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
+      if ((rc = split_planes(qb, ix->q_planes, ix->q_planes + plane, nb, ix->d, ix->dp, s))) return rc;
+      if ((rc = topk_tc_fused(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, nb, ix->ntotal, ix->dp,
+                              !keep_max, ix->qnorm, ix->rnorm, slabs, ix->cand_d, ix->cand_i, s))) return rc;
+      if ((rc = merge_rescore(qb, ix->bank, ix->d, !keep_max, ix->cand_d, ix->cand_i, ncand, k + kFusedSlack, nb, k,
+                              D + q0 * k, I + q0 * k, ix->id_offset, s))) return rc;
+    }
+    return VSCB200_OK;
+  }
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (ix->ntotal + 3) & ~3ll;
   rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s);

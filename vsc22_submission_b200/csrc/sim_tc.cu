@@ -39,8 +39,33 @@ struct SimParams {
   const float* qn;
   const float* rn;
   int tiles_m, tiles_n;
+  // fused top-k mode (kFused): work items = (query block, bank slab); per-thread running top-kFK lists are
+  // flushed per item to cand_d / cand_i [nq, slabs*2*kFK]
+  int slabs;
+  float* cand_d;
+  int32_t* cand_i;
 };
 
+constexpr int kFK = 16;     // per-thread list length of the fused top-k epilogue (k + rescoring slack <= kFK)
+
+// Work decomposition shared by the three warp roles.  Dense mode: item = one 128x128 tile, n fastest.
+// Fused mode: item = (m_blk, slab) and the tiles of the slab are walked consecutively, so a thread's
+// running top-k list lives in registers for the whole item.
+struct ItemIter {
+  int item, step, num_items, slabs, tiles_n;
+  __device__ ItemIter(const SimParams& p, bool fused)
+      : item(blockIdx.x), step(gridDim.x), num_items(fused ? p.tiles_m * p.slabs : p.tiles_m * p.tiles_n),
+        slabs(fused ? p.slabs : p.tiles_n), tiles_n(p.tiles_n) {}
+  __device__ bool valid() const { return item < num_items; }
+  __device__ void advance() { item += step; }
+  __device__ int m_blk() const { return item / slabs; }
+  __device__ int slab() const { return item % slabs; }
+  // tile range [n0, n1) of this item
+  __device__ int n0(bool fused) const { return fused ? static_cast<int>(static_cast<int64_t>(slab()) * tiles_n / slabs) : slab(); }
+  __device__ int n1(bool fused) const { return fused ? static_cast<int>(static_cast<int64_t>(slab() + 1) * tiles_n / slabs) : slab() + 1; }
+};
+
+template <bool kFused>
 __global__ void __launch_bounds__(kTThreads, 1)
 sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
             const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl, SimParams p) {
@@ -69,7 +94,6 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
   const int kblocks = (p.K + kTK - 1) / kTK;
   const int nseg = kblocks < kTSeg ? kblocks : kTSeg;
 
@@ -77,8 +101,8 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      for (ItemIter it(p, kFused); it.valid(); it.advance())
+      for (int n_blk = it.n0(kFused), n_end = it.n1(kFused), m_blk = it.m_blk(); n_blk < n_end; ++n_blk) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kTStageBytes);
@@ -98,7 +122,8 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (ItemIter it(p, kFused); it.valid(); it.advance())
+      for (int n_blk = it.n0(kFused), n_end = it.n1(kFused); n_blk < n_end; ++n_blk) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         int seg = 0, seg_end = kblocks / nseg;        // segment s covers [s*kblocks/nseg, (s+1)*kblocks/nseg)
@@ -134,11 +159,22 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
     float4* stage = stage_all + ew * 256;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+    for (ItemIter it(p, kFused); it.valid(); it.advance()) {
+      const int m_blk = it.m_blk();
+      const int64_t row_base = static_cast<int64_t>(m_blk) * kTM + quad * 32;
+      // fused mode: this thread's running top-kFK of (query row row_base+lane) over its columns of the slab,
+      // sorted best-first; strict comparisons keep the earlier (lower) id among equal scores
+      float ls[kFK];
+      int32_t li[kFK];
+      float qn_row = 0.f;
+      if (kFused) {
+#pragma unroll
+        for (int j = 0; j < kFK; ++j) { ls[j] = -INFINITY; li[j] = -1; }
+        if (p.l2 && row_base + lane < p.nq) qn_row = p.qn[row_base + lane];
+      }
+      for (int n_blk = it.n0(kFused), n_end = it.n1(kFused); n_blk < n_end; ++n_blk) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int64_t row_base = static_cast<int64_t>(m_blk) * kTM + quad * 32;
 #pragma unroll 1
       for (int c = 0; c < kTN / 2 / 32; ++c) {
         const int col0 = half * (kTN / 2) + c * 32;
@@ -158,6 +194,26 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
         }
         if (gcol >= p.nr) continue;   // warp-uniform
+        if (kFused) {
+          // selection key: larger is better (negated squared distance for L2)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float key = f[j];
+            if (p.l2) key = -fmaxf(qn_row + p.rn[min(gcol + j, p.nr - 1)] - 2.0f * key, 0.f);
+            if (gcol + j < p.nr && key > ls[kFK - 1]) {
+              ls[kFK - 1] = key;
+              li[kFK - 1] = static_cast<int32_t>(gcol + j);
+#pragma unroll
+              for (int t = kFK - 1; t > 0; --t) {
+                if (ls[t] > ls[t - 1]) {
+                  const float ts = ls[t]; ls[t] = ls[t - 1]; ls[t - 1] = ts;
+                  const int32_t ti = li[t]; li[t] = li[t - 1]; li[t - 1] = ti;
+                }
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           stage[lane * 8 + (q ^ (lane & 7))] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -172,8 +228,8 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           rn4.w = gc + 3 < p.nr ? p.rn[gc + 3] : 0.f;
         }
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3);
+        for (int it8 = 0; it8 < 8; ++it8) {
+          const int r = it8 * 4 + (lane >> 3);
           const int64_t grow = row_base + r;
           float4 o = stage[r * 8 + (q ^ (r & 7))];
           if (grow < p.nq && gc < p.nr) {
@@ -201,6 +257,18 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }   // tiles of the item
+      if (kFused) {
+        const int64_t grow = row_base + lane;
+        if (grow < p.nq) {
+          const int64_t base = (grow * p.slabs + it.slab()) * (2 * kFK) + half * kFK;
+#pragma unroll
+          for (int j = 0; j < kFK; ++j) {
+            p.cand_d[base + j] = ls[j];
+            p.cand_i[base + j] = li[j];
+          }
+        }
+      }
     }
   }
   tc_fence_before();
@@ -232,32 +300,65 @@ int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, c
   return VSCB200_OK;
 }
 
+static int launch_sim3(const void* Qh, const void* Ql, const void* Rh, const void* Rl, SimParams p, int dp, bool fused,
+                       cudaStream_t stream) {
+  CUtensorMap tQh, tQl, tRh, tRl;
+  int rc;
+  if ((rc = make_tmap_2d(&tQh, Qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nq, dp, dp, kTM, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tQl, Ql, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nq, dp, dp, kTM, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRh, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp, kTN, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRl, Rl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp, kTN, kTK, true))) return rc;
+  p.tiles_m = static_cast<int>((p.nq + kTM - 1) / kTM);
+  const int64_t tn = (p.nr + kTN - 1) / kTN;
+  VSCB_REQUIRE(static_cast<int64_t>(p.tiles_m) * tn < (1ll << 31), "scores_tc: too many tiles");
+  p.tiles_n = static_cast<int>(tn);
+  const int64_t items = fused ? static_cast<int64_t>(p.tiles_m) * p.slabs : static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  const int grid = static_cast<int>(items < device_sm_count() ? items : device_sm_count());
+  ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(p.nq) * p.nr * dp);
+  if (fused) {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    sim3_kernel<true><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+  } else {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    sim3_kernel<false><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+  }
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
 int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
                      int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream) {
   if (nq == 0 || nr == 0) return VSCB200_OK;
   VSCB_REQUIRE(dp % 8 == 0, "scores_tc: dp must be a multiple of 8");
-  CUtensorMap tQh, tQl, tRh, tRl;
-  int rc;
-  if ((rc = make_tmap_2d(&tQh, Qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nq, dp, dp, kTM, kTK, true))) return rc;
-  if ((rc = make_tmap_2d(&tQl, Ql, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nq, dp, dp, kTM, kTK, true))) return rc;
-  if ((rc = make_tmap_2d(&tRh, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nr, dp, dp, kTN, kTK, true))) return rc;
-  if ((rc = make_tmap_2d(&tRl, Rl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nr, dp, dp, kTN, kTK, true))) return rc;
-  SimParams p;
+  SimParams p = {};
   p.S = S; p.ldS = ldS; p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0;
   p.vec4 = (ldS % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) ? 1 : 0;
   p.qn = qn; p.rn = rn;
-  p.tiles_m = static_cast<int>((nq + kTM - 1) / kTM);
-  const int64_t tn = (nr + kTN - 1) / kTN;
-  VSCB_REQUIRE(static_cast<int64_t>(p.tiles_m) * tn < (1ll << 31), "scores_tc: too many tiles");
-  p.tiles_n = static_cast<int>(tn);
-  VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
-  const int64_t num_tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-  const int grid = static_cast<int>(num_tiles < device_sm_count() ? num_tiles : device_sm_count());
-  ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * dp);
-  sim3_kernel<<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
-  count_launch();
-  VSCB_CUDA_OK(cudaGetLastError());
-  return VSCB200_OK;
+  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, false, stream);
+}
+
+// Number of bank slabs per query block for the fused top-k mode: enough work items to fill the GPU
+// (>= 4 per SM when the bank allows), at most 148 (candidate list <= 148*2*kFK per query).
+int fused_topk_slabs(int64_t nq, int64_t nr) {
+  const int64_t tiles_m = (nq + kTM - 1) / kTM, tiles_n = (nr + kTN - 1) / kTN;
+  int64_t s = (4ll * device_sm_count() + tiles_m - 1) / tiles_m;
+  if (s > tiles_n) s = tiles_n;
+  if (s > 148) s = 148;
+  if (s < 1) s = 1;
+  return static_cast<int>(s);
+}
+int fused_topk_list_len() { return kFK; }
+
+// cand_d / cand_i: [nq, slabs * 2 * kFK] keys (larger = better; -distance for L2) and local bank ids (-1 = empty)
+int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp, bool l2,
+                  const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream) {
+  if (nq == 0 || nr == 0) return VSCB200_OK;
+  VSCB_REQUIRE(dp % 8 == 0 && nr < (1ll << 31), "topk_tc_fused: dp must be a multiple of 8 and nr < 2^31");
+  SimParams p = {};
+  p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0; p.qn = qn; p.rn = rn;
+  p.slabs = slabs; p.cand_d = cand_d; p.cand_i = cand_i;
+  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, true, stream);
 }
 
 }  // namespace vscb200
