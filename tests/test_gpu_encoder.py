@@ -47,6 +47,28 @@ def test_gemm_against_fp32(torch):
         assert (out.float() - ref).abs().max().item() <= tol * ref.abs().max().item(), (M, N, K, epi)
 
 
+def test_gemm_cta_pair_mode(torch):
+    """Shapes large enough for the cta_group::2 (CTA pair, M = 256) kernel, including an odd number of
+    128-row blocks (rank 1 of the last pair works on a fully out-of-bounds block) and a ragged tail."""
+    from vsc22_submission_b200 import _lib
+    torch.manual_seed(3)
+    for (M, N, K, epi) in [(25216 + 128 + 5, 768, 768, 1), (19000, 2304, 768, 0), (12800, 768, 3072, 2)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+        out = res.clone() if epi == 2 else torch.empty((M, N), dtype=torch.bfloat16 if epi == 0 else torch.float32,
+                                                       device="cuda")
+        _lib.check(_lib.lib().vscb200_gemm_bf16(_p(A), _p(W), _p(b), _p(out), M, N, K, K, K, N, epi, -1, None))
+        torch.cuda.synchronize()
+        ref = A.float() @ W.float().T + b
+        if epi == 2:
+            ref = ref + res
+        tol = 1e-2 if epi == 0 else 2e-4
+        err = (out.float() - ref).abs()
+        assert err.max().item() <= tol * ref.abs().max().item(), (M, N, K, epi, err.max().item())
+
+
 def test_gemm_epilogues(torch):
     import torch.nn.functional as F
     from vsc22_submission_b200 import _lib

@@ -3,8 +3,8 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled 128x64 / BNx64 bf16 tiles, 4-stage ring)
 //   warp 1      MMA issuer     (tcgen05.mma kind::f16, M=128, N=BN, K=16; fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-11  epilogue       (tcgen05.ld -> smem transpose -> bias / QuickGELU / GELU / residual ->
-//                               coalesced 128-bit global accesses, 4 full 128 B row segments per instruction)
+//   warps 4-11  epilogue       (tcgen05.ld -> bias / QuickGELU / GELU in registers -> 128B-swizzled 32-row box in
+//                               smem -> TMA store (bf16 / fp32) or TMA fp32 reduce-add into the residual stream)
 //
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and a
 // static persistent tile schedule (tile = blockIdx.x + i*gridDim.x, N-blocks fastest so that
@@ -24,6 +24,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+constexpr int kEpiWarpStage = 8192;
 
 struct GemmParams {
   const float* bias;
@@ -42,15 +43,15 @@ struct GemmParams {
 
 constexpr int VSCB_EPI_PATCH_F32 = 3;
 
-template <int BN>
+template <int BN, int kCluster>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (kCluster == 2) ? 5 : ((BN == 256) ? 3 : 5);
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / kCluster) * kBK * 2;   // pair mode: each CTA stages half of the W tile
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStageBytes = kEpiWarps * 32 * 32 * 4;   // per-warp epilogue transpose tiles
+  static constexpr int kStageBytes = kEpiWarps * kEpiWarpStage;   // per-warp epilogue boxes (2 x 4 KB, double-buffered)
   static constexpr int kSmemBytes =
-      kStages * (kABytes + kBBytes) + 256 /*barriers*/ + kStageBytes + 1024 /*align slack*/;
+      kStages * (kABytes + kBBytes) + kStageBytes + 256 /*barriers*/ + 1024 /*align slack*/;
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -70,26 +71,31 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// kCluster == 2: CTA pairs along M share every W tile -- each CTA fetches half of it (BN/2 rows) and
-// TMA-multicasts it into both CTAs' shared memory, halving the L2->SM operand traffic per CTA
-// (A 16 KB + W/2 16 KB per 64-wide K block instead of 48 KB).  A stage is released to both producers by a
-// multicast tcgen05.commit, so the pair advances through the K loop in lockstep.
+// kCluster == 2: a CTA pair (two SMs of one TPC) computes one 256 x BN tile with tcgen05.mma.cta_group::2
+// (M = 256): each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows) -- 32 KB instead of
+// 48 KB of shared-memory fill and operand reads per 64-wide K block, which is what bounds the single-CTA
+// kernel (A 16 KB + W 32 KB read per 512 tensor cycles on a 128 B/clk port that also takes the TMA
+// writes and the epilogue staging).  Rank 0 issues every MMA; both producers' TMA loads complete on
+// rank 0's full barrier; stages and accumulators are released to both CTAs by multicast tcgen05.commit;
+// each CTA drains its own 128 accumulator lanes and the peer's epilogue warps arrive remotely on rank
+// 0's TMEM-empty barrier.
 template <int BN, int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, GemmParams p) {
+  using Cfg = GemmCfg<BN, kCluster>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + kStages * Cfg::kBBytes);
+  uint8_t* stage_all = sB + kStages * Cfg::kBBytes;        // 1024-byte aligned (every operand stage is a multiple of 8 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_all + Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float4* stage_all = reinterpret_cast<float4*>(smem + kStages * (Cfg::kABytes + Cfg::kBBytes) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,19 +103,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kCluster);   // one tcgen05.commit per CTA of the pair
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], kEpiWarps * kCluster);   // rank 0's barrier collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) {
+    if (kCluster > 1) tmem_alloc_cg2<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();    // peer barriers are initialised before any remote arrive / multicast
@@ -133,13 +143,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
-          tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
           if (kCluster > 1) {
-            constexpr int kHalf = Cfg::kBBytes / 2;      // BN/2 rows of the W tile, multicast to both CTAs
-            tma_load_2d_mcast(sB + stage * Cfg::kBBytes + crank * kHalf, &tmB, &full_bar[stage], kb * kBK,
-                              n_blk * BN + static_cast<int>(crank) * (BN / 2), static_cast<uint16_t>(0x3), kEvictLast);
+            // both CTAs' boxes complete on rank 0's barrier, which expects the bytes of the whole pair
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0u);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::kABytes + Cfg::kBBytes));
+            tma_load_2d_cg2(sA + stage * Cfg::kABytes, &tmA, lead_full, kb * kBK, m_blk * kBM, kEvictNormal);
+            tma_load_2d_cg2(sB + stage * Cfg::kBBytes, &tmB, lead_full, kb * kBK,
+                            n_blk * BN + static_cast<int>(crank) * (BN / 2), kEvictLast);
           } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
+            tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -147,8 +160,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kBM, BN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBM * kCluster, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -165,13 +178,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128B swizzle row: +2 in the (addr>>4) field
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kCluster > 1) umma_bf16_ss_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (kCluster > 1) umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
+          if (kCluster > 1) umma_commit_cg2_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
           else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (kCluster > 1) umma_commit_cg2_mcast(&tfull_bar[acc], static_cast<uint16_t>(0x3));
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -179,40 +194,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;           // column half of the tile
-    float4* stage = stage_all + ew * 256;   // 32 rows x 8 float4
+    uint8_t* wstage = stage_all + ew * kEpiWarpStage;   // two 4 KB boxes (1024-byte aligned), or one 32x32 fp32 tile
     constexpr int kChunks = BN / 2 / 32;
+    const bool tma_epi = p.epilogue != VSCB_EPI_PATCH_F32;
+    const bool out_bf16 = p.epilogue == VSCB200_EPI_BF16;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t box_no = 0;
     for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
       const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int64_t row_base = static_cast<int64_t>(m_blk) * kBM + quad * 32;
+      if (tma_epi) {
+        // Tensor-map epilogue: this thread holds 32 consecutive columns of its accumulator row; bias and
+        // activation are applied in registers, the warp's 32-row box (32 fp32 or 64 bf16 columns = 128 B
+        // rows, 128B-swizzled) is written to shared memory once and leaves through the TMA engine -- a
+        // plain store, or an fp32 reduce-add into the residual stream (x += tile is done by the L2, the
+        // SM never reads x).  Ragged M / N edges are clipped by the tensor map.  Boxes are double-buffered.
+        const int step = out_bf16 ? 2 : 1;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; c += step) {
+          const int col0 = half * (BN / 2) + c * 32;
+          const int gcol = n_blk * BN + col0;
+          if (gcol >= p.N || row_base >= p.M) continue;   // warp-uniform
+          uint8_t* box = wstage + (box_no & 1u) * 4096u;
+          ++box_no;
+          if (lane == 0) tma_store_wait_read<1>();        // the store that last read this buffer has drained
+          __syncwarp();
+          for (int sub = 0; sub < step; ++sub) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0 + sub * 32, v);
+            tmem_ld_wait();
+            const int gc0 = gcol + sub * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              if (p.bias != nullptr && gc0 + 4 * q < p.N) {      // N % 8 == 0: a float4 of columns is all-in or all-out
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc0 + 4 * q));
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              if (p.act >= 0) {
+                o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
+                o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+              }
+              if (out_bf16) {
+                v[2 * q] = pack_bf16x2(o.x, o.y);
+                v[2 * q + 1] = pack_bf16x2(o.z, o.w);
+              } else {
+                *reinterpret_cast<float4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
+              }
+            }
+            if (out_bf16) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(box + lane * 128 + (((sub * 4 + q) ^ (lane & 7)) << 4)) =
+                    make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) tma_reduce_add_2d(&tmC, box, gcol, static_cast<int>(row_base));
+            else tma_store_2d(&tmC, box, gcol, static_cast<int>(row_base));
+            tma_store_commit();
+          }
+        }
+      } else {
+      float4* stage = reinterpret_cast<float4*>(wstage);   // 32 rows x 8 float4
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
         const int col0 = half * (BN / 2) + c * 32;
         const int gcol = n_blk * BN + col0;
         uint32_t v[32];
-        // Residual tile of this chunk: all 8 loads are issued up front (they depend on addresses only), so
-        // their HBM latency overlaps the TMEM load and the transpose instead of serialising load->add->store.
-        float4 res[8];
-        if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) {
-          const int gcr = gcol + (lane & 7) * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int64_t grow = row_base + it * 4 + (lane >> 3);
-            res[it] = (grow < p.M && gcr < p.N)
-                          ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.C) + grow * p.ldc + gcr))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
         __syncwarp();                 // tcgen05.ld is .sync.aligned: the warp must be converged
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0, v);
         tmem_ld_wait();
         if (gcol >= p.N) continue;   // warp-uniform
-        // Transpose through this warp's 4 KB staging tile so that every global access of the warp
-        // covers whole 128-byte row segments (row-per-thread TMEM layout -> 4 rows x 128 B per
-        // instruction).  16-byte chunks are XOR-swizzled by the row: conflict-free both ways.
+        // Patch-embed epilogue (rows remapped around the class slot, + positional embedding): transpose
+        // through the warp's staging tile so that every global access covers whole 128-byte row segments.
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           stage[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -229,45 +290,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int64_t grow = row_base + r;
           float4 o = stage[r * 8 + (q ^ (r & 7))];
           o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-          if (p.act >= 0) {
-            o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
-            o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
-          }
           if (grow < p.M && col_ok) {
-            if (p.epilogue == VSCB200_EPI_BF16) {
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + grow * p.ldc + gc) =
-                  make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-            } else if (p.epilogue == VSCB_EPI_PATCH_F32) {
-              const int64_t orow = grow + grow / p.patch_P + 1;
-              const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (grow % p.patch_P + 1) * p.N + gc));
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + gc) =
-                  make_float4(o.x + pe.x, o.y + pe.y, o.z + pe.z, o.w + pe.w);
-            } else {
-              if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) {
-                o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
-              }
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + grow * p.ldc + gc) = o;
-            }
+            const int64_t orow = grow + grow / p.patch_P + 1;
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (grow % p.patch_P + 1) * p.N + gc));
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + orow * p.ldc + gc) =
+                make_float4(o.x + pe.x, o.y + pe.y, o.z + pe.z, o.w + pe.w);
           }
         }
         __syncwarp();                 // the staging tile is rewritten by the next chunk
       }
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCluster > 1) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all<0>();   // shared memory stays valid until the TMA engine has read every box
   }
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();    // no CTA exits while its peer may still multicast into it
-  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (kCluster > 1) cluster_sync_all();    // no CTA exits while its peer may still signal into it
+  if (warp == 2) {
+    if (kCluster > 1) tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
 }
 
 template <int BN, int kCluster>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kCluster>;
   VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
   const int sched_tiles = ((p.tiles_m + kCluster - 1) / kCluster) * p.tiles_n;     // (pair) tiles
@@ -286,7 +342,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster>, tmA, tmB, p));
+  VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster>, tmA, tmB, tmC, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -320,8 +376,16 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
   p.pos = pos; p.patch_P = patch_P;
   p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
   p.tiles_n = (N + BN - 1) / BN;
-  if (pair) return BN == 256 ? launch_gemm<256, 2>(tmA, tmB, p, stream) : launch_gemm<128, 2>(tmA, tmB, p, stream);
-  return BN == 256 ? launch_gemm<256, 1>(tmA, tmB, p, stream) : launch_gemm<128, 1>(tmA, tmB, p, stream);
+  // output tensor map: 32-row boxes of 128 B (64 bf16 / 32 fp32 columns); unused by the patch-embed epilogue
+  CUtensorMap tmC = tmA;
+  if (epilogue == VSCB200_EPI_BF16) {
+    rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldc, 32, 64, true);
+  } else if (epilogue != VSCB_EPI_PATCH_F32) {
+    rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldc, 32, 32, true);
+  }
+  if (rc) return rc;
+  if (pair) return BN == 256 ? launch_gemm<256, 2>(tmA, tmB, tmC, p, stream) : launch_gemm<128, 2>(tmA, tmB, tmC, p, stream);
+  return BN == 256 ? launch_gemm<256, 1>(tmA, tmB, tmC, p, stream) : launch_gemm<128, 1>(tmA, tmB, tmC, p, stream);
 }
 
 }  // namespace vscb200
