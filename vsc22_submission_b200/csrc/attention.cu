@@ -194,9 +194,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
   }   // query-tile loop
 }
 
-int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream) {
+bool attention_tc_supported(int T, int head_dim);
+int attention_tc(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse);
+
+int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream,
+              bool reverse) {
   VSCB_REQUIRE(head_dim == 64, "attention: head_dim must be 64");
   VSCB_REQUIRE(n_frames > 0 && T > 0 && heads > 0, "attention: empty problem");
+  // T <= 256: tcgen05 kernel (attention_tc.cu); longer sequences (ViT-L/14: T = 257) stay on the mma.sync kernel
+  if (attention_tc_supported(T, head_dim) && static_cast<int64_t>(n_frames) * T < (1ll << 31))
+    return attention_tc(qkv, out, n_frames, T, heads, stream, reverse);
   const int Tpad = (T + 15) & ~15;
   const size_t smem = static_cast<size_t>(Tpad) * 128 * 2;
   VSCB_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the single-pass K/V staging");
@@ -216,5 +223,5 @@ int attention(const void* qkv, void* out, int n_frames, int T, int heads, int he
 
 extern "C" int vscb200_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int T, int heads, int head_dim,
                                  void* stream) {
-  return vscb200::attention(qkv_bf16, out_bf16, n_frames, T, heads, head_dim, static_cast<cudaStream_t>(stream));
+  return vscb200::attention(qkv_bf16, out_bf16, n_frames, T, heads, head_dim, static_cast<cudaStream_t>(stream), false);
 }

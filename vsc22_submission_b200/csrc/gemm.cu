@@ -39,6 +39,7 @@ struct GemmParams {
   // (slot 0 of every frame is the class token), plus the positional embedding pos[(m % P) + 1, :].
   const float* pos;
   int patch_P;
+  int reverse;      // walk the tile list from the last M block to the first (kernels.h)
 };
 
 constexpr int VSCB_EPI_PATCH_F32 = 3;
@@ -140,7 +141,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
-        const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
+        const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = (vt / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = vt % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (kCluster > 1) {
@@ -202,7 +204,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     uint32_t box_no = 0;
     for (int tile = sched_first; tile < num_tiles; tile += sched_step) {
-      const int m_blk = (tile / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = tile % p.tiles_n;
+      const int vt = p.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = (vt / p.tiles_n) * kCluster + static_cast<int>(crank), n_blk = vt % p.tiles_n;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int64_t row_base = static_cast<int64_t>(m_blk) * kBM + quad * 32;
@@ -349,7 +352,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
-              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P) {
+              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
+              bool reverse) {
   VSCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
   VSCB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
   VSCB_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N/ldc must be multiples of 8");
@@ -373,7 +377,7 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
   if (rc) return rc;
   GemmParams p;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epilogue = epilogue; p.act = act;
-  p.pos = pos; p.patch_P = patch_P;
+  p.pos = pos; p.patch_P = patch_P; p.reverse = reverse ? 1 : 0;
   p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
   p.tiles_n = (N + BN - 1) / BN;
   // output tensor map: 32-row boxes of 128 B (64 bf16 / 32 fp32 columns); unused by the patch-embed epilogue
@@ -397,5 +401,5 @@ extern "C" int vscb200_gemm_bf16(const void* A, const void* W, const float* bias
     return VSCB200_ERR_INVALID;
   }
   return vscb200::gemm_bf16(A, W, bias, C, M, N, K, lda, ldw, ldc, epilogue, act, static_cast<cudaStream_t>(stream),
-                            nullptr, 0);
+                            nullptr, 0, false);
 }

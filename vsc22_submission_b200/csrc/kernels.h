@@ -1,4 +1,10 @@
 // Internal (C++) launch entry points shared between translation units.
+//
+// `reverse`: walk the rows (LayerNorm), M tiles (GEMM) or frames (attention) from the last to the first.
+// The encoder's activations (x 155 MB, qkv 232 MB, u 310 MB per 256 frames) exceed the 126 MB L2, so a
+// consumer that walks in the producer's order misses on everything (LRU streaming); walking in the
+// opposite order consumes the most recently written -- still L2 resident -- rows first.  vit.cu alternates
+// the direction kernel by kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,10 +14,12 @@ namespace vscb200 {
 constexpr int VSCB_EPI_PATCH_F32_ID = 3;
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
-              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P);
-int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream);
+              int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
+              bool reverse = false);
+int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream,
+              bool reverse = false);
 int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,
-              int out_bf16, cudaStream_t stream);
+              int out_bf16, cudaStream_t stream, bool reverse = false);
 int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream);
 int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream);
 int cls_rows(const float* cls, const float* pos, float* x, int64_t n, int T, int W, cudaStream_t stream);

@@ -7,6 +7,7 @@
 //   -> tail: ln_post tokens | ln_post+GeM+Linear (fused) | ln_post -> conv1x1 GEMM -> GeM+Linear.
 // Residual stream, LayerNorm statistics, softmax, GeM and all accumulators are fp32; GEMM operands bf16.
 // No allocation after create(): the workspace is sized for max_frames.
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -214,14 +215,18 @@ static int forward_chunk(vscb200_vit* m, const float* frames, int n, float* out,
               m->Kp, m->Kp, W, VSCB_EPI_PATCH_F32_ID, -1, s, m->pos, P));
   R(cls_rows(m->cls, m->pos, m->x, n, T, W, s));
   if (sp.pre_norm) R(layernorm(m->x, m->ln_pre_w, m->ln_pre_b, m->x, M, W, sp.ln_eps, 0, s));
+  // zig-zag walk (kernels.h): every kernel consumes its input starting from the rows its producer wrote last
+  static const bool zigzag = [] { const char* e = getenv("VSCB200_ZIGZAG"); return e ? atoi(e) != 0 : true; }();
+  bool rev = false;
+  auto dir = [&]() { const bool r = rev; if (zigzag) rev = !rev; return r; };
   for (const LayerW& l : m->layers) {
-    R(layernorm(m->x, l.ln1_w, l.ln1_b, m->h, M, W, sp.ln_eps, 1, s));
-    R(gemm_bf16(m->h, l.qkv_w, l.qkv_b, m->qkv, M, 3 * W, W, W, W, 3 * W, VSCB200_EPI_BF16, -1, s, nullptr, 0));
-    R(attention(m->qkv, m->ao, n, T, sp.heads, 64, s));
-    R(gemm_bf16(m->ao, l.proj_w, l.proj_b, m->x, M, W, W, W, W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0));
-    R(layernorm(m->x, l.ln2_w, l.ln2_b, m->h, M, W, sp.ln_eps, 1, s));
-    R(gemm_bf16(m->h, l.fc1_w, l.fc1_b, m->u, M, 4 * W, W, W, W, 4 * W, VSCB200_EPI_BF16, sp.act, s, nullptr, 0));
-    R(gemm_bf16(m->u, l.fc2_w, l.fc2_b, m->x, M, W, 4 * W, 4 * W, 4 * W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0));
+    R(layernorm(m->x, l.ln1_w, l.ln1_b, m->h, M, W, sp.ln_eps, 1, s, dir()));
+    R(gemm_bf16(m->h, l.qkv_w, l.qkv_b, m->qkv, M, 3 * W, W, W, W, 3 * W, VSCB200_EPI_BF16, -1, s, nullptr, 0, dir()));
+    R(attention(m->qkv, m->ao, n, T, sp.heads, 64, s, dir()));
+    R(gemm_bf16(m->ao, l.proj_w, l.proj_b, m->x, M, W, W, W, W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir()));
+    R(layernorm(m->x, l.ln2_w, l.ln2_b, m->h, M, W, sp.ln_eps, 1, s, dir()));
+    R(gemm_bf16(m->h, l.fc1_w, l.fc1_b, m->u, M, 4 * W, W, W, W, 4 * W, VSCB200_EPI_BF16, sp.act, s, nullptr, 0, dir()));
+    R(gemm_bf16(m->u, l.fc2_w, l.fc2_b, m->x, M, W, 4 * W, 4 * W, 4 * W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir()));
   }
   if (sp.tail == VSCB200_TAIL_TOKENS) {
     R(layernorm(m->x, m->ln_post_w, m->ln_post_b, out, M, W, sp.ln_eps, 0, s));

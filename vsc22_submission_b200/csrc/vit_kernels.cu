@@ -13,9 +13,10 @@ constexpr int kLnMaxVec = 8;   // float4 per lane -> width <= 1024
 template <bool kOutBf16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 void* __restrict__ y, int64_t rows, int width, float eps) {
+                 void* __restrict__ y, int64_t rows, int width, float eps, int reverse) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned bid = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int64_t row = static_cast<int64_t>(bid) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = width >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + row * width);
@@ -66,16 +67,16 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,
-              int out_bf16, cudaStream_t stream) {
+              int out_bf16, cudaStream_t stream, bool reverse) {
   VSCB_REQUIRE(width % 4 == 0 && width <= 128 * kLnMaxVec, "layernorm: width must be a multiple of 4 and <= 1024");
   if (rows == 0) return VSCB200_OK;
   const int rows_per_block = 8;
   const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
   ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * width * (out_bf16 ? 6 : 8));
   if (out_bf16)
-    layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps);
+    layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0);
   else
-    layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps);
+    layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -281,7 +282,7 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
 extern "C" {
 int vscb200_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width,
                       float eps, int out_bf16, void* stream) {
-  return vscb200::layernorm(x, gamma, beta, y, rows, width, eps, out_bf16, static_cast<cudaStream_t>(stream));
+  return vscb200::layernorm(x, gamma, beta, y, rows, width, eps, out_bf16, static_cast<cudaStream_t>(stream), false);
 }
 int vscb200_cast_f32_bf16(const float* x, void* y_bf16, int64_t count, void* stream) {
   return vscb200::cast_f32_bf16_padded(x, y_bf16, count, 1, 1, static_cast<cudaStream_t>(stream));
