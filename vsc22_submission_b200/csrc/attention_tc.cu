@@ -29,9 +29,126 @@ constexpr int kAtcOCol = 128;        // O accumulator columns [128, 192): S is d
 
 struct AtcParams {
   __nv_bfloat16* out;
-  int T, Tpad, heads, W, mtiles, reverse;
+  int T, Tpad, heads, W, mtiles, reverse, dbg;
   float scale_log2e;
 };
+
+
+// fp32 pair -> packed bf16x2 on the integer ALU (round-half-up on the magnitude: +0x8000, keep the high halves).
+// cvt.rn.bf16x2.f32 (F2FP) issues on the XU pipe, which this kernel saturates with its exponentials; finite
+// inputs only (probabilities in [0, 256], normalised outputs).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
+// Softmax of this thread's query row over S (fp32, TMEM columns [0, Tpad) of `tlane`), P written back in place
+// as packed bf16 pairs (columns [0, Tpad/2)).  Returns 1 / row sum.  Warp-collective (tcgen05.ld/st).
+__device__ __forceinline__ float softmax_row_tmem(uint32_t tlane, int T, int Tpad, float scale_log2e, int dbg = 0) {
+  const int nfull = Tpad >> 5;
+  const bool tail16 = (Tpad & 31) != 0;
+  // ---- pass 1: row maximum over the valid keys (four independent chains; the next chunk's TMEM load is in
+  //      flight while the current one is reduced)
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < (dbg ? 1 : nfull); ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tlane + c * 32, v);
+    tmem_ld_wait();
+    const int lim = T - c * 32;
+    if (lim >= 32) {                               // warp-uniform fast path: no masking
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+        m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        m2 = fmaxf(m2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+        m3 = fmaxf(m3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < lim) m0 = fmaxf(m0, __uint_as_float(v[j]));
+    }
+  }
+  if (tail16) {
+    uint32_t v[16];
+    tmem_ld_32x16(tlane + nfull * 32, v);
+    tmem_ld_wait();
+    const int lim = T - nfull * 32;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < lim) m2 = fmaxf(m2, __uint_as_float(v[j]));
+  }
+  const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2e;
+  // ---- pass 2: p = 2^(s*scale - max*scale), row sum (four chains), P -> TMEM (bf16 pairs, in place over S)
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  auto exp_chunk = [&](const uint32_t (&cur)[32], int c) {
+    uint32_t pk[16];
+    const int lim = T - c * 32;
+    if (lim >= 32) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2e, -mxs));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), scale_log2e, -mxs));
+        const float p2 = ex2_approx(fmaf(__uint_as_float(cur[j + 2]), scale_log2e, -mxs));
+        const float p3 = ex2_approx(fmaf(__uint_as_float(cur[j + 3]), scale_log2e, -mxs));
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        pk[j >> 1] = pack_bf16x2_alu(p0, p1);
+        pk[(j >> 1) + 1] = pack_bf16x2_alu(p2, p3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float p0 = ex2_approx(fmaf(__uint_as_float(cur[j]), scale_log2e, -mxs));
+        float p1 = ex2_approx(fmaf(__uint_as_float(cur[j + 1]), scale_log2e, -mxs));
+        if (j >= lim) p0 = 0.f;
+        if (j + 1 >= lim) p1 = 0.f;
+        l0 += p0; l1 += p1;
+        pk[j >> 1] = pack_bf16x2_alu(p0, p1);
+      }
+    }
+    // P of chunk c lands on columns [16c, 16c+16): inside S chunks <= c, all consumed; chunk c+1 (in flight)
+    // starts at column 32(c+1) > 16c+16
+    tmem_st_32x16(tlane + c * 16, pk);
+  };
+#pragma unroll 1
+  for (int c = 0; c < nfull; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tlane + c * 32, v);
+    tmem_ld_wait();
+    exp_chunk(v, c);
+  }
+  if (tail16) {
+    uint32_t v[16], pk[8];
+    tmem_ld_32x16(tlane + nfull * 32, v);
+    tmem_ld_wait();
+    const int lim = T - nfull * 32;
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -mxs));
+      float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -mxs));
+      if (j >= lim) p0 = 0.f;
+      if (j + 1 >= lim) p1 = 0.f;
+      l2 += p0; l3 += p1;
+      pk[j >> 1] = pack_bf16x2_alu(p0, p1);
+    }
+    tmem_st_32x8(tlane + nfull * 16, pk);
+  }
+  tmem_st_wait();
+  return 1.0f / ((l0 + l1) + (l2 + l3));
+}
+
+// 32 fp32 accumulator columns * inv_l -> 32 bf16 (64 contiguous bytes of the output row)
+__device__ __forceinline__ void store_o_half(__nv_bfloat16* dst, const uint32_t (&v)[32], float inv_l) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 o;
+    o.x = pack_bf16x2_alu(__uint_as_float(v[8 * q]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l);
+    o.y = pack_bf16x2_alu(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
+    o.z = pack_bf16x2_alu(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
+    o.w = pack_bf16x2_alu(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
+    *reinterpret_cast<uint4*>(dst + q * 8) = o;
+  }
+}
 
 __global__ void __launch_bounds__(kAtcThreads)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AtcParams p) {
@@ -96,85 +213,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int rbase = mt * 128 + warp * 32;             // first query row of this warp inside the frame
     const bool warp_valid = rbase < p.T;                // warp-uniform
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int nfull = p.Tpad >> 5;
-    const bool tail16 = (p.Tpad & 31) != 0;
     float inv_l = 0.f;
     mbar_wait(bar_s, 0);
     tc_fence_after();
-    if (warp_valid) {
-      // ---- pass 1: row maximum over the valid keys
-      float mx = -INFINITY;
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tlane + c * 32, v);
-        tmem_ld_wait();
-        const int lim = p.T - c * 32;
-        if (lim >= 32) {                                 // warp-uniform fast path: no masking
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
-        }
-      }
-      if (tail16) {
-        uint32_t v[16];
-        tmem_ld_32x16(tlane + nfull * 32, v);
-        tmem_ld_wait();
-        const int lim = p.T - nfull * 32;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
-      }
-      const float mxs = mx * p.scale_log2e;
-      // ---- pass 2: p = 2^(s*scale - max*scale), row sum, P -> TMEM (bf16 pairs, in place over S)
-      float l = 0.f;
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t v[32], pk[16];
-        tmem_ld_32x32(tlane + c * 32, v);
-        tmem_ld_wait();
-        const int lim = p.T - c * 32;
-        if (lim >= 32) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mxs));
-            l += p0 + p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mxs));
-            if (j >= lim) p0 = 0.f;
-            if (j + 1 >= lim) p1 = 0.f;
-            l += p0 + p1;
-            pk[j >> 1] = pack_bf16x2(p0, p1);
-          }
-        }
-        tmem_st_32x16(tlane + c * 16, pk);
-      }
-      if (tail16) {
-        uint32_t v[16], pk[8];
-        tmem_ld_32x16(tlane + nfull * 32, v);
-        tmem_ld_wait();
-        const int lim = p.T - nfull * 32;
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), p.scale_log2e, -mxs));
-          if (j >= lim) p0 = 0.f;
-          if (j + 1 >= lim) p1 = 0.f;
-          l += p0 + p1;
-          pk[j >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_32x8(tlane + nfull * 16, pk);
-      }
-      tmem_st_wait();
-      inv_l = 1.0f / l;
-    }
+    if (warp_valid) inv_l = softmax_row_tmem(tlane, p.T, p.Tpad, p.scale_log2e);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
@@ -189,23 +231,174 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(tlane + kAtcOCol + hc * 32, v);
         tmem_ld_wait();
-        if (row < p.T) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * q]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + hc * 32 + q * 8) = o;
-          }
-        }
+        if (row < p.T) store_o_half(orow + hc * 32, v, inv_l);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<kAtcTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------ persistent ping-pong variant (128 < T <= 256)
+// One CTA per SM walks (frame, head) units.  Both 128-query tiles of a unit are in flight at once, each owned
+// by one softmax warpgroup with its own 256 TMEM columns, so one warpgroup's exponentials overlap the other's
+// MMAs and epilogue; Q/K/V of the NEXT unit are prefetched by a TMA producer warp into the second smem stage.
+//
+//   warps 0-3 / 4-7   softmax + epilogue warpgroups (tile 0 / tile 1; thread = query row)
+//   warp 8            TMA producer: Q [256 x 64], K, V [Tpad x 64] of unit i+1 while unit i computes
+//   warp 9            TMEM allocator (512 columns); lane 0 issues every MMA in the order
+//                     S0(u) S1(u) PV0(u) PV1(u) S0(u+1) ... each gated by the mbarrier of the data it needs
+constexpr int kAppThreads = 320;
+
+__global__ void __launch_bounds__(kAppThreads, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AtcParams p,
+                    int n_units) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int kv_bytes = p.Tpad * 128;
+  const int stage_bytes = 32768 + 2 * kv_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* qk_full = bars;          // [2] per smem stage: Q + K landed
+  uint64_t* qk_empty = bars + 2;     //     both S MMAs of the unit have read them
+  uint64_t* v_full = bars + 4;       //     V landed
+  uint64_t* v_empty = bars + 6;      //     both P.V MMAs of the unit have read it
+  uint64_t* s_full = bars + 8;       // [2] per warpgroup
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 12;
+  uint64_t* o_empty = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 9) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&qk_full[i], 1); mbar_init(&qk_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+        mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto unit_frame_head = [&](int unit, int& frame, int& head) {
+    const int f = unit / p.heads;
+    head = unit % p.heads;
+    frame = p.reverse ? (n_units / p.heads - 1 - f) : f;
+  };
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int it = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        const int st = it & 1;
+        int frame, head;
+        unit_frame_head(unit, frame, head);
+        const int row0 = frame * p.T;
+        uint8_t* sQ = smem + st * stage_bytes;
+        const uint32_t par = (it >> 1) & 1;
+        mbar_wait(&qk_empty[st], par ^ 1);
+        mbar_expect_tx(&qk_full[st], 32768 + kv_bytes);
+        tma_load_2d(sQ, &tmQ, &qk_full[st], head * 64, row0, kEvictFirst);
+        tma_load_2d(sQ + 32768, &tmKV, &qk_full[st], p.W + head * 64, row0, kEvictFirst);
+        mbar_wait(&v_empty[st], par ^ 1);
+        mbar_expect_tx(&v_full[st], kv_bytes);
+        tma_load_2d(sQ + 32768 + kv_bytes, &tmKV, &v_full[st], 2 * p.W + head * 64, row0, kEvictFirst);
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16_f32(128, p.Tpad);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, 64);
+      const int ksteps = p.Tpad >> 4;
+      const int n_it = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      auto issue_s = [&](int w, int it) {
+        const int st = it & 1;
+        const uint32_t sQ = smem_u32(smem + st * stage_bytes);
+        mbar_wait(&qk_full[st], (it >> 1) & 1);
+        mbar_wait(&o_empty[w], (it & 1) ^ 1);           // the warpgroup has drained O of its previous unit
+        tc_fence_after();
+        const uint64_t qd = make_desc_k_sw128(sQ + w * 16384), kd = make_desc_k_sw128(sQ + 32768);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(&s_full[w]);
+      };
+      auto issue_pv = [&](int w, int it) {
+        const int st = it & 1;
+        const uint64_t vd = make_desc_mn_sw128(smem_u32(smem + st * stage_bytes) + 32768 + kv_bytes);
+        mbar_wait(&v_full[st], (it >> 1) & 1);
+        mbar_wait(&p_full[w], it & 1);
+        tc_fence_after();
+        for (int i = 0; i < ksteps; ++i)
+          umma_bf16_ts(tmem_base + w * 256 + kAtcOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
+                       idesc_o, i ? 1u : 0u);
+        umma_commit(&o_full[w]);
+      };
+      // The two warpgroups run half a period apart: while one is in its exponentials (XU-bound) the other one's
+      // MMAs and epilogue run, so they do not queue on the same XU pipe at the same time.
+      if (n_it > 0) issue_s(0, 0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it > 0) {
+          issue_pv(1, it - 1);
+          umma_commit(&v_empty[(it - 1) & 1]);
+        }
+        issue_s(1, it);
+        umma_commit(&qk_empty[it & 1]);
+        issue_pv(0, it);
+        if (it + 1 < n_it) issue_s(0, it + 1);
+      }
+      if (n_it > 0) {
+        issue_pv(1, n_it - 1);
+        umma_commit(&v_empty[(n_it - 1) & 1]);
+      }
+    }
+  } else {
+    const int w = warp >> 2, quad = warp & 3;
+    const int rbase = w * 128 + quad * 32;
+    const bool warp_valid = rbase < p.T;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + w * 256;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      int frame, head;
+      unit_frame_head(unit, frame, head);
+      float inv_l = 0.f;
+      mbar_wait(&s_full[w], ph);
+      tc_fence_after();
+      if (warp_valid) inv_l = softmax_row_tmem(tlane, p.T, p.Tpad, p.scale_log2e, p.dbg);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[w]);
+      mbar_wait(&o_full[w], ph);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      if (warp_valid) {
+        tmem_ld_32x32(tlane + kAtcOCol, v0);
+        tmem_ld_32x32(tlane + kAtcOCol + 32, v1);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[w]);          // TMEM is free for S of the next unit before the stores
+      const int row = rbase + lane;
+      if (warp_valid && row < p.T) {
+        __nv_bfloat16* orow = p.out + (static_cast<int64_t>(frame) * p.T + row) * p.W + head * 64;
+        store_o_half(orow, v0, inv_l);
+        store_o_half(orow + 32, v1, inv_l);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 bool attention_tc_supported(int T, int head_dim) {
@@ -224,7 +417,22 @@ int attention_tc(const void* qkv, void* out, int n_frames, int T, int heads, cud
   AtcParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.T = T; p.Tpad = Tpad; p.heads = heads; p.W = W; p.mtiles = (T + 127) / 128; p.reverse = reverse ? 1 : 0;
+  { const char* e = getenv("VSCB200_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.scale_log2e = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
+  static const int no_pp = [] { const char* e = getenv("VSCB200_ATTN_NO_PINGPONG"); return e ? atoi(e) : 0; }();
+  if (p.mtiles == 2 && !no_pp) {
+    CUtensorMap tmQ2;
+    if ((rc = make_tmap_2d(&tmQ2, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, 256, 64, true))) return rc;
+    const int n_units = n_frames * heads;
+    const int smem_pp = 2 * (32768 + 2 * Tpad * 128) + 256 + 1024;
+    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp));
+    const int grid_pp = n_units < device_sm_count() ? n_units : device_sm_count();
+    ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * 64);
+    attention_pp_kernel<<<grid_pp, kAppThreads, smem_pp, stream>>>(tmQ2, tmKV, p, n_units);
+    count_launch();
+    VSCB_CUDA_OK(cudaGetLastError());
+    return VSCB200_OK;
+  }
   // >= 80 KB per CTA keeps residency at two CTAs per SM (each owns 256 of the 512 TMEM columns)
   int smem = 16384 + 2 * Tpad * 128 + 64 + 1024;
   if (smem < 80 * 1024) smem = 80 * 1024;
