@@ -42,7 +42,12 @@ def test_golden_search_small(faiss, golden_dir):
 
 @pytest.mark.parametrize("nb,nq,d,k,metric", [(5, 3, 3, 2, 1), (1000, 37, 64, 10, 0), (20000, 256, 512, 10, 0),
                                                (4000, 64, 512, 1024, 0), (777, 33, 20, 5, 1), (3000, 100, 512, 1, 0),
-                                               (9, 4, 512, 16, 0)])
+                                               (9, 4, 512, 16, 0),
+                                               # streaming form (nq <= 128 rows against a large bank, sim_stream.cu)
+                                               (70000, 40, 512, 10, 0), (40000, 1, 64, 1, 1), (50000, 128, 512, 5, 0),
+                                               (33000, 17, 40, 26, 1), (100001, 8, 512, 10, 0),
+                                               # few rows x many columns, large k: two-level selection (select.cu)
+                                               (70001, 5, 64, 1024, 0), (66000, 3, 32, 100, 1)])
 def test_search_matches_oracle(faiss, nb, nq, d, k, metric):
     from oracle import faiss_np
     rng = np.random.default_rng(nb + nq)
@@ -75,6 +80,17 @@ def test_exact_ties_resolve_to_lower_id(faiss):
     ix.add(xb)
     D, I = ix.search(np.array([[1, 0, 0, 0]], np.float32), 5)
     assert I.tolist() == [[100, 0, 1, 2, 3]] and D.tolist() == [[2.0, 1.0, 1.0, 1.0, 1.0]]
+
+
+def test_streaming_exact_ties_resolve_to_lower_id(faiss):
+    """Ties across and inside the 32-row groups of the streaming search."""
+    ix = faiss.IndexFlat(8, faiss.METRIC_INNER_PRODUCT)
+    xb = np.zeros((40000, 8), np.float32)
+    xb[:, 0] = 1.0
+    xb[33333, 0] = 2.0
+    ix.add(xb)
+    D, I = ix.search(np.array([[1, 0, 0, 0, 0, 0, 0, 0]], np.float32), 6)
+    assert I.tolist() == [[33333, 0, 1, 2, 3, 4]] and D.tolist() == [[2.0, 1.0, 1.0, 1.0, 1.0, 1.0]]
 
 
 @pytest.mark.parametrize("metric", [0, 1])

@@ -20,6 +20,7 @@ int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void*
                      int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream);
 int fused_topk_slabs(int64_t nq, int64_t nr);
 int fused_topk_list_len();
+int fused_topk_group_rows();
 int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp, bool l2,
                   const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream);
 int merge_rescore(const float* Q, const float* bank, int d, bool l2, const float* cand_d, const int32_t* cand_i,
@@ -51,6 +52,8 @@ struct vscb200_index {
   float* cand_d = nullptr; size_t cand_d_bytes = 0;   // fused top-k epilogue candidates [nq, slabs*2*kFK]
   int32_t* cand_i = nullptr; size_t cand_i_bytes = 0;
   int no_fused = 0;
+  int no_stream = 0;
+  float* gmax = nullptr; size_t gmax_bytes = 0;       // streaming search: per (32-row group, query) maxima
   cudaStream_t own_stream = nullptr;
   cudaStream_t last_stream = nullptr;   // stream of the most recent call (orders the final frees)
   int force_simt = 0;
@@ -202,6 +205,8 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
   ix->force_simt = (e && atoi(e)) ? 1 : 0;
   const char* nf = getenv("VSCB200_NO_FUSED_TOPK");
   ix->no_fused = (nf && atoi(nf)) ? 1 : 0;
+  const char* ns = getenv("VSCB200_NO_STREAM_SEARCH");
+  ix->no_stream = (ns && atoi(ns)) ? 1 : 0;
   *out = ix;
   return VSCB200_OK;
 }
@@ -211,7 +216,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
   void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
-                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i};
+                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax};
   if (ix->own_stream && s == ix->own_stream) {
     cudaStreamSynchronize(s);     // own stream is destroyed below: drain it, then free un-ordered
     s = nullptr;
@@ -265,6 +270,38 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   int rc = flush_pending(ix, s);
   if (rc) return rc;
   const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
+  // A few query rows against a large bank (the reference's per-video call pattern): the bank is streamed from
+  // HBM once, per-group maxima select k + slack groups of 32 rows per query, which are rescored exactly.
+  const int kStreamSlack = 6;
+  if (!ix->force_simt && !ix->no_stream && nq >= 1 && nq <= 128 && k + kStreamSlack <= 32 && ix->ntotal >= 32768 &&
+      ix->ntotal < (1ll << 31) - 256) {
+    const int Npad = static_cast<int>((nq + 15) & ~15ll);
+    const int64_t G = (ix->ntotal + 31) / 32;
+    const int kg = static_cast<int>(std::min<int64_t>(k + kStreamSlack, G));
+    if ((rc = grow(&ix->gmax, &ix->gmax_bytes, static_cast<size_t>(G) * Npad * sizeof(float), s))) return rc;
+    if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float), s))) return rc;
+    if ((rc = row_sqnorm(q, nq, ix->d, ix->qnorm, s))) return rc;
+    const size_t plane = static_cast<size_t>(nq) * ix->dp;
+    if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
+    if ((rc = split_planes(q, ix->q_planes, ix->q_planes + plane, nq, ix->d, ix->dp, s))) return rc;
+    if ((rc = sim_stream_groupmax(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, nq, ix->ntotal, ix->dp,
+                                  !keep_max, ix->qnorm, ix->rnorm, ix->gmax, Npad, s))) return rc;
+    const int chunks = group_topk_chunks(G);
+    if (chunks <= 256) {
+      // per-chunk top groups (one CTA per 256 groups), merged inside the rescoring kernel
+      const size_t ncg = static_cast<size_t>(chunks) * kg;
+      if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nq) * ncg * sizeof(float), s))) return rc;
+      if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nq) * ncg * sizeof(int32_t), s))) return rc;
+      if ((rc = group_topk(ix->gmax, G, Npad, static_cast<int>(nq), kg, chunks, ix->cand_d, ix->cand_i, s))) return rc;
+      return group_rescore(q, ix->bank, ix->d, !keep_max, ix->ntotal, nullptr, ix->cand_d, ix->cand_i, static_cast<int>(ncg),
+                           kg, nq, k, D, I, ix->id_offset, s);
+    }
+    if ((rc = grow(&ix->Dtmp, &ix->Dtmp_bytes, static_cast<size_t>(nq) * kg * sizeof(float), s))) return rc;
+    if ((rc = grow(&ix->Itmp, &ix->Itmp_bytes, static_cast<size_t>(nq) * kg * sizeof(int64_t), s))) return rc;
+    if ((rc = topk_rows(ix->gmax, 1, nq, G, kg, true, ix->Dtmp, ix->Itmp, 0, s, Npad))) return rc;
+    return group_rescore(q, ix->bank, ix->d, !keep_max, ix->ntotal, ix->Itmp, nullptr, nullptr, 0, kg, nq, k, D, I,
+                         ix->id_offset, s);
+  }
   // Small k on a large bank: top-k fused into the scoring kernel's epilogue (no score block in HBM), then a
   // per-query merge + exact rescoring of the survivors.
   const int kFusedSlack = 6;
@@ -285,8 +322,9 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
       if ((rc = split_planes(qb, ix->q_planes, ix->q_planes + plane, nb, ix->d, ix->dp, s))) return rc;
       if ((rc = topk_tc_fused(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, nb, ix->ntotal, ix->dp,
                               !keep_max, ix->qnorm, ix->rnorm, slabs, ix->cand_d, ix->cand_i, s))) return rc;
-      if ((rc = merge_rescore(qb, ix->bank, ix->d, !keep_max, ix->cand_d, ix->cand_i, ncand, k + kFusedSlack, nb, k,
-                              D + q0 * k, I + q0 * k, ix->id_offset, s))) return rc;
+      if ((rc = group_rescore(qb, ix->bank, ix->d, !keep_max, ix->ntotal, nullptr, ix->cand_d, ix->cand_i, ncand,
+                              k + kFusedSlack, nb, k, D + q0 * k, I + q0 * k, ix->id_offset, s,
+                              fused_topk_group_rows()))) return rc;
     }
     return VSCB200_OK;
   }

@@ -35,8 +35,18 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
 int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
 int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
                  float* out, cudaStream_t stream);
+// row r = S + r*ldS, element i of a row at [i*es] (es = 1: dense rows; es > 1: a column of a row-major matrix)
 int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
-              int64_t id_offset, cudaStream_t stream);
+              int64_t id_offset, cudaStream_t stream, int64_t es = 1);
+// sim_stream.cu: streaming search for a few query rows (group maxima + exact rescoring of the best groups)
+int sim_stream_groupmax(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp,
+                        bool l2, const float* qn, const float* rn, float* gmax, int Npad, cudaStream_t stream);
+int group_topk_chunks(int64_t G);
+int group_topk(const float* gmax, int64_t G, int Npad, int nq, int kg, int chunks, float* cand_v, int32_t* cand_g,
+               cudaStream_t stream);
+int group_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nr, const int64_t* gsel, const float* cand_v,
+                  const int32_t* cand_g, int ncg, int kg, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset,
+                  cudaStream_t stream, int gs = 32);
 int rescore_sort(const float* Q, const float* bank, int d, bool l2, const int64_t* Iin, int kin, int64_t nq, int k,
                  float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
 // Q != nullptr: S holds tensor-core scores; borderline pairs and reported distances are recomputed in fp32

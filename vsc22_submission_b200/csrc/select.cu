@@ -22,16 +22,22 @@ __device__ __forceinline__ uint32_t okey(float f, bool keep_max) {
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int k, int kpad, int keep_max_i,
-                   float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset) {
+topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t es, int64_t n_all, int64_t seg_len, int k, int kpad,
+                   int keep_max_i, float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset,
+                   const int64_t* __restrict__ ids_in) {
   extern __shared__ unsigned long long cand[];     // [kpad] (key << 32) | ~idx
   __shared__ unsigned int hist[256];
   __shared__ unsigned int s_prefix, s_remaining, s_gt_slots, s_warp_tot[kSelThreads / 32];
   const bool keep_max = keep_max_i != 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* row = S + static_cast<int64_t>(blockIdx.x) * ldS;
-  float* Dr = D + static_cast<int64_t>(blockIdx.x) * k;
-  int64_t* Ir = I + static_cast<int64_t>(blockIdx.x) * k;
+  // blockIdx.y = segment of the row (two-level selection for few rows x many columns): this CTA selects among
+  // columns [seg0, seg0 + n) and writes its k results at slot (row * gridDim.y + segment)
+  const int64_t seg0 = static_cast<int64_t>(blockIdx.y) * seg_len;
+  const int64_t n = n_all - seg0 < seg_len ? n_all - seg0 : seg_len;
+  const float* row = S + static_cast<int64_t>(blockIdx.x) * ldS + seg0 * es;
+  const int64_t* ids_row = ids_in ? ids_in + static_cast<int64_t>(blockIdx.x) * n_all + seg0 : nullptr;
+  float* Dr = D + (static_cast<int64_t>(blockIdx.x) * gridDim.y + blockIdx.y) * k;
+  int64_t* Ir = I + (static_cast<int64_t>(blockIdx.x) * gridDim.y + blockIdx.y) * k;
   const int kk = static_cast<int>(n < k ? n : k);    // entries that exist
 
   for (int i = tid; i < kpad; i += kSelThreads) cand[i] = 0ull;
@@ -46,7 +52,7 @@ topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int k, i
       __syncthreads();
       const uint32_t prefix = s_prefix;
       for (int64_t i = tid; i < n; i += kSelThreads) {
-        const uint32_t key = okey(row[i], keep_max);
+        const uint32_t key = okey(row[i * es], keep_max);
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
       }
       __syncthreads();
@@ -73,7 +79,7 @@ topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int k, i
       uint32_t key = 0;
       bool gt = false, eq = false;
       if (i < n) {
-        key = okey(row[i], keep_max);
+        key = okey(row[i * es], keep_max);
         gt = key > kth;
         eq = (key == kth) && (eq_seen < need_eq);
       }
@@ -117,8 +123,8 @@ topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int k, i
   for (int j = tid; j < k; j += kSelThreads) {
     if (j < kk) {
       const uint32_t idx = ~static_cast<uint32_t>(cand[j] & 0xFFFFFFFFull);
-      Dr[j] = row[idx];
-      Ir[j] = id_offset + idx;
+      Dr[j] = row[static_cast<int64_t>(idx) * es];
+      Ir[j] = ids_row ? ids_row[idx] : id_offset + seg0 + idx;
     } else {
       Dr[j] = keep_max ? -FLT_MAX : FLT_MAX;
       Ir[j] = -1;
@@ -127,16 +133,50 @@ topk_select_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int k, i
 }
 
 int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
-              int64_t id_offset, cudaStream_t stream) {
+              int64_t id_offset, cudaStream_t stream, int64_t es) {
   VSCB_REQUIRE(k >= 1 && k <= 2048, "search: k must be in [1, 2048]");
   VSCB_REQUIRE(n < (1ll << 32), "search: at most 2^32-1 bank rows per device");
   if (nq == 0) return VSCB200_OK;
   int kpad = 2;
   while (kpad < k) kpad <<= 1;
   ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * n * 4);
-  topk_select_kernel<<<static_cast<unsigned>(nq), kSelThreads, kpad * sizeof(unsigned long long), stream>>>(
-      S, ldS, n, k, kpad, keep_max ? 1 : 0, D, I, id_offset);
+  // Few rows x many columns (the per-video k = 1024 searches of M/infer/infer_matching.py:232): one CTA per row
+  // leaves the GPU idle.  Two levels: every row is cut into segments selected by their own CTAs, then the
+  // nsplit * k survivors per row are selected again.  Ties keep resolving to the lower id: a lower segment holds
+  // lower ids and each segment's output is already ordered.
+  int64_t nsplit = 1;
+  if (nq < 2 * device_sm_count() && n >= 65536 && n >= 16ll * k) {
+    nsplit = (4ll * device_sm_count() + nq - 1) / nq;
+    if (nsplit > n / (8ll * k)) nsplit = n / (8ll * k);
+    if (nsplit > 64) nsplit = 64;
+  }
+  if (nsplit <= 1) {
+    topk_select_kernel<<<static_cast<unsigned>(nq), kSelThreads, kpad * sizeof(unsigned long long), stream>>>(
+        S, ldS, es, n, n, k, kpad, keep_max ? 1 : 0, D, I, id_offset, nullptr);
+    count_launch();
+    VSCB_CUDA_OK(cudaGetLastError());
+    return VSCB200_OK;
+  }
+  const int64_t seg_len = (n + nsplit - 1) / nsplit;
+  nsplit = (n + seg_len - 1) / seg_len;
+  float* Dp = nullptr;
+  int64_t* Ip = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&Dp), static_cast<size_t>(nq) * nsplit * k * sizeof(float), stream);
+  if (rc) return rc;
+  if ((rc = pool_alloc(reinterpret_cast<void**>(&Ip), static_cast<size_t>(nq) * nsplit * k * sizeof(int64_t), stream))) {
+    pool_free(Dp, stream);
+    return rc;
+  }
+  topk_select_kernel<<<dim3(static_cast<unsigned>(nq), static_cast<unsigned>(nsplit)), kSelThreads,
+                       kpad * sizeof(unsigned long long), stream>>>(S, ldS, es, n, seg_len, k, kpad, keep_max ? 1 : 0, Dp, Ip,
+                                                                    id_offset, nullptr);
   count_launch();
+  const int64_t n2 = nsplit * k;
+  topk_select_kernel<<<static_cast<unsigned>(nq), kSelThreads, kpad * sizeof(unsigned long long), stream>>>(
+      Dp, n2, 1, n2, n2, k, kpad, keep_max ? 1 : 0, D, I, 0, Ip);
+  count_launch();
+  pool_free(Dp, stream);
+  pool_free(Ip, stream);
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
@@ -147,7 +187,7 @@ int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool ke
 // fp32 from the original fp32 descriptors (the arithmetic faiss IndexFlat performs), re-sorts and keeps k:
 // reported scores are fp32 dot products and the order can only differ from an fp32 brute force where two
 // scores agree to fp32 rounding.
-constexpr int kRescoreThreads = 128;
+constexpr int kRescoreThreads = 256;
 
 __global__ void __launch_bounds__(kRescoreThreads)
 rescore_sort_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2,
@@ -163,26 +203,37 @@ rescore_sort_kernel(const float* __restrict__ Q, const float* __restrict__ bank,
   for (int c = tid; c < d; c += kRescoreThreads) sq[c] = Q[row * d + c];
   for (int i = tid; i < kpad; i += kRescoreThreads) cand[i] = 0ull;
   __syncthreads();
-  for (int c = warp; c < kin; c += kRescoreThreads / 32) {
-    const int64_t id = Iin[row * kin + c];
-    if (id < 0) continue;                                  // padding (k > ntotal)
-    const float* r = bank + id * d;
-    float acc = 0.f;
+  // four survivors per warp per round: independent row reads, so their HBM latencies overlap
+  for (int c0 = warp * 4; c0 < kin; c0 += (kRescoreThreads / 32) * 4) {
+    int64_t ids[4];
+    const float* rp[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ids[u] = (c0 + u < kin) ? Iin[row * kin + c0 + u] : -1;     // -1: padding (k > ntotal)
+      rp[u] = bank + (ids[u] >= 0 ? ids[u] : 0) * d;
+    }
     for (int j = lane; j < d; j += 32) {
-      if (l2) {
-        const float df = sq[j] - r[j];
-        acc = fmaf(df, df, acc);
-      } else {
-        acc = fmaf(sq[j], r[j], acc);
+      const float qj = sq[j];
+      float rv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rv[u] = rp[u][j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (l2) { const float df = qj - rv[u]; acc[u] = fmaf(df, df, acc[u]); }
+        else acc[u] = fmaf(qj, rv[u], acc[u]);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      sval[c] = acc;
-      // key 0 is reserved for empty slots: okey() of a finite float is never 0
-      cand[c] = (static_cast<unsigned long long>(okey(acc, keep_max)) << 32) |
-                static_cast<uint32_t>(~static_cast<uint32_t>(id));
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      if (lane == 0 && ids[u] >= 0) {
+        sval[c0 + u] = acc[u];
+        // key 0 is reserved for empty slots: okey() of a finite float is never 0
+        cand[c0 + u] = (static_cast<unsigned long long>(okey(acc[u], keep_max)) << 32) |
+                       static_cast<uint32_t>(~static_cast<uint32_t>(ids[u]));
+      }
     }
   }
   __syncthreads();

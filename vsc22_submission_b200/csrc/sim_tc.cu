@@ -47,6 +47,7 @@ struct SimParams {
 };
 
 constexpr int kFK = 16;     // per-thread list length of the fused top-k epilogue (k + rescoring slack <= kFK)
+constexpr int kFG = 8;      // rows per candidate group of the fused epilogue
 
 // Work decomposition shared by the three warp roles.  Dense mode: item = one 128x128 tile, n fastest.
 // Fused mode: item = (m_blk, slab) and the tiles of the slab are walked consecutively, so a thread's
@@ -195,14 +196,23 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
         }
         if (gcol >= p.nr) continue;   // warp-uniform
         if (kFused) {
-          // selection key: larger is better (negated squared distance for L2)
+          // Candidates are GROUPS of kFG = 8 consecutive bank rows, keyed by the group's best selection key
+          // (larger is better; negated squared distance for L2): 8x fewer list updates than per-pair
+          // candidates, and the k best rows are always inside the k groups with the best maxima, which
+          // group_rescore_kernel rescans exactly.
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float key = f[j];
-            if (p.l2) key = -fmaxf(qn_row + p.rn[min(gcol + j, p.nr - 1)] - 2.0f * key, 0.f);
-            if (gcol + j < p.nr && key > ls[kFK - 1]) {
-              ls[kFK - 1] = key;
-              li[kFK - 1] = static_cast<int32_t>(gcol + j);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float gm = -INFINITY;
+#pragma unroll
+            for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+              float key = f[j];
+              if (p.l2) key = 2.0f * key - p.rn[min(gcol + j, p.nr - 1)];
+              if (gcol + j < p.nr) gm = fmaxf(gm, key);
+            }
+            if (p.l2) gm = -fmaxf(qn_row - gm, 0.f);
+            if (gm > ls[kFK - 1]) {
+              ls[kFK - 1] = gm;
+              li[kFK - 1] = static_cast<int32_t>((gcol >> 3) + g8);
 #pragma unroll
               for (int t = kFK - 1; t > 0; --t) {
                 if (ls[t] > ls[t - 1]) {
@@ -349,8 +359,10 @@ int fused_topk_slabs(int64_t nq, int64_t nr) {
   return static_cast<int>(s);
 }
 int fused_topk_list_len() { return kFK; }
+int fused_topk_group_rows() { return kFG; }
 
-// cand_d / cand_i: [nq, slabs * 2 * kFK] keys (larger = better; -distance for L2) and local bank ids (-1 = empty)
+// cand_d / cand_i: [nq, slabs * 2 * kFK] group keys (larger = better; -distance for L2) and group ids = row / kFG
+// (-1 = empty)
 int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp, bool l2,
                   const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream) {
   if (nq == 0 || nr == 0) return VSCB200_OK;

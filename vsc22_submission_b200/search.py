@@ -170,9 +170,34 @@ def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch
 # ------------------------------------------------------------------------------------------------
 # the reference's function signatures (lists of VideoFeature-like objects, numpy features)
 # ------------------------------------------------------------------------------------------------
-def _cat(features: Sequence, device) -> torch.Tensor:
-    arr = np.concatenate([np.asarray(f.feature, dtype=np.float32) for f in features], axis=0)
-    return torch.from_numpy(np.ascontiguousarray(arr)).to(device, non_blocking=False)
+_PINNED = {}      # staging buffers (page-locked host memory), reused across calls: name -> uint8 tensor
+
+
+def _pinned(name: str, nbytes: int) -> torch.Tensor:
+    buf = _PINNED.get(name)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _PINNED[name] = buf
+    return buf
+
+
+def _cat(features: Sequence, device, name: str = "cat") -> torch.Tensor:
+    """Concatenate the per-video feature arrays straight into a page-locked staging buffer (one pass over the
+    host data) and upload it with one asynchronous copy."""
+    rows = sum(int(f.feature.shape[0]) for f in features)
+    d = int(features[0].feature.shape[1])
+    stage = _pinned(name, rows * d * 4)[: rows * d * 4].view(torch.float32).view(rows, d)
+    torch.cuda.current_stream(device).synchronize()      # the previous upload from this buffer has drained
+    np.concatenate([np.asarray(f.feature, dtype=np.float32) for f in features], axis=0, out=stage.numpy())
+    return stage.to(device, non_blocking=True)
+
+
+def _to_host(t: torch.Tensor, name: str) -> np.ndarray:
+    """Device -> page-locked host buffer -> numpy array owned by the caller."""
+    stage = _pinned(name, t.numel() * 4)[: t.numel() * 4].view(torch.float32).view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return stage.numpy().copy()
 
 
 def _split(features: Sequence, arr: np.ndarray) -> List:
@@ -197,9 +222,9 @@ def score_normalize(queries, refs, score_norm_refs, l2_normalize: bool = True, r
     """score_normalization.py:33-104."""
     _check_disjoint(refs, score_norm_refs)
     dev = torch.device(device)
-    q_t, r_t, _ = score_normalize_tensors(_cat(queries, dev), _cat(refs, dev), _cat(score_norm_refs, dev),
+    q_t, r_t, _ = score_normalize_tensors(_cat(queries, dev, "q"), _cat(refs, dev, "r"), _cat(score_norm_refs, dev, "z"),
                                           l2_normalize, replace_dim, beta, nk)
-    return _split(queries, q_t.cpu().numpy()), _split(refs, r_t.cpu().numpy())
+    return _split(queries, _to_host(q_t, "qo")), _split(refs, _to_host(r_t, "ro"))
 
 
 def query_score_normalize(queries, score_norm_refs, video_scores: dict, score_threshold: float = 0.001,
@@ -208,10 +233,10 @@ def query_score_normalize(queries, score_norm_refs, video_scores: dict, score_th
     """score_normalization.py:107-148 (video-score gate: bias = -100 below the threshold, :142-143)."""
     dev = torch.device(device)
     gated = np.concatenate([np.full(q.feature.shape[0], video_scores[q.video_id] < score_threshold) for q in queries])
-    q_t, _, _ = score_normalize_tensors(_cat(queries, dev), None, _cat(score_norm_refs, dev), l2_normalize,
+    q_t, _, _ = score_normalize_tensors(_cat(queries, dev, "q"), None, _cat(score_norm_refs, dev, "z"), l2_normalize,
                                         replace_dim, beta, nk, low_var_dim_=low_var_dim,
                                         gated_rows=torch.from_numpy(gated))
-    return _split(queries, q_t.cpu().numpy())
+    return _split(queries, _to_host(q_t, "qo"))
 
 
 def ref_score_normalize(refs, score_norm_refs, l2_normalize: bool = True, replace_dim: bool = True,
@@ -221,6 +246,6 @@ def ref_score_normalize(refs, score_norm_refs, l2_normalize: bool = True, replac
     dev = torch.device(device)
     lvd = -1
     if replace_dim:
-        lvd = low_var_dim(_cat(score_norm_refs, dev))
-    r_t = sn_transform(_cat(refs, dev), lvd, l2_normalize, fill=1.0)
-    return _split(refs, r_t.cpu().numpy())
+        lvd = low_var_dim(_cat(score_norm_refs, dev, "z"))
+    r_t = sn_transform(_cat(refs, dev, "r"), lvd, l2_normalize, fill=1.0)
+    return _split(refs, _to_host(r_t, "ro"))
