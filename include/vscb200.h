@@ -140,6 +140,35 @@ int vscb200_vit_forward_host(vscb200_vit* m, const float* frames_host, int64_t n
 int64_t vscb200_vit_out_elems_per_frame(const vscb200_vit* m);
 
 /* ------------------------------------------------------------------------------------------------
+ * (A) Swin-V2 frame encoder.  Replaces the TorchScript module `swinv2_v1xx` called at
+ *     D/infer/src/extractor.py:25 / D/infer/extract_query_feats.py:148 (architecture:
+ *     D/train/train_v106/vsc/baseline/model_factory/backbones/swinv2.py:502-633, config_v106.py:8-24).
+ *     head_dim is 32 in every stage (heads[i] * 32 == embed << i), window side 4 / 8 / 16.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vscb200_swin vscb200_swin;
+
+typedef struct vscb200_swin_spec {
+  int img, patch, embed, n_stages;
+  int depths[4];
+  int heads[4];
+  int window;
+  int pretrained_windows[4]; /* swinv2.py:107-112: normalisation of the log-spaced relative coordinates */
+  int out_dim;
+  float ln_eps;
+  float gem_p;
+} vscb200_swin_spec;
+
+int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_swin** out);
+void vscb200_swin_destroy(vscb200_swin* m);
+/* Upload one named fp32 parameter (device pointer); names are the reference's state-dict names
+ * (patch_embed.proj.weight ... layers.<i>.blocks.<j>.attn.qkv.weight ... output_proj.bias). */
+int vscb200_swin_set_param(vscb200_swin* m, const char* name, const float* w_dev, int64_t count, void* stream);
+/* model(frames): frames [n,3,img,img] float32 NCHW contiguous (device) -> out (device) [n,out_dim] */
+int vscb200_swin_forward(vscb200_swin* m, const float* frames_dev, int64_t n, float* out_dev, void* stream);
+int vscb200_swin_forward_host(vscb200_swin* m, const float* frames_host, int64_t n, float* out_host);
+int vscb200_swin_out_dim(const vscb200_swin* m);
+
+/* ------------------------------------------------------------------------------------------------
  * Building blocks exported for unit tests and micro-benchmarks.
  * ---------------------------------------------------------------------------------------------- */
 #define VSCB200_EPI_BF16 0          /* C_bf16 = act(A*W^T + bias)            */

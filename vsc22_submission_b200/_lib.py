@@ -25,6 +25,12 @@ class VitSpecC(C.Structure):
                                        "tail", "out_dim", "gem_hidden")] + [("ln_eps", C.c_float), ("gem_p", C.c_float)]
 
 
+class SwinSpecC(C.Structure):
+    _fields_ = [("img", C.c_int), ("patch", C.c_int), ("embed", C.c_int), ("n_stages", C.c_int), ("depths", C.c_int * 4),
+                ("heads", C.c_int * 4), ("window", C.c_int), ("pretrained_windows", C.c_int * 4), ("out_dim", C.c_int),
+                ("ln_eps", C.c_float), ("gem_p", C.c_float)]
+
+
 class Vscb200Error(RuntimeError):
     pass
 
@@ -64,6 +70,12 @@ SIGNATURES = {
     "vscb200_vit_forward": (_i, [_p, _p, _i64, _p, _p]),
     "vscb200_vit_forward_host": (_i, [_p, _p, _i64, _p]),
     "vscb200_vit_out_elems_per_frame": (_i64, [_p]),
+    "vscb200_swin_create": (_i, [C.POINTER(SwinSpecC), _i, C.POINTER(_p)]),
+    "vscb200_swin_destroy": (None, [_p]),
+    "vscb200_swin_set_param": (_i, [_p, C.c_char_p, _p, _i64, _p]),
+    "vscb200_swin_forward": (_i, [_p, _p, _i64, _p, _p]),
+    "vscb200_swin_forward_host": (_i, [_p, _p, _i64, _p]),
+    "vscb200_swin_out_dim": (_i, [_p]),
     "vscb200_gemm_bf16": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
     "vscb200_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "vscb200_attention": (_i, [_p, _p, _i, _i, _i, _i, _p]),

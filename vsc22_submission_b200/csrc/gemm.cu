@@ -40,6 +40,11 @@ struct GemmParams {
   const float* pos;
   int patch_P;
   int reverse;      // walk the tile list from the last M block to the first (kernels.h)
+  // Swin-V2 cosine attention (swinv2.py:160-163), fused into the QKV projection: every 32-column chunk with
+  // column < qk_norm_cols is one head's q or k vector of this row -> L2-normalised (F.normalize, eps 1e-12);
+  // q chunks (column < qk_norm_cols / 2) are also multiplied by their head's clamped exp(logit_scale).
+  int qk_norm_cols;
+  const float* qscale;
 };
 
 constexpr int VSCB_EPI_PATCH_F32 = 3;
@@ -230,6 +235,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0 + sub * 32, v);
             tmem_ld_wait();
             const int gc0 = gcol + sub * 32;
+            float rnorm = 1.0f;
+            const bool qk_norm = gc0 < p.qk_norm_cols;        // warp-uniform
+            if (qk_norm) {
+              float ss = 0.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc0 + 4 * q));
+                const float a = __uint_as_float(v[4 * q]) + b4.x, b = __uint_as_float(v[4 * q + 1]) + b4.y;
+                const float c2 = __uint_as_float(v[4 * q + 2]) + b4.z, d2 = __uint_as_float(v[4 * q + 3]) + b4.w;
+                ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c2, c2, ss); ss = fmaf(d2, d2, ss);
+              }
+              rnorm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+              if (gc0 < (p.qk_norm_cols >> 1)) rnorm *= __ldg(p.qscale + (gc0 >> 5));
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
@@ -238,6 +258,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc0 + 4 * q));
                 o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
               }
+              if (qk_norm) { o.x *= rnorm; o.y *= rnorm; o.z *= rnorm; o.w *= rnorm; }
               if (p.act >= 0) {
                 o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
                 o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
@@ -353,7 +374,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
               int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
-              bool reverse) {
+              bool reverse, int qk_norm_cols, const float* qscale) {
   VSCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
   VSCB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
   VSCB_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N/ldc must be multiples of 8");
@@ -378,6 +399,9 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
   GemmParams p;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epilogue = epilogue; p.act = act;
   p.pos = pos; p.patch_P = patch_P; p.reverse = reverse ? 1 : 0;
+  VSCB_REQUIRE(qk_norm_cols == 0 || (epilogue == VSCB200_EPI_BF16 && qk_norm_cols % 64 == 0 && qk_norm_cols <= N && qscale != nullptr),
+               "gemm: the q/k normalisation epilogue needs bf16 output and whole 32-column heads");
+  p.qk_norm_cols = qk_norm_cols; p.qscale = qscale;
   p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
   p.tiles_n = (N + BN - 1) / BN;
   // output tensor map: 32-row boxes of 128 B (64 bf16 / 32 fp32 columns); unused by the patch-embed epilogue
@@ -401,5 +425,5 @@ extern "C" int vscb200_gemm_bf16(const void* A, const void* W, const float* bias
     return VSCB200_ERR_INVALID;
   }
   return vscb200::gemm_bf16(A, W, bias, C, M, N, K, lda, ldw, ldc, epilogue, act, static_cast<cudaStream_t>(stream),
-                            nullptr, 0, false);
+                            nullptr, 0, false, 0, nullptr);
 }

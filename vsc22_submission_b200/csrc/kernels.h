@@ -15,7 +15,7 @@ constexpr int VSCB_EPI_PATCH_F32_ID = 3;
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
               int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
-              bool reverse = false);
+              bool reverse = false, int qk_norm_cols = 0, const float* qscale = nullptr);
 int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream,
               bool reverse = false);
 int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,

@@ -269,8 +269,11 @@ def encoder_from_state_dict(sd: Dict[str, torch.Tensor], max_frames: int = 256) 
                        ln_eps=1e-6, tail="gem_conv_linear", out_dim=sd["model.embeddings.1.weight"].shape[0],
                        gem_hidden=sd["model.embeddings.0.conv.weight"].shape[0])
         return B200ViTEncoder(spec, weights_from_sscd_timm_state_dict(sd, layers), max_frames)
-    raise RuntimeError("encoder_from_state_dict: unrecognised checkpoint (only the ViT encoders of the reference's "
-                       "inference path are implemented so far; Swin-V2 is the next SURVEY.md 8a row)")
+    if "patch_embed.proj.weight" in keys and "layers.0.blocks.0.attn.logit_scale" in keys:             # swinv2_v1xx
+        from .swin_encoder import B200SwinEncoder, spec_from_state_dict
+        return B200SwinEncoder(spec_from_state_dict(sd), sd, min(max_frames, 64))
+    raise RuntimeError("encoder_from_state_dict: unrecognised checkpoint (implemented: CLIP ViT, timm ViT + GeM head, "
+                       "Swin-V2 -- the encoders on the reference's inference path)")
 
 
 _orig_jit_load = None
