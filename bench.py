@@ -34,6 +34,16 @@ BATCH = 256                # encoder plan max_frames
 SIM_NQ, SIM_NR, SIM_NZ, SIM_D, SIM_K = 10_000, 40_000, 40_000, 512, 10   # configs[2]
 
 
+def load_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
+    capture (profiles/r01_traffic.json; a number measured under the profiler, never a timing)."""
+    p = os.path.join(REPO, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -191,7 +201,7 @@ def bench_encoder(args, world, rank, peaks):
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all projections + patch embed)",
                 "achieved": gemm_tflops, "peak": roof_peak, "unit": "TFLOP/s", "frac": gemm_tflops / roof_peak,
                 "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
-                "traffic": None, "launches": gm["launches"],
+                "traffic": load_traffic("gemm_bf16_kernel"), "launches": gm["launches"],
                 "share_of_step": gm["ms"] / ms if ms > 0 else None,
                 "whole_step_tflops": value / world * spec.flops_per_frame() / 1e12,
                 "whole_step_frac": value / world * spec.flops_per_frame() / 1e12 / roof_peak,
@@ -221,13 +231,15 @@ def cpu_baseline_encoder(frames_cpu_fn, seconds_budget=20.0):
 
 
 # ------------------------------------------------------------------------------------------------ similarity
-def make_sim_data(device, rank=0):
+def make_sim_data(device, world=1, rank=0):
+    """Queries (replicated) and THIS RANK's shard of the reference / noise banks.  Weak scaling: every rank holds
+    SIM_NR + SIM_NZ bank rows, the global banks have world x that many (ids offset by rank * SIM_NR)."""
     import torch
     def unit(n, seed):
         g = torch.Generator(device=device).manual_seed(seed)
         x = torch.randn((n, SIM_D), generator=g, device=device)
         return x / x.norm(dim=1, keepdim=True)
-    return unit(SIM_NQ, 2), unit(SIM_NR, 3), unit(SIM_NZ, 4)
+    return unit(SIM_NQ, 2), unit(SIM_NR, 3 + 100 * rank), unit(SIM_NZ, 4 + 100 * rank)
 
 
 def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
@@ -273,13 +285,8 @@ def bench_sim(args, world, rank, peaks):
 
     from vsc22_submission_b200 import _lib
     dev = torch.device("cuda", torch.cuda.current_device())
-    Q, R, Z = make_sim_data(dev)
-    from vsc22_submission_b200.sharding import shard_range
-    def shard(x):
-        a, b = shard_range(x.shape[0], world, rank)
-        return x[a:b].contiguous(), a
-    R_s, row0 = shard(R)
-    Z_s, _ = shard(Z)
+    Q, R, Z = make_sim_data(dev, world, rank)
+    R_s, Z_s, row0 = R, Z, rank * SIM_NR
     for _ in range(args.warmup):
         D, I = sim_step_device(Q, R_s, Z_s, world, rank, row0)
     barrier_sync(world)
@@ -302,7 +309,7 @@ def bench_sim(args, world, rank, peaks):
     launches = _lib.launch_count() - n0
     _lib.prof_enable(False)
     prof = _lib.prof_collect()
-    pairs = SIM_NQ * (SIM_NR + SIM_NZ)
+    pairs = SIM_NQ * (SIM_NR + SIM_NZ) * world
     value = pairs / (ms / 1e3)
     # e2e through the reference-facing API: lists of per-video host feature arrays through score_normalize
     # (score_normalization.py:33-104), the normalised features added video by video to a faiss-style index
@@ -341,12 +348,12 @@ def bench_sim(args, world, rank, peaks):
                       ".search on numpy arrays",
                "idx_agree_with_device_path": float((Ih == I.cpu().numpy()).mean())}
         stream = bench_sim_stream(peaks)
-    flops = 2.0 * SIM_D * pairs
+    flops = 2.0 * SIM_D * pairs / world            # per GPU
     bytes_alg = (SIM_NQ + SIM_NR + SIM_NZ) * SIM_D * 4 + SIM_NQ * SIM_K * 12
     sc = prof["scores"]
     roof = {"bound": "tensor", "kernel": "similarity scores kernel (both banks)",
             "achieved": (sc["work"] / (sc["ms"] / 1e3) / 1e12) if sc["ms"] > 0 else 0.0, "peak": peaks["bf16_tflops"],
-            "unit": "TFLOP/s", "peak_source": f"{peaks['source']} bf16_tflops (burst)", "traffic": None,
+            "unit": "TFLOP/s", "peak_source": f"{peaks['source']} bf16_tflops (burst)", "traffic": load_traffic("sim3_kernel"),
             "whole_step_tensor_frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
             "whole_step_hbm_frac": bytes_alg / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
             "kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}}
@@ -359,6 +366,7 @@ def bench_sim(args, world, rank, peaks):
             "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
                                    "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
                        "k": SIM_K, "l2_flush": "256 MiB write between steps",
+                       "scaling": "weak (every rank holds a 40k + 40k row bank shard; global banks = world x that)",
                        "sharding": "bank rows over ranks + all-gather of partial top-k" if world > 1 else "single GPU"}}
 
 
@@ -405,7 +413,8 @@ def bench_sim_stream(peaks, nq=40, nr=1_000_000, k=10, iters=10):
             "roofline": {"bound": "hbm", "kernel": "sim_stream_kernel (bank streamed once; group maxima out)",
                          "achieved": bytes_alg / (kern / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": bytes_alg / (kern / 1e3) / 1e9 / peaks["hbm_gbs"],
-                         "peak_source": f"{peaks['source']} hbm_gbs (copy bandwidth)", "traffic": None,
+                         "peak_source": f"{peaks['source']} hbm_gbs (copy bandwidth)", "traffic": load_traffic("sim_stream_kernel"),
+                         "algorithmic_bytes": bytes_alg,
                          "kernel_ms": kern, "whole_call_achieved": bytes_alg / (call / 1e3) / 1e9,
                          "whole_call_frac": bytes_alg / (call / 1e3) / 1e9 / peaks["hbm_gbs"]}}
 

@@ -6,6 +6,7 @@
 // vsc/exhaustive_search.py:62,74; score_normalization.py:95; M/infer/infer_matching.py:232-235.
 #include <float.h>
 
+#include "exact.cuh"
 #include "host_util.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -207,27 +208,15 @@ rescore_sort_kernel(const float* __restrict__ Q, const float* __restrict__ bank,
   for (int c0 = warp * 4; c0 < kin; c0 += (kRescoreThreads / 32) * 4) {
     int64_t ids[4];
     const float* rp[4];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       ids[u] = (c0 + u < kin) ? Iin[row * kin + c0 + u] : -1;     // -1: padding (k > ntotal)
       rp[u] = bank + (ids[u] >= 0 ? ids[u] : 0) * d;
     }
-    for (int j = lane; j < d; j += 32) {
-      const float qj = sq[j];
-      float rv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rv[u] = rp[u][j];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (l2) { const float df = qj - rv[u]; acc[u] = fmaf(df, df, acc[u]); }
-        else acc[u] = fmaf(qj, rv[u], acc[u]);
-      }
-    }
+    exact_rows_warp<4>(sq, rp, d, lane, l2 != 0, acc);            // the shared summation order (exact.cuh)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
       if (lane == 0 && ids[u] >= 0) {
         sval[c0 + u] = acc[u];
         // key 0 is reserved for empty slots: okey() of a finite float is never 0
@@ -322,14 +311,10 @@ merge_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank
     const unsigned long long cc = cand[c];
     if (cc == 0ull) continue;
     const uint32_t id = ~static_cast<uint32_t>(cc & 0xFFFFFFFFull);
-    const float* r = bank + static_cast<int64_t>(id) * d;
-    float acc = 0.f;
-    for (int j = lane; j < d; j += 32) {
-      if (l2) { const float df = sq[j] - r[j]; acc = fmaf(df, df, acc); }
-      else acc = fmaf(sq[j], r[j], acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float* const rp1[1] = {bank + static_cast<int64_t>(id) * d};
+    float acc1[1];
+    exact_rows_warp<1>(sq, rp1, d, lane, l2 != 0, acc1);
+    const float acc = acc1[0];
     if (lane == 0) cand[c] = (static_cast<unsigned long long>(okey(acc, keep_max)) << 32) | static_cast<uint32_t>(~id);
   }
   __syncthreads();
@@ -484,14 +469,10 @@ range_fill_kernel(RangeArgs a, const unsigned long long* __restrict__ offsets, f
     const unsigned long long cnt = pos - pos0;
     for (unsigned long long j = warp; j < cnt; j += kRangeThreads / 32) {
       const int64_t id = I[pos0 + j];
-      const float* r = a.bank + id * a.d;
-      float acc = 0.f;
-      for (int c = lane; c < a.d; c += 32) {
-        if (!a.keep_max) { const float df = rg_q[c] - r[c]; acc = fmaf(df, df, acc); }
-        else acc = fmaf(rg_q[c], r[c], acc);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float* const rp1[1] = {a.bank + id * a.d};
+      float acc1[1];
+      exact_rows_warp<1>(rg_q, rp1, a.d, lane, !a.keep_max, acc1);
+      const float acc = acc1[0];
       if (lane == 0) {
         D[pos0 + j] = acc;
         I[pos0 + j] = id_offset + id;

@@ -17,6 +17,7 @@
 // scores, no dense score block.
 #include <float.h>
 
+#include "exact.cuh"
 #include "host_util.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -328,7 +329,7 @@ group_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank
     const float* rp[4];
     int64_t ids[4];
     bool ok[4];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int c = c0 + u;
@@ -337,23 +338,9 @@ group_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank
       ok[u] = g >= 0 && ids[u] < nr;
       rp[u] = bank + (ok[u] ? ids[u] : 0) * d;
     }
-    // Same summation order as every other exact-rescoring kernel (select.cu): lane-strided fmaf chain, then
-    // a butterfly reduction -- a pair's reported score does not depend on which search path produced it.
-    for (int j = lane; j < d; j += 32) {
-      const float qj = sq[j];
-      float rv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rv[u] = __ldg(rp[u] + j);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (l2) { const float df = qj - rv[u]; acc[u] = fmaf(df, df, acc[u]); }
-        else acc[u] = fmaf(qj, rv[u], acc[u]);
-      }
-    }
+    exact_rows_warp<4>(sq, rp, d, lane, l2 != 0, acc);       // the shared summation order (exact.cuh)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
       if (lane == 0 && ok[u])
         cand[c0 + u] = (static_cast<unsigned long long>(okey_u(acc[u], keep_max)) << 32) |
                        static_cast<uint32_t>(~static_cast<uint32_t>(ids[u]));
