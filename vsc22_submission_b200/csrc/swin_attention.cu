@@ -34,23 +34,80 @@ __device__ __forceinline__ uint32_t pack_bf16x2_alu2(float lo, float hi) {
   return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 
-// z[j] = S[j] + bias(i, j) (+ mask) for the 32 (or 16) columns of chunk c; natural-log domain
-template <int WS, int NCOL>
+// z[jj] = S[jj] + bias(i, j) (+ mask) for the NCOL columns j = 32c + jj of chunk c (natural-log domain).
+//   bias: tab[(yi - yj + WS-1) * TS + (xi - xj + WS-1)] = tp[-(yj_local * TS + xj)] with tp = tab + base_i - c * rows_per_chunk * TS:
+//         one LDS with a compile-time offset per score;
+//   mask: the shift is WS / 2, so a column's x-region is a compile-time function of jj and its y-region is uniform over
+//         the chunk (WS >= 8) or compile-time (WS = 4): pen[ry][rx] (-100 where the region differs from the row's) is
+//         precomputed per thread and only edge windows of shifted blocks take this variant.
+template <int WS, int NCOL, bool kMasked>
 __device__ __forceinline__ void add_bias_mask(float (&z)[32], const uint32_t (&v)[32], const float* tab, int base_i, int c,
-                                              bool masked, int ry_i, int rx_i, bool edge_y, bool edge_x, int shift) {
+                                              const float (&pen)[2][2]) {
   constexpr int TS = 2 * WS - 1;
+  constexpr int kRowsPerChunk = 32 / WS > 0 ? 32 / WS : 1;      // window rows covered by a 32-column chunk
+  const float* tp = tab + base_i - c * kRowsPerChunk * TS;
+  const bool ry_chunk = c * kRowsPerChunk >= WS / 2;             // WS >= 8: all rows of the chunk are on one side
+  const float pen_c0 = ry_chunk ? pen[1][0] : pen[0][0], pen_c1 = ry_chunk ? pen[1][1] : pen[0][1];
 #pragma unroll
   for (int jj = 0; jj < NCOL; ++jj) {
-    const int j = c * 32 + jj;
-    const int yj = j / WS, xj = j % WS;              // WS is a power of two
-    float b = tab[base_i - (yj * TS + xj)];
-    if (masked) {
-      const int ryj = (edge_y && yj >= WS - shift) ? 1 : 0;
-      const int rxj = (edge_x && xj >= WS - shift) ? 1 : 0;
-      if (ryj != ry_i || rxj != rx_i) b -= 100.0f;
+    const int yl = jj / WS, xj = jj % WS;                        // compile-time
+    float zz = __uint_as_float(v[jj]) + tp[-(yl * TS + xj)];
+    if (kMasked) {
+      const bool rx = xj >= WS / 2;
+      if (WS >= 8) zz += rx ? pen_c1 : pen_c0;
+      else zz += pen[yl >= WS / 2 ? 1 : 0][rx ? 1 : 0];
     }
-    z[jj] = __uint_as_float(v[jj]) + b;
+    z[jj] = zz;
   }
+}
+
+// Softmax of one query row of a window over S (TMEM, fp32) + bias + mask; P written back in place as bf16 pairs.
+template <int WS, bool kMasked>
+__device__ __forceinline__ float softmax_row(uint32_t tlane, const float* tab, int base_i, const float (&pen)[2][2]) {
+  constexpr int N = WS * WS;
+  constexpr int kChunks = N >= 32 ? N / 32 : 1;
+  constexpr int kCols = N >= 32 ? 32 : 16;
+  // ---- pass 1: row maximum of z = s + bias + mask
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t v[32];
+    float z[32];
+    if (kCols == 32) tmem_ld_32x32(tlane + c * 32, v);
+    else tmem_ld_32x16(tlane, reinterpret_cast<uint32_t(&)[16]>(v));
+    tmem_ld_wait();
+    add_bias_mask<WS, kCols, kMasked>(z, v, tab, base_i, c, pen);
+#pragma unroll
+    for (int j = 0; j < kCols; j += 4) {
+      m0 = fmaxf(m0, z[j]); m1 = fmaxf(m1, z[j + 1]); m2 = fmaxf(m2, z[j + 2]); m3 = fmaxf(m3, z[j + 3]);
+    }
+  }
+  const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * 1.4426950408889634f;
+  // ---- pass 2: p = exp(z - max), row sum, P -> TMEM as bf16 pairs (in place over S)
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t v[32], pk[16];
+    float z[32];
+    if (kCols == 32) tmem_ld_32x32(tlane + c * 32, v);
+    else tmem_ld_32x16(tlane, reinterpret_cast<uint32_t(&)[16]>(v));
+    tmem_ld_wait();
+    add_bias_mask<WS, kCols, kMasked>(z, v, tab, base_i, c, pen);
+#pragma unroll
+    for (int j = 0; j < kCols; j += 4) {
+      const float p0 = ex2_approx(fmaf(z[j], 1.4426950408889634f, -mxs));
+      const float p1 = ex2_approx(fmaf(z[j + 1], 1.4426950408889634f, -mxs));
+      const float p2 = ex2_approx(fmaf(z[j + 2], 1.4426950408889634f, -mxs));
+      const float p3 = ex2_approx(fmaf(z[j + 3], 1.4426950408889634f, -mxs));
+      l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+      pk[j >> 1] = pack_bf16x2_alu2(p0, p1);
+      pk[(j >> 1) + 1] = pack_bf16x2_alu2(p2, p3);
+    }
+    if (kCols == 32) tmem_st_32x16(tlane + c * 16, pk);
+    else tmem_st_32x8(tlane, reinterpret_cast<uint32_t(&)[8]>(pk));
+  }
+  tmem_st_wait();
+  return 1.0f / ((l0 + l1) + (l2 + l3));
 }
 
 template <int WS>
@@ -194,7 +251,13 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
         const bool edge_y = p.shift > 0 && (wf / p.nWx) == (p.nW_per_frame / p.nWx) - 1;
         const bool edge_x = p.shift > 0 && (wf % p.nWx) == p.nWx - 1;
         const bool masked = edge_y || edge_x;
-        const int ry_i = (edge_y && yi >= WS - p.shift) ? 1 : 0, rx_i = (edge_x && xi >= WS - p.shift) ? 1 : 0;
+        const int ry_i = (edge_y && yi >= WS / 2) ? 1 : 0, rx_i = (edge_x && xi >= WS / 2) ? 1 : 0;
+        float pen[2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            pen[a][b] = ((edge_y && a != ry_i) || (edge_x && b != rx_i)) ? -100.0f : 0.0f;
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t ph = (2 * it + hh) & 1;
@@ -203,46 +266,8 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
           mbar_wait(&s_full[w], ph);
           tc_fence_after();
           if (warp_valid) {
-            constexpr int kChunks = N >= 32 ? N / 32 : 1;
-            constexpr int kCols = N >= 32 ? 32 : 16;
-            // ---- pass 1: row maximum of z = s + bias + mask
-            float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-              uint32_t v[32];
-              float z[32];
-              if (kCols == 32) tmem_ld_32x32(tlane + c * 32, v);
-              else tmem_ld_32x16(tlane, reinterpret_cast<uint32_t(&)[16]>(v));
-              tmem_ld_wait();
-              add_bias_mask<WS, kCols>(z, v, tab, row_ok ? base_i : (WS - 1) * TS + WS - 1, c, masked, ry_i, rx_i, edge_y, edge_x,
-                                       p.shift);
-#pragma unroll
-              for (int j = 0; j < kCols; j += 2) { m0 = fmaxf(m0, z[j]); m1 = fmaxf(m1, z[j + 1]); }
-            }
-            const float mxs = fmaxf(m0, m1) * 1.4426950408889634f;
-            // ---- pass 2: p = exp(z - max), row sum, P -> TMEM as bf16 pairs (in place over S)
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-              uint32_t v[32], pk[16];
-              float z[32];
-              if (kCols == 32) tmem_ld_32x32(tlane + c * 32, v);
-              else tmem_ld_32x16(tlane, reinterpret_cast<uint32_t(&)[16]>(v));
-              tmem_ld_wait();
-              add_bias_mask<WS, kCols>(z, v, tab, row_ok ? base_i : (WS - 1) * TS + WS - 1, c, masked, ry_i, rx_i, edge_y, edge_x,
-                                       p.shift);
-#pragma unroll
-              for (int j = 0; j < kCols; j += 2) {
-                const float p0 = ex2_approx(fmaf(z[j], 1.4426950408889634f, -mxs));
-                const float p1 = ex2_approx(fmaf(z[j + 1], 1.4426950408889634f, -mxs));
-                l0 += p0; l1 += p1;
-                pk[j >> 1] = pack_bf16x2_alu2(p0, p1);
-              }
-              if (kCols == 32) tmem_st_32x16(tlane + c * 16, pk);
-              else tmem_st_32x8(tlane, reinterpret_cast<uint32_t(&)[8]>(pk));
-            }
-            tmem_st_wait();
-            inv_l = 1.0f / (l0 + l1);
+            if (masked) inv_l = softmax_row<WS, true>(tlane, tab, row_ok ? base_i : (WS - 1) * TS + WS - 1, pen);
+            else inv_l = softmax_row<WS, false>(tlane, tab, row_ok ? base_i : (WS - 1) * TS + WS - 1, pen);
           }
           tc_fence_before();
           __syncwarp();
