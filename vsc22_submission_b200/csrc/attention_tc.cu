@@ -271,6 +271,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (warp == 9) {
     if (lane == 0) {
       prefetch_tmap(&tmQ);
@@ -288,6 +289,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   auto unit_frame_head = [&](int unit, int& frame, int& head) {
     const int f = unit / p.heads;
@@ -428,7 +430,7 @@ int attention_tc(const void* qkv, void* out, int n_frames, int T, int heads, cud
     VSCB_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp));
     const int grid_pp = n_units < device_sm_count() ? n_units : device_sm_count();
     ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * 64);
-    attention_pp_kernel<<<grid_pp, kAppThreads, smem_pp, stream>>>(tmQ2, tmKV, p, n_units);
+    VSCB_CUDA_OK(launch_pdl(attention_pp_kernel, dim3(grid_pp), dim3(kAppThreads), smem_pp, stream, tmQ2, tmKV, p, n_units));
     count_launch();
     VSCB_CUDA_OK(cudaGetLastError());
     return VSCB200_OK;

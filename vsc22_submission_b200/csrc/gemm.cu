@@ -105,6 +105,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -131,6 +132,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (kCluster > 1) cluster_sync_all();    // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the previous kernel's tail; its results are visible from here
 
   // Tile schedule.  kCluster == 1: tile = blockIdx.x + i*gridDim.x.  kCluster == 2: the pair walks
   // "pair tiles" (two consecutive M blocks x one N block); rank r takes M block 2*pm + r.
@@ -359,13 +361,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster>, tmA, tmB, tmC, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());

@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "host_util.h"
 
 #include <atomic>
@@ -48,6 +50,11 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
     return VSCB200_ERR_CUDA;
   }
   return VSCB200_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VSCB200_PDL"); return e ? atoi(e) != 0 : false; }();
+  return on;
 }
 
 int device_sm_count() {

@@ -41,6 +41,24 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
                  uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 
 int device_sm_count();
+bool pdl_enabled();     // VSCB200_PDL=1: launch with programmatic stream serialization (measured: no gain, off by default)
+
+// <<<>>> with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
+// stream drains; it must execute griddepcontrol.wait (ptx.cuh pdl_wait) before touching global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // Caching device allocator for the index's transient buffers (score workspace, staging, operand
 // planes).  The reference builds a fresh faiss index per score_normalize call

@@ -314,6 +314,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Programmatic dependent launch: a kernel lets its successor in the stream start early (prologue: barrier init,
+// TMEM allocation, tensor-map prefetch, on SMs that have drained) and the successor waits here for the
+// predecessor's completion and memory flush before it touches global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -14,6 +14,8 @@ template <bool kOutBf16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ y, int64_t rows, int width, float eps, int reverse) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const unsigned bid = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int64_t row = static_cast<int64_t>(bid) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -74,9 +76,9 @@ int layernorm(const float* x, const float* gamma, const float* beta, void* y, in
   const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
   ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * width * (out_bf16 ? 6 : 8));
   if (out_bf16)
-    layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0);
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0));
   else
-    layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0);
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -128,11 +130,41 @@ __global__ void im2row_kernel(const float* __restrict__ frames, __nv_bfloat16* _
   reinterpret_cast<uint32_t*>(patches)[idx] = pack_bf16x2(v.x, v.y);
 }
 
+// Fast path (patch % 4 == 0, no K padding): one thread per 4 consecutive pixels of an image row -- a 128-bit
+// coalesced read of the frame, one 8-byte store into the patch row (4 threads fill a 32-byte sector).
+__global__ void __launch_bounds__(256)
+im2row_vec4_kernel(const float4* __restrict__ frames, uint2* __restrict__ patches, int64_t total, int img, int patch) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = img >> 2;                                   // float4 per image row
+  const int x4 = static_cast<int>(idx % q);
+  const int64_t t = idx / q;
+  const int y = static_cast<int>(t % img);
+  const int64_t fc = t / img;
+  const int c = static_cast<int>(fc % 3);
+  const int64_t f = fc / 3;
+  const int grid = img / patch, x = x4 * 4;
+  const int py = y / patch, i = y % patch, px = x / patch, j = x % patch;
+  const int K = 3 * patch * patch;
+  const int64_t dst = ((f * grid + py) * grid + px) * K + (c * patch + i) * patch + j;     // bf16 elements
+  const float4 v = ldg_nc_f4(frames + idx);
+  patches[dst >> 2] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
 int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream) {
   VSCB_REQUIRE(patch % 2 == 0 && img % patch == 0 && Kp % 2 == 0, "im2row: patch must be even and divide img");
   const int P = (img / patch) * (img / patch);
+  if (n == 0) return VSCB200_OK;
+  if (patch % 4 == 0 && Kp == 3 * patch * patch && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
+    const int64_t total4 = n * 3 * img * (img / 4);
+    ProfScope prof(kProfVitOther, stream, static_cast<double>(total4) * 24);
+    im2row_vec4_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(frames), reinterpret_cast<uint2*>(patches), total4, img, patch);
+    count_launch();
+    VSCB_CUDA_OK(cudaGetLastError());
+    return VSCB200_OK;
+  }
   const int64_t total = n * P * (Kp / 2);
-  if (total == 0) return VSCB200_OK;
   ProfScope prof(kProfVitOther, stream, static_cast<double>(total) * 2 * 6);
   im2row_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
       frames, reinterpret_cast<__nv_bfloat16*>(patches), n, img, patch, Kp);
@@ -166,8 +198,7 @@ constexpr int kTailThreads = 256;
 template <bool kLN>
 __global__ void __launch_bounds__(kTailThreads)
 gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ head_w, const float* __restrict__ head_b, float* __restrict__ out, int T,
-                int C, int out_dim, float eps, float p) {
+                float* __restrict__ pooled, int T, int C, float eps, float p) {
   extern __shared__ float tail_smem[];   // [C] pooled sums / g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = kTailThreads >> 5;
   const int64_t f = blockIdx.x;
@@ -244,18 +275,45 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
     }
   }
   __syncthreads();
+  // pooled descriptor g[f, :] (fp32); the Linear runs as its own kernel that reuses every weight row over 8 frames
   for (int c = tid; c < C; c += kTailThreads) {
     const float m = tail_smem[c] / T;
-    tail_smem[c] = cube ? cbrtf(m) : powf(m, 1.0f / p);
+    pooled[f * C + c] = cube ? cbrtf(m) : powf(m, 1.0f / p);
   }
+}
+
+// out[f, o] = head_b[o] + sum_c head_w[o, c] * g[f, c]; CTA = 8 frames x 64 outputs, g of the 8 frames in smem,
+// one warp per output row at a time (coalesced weight read, 8 accumulators)
+constexpr int kHlFrames = 8, kHlOuts = 64;
+__global__ void __launch_bounds__(256)
+head_linear_kernel(const float* __restrict__ g, const float* __restrict__ head_w, const float* __restrict__ head_b,
+                   float* __restrict__ out, int64_t n, int C, int out_dim) {
+  extern __shared__ float hl_smem[];                       // [kHlFrames][C]
+  const int64_t f0 = static_cast<int64_t>(blockIdx.x) * kHlFrames;
+  const int o0 = blockIdx.y * kHlOuts;
+  const int nf = static_cast<int>(n - f0 < kHlFrames ? n - f0 : kHlFrames);
+  for (int i = threadIdx.x; i < kHlFrames * C; i += 256) hl_smem[i] = (i / C < nf) ? g[f0 * C + i] : 0.f;
   __syncthreads();
-  for (int o = warp; o < out_dim; o += nwarp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = o0 + warp; o < o0 + kHlOuts && o < out_dim; o += 8) {
     const float* wr = head_w + static_cast<int64_t>(o) * C;
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a += wr[c] * tail_smem[c];
+    float a[kHlFrames];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) out[f * out_dim + o] = a + head_b[o];
+    for (int u = 0; u < kHlFrames; ++u) a[u] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wv = __ldg(wr + c);
+#pragma unroll
+      for (int u = 0; u < kHlFrames; ++u) a[u] += wv * hl_smem[u * C + c];
+    }
+#pragma unroll
+    for (int u = 0; u < kHlFrames; ++u) {
+#pragma unroll
+      for (int s2 = 16; s2 > 0; s2 >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], s2);
+    }
+    if (lane == 0) {
+      const float b = head_b[o];
+      for (int u = 0; u < nf; ++u) out[(f0 + u) * out_dim + o] = a[u] + b;
+    }
   }
 }
 
@@ -265,14 +323,23 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
   if (n == 0) return VSCB200_OK;
   VSCB_REQUIRE(!fuse_ln || (C % 4 == 0 && C <= 128 * kLnMaxVec), "gem_head: fused LN needs width % 4 == 0 and <= 1024");
   const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  const size_t hl_smem_bytes = static_cast<size_t>(kHlFrames) * C * sizeof(float);
+  VSCB_REQUIRE(hl_smem_bytes <= 200 * 1024, "gem_head: width too large for the head kernel");
+  VSCB_CUDA_OK(cudaFuncSetAttribute(head_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hl_smem_bytes)));
+  float* pooled = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&pooled), static_cast<size_t>(n) * C * sizeof(float), stream);
+  if (rc) return rc;
   ProfScope prof(kProfVitOther, stream, static_cast<double>(n) * T * C * 4);
   if (fuse_ln)
-    gem_head_kernel<true><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, head_w, head_b,
-                                                                                   out, T, C, out_dim, eps, p);
+    gem_head_kernel<true><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
   else
-    gem_head_kernel<false><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, head_w, head_b,
-                                                                                    out, T, C, out_dim, eps, p);
+    gem_head_kernel<false><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
   count_launch();
+  dim3 grid(static_cast<unsigned>((n + kHlFrames - 1) / kHlFrames), static_cast<unsigned>((out_dim + kHlOuts - 1) / kHlOuts));
+  head_linear_kernel<<<grid, 256, hl_smem_bytes, stream>>>(pooled, head_w, head_b, out, n, C,
+                                                                                              out_dim);
+  count_launch();
+  pool_free(pooled, stream);
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
