@@ -169,6 +169,15 @@ int vscb200_swin_forward_host(vscb200_swin* m, const float* frames_host, int64_t
 int vscb200_swin_out_dim(const vscb200_swin* m);
 
 /* ------------------------------------------------------------------------------------------------
+ * Ensemble tail: per-model row L2 normalisation -> concatenation -> PCA.transform
+ * ((X - mean_) @ components_.T), D/infer/concat_pca_sn.py:56-64, D/infer/extract_query_feats.py:169-204,
+ * M/infer/infer_matching.py:140-145.  parts_dev: n_parts (<= 8) device pointers [n, dims[i]] fp32 (HOST array of
+ * pointers); mean_dev [sum dims]; components_dev [out_dim, sum dims] (sklearn PCA.components_); out_dev [n, out_dim].
+ * ---------------------------------------------------------------------------------------------- */
+int vscb200_ensemble_pca(const float* const* parts_dev, const int* dims, int n_parts, int64_t n, const float* mean_dev,
+                         const float* components_dev, int out_dim, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Building blocks exported for unit tests and micro-benchmarks.
  * ---------------------------------------------------------------------------------------------- */
 #define VSCB200_EPI_BF16 0          /* C_bf16 = act(A*W^T + bias)            */

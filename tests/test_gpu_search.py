@@ -221,3 +221,22 @@ def test_dense_scores_fp32_equivalent(faiss):
         # error scales with |q||r| (= 1 here): 2^-18-level operand representation, <= ~8e-6 worst case
         assert (S.double() - ref).abs().max().item() < 1e-5
         assert (S.double() - ref).pow(2).mean().sqrt().item() < 2e-6
+
+
+def test_ensemble_pca_tail_matches_oracle():
+    """per-model normalize -> concat -> PCA.transform (concat_pca_sn.py:56-61) on the device."""
+    import torch
+    from oracle import pca_np
+    from vsc22_submission_b200.ensemble import B200PCA
+    rng = np.random.default_rng(4)
+    dims = (512, 512, 512, 512)
+    parts = [rng.standard_normal((1000, d)).astype(np.float32) * (i + 1) for i, d in enumerate(dims)]
+    parts[2][5] = 0.0
+    mean = (rng.standard_normal(sum(dims)) * 0.01).astype(np.float32)
+    comp = np.linalg.qr(rng.standard_normal((sum(dims), 512)))[0].T.astype(np.float32)
+    ref = pca_np.ensemble_pca(parts, mean, comp)
+    pca = B200PCA(mean, comp)
+    got = pca.transform_parts([torch.from_numpy(p).cuda() for p in parts]).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    assert np.abs(pca.transform_parts_host(parts) - got).max() == 0.0
+    assert pca.transform_parts([torch.zeros((0, d), device="cuda") for d in dims]).shape == (0, 512)

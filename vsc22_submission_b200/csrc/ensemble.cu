@@ -1,0 +1,79 @@
+// Ensemble tail between the encoders and the index:
+//   per-model sklearn `normalize` (row L2) -> concatenate -> PCA.transform = (X - mean_) @ components_.T
+// Reference: D/infer/concat_pca_sn.py:56-64 (reference bank), D/infer/extract_query_feats.py:169-204 and
+// M/infer/infer_matching.py:140-145 (queries) -- numpy/sklearn on the host, one call per video.  Here: one
+// gather kernel (normalise + concatenate + centre, warp per frame) and the exact-fp32 FFMA tile kernel of sim.cu
+// for the [n, D] x [out, D]^T projection; every descriptor of a batch in one call, nothing leaves the device.
+#include "host_util.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vscb200 {
+
+constexpr int kEnsMaxParts = 8;
+struct EnsParts {
+  const float* ptr[kEnsMaxParts];
+  int dim[kEnsMaxParts];
+  int off[kEnsMaxParts];
+  int n_parts;
+};
+
+// xc[row, off_p + c] = parts[p][row, c] / max(||parts[p][row]||, tiny) - mean[off_p + c]
+// (sklearn.preprocessing.normalize leaves all-zero rows untouched: norm 0 -> divide by 1)
+__global__ void __launch_bounds__(256)
+ensemble_center_kernel(EnsParts parts, const float* __restrict__ mean, float* __restrict__ xc, int64_t n, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  for (int p = 0; p < parts.n_parts; ++p) {
+    const float* src = parts.ptr[p] + row * parts.dim[p];
+    float ss = 0.f;
+    for (int c = lane; c < parts.dim[p]; c += 32) { const float v = src[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    const float inv = nrm > 0.f ? 1.0f / nrm : 1.0f;
+    float* dst = xc + row * D + parts.off[p];
+    const float* mu = mean + parts.off[p];
+    for (int c = lane; c < parts.dim[p]; c += 32) dst[c] = src[c] * inv - mu[c];
+  }
+}
+
+}  // namespace vscb200
+
+using namespace vscb200;
+
+extern "C" int vscb200_ensemble_pca(const float* const* parts_dev, const int* dims, int n_parts, int64_t n,
+                                    const float* mean_dev, const float* components_dev, int out_dim, float* out_dev,
+                                    void* stream_v) {
+  VSCB_REQUIRE(parts_dev && dims && n_parts >= 1 && n_parts <= kEnsMaxParts, "ensemble_pca: 1..8 descriptor sets");
+  VSCB_REQUIRE(n >= 0 && out_dim > 0 && mean_dev && components_dev && (n == 0 || out_dev), "ensemble_pca: null argument");
+  if (n == 0) return VSCB200_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_v);
+  EnsParts parts = {};
+  parts.n_parts = n_parts;
+  int D = 0;
+  for (int p = 0; p < n_parts; ++p) {
+    VSCB_REQUIRE(parts_dev[p] != nullptr && dims[p] > 0, "ensemble_pca: bad descriptor set");
+    parts.ptr[p] = parts_dev[p];
+    parts.dim[p] = dims[p];
+    parts.off[p] = D;
+    D += dims[p];
+  }
+  float* xc = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&xc), static_cast<size_t>(n) * D * sizeof(float), s);
+  if (rc) return rc;
+  {
+    ProfScope prof(kProfVitOther, s, static_cast<double>(n) * D * 8);
+    ensemble_center_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(parts, mean_dev, xc, n, D);
+    count_launch();
+  }
+  for (int64_t r0 = 0; r0 < n && rc == VSCB200_OK; r0 += 65535ll * 64) {
+    const int64_t nb = n - r0 < 65535ll * 64 ? n - r0 : 65535ll * 64;
+    rc = scores_simt(xc + r0 * D, components_dev, out_dev + r0 * out_dim, nb, out_dim, D, out_dim, false, nullptr, nullptr, s);
+  }
+  pool_free(xc, s);
+  if (rc) return rc;
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
