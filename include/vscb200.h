@@ -178,6 +178,21 @@ int vscb200_ensemble_pca(const float* const* parts_dev, const int* dims, int n_p
                          const float* components_dev, int out_dim, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Candidate-pair frame-similarity matrices: `np.matmul(a, b.T)` (+ similarity_bias) of
+ * vsc/baseline/localization.py:32-35,52-57 for ALL candidate pairs in one launch, and the per-row top-k that
+ * opens the temporal-network alignment (vcsl/vta.py:262-265).  q_dev [all query frames, d], r_dev [all ref frames, d];
+ * pair p = rows [q_off[p], q_off[p]+q_len[p]) x [r_off[p], r_off[p]+r_len[p]); its row-major [q_len, r_len] block starts at
+ * sims_dev + s_off[p].  Top-k rows of pair p start at row_off[p] in topv/topi [sum q_len, k] (-1 / -FLT_MAX padding).
+ * All descriptor arrays are device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+int vscb200_pair_sims(const float* q_dev, const float* r_dev, int d, int64_t n_pairs, const int64_t* q_off_dev,
+                      const int32_t* q_len_dev, const int64_t* r_off_dev, const int32_t* r_len_dev, const int64_t* s_off_dev,
+                      float bias, float* sims_dev, void* stream);
+int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_len_dev, const int32_t* r_len_dev,
+                      const int64_t* s_off_dev, const int64_t* row_off_dev, int k, float* topv_dev, int32_t* topi_dev,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Building blocks exported for unit tests and micro-benchmarks.
  * ---------------------------------------------------------------------------------------------- */
 #define VSCB200_EPI_BF16 0          /* C_bf16 = act(A*W^T + bias)            */

@@ -240,3 +240,39 @@ def test_ensemble_pca_tail_matches_oracle():
     assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
     assert np.abs(pca.transform_parts_host(parts) - got).max() == 0.0
     assert pca.transform_parts([torch.zeros((0, d), device="cuda") for d in dims]).shape == (0, 512)
+
+
+def test_pair_similarity_matrices_and_topk():
+    """per-candidate-pair `a @ b.T + bias` (localization.py:32-35,52-57) and the per-row top-k that
+    opens vcsl.vta.tn (vta.py:262-265), all pairs in one launch, against numpy."""
+    import dataclasses
+    from vsc22_submission_b200.localization import PairSimilarity
+
+    @dataclasses.dataclass
+    class VF:
+        video_id: str
+        feature: np.ndarray
+
+    @dataclasses.dataclass
+    class Cand:
+        query_id: str
+        ref_id: str
+
+    rng = np.random.default_rng(9)
+    qs = [VF(f"Q{i}", rng.standard_normal((int(rng.integers(1, 150)), 512)).astype(np.float32)) for i in range(12)]
+    rs = [VF(f"R{i}", rng.standard_normal((int(rng.integers(1, 200)), 512)).astype(np.float32)) for i in range(15)]
+    rs[3] = VF("R3", rng.standard_normal((3, 512)).astype(np.float32))          # fewer reference frames than k
+    cands = [Cand(f"Q{int(rng.integers(12))}", f"R{int(rng.integers(15))}") for _ in range(60)] + [Cand("Q0", "R3")]
+    ps = PairSimilarity(qs, rs, similarity_bias=0.5)
+    qd, rd = {v.video_id: v.feature for v in qs}, {v.video_id: v.feature for v in rs}
+    got = ps.similarities_topk(cands, top_k=5)
+    assert [g[0] for g in got] == [f"{c.query_id}-{c.ref_id}" for c in cands]
+    for c, (_, sims, ti, tv) in zip(cands, got):
+        ref = np.matmul(qd[c.query_id], rd[c.ref_id].T) + 0.5
+        assert sims.shape == ref.shape and np.abs(sims - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+        top = min(5, ref.shape[1])
+        order = np.argsort(-sims, kind="stable")[:, :top]                     # on OUR fp32 values: exact expectation
+        np.testing.assert_array_equal(ti, order)
+        np.testing.assert_array_equal(tv, np.take_along_axis(sims, order, axis=-1))
+    plain = ps.similarities(cands[:3])
+    assert all(np.array_equal(a[1], b[1]) for a, b in zip(plain, got[:3])) and ps.similarities([]) == []
