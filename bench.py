@@ -327,6 +327,7 @@ def bench_sim(args, world, rank, peaks):
     # (vsc/index.py:87-94) and one search over all query rows -- host buffers in, host results out
     e2e = None
     stream = None
+    dense = None
     if world == 1:
         import dataclasses
 
@@ -359,6 +360,7 @@ def bench_sim(args, world, rank, peaks):
                       ".search on numpy arrays",
                "idx_agree_with_device_path": float((Ih == I.cpu().numpy()).mean())}
         stream = bench_sim_stream(peaks)
+        dense = bench_sim_dense(peaks)
     flops = 2.0 * SIM_D * pairs / world            # per GPU
     bytes_alg = (SIM_NQ + SIM_NR + SIM_NZ) * SIM_D * 4 + SIM_NQ * SIM_K * 12
     sc = prof["scores"]
@@ -372,7 +374,7 @@ def bench_sim(args, world, rank, peaks):
     roof["note"] = ("fp32-equivalent scores = 3 bf16 MMAs per product (hi.hi + lo.hi + hi.lo): the kernel's ceiling is "
                     "1/3 of the bf16 peak; config 3 as stated is tensor-bound, the HBM-bound form is 'stream'")
     return {"metric": "sim-pairs/sec", "value": value, "unit": "sim-pairs/sec", "ms_per_step": ms, "e2e": e2e,
-            "stream": stream,
+            "stream": stream, "dense": dense,
             "gpu_launches": int(launches), "roofline": roof, "dtype": "f32",
             "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
                                    "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
@@ -428,6 +430,41 @@ def bench_sim_stream(peaks, nq=40, nr=1_000_000, k=10, iters=10):
                          "algorithmic_bytes": bytes_alg,
                          "kernel_ms": kern, "whole_call_achieved": bytes_alg / (call / 1e3) / 1e9,
                          "whole_call_frac": bytes_alg / (call / 1e3) / 1e9 / peaks["hbm_gbs"]}}
+
+
+def bench_sim_dense(peaks, n=40_000, iters=3):
+    """BASELINE configs[4] form: the dense n x n frame-similarity matrix (fp32, written to
+    HBM: n*n*4 B) and the per-row top-5 that feeds the temporal-network alignment (vta.py:262-265)."""
+    import torch
+
+    from vsc22_submission_b200 import _lib, search
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(6)
+    X = torch.nn.functional.normalize(torch.randn((n, SIM_D), generator=g, device=dev))
+    ix = search.DeviceIndex(SIM_D)
+    ix.add(X)
+    S = ix.scores(X[:1024])
+    del S
+    ts, tk = [], []
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        S = ix.scores(X)
+        e1.record()
+        D, I = ix.search(X, 5)
+        e2.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1)); tk.append(e1.elapsed_time(e2))
+        del S
+    ms, ms_k = min(ts), min(tk)
+    self_hit = float((I[:, 0] == torch.arange(n, device=dev)).float().mean().item())
+    torch.cuda.empty_cache()
+    return {"workload": f"dense {n} x {n} x {SIM_D} similarity matrix (fp32 out, {n * n * 4 / 1e9:.1f} GB) + per-row top-5",
+            "dense_ms": ms, "top5_ms": ms_k, "pairs_per_sec_dense": n * n / (ms / 1e3), "top1_is_self": self_hit,
+            "roofline": {"bound": "hbm-write / tensor (balanced)", "hbm_write_frac": n * n * 4 / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                         "tensor_frac": 2.0 * n * n * SIM_D / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
+                         "note": "3 bf16 MMAs per product: tensor ceiling 1/3"}}
 
 
 def cpu_baseline_sim():
@@ -520,7 +557,7 @@ def main():
         if enc_res is None:
             line.update(metric="sim-pairs/sec", unit="sim-pairs/sec", value=sim["value"], ms_per_step=sim["ms_per_step"],
                         e2e=sim["e2e"], gpu_launches=sim["gpu_launches"], roofline=sim["roofline"], dtype="f32",
-                        config=sim["config"])
+                        config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"))
         else:
             line["sim"] = sim
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
