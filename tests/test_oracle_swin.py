@@ -60,3 +60,23 @@ def test_oracle_matches_live_reference_class():
     with torch.no_grad():
         ref = model(x)
     np.testing.assert_allclose(swin_ref.forward(spec, w, x).numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference is only present in the authoring container")
+def test_spec_is_recovered_from_a_reference_state_dict():
+    """install_jit_load_hook path: the architecture of a swinv2 checkpoint is read off its state dict
+    (parameter shapes + the registered buffers relative_position_index / attn_mask / relative_coords_table)."""
+    from vsc22_submission_b200.swin_encoder import param_names, spec_from_state_dict
+    mod = refload.swinv2_module()
+    for kw in (dict(img_size=128, patch_size=4, embed_dim=64, depths=[2, 2, 2, 2], num_heads=[2, 4, 8, 16], window_size=8,
+                    pretrained_window_sizes=[6, 6, 6, 3], output_dim=64),
+               dict(img_size=256, patch_size=4, embed_dim=128, depths=[2, 2, 2, 2], num_heads=[4, 8, 16, 32], window_size=16,
+                    pretrained_window_sizes=[12, 12, 12, 6], output_dim=512)):
+        model = mod.SwinTransformerV2(pretrained=None, **kw)
+        sd = model.state_dict()
+        spec = spec_from_state_dict(sd)
+        assert (spec.img, spec.patch, spec.embed, list(spec.depths), list(spec.heads), spec.window,
+                list(spec.pretrained_windows), spec.out_dim) == (
+            kw["img_size"], kw["patch_size"], kw["embed_dim"], kw["depths"], kw["num_heads"], kw["window_size"],
+            kw["pretrained_window_sizes"], kw["output_dim"])
+        assert set(param_names(spec)) == {k for k, _ in model.named_parameters()}
