@@ -221,6 +221,55 @@ def bench_encoder(args, world, rank, peaks):
             "roofline": roofline, "dev_vs_host_maxabs": dev_vs_host, "enc": enc, "frames": frames, "out": out}
 
 
+def bench_swin(args):
+    """Second encoder family on the reference's path (swinv2_v106/107/115: SwinV2-B 256x256, config_v106.py:8-24):
+    device-resident frames, 1024 synthetic frames per step, plan chunk 128; parity of 2 frames vs the fp32 oracle."""
+    import numpy as np
+    import torch
+
+    from oracle import swin_ref
+    from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SWINV2_B_256, random_weights
+    dev = torch.device("cuda", torch.cuda.current_device())
+    w = random_weights(SWINV2_B_256, seed=0)
+    enc = B200SwinEncoder(SWINV2_B_256, w, max_frames=128).to(dev).eval()
+    n = 1024
+    frames = torch.randn((n, 3, 256, 256), generator=torch.Generator(device=dev).manual_seed(7), device=dev).clamp_(-1, 1)
+    for _ in range(2):
+        out = enc(frames)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = enc(frames)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    ref = swin_ref.forward(swin_ref.SWINV2_B_256, w, frames[:2].cpu()).numpy()
+    got = out[:2].cpu().numpy()
+    rel = float((np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
+    fps = n / (ms / 1e3)
+    return {"metric": "frame-descriptors/sec", "value": fps, "ms_per_step": ms, "frames_per_step": n,
+            "tflops": fps * SWINV2_B_256.flops_per_frame() / 1e12, "flops_per_frame": SWINV2_B_256.flops_per_frame(),
+            "parity_rel_l2_max_vs_fp32_oracle": rel,
+            "config": {"workload": "SwinV2-B 256x256 window 16 (config_v106.py), random init, bf16 operands, 1 GPU"}}
+
+
+def h2d_bandwidth_gbs():
+    """Pinned host -> device copy rate of this box (the ceiling of every e2e number that ships fp32 frames)."""
+    import torch
+    host = torch.empty(1 << 28, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+    dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        dev.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return 4 * (1 << 28) / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
 def cpu_baseline_encoder(frames_cpu_fn, seconds_budget=20.0):
     """The oracle port of the reference ViT forward (torch fp32, all host cores) on a bounded sample."""
     import torch
@@ -560,6 +609,9 @@ def main():
                         config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"))
         else:
             line["sim"] = sim
+    if rank == 0 and world == 1 and args.workload == "both":
+        line["swin"] = bench_swin(args)
+        line["h2d_pinned_gbs"] = h2d_bandwidth_gbs()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g = torch.Generator().manual_seed(1)
         if args.workload in ("both", "encoder"):

@@ -67,9 +67,11 @@ struct vscb200_swin {
   void* ao = nullptr;       // bf16 [M0, C0]
   void* u = nullptr;        // bf16 [M0, 4 C0]
   void* patches = nullptr;  // bf16 [M0, Kp]
-  float* frames_stage = nullptr;
-  float* out_stage = nullptr;
-  cudaStream_t own_stream = nullptr;
+  float* frames_stage2[2] = {nullptr, nullptr};
+  float* out_stage2[2] = {nullptr, nullptr};
+  float* out_pinned2[2] = {nullptr, nullptr};
+  cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool finalized = false;
   std::vector<void*> allocs;
   std::map<std::string, bool> loaded;
@@ -166,9 +168,17 @@ int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_s
 void vscb200_swin_destroy(vscb200_swin* m) {
   if (!m) return;
   for (void* p : m->allocs) cudaFree(p);
-  if (m->frames_stage) cudaFree(m->frames_stage);
-  if (m->out_stage) cudaFree(m->out_stage);
+  for (int b = 0; b < 2; ++b) {
+    if (m->frames_stage2[b]) cudaFree(m->frames_stage2[b]);
+    if (m->out_stage2[b]) cudaFree(m->out_stage2[b]);
+    if (m->out_pinned2[b]) cudaFreeHost(m->out_pinned2[b]);
+    if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
+    if (m->ev_comp[b]) cudaEventDestroy(m->ev_comp[b]);
+    if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
+  }
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->in_stream) cudaStreamDestroy(m->in_stream);
+  if (m->out_stream) cudaStreamDestroy(m->out_stream);
   delete m;
 }
 
@@ -300,21 +310,50 @@ int vscb200_swin_forward(vscb200_swin* m, const float* frames, int64_t n, float*
 }
 
 int vscb200_swin_forward_host(vscb200_swin* m, const float* frames_host, int64_t n, float* out_host) {
+  // Same double-buffered pipeline as vscb200_vit_forward_host: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels
+  // of chunk i; descriptors land in page-locked buffers and are handed to the caller one chunk later.
   VSCB_REQUIRE(m && (n == 0 || (frames_host && out_host)), "swin_forward_host: null argument");
   const int64_t in_per = 3LL * m->spec.img * m->spec.img, out_per = m->spec.out_dim;
   if (!m->own_stream) {
     VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
-    VSCB_CUDA_OK(cudaMalloc(&m->frames_stage, static_cast<size_t>(m->max_frames) * in_per * 4));
-    VSCB_CUDA_OK(cudaMalloc(&m->out_stage, static_cast<size_t>(m->max_frames) * out_per * 4));
+    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
+      VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+      VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
+      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
+    }
   }
-  for (int64_t f0 = 0; f0 < n; f0 += m->max_frames) {
+  int64_t chunk = 0, last_f0 = 0;
+  int last_nc = 0, last_b = 0;
+  for (int64_t f0 = 0; f0 < n; f0 += m->max_frames, ++chunk) {
+    const int b = static_cast<int>(chunk & 1);
     const int nc = static_cast<int>(n - f0 < m->max_frames ? n - f0 : m->max_frames);
-    VSCB_CUDA_OK(cudaMemcpyAsync(m->frames_stage, frames_host + f0 * in_per, static_cast<size_t>(nc) * in_per * 4,
-                                 cudaMemcpyHostToDevice, m->own_stream));
-    int rc = swin_forward_chunk(m, m->frames_stage, nc, m->out_stage, m->own_stream);
+    if (chunk >= 2) VSCB_CUDA_OK(cudaStreamWaitEvent(m->in_stream, m->ev_comp[b], 0));
+    VSCB_CUDA_OK(cudaMemcpyAsync(m->frames_stage2[b], frames_host + f0 * in_per, static_cast<size_t>(nc) * in_per * 4,
+                                 cudaMemcpyHostToDevice, m->in_stream));
+    VSCB_CUDA_OK(cudaEventRecord(m->ev_in[b], m->in_stream));
+    VSCB_CUDA_OK(cudaStreamWaitEvent(m->own_stream, m->ev_in[b], 0));
+    if (chunk >= 2) VSCB_CUDA_OK(cudaStreamWaitEvent(m->own_stream, m->ev_out[b], 0));
+    int rc = swin_forward_chunk(m, m->frames_stage2[b], nc, m->out_stage2[b], m->own_stream);
     if (rc) return rc;
-    VSCB_CUDA_OK(cudaMemcpyAsync(out_host + f0 * out_per, m->out_stage, static_cast<size_t>(nc) * out_per * 4,
-                                 cudaMemcpyDeviceToHost, m->own_stream));
+    VSCB_CUDA_OK(cudaEventRecord(m->ev_comp[b], m->own_stream));
+    VSCB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, m->ev_comp[b], 0));
+    VSCB_CUDA_OK(cudaMemcpyAsync(m->out_pinned2[b], m->out_stage2[b], static_cast<size_t>(nc) * out_per * 4,
+                                 cudaMemcpyDeviceToHost, m->out_stream));
+    VSCB_CUDA_OK(cudaEventRecord(m->ev_out[b], m->out_stream));
+    if (chunk >= 1) {
+      VSCB_CUDA_OK(cudaEventSynchronize(m->ev_out[b ^ 1]));
+      memcpy(out_host + (f0 - m->max_frames) * out_per, m->out_pinned2[b ^ 1], static_cast<size_t>(m->max_frames) * out_per * 4);
+    }
+    last_f0 = f0; last_nc = nc; last_b = b;
+  }
+  if (last_nc > 0) {
+    VSCB_CUDA_OK(cudaEventSynchronize(m->ev_out[last_b]));
+    memcpy(out_host + last_f0 * out_per, m->out_pinned2[last_b], static_cast<size_t>(last_nc) * out_per * 4);
   }
   VSCB_CUDA_OK(cudaStreamSynchronize(m->own_stream));
   return VSCB200_OK;

@@ -45,6 +45,7 @@ struct vscb200_vit {
   // host-API staging
   float* frames_stage2[2] = {nullptr, nullptr};
   float* out_stage2[2] = {nullptr, nullptr};
+  float* out_pinned2[2] = {nullptr, nullptr};   // page-locked landing buffers: a D2H into pageable memory would block the host
   cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
@@ -136,6 +137,7 @@ void vscb200_vit_destroy(vscb200_vit* m) {
   for (int b = 0; b < 2; ++b) {
     if (m->frames_stage2[b]) cudaFree(m->frames_stage2[b]);
     if (m->out_stage2[b]) cudaFree(m->out_stage2[b]);
+    if (m->out_pinned2[b]) cudaFreeHost(m->out_pinned2[b]);
     if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
     if (m->ev_comp[b]) cudaEventDestroy(m->ev_comp[b]);
     if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
@@ -270,12 +272,14 @@ int vscb200_vit_forward_host(vscb200_vit* m, const float* frames_host, int64_t n
     for (int b = 0; b < 2; ++b) {
       VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
       VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+      VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
       VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
       VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
       VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
     }
   }
-  int64_t chunk = 0;
+  int64_t chunk = 0, last_f0 = 0;
+  int last_nc = 0, last_b = 0;
   for (int64_t f0 = 0; f0 < n; f0 += m->max_frames, ++chunk) {
     const int b = static_cast<int>(chunk & 1);
     const int nc = static_cast<int>(n - f0 < m->max_frames ? n - f0 : m->max_frames);
@@ -289,12 +293,23 @@ int vscb200_vit_forward_host(vscb200_vit* m, const float* frames_host, int64_t n
     if (rc) return rc;
     VSCB_CUDA_OK(cudaEventRecord(m->ev_comp[b], m->own_stream));
     VSCB_CUDA_OK(cudaStreamWaitEvent(m->out_stream, m->ev_comp[b], 0));
-    VSCB_CUDA_OK(cudaMemcpyAsync(out_host + f0 * out_per, m->out_stage2[b], static_cast<size_t>(nc) * out_per * 4,
+    // D2H lands in a page-locked buffer (a copy into the caller's pageable array would block this thread until the
+    // chunk's kernels finish, so the next chunk's H2D would no longer overlap them); the previous chunk's descriptors
+    // are handed to the caller while this chunk computes.
+    VSCB_CUDA_OK(cudaMemcpyAsync(m->out_pinned2[b], m->out_stage2[b], static_cast<size_t>(nc) * out_per * 4,
                                  cudaMemcpyDeviceToHost, m->out_stream));
     VSCB_CUDA_OK(cudaEventRecord(m->ev_out[b], m->out_stream));
+    if (chunk >= 1) {
+      VSCB_CUDA_OK(cudaEventSynchronize(m->ev_out[b ^ 1]));
+      memcpy(out_host + (f0 - m->max_frames) * out_per, m->out_pinned2[b ^ 1], static_cast<size_t>(m->max_frames) * out_per * 4);
+    }
+    last_f0 = f0; last_nc = nc; last_b = b;
+  }
+  if (last_nc > 0) {
+    VSCB_CUDA_OK(cudaEventSynchronize(m->ev_out[last_b]));
+    memcpy(out_host + last_f0 * out_per, m->out_pinned2[last_b], static_cast<size_t>(last_nc) * out_per * 4);
   }
   VSCB_CUDA_OK(cudaStreamSynchronize(m->own_stream));
-  VSCB_CUDA_OK(cudaStreamSynchronize(m->out_stream));
   return VSCB200_OK;
 }
 
