@@ -30,7 +30,8 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 N_FRAMES = 10_000          # configs[1]: 10k synthetic frames
-BATCH = 256                # encoder plan max_frames
+BATCH = 512                # encoder plan chunk (max_frames): the 10k-frame job is walked in chunks of 512 frames
+                           # (measured: 256 -> 22.2k, 384 -> 22.7k, 512 -> 23.1k, 768 -> 23.1k frames/s; tools/sweep_batch.py)
 SIM_NQ, SIM_NR, SIM_NZ, SIM_D, SIM_K = 10_000, 40_000, 40_000, 512, 10   # configs[2]
 
 
@@ -593,7 +594,7 @@ def main():
                     gpu_launches=enc_res["gpu_launches"], clocks=enc_res["clocks"], roofline=enc_res["roofline"])
         line["config"] = {"workload": "configs[1]: ViT-B/16 224x224 bf16 frame encoder, 10k synthetic frames per GPU per step",
                           "arch": "CLIPModel(224,16,768,12,12) + gem(p=3)/Linear(768->512) tail, random init (seed 0)",
-                          "frames_per_step_per_gpu": N_FRAMES, "batch": BATCH, "tokens": 197,
+                          "frames_per_step_per_gpu": N_FRAMES, "plan_chunk_frames": BATCH, "tokens": 197,
                           "flops_per_frame": enc_res["enc"].spec.flops_per_frame(),
                           "cache": "6.0 GB of input frames per step, far larger than the 126 MB L2 (no flush needed)",
                           "parallelism": f"dp{world} (frames sharded over ranks, no data-path collective)",

@@ -25,8 +25,10 @@ using namespace vscb200;
 
 namespace vscb200 {
 int window_gather_bf16(const float* x, void* h, int64_t n, int res, int ws, int shift, int C, cudaStream_t stream);
+// h_next != nullptr: the updated rows are also written as bf16 in the row order of the next consumer (ws_next x ws_next
+// windows shifted by shift_next; ws_next == res, shift 0: token order)
 int ln_residual_scatter(const float* y, const float* gamma, const float* beta, float* x, int64_t n, int res, int ws, int shift,
-                        int C, float eps, cudaStream_t stream);
+                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next);
 int patch_merge_gather(const float* x, void* out, int64_t n, int res, int C, cudaStream_t stream);
 int cpb_table(const float* w0, const float* b0, const float* w2, float* table, int ws, int pretrained_ws, int heads,
               cudaStream_t stream);
@@ -270,18 +272,20 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
     for (size_t j = 0; j < st.blocks.size(); ++j) {
       const SwinBlockW& b = st.blocks[j];
       const int shift = (res > sp.window && (j & 1)) ? sp.window / 2 : 0;     // swinv2.py:223-226, 411
-      // ---- (shifted) window attention branch
-      R(window_gather_bf16(m->x, m->h, n, res, ws, shift, C, s));
+      // ---- (shifted) window attention branch.  Only the first block of a stage gathers its input rows itself: every
+      //      later block finds them written, in its own window order, by the previous block's res-post-norm kernel.
+      if (j == 0) R(window_gather_bf16(m->x, m->h, n, res, ws, shift, C, s));
       R(gemm_bf16(m->h, b.qkv_w, b.qkv_bias, m->qkv, M, 3 * C, C, C, C, 3 * C, VSCB200_EPI_BF16, -1, s, nullptr, 0, false,
                   2 * C, b.qscale));
       R(swin_attention(m->qkv, m->ao, b.table, static_cast<int64_t>(n) * nW, nW, nWx, ws, shift, st.heads, s));
       R(gemm_bf16(m->ao, b.proj_w, b.proj_b, m->y, M, C, C, C, C, C, VSCB200_EPI_F32, -1, s, nullptr, 0));
-      R(ln_residual_scatter(m->y, b.norm1_w, b.norm1_b, m->x, n, res, ws, shift, C, eps, s));
+      R(ln_residual_scatter(m->y, b.norm1_w, b.norm1_b, m->x, n, res, ws, shift, C, eps, s, m->h, res, 0));   // h: MLP input
       // ---- MLP branch (token order: identity map)
-      R(window_gather_bf16(m->x, m->h, n, res, res, 0, C, s));
       R(gemm_bf16(m->h, b.fc1_w, b.fc1_b, m->u, M, 4 * C, C, C, C, 4 * C, VSCB200_EPI_BF16, VSCB200_ACT_GELU, s, nullptr, 0));
       R(gemm_bf16(m->u, b.fc2_w, b.fc2_b, m->y, M, C, 4 * C, 4 * C, 4 * C, C, VSCB200_EPI_F32, -1, s, nullptr, 0));
-      R(ln_residual_scatter(m->y, b.norm2_w, b.norm2_b, m->x, n, res, res, 0, C, eps, s));
+      const bool more = j + 1 < st.blocks.size();
+      const int next_shift = (res > sp.window && ((j + 1) & 1)) ? sp.window / 2 : 0;
+      R(ln_residual_scatter(m->y, b.norm2_w, b.norm2_b, m->x, n, res, res, 0, C, eps, s, more ? m->h : nullptr, ws, next_shift));
     }
     if (i + 1 < m->stages.size()) {
       R(patch_merge_gather(m->x, m->h, n, res, C, s));

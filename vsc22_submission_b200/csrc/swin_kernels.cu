@@ -27,6 +27,15 @@ __device__ __forceinline__ int win_row_to_token(const WinMap& m, int r_in_frame)
   return y * m.res + x;
 }
 
+// token index inside the frame -> its row in (shifted) window order (inverse of win_row_to_token)
+__device__ __forceinline__ int token_to_win_row(const WinMap& m, int tok) {
+  int y = tok / m.res - m.shift, x = tok % m.res - m.shift;
+  if (y < 0) y += m.res;
+  if (x < 0) x += m.res;
+  const int N = m.ws * m.ws;
+  return ((y / m.ws) * m.nWx + x / m.ws) * N + (y % m.ws) * m.ws + x % m.ws;
+}
+
 __global__ void __launch_bounds__(256)
 window_gather_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h, int64_t rows, int C, WinMap m) {
   const int lane = threadIdx.x & 31;
@@ -60,7 +69,8 @@ constexpr int kSwLnMaxVec = 8;    // float4 per lane -> C <= 1024
 
 __global__ void __launch_bounds__(256)
 ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                           float* __restrict__ x, int64_t rows, int C, float eps, WinMap m) {
+                           float* __restrict__ x, int64_t rows, int C, float eps, WinMap m, __nv_bfloat16* __restrict__ h_next,
+                           WinMap m_next) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -95,6 +105,9 @@ ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict_
   const int64_t frame = row / L;
   const int tok = win_row_to_token(m, static_cast<int>(row % L));
   float4* xr = reinterpret_cast<float4*>(x + (frame * L + tok) * C);
+  // the updated row is also the next GEMM's A operand: written as bf16 straight into that consumer's row order
+  // (token order for the MLP, the next block's shifted-window order for its QKV projection) -- no gather/cast pass
+  uint2* hr = h_next ? reinterpret_cast<uint2*>(h_next + (frame * L + token_to_win_row(m_next, tok)) * C) : nullptr;
 #pragma unroll
   for (int i = 0; i < kSwLnMaxVec; ++i) {
     const int c = lane + 32 * i;
@@ -107,18 +120,21 @@ ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict_
       r.z += (v[i].z - mean) * rstd * gm.z + bt.z;
       r.w += (v[i].w - mean) * rstd * gm.w + bt.w;
       xr[c] = r;
+      if (hr) hr[c] = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
     }
   }
 }
 
 int ln_residual_scatter(const float* y, const float* gamma, const float* beta, float* x, int64_t n, int res, int ws, int shift,
-                        int C, float eps, cudaStream_t stream) {
+                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next) {
   VSCB_REQUIRE(C % 4 == 0 && C <= 128 * kSwLnMaxVec && res % ws == 0, "ln_residual_scatter: C must be a multiple of 4, <= 1024");
   const int64_t rows = n * res * res;
   if (rows == 0) return VSCB200_OK;
   WinMap m{res, ws, shift, res / ws};
   ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * C * 12);
-  ln_residual_scatter_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(y, gamma, beta, x, rows, C, eps, m);
+  WinMap mn{res, ws_next > 0 ? ws_next : res, shift_next, ws_next > 0 ? res / ws_next : 1};
+  ln_residual_scatter_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      y, gamma, beta, x, rows, C, eps, m, reinterpret_cast<__nv_bfloat16*>(h_next), mn);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
