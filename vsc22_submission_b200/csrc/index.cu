@@ -23,8 +23,6 @@ int fused_topk_list_len();
 int fused_topk_group_rows();
 int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp, bool l2,
                   const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream);
-int merge_rescore(const float* Q, const float* bank, int d, bool l2, const float* cand_d, const int32_t* cand_i,
-                  int ncand, int kmid, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
 }  // namespace vscb200
 
 struct vscb200_index {

@@ -269,102 +269,6 @@ int rescore_sort(const float* Q, const float* bank, int d, bool l2, const int64_
   return VSCB200_OK;
 }
 
-// ------------------------------------------------------------------ merge of fused-epilogue candidates
-// cand_d/cand_i: [nq, ncand] keys (larger = better) + local ids from sim3_kernel<true>.  Per query: sort the
-// candidates by (key, lower id), keep kmid = k + slack, rescore those exactly in fp32, sort, emit k.
-__global__ void __launch_bounds__(kRescoreThreads)
-merge_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2,
-                     const float* __restrict__ cand_d, const int32_t* __restrict__ cand_i, int ncand, int cpad,
-                     int kmid, int mpad, int k, float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset) {
-  extern __shared__ unsigned long long mg_smem[];          // [cpad] composite keys, then [d] floats
-  unsigned long long* cand = mg_smem;
-  float* sq = reinterpret_cast<float*>(mg_smem + cpad);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t row = blockIdx.x;
-  const bool keep_max = !l2;
-  for (int c = tid; c < d; c += kRescoreThreads) sq[c] = Q[row * d + c];
-  for (int i = tid; i < cpad; i += kRescoreThreads) {
-    unsigned long long c = 0ull;
-    if (i < ncand) {
-      const int32_t id = cand_i[row * ncand + i];
-      if (id >= 0)
-        c = (static_cast<unsigned long long>(okey(cand_d[row * ncand + i], true)) << 32) |
-            static_cast<uint32_t>(~static_cast<uint32_t>(id));
-    }
-    cand[i] = c;
-  }
-  __syncthreads();
-  for (int size = 2; size <= cpad; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (cpad >> 1); i += kRescoreThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const unsigned long long a = cand[lo], b = cand[hi];
-        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
-  // exact rescoring of the kmid best (in place: slots [0, kmid) get (exact key, id); the rest is cleared)
-  for (int c = warp; c < kmid; c += kRescoreThreads / 32) {
-    const unsigned long long cc = cand[c];
-    if (cc == 0ull) continue;
-    const uint32_t id = ~static_cast<uint32_t>(cc & 0xFFFFFFFFull);
-    const float* const rp1[1] = {bank + static_cast<int64_t>(id) * d};
-    float acc1[1];
-    exact_rows_warp<1>(sq, rp1, d, lane, l2 != 0, acc1);
-    const float acc = acc1[0];
-    if (lane == 0) cand[c] = (static_cast<unsigned long long>(okey(acc, keep_max)) << 32) | static_cast<uint32_t>(~id);
-  }
-  __syncthreads();
-  for (int i = kmid + tid; i < mpad; i += kRescoreThreads) cand[i] = 0ull;
-  __syncthreads();
-  for (int size = 2; size <= mpad; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < (mpad >> 1); i += kRescoreThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const unsigned long long a = cand[lo], b = cand[hi];
-        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
-      }
-      __syncthreads();
-    }
-  }
-  for (int j = tid; j < k; j += kRescoreThreads) {
-    const unsigned long long c = cand[j];
-    if (c != 0ull) {
-      const uint32_t key = static_cast<uint32_t>(c >> 32);
-      const uint32_t ok = keep_max ? key : ~key;
-      const uint32_t u = (ok & 0x80000000u) ? (ok ^ 0x80000000u) : ~ok;
-      D[row * k + j] = __uint_as_float(u);
-      I[row * k + j] = id_offset + static_cast<int64_t>(~static_cast<uint32_t>(c & 0xFFFFFFFFull));
-    } else {
-      D[row * k + j] = keep_max ? -FLT_MAX : FLT_MAX;
-      I[row * k + j] = -1;
-    }
-  }
-}
-
-int merge_rescore(const float* Q, const float* bank, int d, bool l2, const float* cand_d, const int32_t* cand_i,
-                  int ncand, int kmid, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset, cudaStream_t stream) {
-  if (nq == 0) return VSCB200_OK;
-  int cpad = 2, mpad = 2;
-  while (cpad < ncand) cpad <<= 1;
-  if (kmid > ncand) kmid = ncand;
-  while (mpad < kmid) mpad <<= 1;
-  const size_t smem = cpad * sizeof(unsigned long long) + static_cast<size_t>(d) * sizeof(float);
-  VSCB_REQUIRE(smem <= 200 * 1024, "merge_rescore: too many candidates / dimension too large");
-  VSCB_CUDA_OK(cudaFuncSetAttribute(merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * ncand * 8);
-  merge_rescore_kernel<<<static_cast<unsigned>(nq), kRescoreThreads, smem, stream>>>(Q, bank, d, l2 ? 1 : 0, cand_d, cand_i,
-                                                                                     ncand, cpad, kmid, mpad, k, D, I, id_offset);
-  count_launch();
-  VSCB_CUDA_OK(cudaGetLastError());
-  return VSCB200_OK;
-}
-
 // ------------------------------------------------------------------ range search
 // S holds tensor-core scores (fp32-equivalent to ~1e-6 relative to |q||r|).  Pairs whose score lies
 // within that error of the threshold are decided on an exact fp32 recomputation, and every reported
