@@ -224,7 +224,7 @@ def bench_encoder(args, world, rank, peaks):
 
 def bench_swin(args):
     """Second encoder family on the reference's path (swinv2_v106/107/115: SwinV2-B 256x256, config_v106.py:8-24):
-    device-resident frames, 1024 synthetic frames per step, plan chunk 128; parity of 2 frames vs the fp32 oracle."""
+    device-resident frames, 1024 synthetic frames per step, plan chunk 256; parity of 2 frames vs the fp32 oracle."""
     import numpy as np
     import torch
 
@@ -232,7 +232,7 @@ def bench_swin(args):
     from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SWINV2_B_256, random_weights
     dev = torch.device("cuda", torch.cuda.current_device())
     w = random_weights(SWINV2_B_256, seed=0)
-    enc = B200SwinEncoder(SWINV2_B_256, w, max_frames=128).to(dev).eval()
+    enc = B200SwinEncoder(SWINV2_B_256, w, max_frames=256).to(dev).eval()
     n = 1024
     frames = torch.randn((n, 3, 256, 256), generator=torch.Generator(device=dev).manual_seed(7), device=dev).clamp_(-1, 1)
     for _ in range(2):

@@ -30,6 +30,7 @@ constexpr int kAtcOCol = 128;        // O accumulator columns [128, 192): S is d
 struct AtcParams {
   __nv_bfloat16* out;
   int T, Tpad, heads, W, mtiles, reverse, dbg;
+  int extra;        // tokens past 256 (T = 257 of a ViT-L/14: one class token on a 16 x 16 grid), handled outside the MMAs
   float scale_log2e;
 };
 
@@ -43,7 +44,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
 
 // Softmax of this thread's query row over S (fp32, TMEM columns [0, Tpad) of `tlane`), P written back in place
 // as packed bf16 pairs (columns [0, Tpad/2)).  Returns 1 / row sum.  Warp-collective (tcgen05.ld/st).
-__device__ __forceinline__ float softmax_row_tmem(uint32_t tlane, int T, int Tpad, float scale_log2e, int dbg = 0) {
+// `sx[0..nx)`: raw scores of extra keys that are not in TMEM (computed by the caller); they take part in the max and the
+// sum and their probabilities come back in `px`.
+__device__ __forceinline__ float softmax_row_tmem(uint32_t tlane, int T, int Tpad, float scale_log2e, int dbg = 0,
+                                                  const float* sx = nullptr, int nx = 0, float* px = nullptr) {
   const int nfull = Tpad >> 5;
   const bool tail16 = (Tpad & 31) != 0;
   // ---- pass 1: row maximum over the valid keys (four independent chains; the next chunk's TMEM load is in
@@ -78,6 +82,7 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t tlane, int T, int Tpa
     for (int j = 0; j < 16; ++j)
       if (j < lim) m2 = fmaxf(m2, __uint_as_float(v[j]));
   }
+  for (int e = 0; e < nx; ++e) m3 = fmaxf(m3, sx[e]);
   const float mxs = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2e;
   // ---- pass 2: p = 2^(s*scale - max*scale), row sum (four chains), P -> TMEM (bf16 pairs, in place over S)
   float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
@@ -134,6 +139,10 @@ __device__ __forceinline__ float softmax_row_tmem(uint32_t tlane, int T, int Tpa
     tmem_st_32x8(tlane + nfull * 16, pk);
   }
   tmem_st_wait();
+  for (int e = 0; e < nx; ++e) {
+    px[e] = ex2_approx(fmaf(sx[e], scale_log2e, -mxs));
+    l3 += px[e];
+  }
   return 1.0f / ((l0 + l1) + (l2 + l3));
 }
 
@@ -240,7 +249,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 4) tmem_dealloc<kAtcTmemCols>(tmem_base);
 }
 
-// ------------------------------------------------------------------ persistent ping-pong variant (128 < T <= 256)
+// ---- SIMT helpers for the tokens past 256 (attention_pp_kernel, extra > 0): 64-wide bf16 rows of a 128B-swizzled tile
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+// row r of a tile whose rows are 128 bytes (64 bf16), 16-byte chunk c stored at c ^ (r & 7)
+__device__ __forceinline__ uint4 tile_chunk(const uint8_t* tile, int r, int c) {
+  return *reinterpret_cast<const uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ float dot64(const uint8_t* ta, int ra, const uint8_t* tb, int rb) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float a[8], b[8];
+    unpack8(tile_chunk(ta, ra, c), a);
+    unpack8(tile_chunk(tb, rb, c), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(a[i], b[i], acc);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------ persistent ping-pong variant (128 < T <= 264)
 // One CTA per SM walks (frame, head) units.  Both 128-query tiles of a unit are in flight at once, each owned
 // by one softmax warpgroup with its own 256 TMEM columns, so one warpgroup's exponentials overlap the other's
 // MMAs and epilogue; Q/K/V of the NEXT unit are prefetched by a TMA producer warp into the second smem stage.
@@ -251,14 +286,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 //                     S0(u) S1(u) PV0(u) PV1(u) S0(u+1) ... each gated by the mbarrier of the data it needs
 constexpr int kAppThreads = 320;
 
+template <int kExtra>     // tokens past 256: 0, or 1 (T = 257)
 __global__ void __launch_bounds__(kAppThreads, 1)
-attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AtcParams p,
-                    int n_units) {
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmX, AtcParams p, int n_units) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int kv_bytes = p.Tpad * 128;
-  const int stage_bytes = 32768 + 2 * kv_bytes;
+  // T = 256 + extra (ViT-L/14: 257): the 256 x 256 block runs on the tensor cores as usual; the extra KEYS are folded in by
+  // the softmax threads (one 64-long dot product per row and key, a rank-1 update of O) and the extra QUERY rows are
+  // computed whole by the otherwise idle lanes of the producer warp.  Their Q / K / V rows ride in three 8-row boxes.
+  constexpr int extra = kExtra;
+  const int stage_bytes = 32768 + 2 * kv_bytes + (extra ? 3072 : 0);
+  const int x_off = 32768 + 2 * kv_bytes;     // Qx | Kx | Vx, 1 KB each
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
   uint64_t* qk_full = bars;          // [2] per smem stage: Q + K landed
   uint64_t* qk_empty = bars + 2;     //     both S MMAs of the unit have read them
@@ -277,7 +318,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       prefetch_tmap(&tmQ);
       prefetch_tmap(&tmKV);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&qk_full[i], 1); mbar_init(&qk_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+        // extra tokens: the 8 softmax warps and the producer warp read the staged rows too and release them themselves
+        mbar_init(&qk_full[i], 1); mbar_init(&qk_empty[i], extra ? 10 : 1);
+        mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], extra ? 10 : 1);
         mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
       }
       fence_barrier_init();
@@ -298,9 +341,63 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   };
 
   if (warp == 8) {
-    if (lane == 0) {
-      int it = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+    // extra query rows of one unit, whole warp: scores against the 256 staged keys + the extra keys, softmax, P.V
+    auto extra_rows = [&](int unit, int it) {
+      const int st = it & 1;
+      int frame, head;
+      unit_frame_head(unit, frame, head);
+      const uint8_t* sQ = smem + st * stage_bytes;
+      const uint8_t *sK = sQ + 32768, *sV = sK + kv_bytes, *sQx = sQ + x_off, *sKx = sQx + 1024, *sVx = sKx + 1024;
+      mbar_wait(&qk_full[st], (it >> 1) & 1);
+      mbar_wait(&v_full[st], (it >> 1) & 1);
+      {
+        constexpr int e = 0;
+        float sc[9];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sc[i] = dot64(sQx, e, sK, lane + 32 * i);
+        sc[8] = lane < extra ? dot64(sQx, e, sKx, lane) : -INFINITY;
+        float mx = sc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, sc[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float l = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          sc[i] = ex2_approx((sc[i] - mx) * p.scale_log2e);
+          l += sc[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        float a0 = 0.f, a1 = 0.f;                     // output columns 2*lane, 2*lane + 1
+        const uint8_t* vcol = sV + (lane & 3) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll 4
+          for (int jj = 0; jj < 32; ++jj) {
+            const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
+            const int j = 32 * i + jj;
+            const uint32_t vv = *reinterpret_cast<const uint32_t*>(vcol + j * 128 + (((lane >> 2) ^ (j & 7)) << 4));
+            a0 = fmaf(pj, __uint_as_float(vv << 16), a0);
+            a1 = fmaf(pj, __uint_as_float(vv & 0xFFFF0000u), a1);
+          }
+        }
+        {
+          const float pj = __shfl_sync(0xffffffffu, sc[8], 0);
+          const uint32_t vv = *reinterpret_cast<const uint32_t*>(sVx + ((lane >> 2) << 4) + (lane & 3) * 4);
+          a0 = fmaf(pj, __uint_as_float(vv << 16), a0);
+          a1 = fmaf(pj, __uint_as_float(vv & 0xFFFF0000u), a1);
+        }
+        const float inv = 1.0f / l;
+        __nv_bfloat16* orow = p.out + (static_cast<int64_t>(frame) * p.T + 256 + e) * p.W + head * 64;
+        *reinterpret_cast<uint32_t*>(orow + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&qk_empty[st]); mbar_arrive(&v_empty[st]); }
+    };
+    int it = 0, prev_unit = -1;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+      if (lane == 0) {
         const int st = it & 1;
         int frame, head;
         unit_frame_head(unit, frame, head);
@@ -308,14 +405,23 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint8_t* sQ = smem + st * stage_bytes;
         const uint32_t par = (it >> 1) & 1;
         mbar_wait(&qk_empty[st], par ^ 1);
-        mbar_expect_tx(&qk_full[st], 32768 + kv_bytes);
+        mbar_expect_tx(&qk_full[st], 32768 + kv_bytes + (extra ? 2048 : 0));
         tma_load_2d(sQ, &tmQ, &qk_full[st], head * 64, row0, kEvictFirst);
         tma_load_2d(sQ + 32768, &tmKV, &qk_full[st], p.W + head * 64, row0, kEvictFirst);
+        if (extra) {
+          tma_load_2d(sQ + x_off, &tmX, &qk_full[st], head * 64, row0 + 256, kEvictFirst);
+          tma_load_2d(sQ + x_off + 1024, &tmX, &qk_full[st], p.W + head * 64, row0 + 256, kEvictFirst);
+        }
         mbar_wait(&v_empty[st], par ^ 1);
-        mbar_expect_tx(&v_full[st], kv_bytes);
+        mbar_expect_tx(&v_full[st], kv_bytes + (extra ? 1024 : 0));
         tma_load_2d(sQ + 32768 + kv_bytes, &tmKV, &v_full[st], 2 * p.W + head * 64, row0, kEvictFirst);
+        if (extra) tma_load_2d(sQ + x_off + 2048, &tmX, &v_full[st], 2 * p.W + head * 64, row0 + 256, kEvictFirst);
       }
+      __syncwarp();
+      if (extra && prev_unit >= 0) extra_rows(prev_unit, it - 1);     // while this unit's loads are in flight
+      prev_unit = unit;
     }
+    if (extra && prev_unit >= 0) extra_rows(prev_unit, it - 1);
   } else if (warp == 9) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16_f32(128, p.Tpad);
@@ -373,9 +479,18 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int frame, head;
       unit_frame_head(unit, frame, head);
       float inv_l = 0.f;
+      float sx[1] = {-INFINITY}, px[1] = {0.f};
+      const int st = it & 1;
+      const uint8_t* sQ = smem + st * stage_bytes;
+      if (extra) {                                       // this row's score against the key past 256
+        mbar_wait(&qk_full[st], (it >> 1) & 1);
+        sx[0] = dot64(sQ, rbase + lane, sQ + x_off + 1024, 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qk_empty[st]);
+      }
       mbar_wait(&s_full[w], ph);
       tc_fence_after();
-      if (warp_valid) inv_l = softmax_row_tmem(tlane, p.T, p.Tpad, p.scale_log2e, p.dbg);
+      if (warp_valid) inv_l = softmax_row_tmem(tlane, p.T < 256 ? p.T : 256, p.Tpad, p.scale_log2e, p.dbg, sx, extra, px);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[w]);
@@ -390,6 +505,22 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[w]);          // TMEM is free for S of the next unit before the stores
+      if (extra) {                                       // O += p_x * v_x for the keys past 256 (fp32, rank-1 per key)
+        mbar_wait(&v_full[st], (it >> 1) & 1);
+        const uint8_t* sVx = sQ + x_off + 2048;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float vf[8];
+          unpack8(tile_chunk(sVx, 0, c), vf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (c < 4) v0[8 * c + i] = __float_as_uint(fmaf(px[0], vf[i], __uint_as_float(v0[8 * c + i])));
+            else v1[8 * (c - 4) + i] = __float_as_uint(fmaf(px[0], vf[i], __uint_as_float(v1[8 * (c - 4) + i])));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_empty[st]);
+      }
       const int row = rbase + lane;
       if (warp_valid && row < p.T) {
         __nv_bfloat16* orow = p.out + (static_cast<int64_t>(frame) * p.T + row) * p.W + head * 64;
@@ -405,11 +536,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 bool attention_tc_supported(int T, int head_dim) {
   static const int off = [] { const char* e = getenv("VSCB200_ATTN_MMA_SYNC"); return e ? atoi(e) : 0; }();
-  return !off && head_dim == 64 && ((T + 15) & ~15) <= 256;
+  return !off && head_dim == 64 && (((T + 15) & ~15) <= 256 || T == 257);
 }
 
 int attention_tc(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse) {
-  const int Tpad = (T + 15) & ~15;
+  const int extra = T > 256 ? T - 256 : 0;            // 257 = 256 + class token: the tokens past 256 bypass the MMAs
+  const int Tpad = extra ? 256 : (T + 15) & ~15;
   const int W = heads * 64;
   const int64_t M = static_cast<int64_t>(n_frames) * T;
   CUtensorMap tmQ, tmKV;
@@ -418,19 +550,24 @@ int attention_tc(const void* qkv, void* out, int n_frames, int T, int heads, cud
   if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, Tpad, 64, true))) return rc;
   AtcParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.T = T; p.Tpad = Tpad; p.heads = heads; p.W = W; p.mtiles = (T + 127) / 128; p.reverse = reverse ? 1 : 0;
+  p.T = T; p.Tpad = Tpad; p.heads = heads; p.W = W; p.mtiles = extra ? 2 : (T + 127) / 128; p.reverse = reverse ? 1 : 0;
+  p.extra = extra;
   { const char* e = getenv("VSCB200_ATTN_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.scale_log2e = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
   static const int no_pp = [] { const char* e = getenv("VSCB200_ATTN_NO_PINGPONG"); return e ? atoi(e) : 0; }();
   if (p.mtiles == 2 && !no_pp) {
     CUtensorMap tmQ2;
     if ((rc = make_tmap_2d(&tmQ2, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, 256, 64, true))) return rc;
+    CUtensorMap tmX = tmKV;
+    if (extra && (rc = make_tmap_2d(&tmX, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, 8, 64, true))) return rc;
     const int n_units = n_frames * heads;
-    const int smem_pp = 2 * (32768 + 2 * Tpad * 128) + 256 + 1024;
-    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp));
+    const int smem_pp = 2 * (32768 + 2 * Tpad * 128 + (extra ? 3072 : 0)) + 256 + 1024;
+    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp));
+    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pp));
     const int grid_pp = n_units < device_sm_count() ? n_units : device_sm_count();
     ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * 64);
-    VSCB_CUDA_OK(launch_pdl(attention_pp_kernel, dim3(grid_pp), dim3(kAppThreads), smem_pp, stream, tmQ2, tmKV, p, n_units));
+    if (extra) VSCB_CUDA_OK(launch_pdl(attention_pp_kernel<1>, dim3(grid_pp), dim3(kAppThreads), smem_pp, stream, tmQ2, tmKV, tmX, p, n_units));
+    else VSCB_CUDA_OK(launch_pdl(attention_pp_kernel<0>, dim3(grid_pp), dim3(kAppThreads), smem_pp, stream, tmQ2, tmKV, tmX, p, n_units));
     count_launch();
     VSCB_CUDA_OK(cudaGetLastError());
     return VSCB200_OK;

@@ -271,7 +271,7 @@ def encoder_from_state_dict(sd: Dict[str, torch.Tensor], max_frames: int = 256) 
         return B200ViTEncoder(spec, weights_from_sscd_timm_state_dict(sd, layers), max_frames)
     if "patch_embed.proj.weight" in keys and "layers.0.blocks.0.attn.logit_scale" in keys:             # swinv2_v1xx
         from .swin_encoder import B200SwinEncoder, spec_from_state_dict
-        return B200SwinEncoder(spec_from_state_dict(sd), sd, min(max_frames, 64))
+        return B200SwinEncoder(spec_from_state_dict(sd), sd, max_frames)
     raise RuntimeError("encoder_from_state_dict: unrecognised checkpoint (implemented: CLIP ViT, timm ViT + GeM head, "
                        "Swin-V2 -- the encoders on the reference's inference path)")
 
