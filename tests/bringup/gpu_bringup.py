@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """GPU bring-up diagnostics: each stage runs in its own process (a trapped kernel poisons the CUDA
-context) under a timeout.  `python tools/gpu_bringup.py` runs all stages; `... <stage>` runs one."""
+context) under a timeout.  `python tests/bringup/gpu_bringup.py` runs all stages; `... <stage>` runs one."""
 import ctypes as C
 import os
 import subprocess
 import sys
 import time
 
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 
 STAGES = ["sim_precision", "gemm_sustained", "gemm_small", "gemm_shapes", "gemm_epilogues", "layernorm", "attention", "index", "vit_small", "vit_b16"]

@@ -2,7 +2,7 @@
 """Swin-V2 bring-up: small configurations against the fp32 oracle, stage by stage (truncated depths)."""
 import os, sys, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import swin_ref
 from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SwinSpec, random_weights, SWINV2_B_256
 
