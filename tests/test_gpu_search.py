@@ -276,3 +276,55 @@ def test_pair_similarity_matrices_and_topk():
         np.testing.assert_array_equal(tv, np.take_along_axis(sims, order, axis=-1))
     plain = ps.similarities(cands[:3])
     assert all(np.array_equal(a[1], b[1]) for a, b in zip(plain, got[:3])) and ps.similarities([]) == []
+
+
+def _videos(prefix, arr, lens):
+    import dataclasses
+
+    @dataclasses.dataclass
+    class VF:
+        video_id: str
+        feature: np.ndarray
+        timestamps: np.ndarray = None
+
+    out, i = [], 0
+    for n, ln in enumerate(lens):
+        out.append(VF(f"{prefix}{n:06d}", arr[i:i + int(ln)]))
+        i += int(ln)
+    return out
+
+
+def test_score_normalize_matches_reference_golden(golden_dir):
+    """search.score_normalize (device) == the reference's own score_normalize on the golden descriptors
+    (score_normalization.py:33-104, fixture made by tests/golden/make_golden.py through the unmodified vsc package)."""
+    from vsc22_submission_b200 import search
+    g = np.load(os.path.join(golden_dir, "search_small.npz"))
+    q, r, z = (_videos(p, g[k], g[l]) for p, k, l in (("Q", "q_raw", "q_len"), ("R", "r_raw", "r_len"), ("N", "z_raw", "z_len")))
+    sq, sr = search.score_normalize(q, r, z, beta=1.2)
+    got_q, got_r = np.concatenate([v.feature for v in sq]), np.concatenate([v.feature for v in sr])
+    np.testing.assert_allclose(got_q, g["sn_q"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(got_r, g["sn_r"], rtol=2e-5, atol=2e-6)
+    assert [v.video_id for v in sq] == [v.video_id for v in q] and sq[0].feature.shape == q[0].feature.shape
+    with pytest.raises(Exception, match="against VSC rules"):
+        search.score_normalize(q, r, r, beta=1.2)
+
+
+def test_query_and_ref_score_normalize_match_oracle():
+    """query_score_normalize (video-score gate, nk > 1, fixed low_var_dim) and ref_score_normalize
+    (score_normalization.py:107-192) against the numpy restatement; a bank large enough for the tensor-core path."""
+    from oracle import score_norm_np
+    from vsc22_submission_b200 import search
+    rng = np.random.default_rng(12)
+    d = 64
+    qa, za = rng.standard_normal((90, d)).astype(np.float32), rng.standard_normal((5000, d)).astype(np.float32)
+    ra = rng.standard_normal((300, d)).astype(np.float32)
+    q, z, r = _videos("Q", qa, [30, 40, 20]), _videos("N", za, [2500, 2500]), _videos("R", ra, [100, 200])
+    scores = {"Q000000": 0.5, "Q000001": 0.0, "Q000002": 0.9}
+    gated = np.concatenate([np.full(30, False), np.full(40, True), np.full(20, False)])
+    got = np.concatenate([v.feature for v in search.query_score_normalize(q, z, scores, low_var_dim=5, beta=1.2, nk=2)])
+    ref = score_norm_np.query_score_normalize(qa, za, gated, low_var_dim_=5, beta=1.2, nk=2)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+    assert (got[30:70, -1] == -100.0).all()
+    got_r = np.concatenate([v.feature for v in search.ref_score_normalize(r, z)])
+    ref_r, _ = score_norm_np.ref_score_normalize(ra, za)
+    np.testing.assert_allclose(got_r, ref_r, rtol=2e-5, atol=2e-6)
