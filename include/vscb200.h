@@ -91,6 +91,23 @@ void vscb200_free(void* p);
 int vscb200_index_scores(vscb200_index* ix, const float* q_dev, int64_t nq, float* S_dev, int64_t ldS,
                          void* stream);
 
+/* Global (cross-query) candidate search -- vsc/index.py:142-165 `_global_threshold_knn_search` with
+ * vsc/exhaustive_search.py:206-292 `range_search_max_results` (adaptive radius, <= 2K survivors), and, with a
+ * threshold, the search loop of M/infer/infer_matching.py:229-247.  Finds the `global_k` best (query row, bank row)
+ * pairs over ALL nq query rows (global_k <= 0: no limit), optionally restricted to pairs strictly better than
+ * `thresh` (use_thresh != 0; '>' IP / '<' L2).  Scores are exact fp32; order: best first, ties by (query row,
+ * bank row).  The result stays inside the index until the next global search; *n_found_host receives its length. */
+int vscb200_index_global_search(vscb200_index* ix, const float* q_dev, int64_t nq, int64_t global_k, int use_thresh,
+                                float thresh, int64_t* n_found_host, void* stream);
+/* copy the retained result: scores [n] float32, query rows [n] int64, bank rows [n] int64 (device or host memory) */
+int vscb200_index_global_results(vscb200_index* ix, float* scores, int64_t* qrows, int64_t* brows, void* stream);
+/* Reduce the retained frame pairs to (query video, ref video) candidates scored by their best frame pair, sorted
+ * best first -- vsc/index.py:119-140 + vsc/candidates.py:24-40 (MaxScoreAggregation + sort), infer_matching.py:248-256.
+ * q_offsets_dev [nqv+1] / r_offsets_dev [nrv+1] (int64, device): first row of each video in the query matrix / bank. */
+int vscb200_index_global_video_pairs(vscb200_index* ix, const int64_t* q_offsets_dev, int64_t nqv,
+                                     const int64_t* r_offsets_dev, int64_t nrv, int64_t* n_pairs_host, void* stream);
+int vscb200_index_video_pair_results(vscb200_index* ix, float* scores, int64_t* qvideo, int64_t* rvideo, void* stream);
+
 /* Fused score normalisation prologue (vsc/baseline/score_normalization.py:71-103):
  * out[n, d] = [ l2norm(drop(x, drop_dim)) , last ] where last is `fill` (1.0 for references, :99-101)
  * or, when bias_dev != NULL, bias_dev[row] (queries, :96-97).  x: [n, d] -> out: [n, d]. */

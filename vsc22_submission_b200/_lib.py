@@ -61,6 +61,10 @@ SIGNATURES = {
     "vscb200_index_range_search_host": (_i, [_p, _p, _i64, _f, _p, C.POINTER(_p), C.POINTER(_p)]),
     "vscb200_free": (None, [_p]),
     "vscb200_index_scores": (_i, [_p, _p, _i64, _p, _i64, _p]),
+    "vscb200_index_global_search": (_i, [_p, _p, _i64, _i64, _i, _f, C.POINTER(_i64), _p]),
+    "vscb200_index_global_results": (_i, [_p, _p, _p, _p, _p]),
+    "vscb200_index_global_video_pairs": (_i, [_p, _p, _i64, _p, _i64, C.POINTER(_i64), _p]),
+    "vscb200_index_video_pair_results": (_i, [_p, _p, _p, _p, _p]),
     "vscb200_sn_transform": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p]),
     "vscb200_low_var_dim": (_i, [_p, _i64, _i, C.POINTER(_i), _p]),
     "vscb200_sn_bias": (_i, [_p, _i64, _i, _i, _f, _p, _p]),

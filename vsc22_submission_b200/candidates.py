@@ -1,0 +1,180 @@
+"""Video-level candidate generation with the search, the global top-K selection and the per-video-pair
+reduction all on the device.
+
+Mirrors, with the same names / argument meaning:
+
+* ``VideoIndex`` (``add`` / ``search(queries, global_k)``)  -- VSC22-Descriptor-Track-1st/infer/vsc/index.py:74-177
+  (``global_k >= 0``: global-threshold search, :142-165 over vsc/exhaustive_search.py:206-292; ``global_k < 0``:
+  plain kNN with k = -global_k, :167-177)
+* ``MaxScoreAggregation`` / ``CandidateGeneration.query``   -- vsc/candidates.py:24-40
+* ``threshold_candidates``  -- the search section of VSC22-Matching-Track-1st/infer/infer_matching.py:217-256
+  (every (query video, ref video) whose best frame pair beats ``SEARCH_THRESHOLD``, best first)
+
+The reference walks every retrieved frame pair in Python (index.py:123-135, :158-160 -- ~10 M tuples at test scale)
+and falls back to a CPU range search for dense rows (exhaustive_search.py:70-89).  Here one C-ABI call produces the
+exact global top-K on the device (csrc/global_topk.cu) and a second one reduces it to video pairs; Python only
+builds the (few) result objects.  ``VideoFeature``-like inputs are duck-typed (``.video_id``, ``.feature``,
+``.timestamps``); results use the reference's own ``PairMatch`` / ``PairMatches`` / ``CandidatePair`` classes when the
+reference's ``vsc`` package is importable, and field-compatible stand-ins otherwise.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import search as _search
+from .search import METRIC_INNER_PRODUCT, METRIC_L2, DeviceIndex  # noqa: F401
+
+
+class _PairMatch(NamedTuple):            # vsc/index.py:48-51
+    query_timestamps: Tuple[float, float]
+    ref_timestamps: Tuple[float, float]
+    score: float
+
+
+class _PairMatches(NamedTuple):          # vsc/index.py:54-71
+    query_id: str
+    ref_id: str
+    matches: list
+
+    def records(self):
+        for m in self.matches:
+            yield {"query_id": self.query_id, "ref_id": self.ref_id, "query_start": m.query_timestamps[0],
+                   "query_end": m.query_timestamps[1], "ref_start": m.ref_timestamps[0],
+                   "ref_end": m.ref_timestamps[1], "score": m.score}
+
+
+class _CandidatePair(NamedTuple):        # vsc/metrics.py:43-47
+    query_id: str
+    ref_id: str
+    score: float
+
+
+def _result_types():
+    try:
+        from vsc.index import PairMatch, PairMatches
+        from vsc.metrics import CandidatePair
+        return PairMatch, PairMatches, CandidatePair
+    except Exception:
+        return _PairMatch, _PairMatches, _CandidatePair
+
+
+def _timestamps(ts: np.ndarray, idx: int) -> Tuple[float, float]:
+    """VideoMetadata.get_timestamps (vsc/index.py:26-30): N -> (t, t); Nx2 -> (start, end)."""
+    t = ts[idx]
+    if ts.ndim == 1:
+        return (t, t)
+    return (t[0], t[1])
+
+
+def _offsets(videos: Sequence) -> np.ndarray:
+    off = np.zeros(len(videos) + 1, dtype=np.int64)
+    np.cumsum([int(v.feature.shape[0]) for v in videos], out=off[1:])
+    return off
+
+
+class VideoIndex:
+    """Flat index over the frames of a list of reference videos (vsc/index.py:74-94)."""
+
+    def __init__(self, dim: int, codec_str: str = "Flat", metric: int = METRIC_INNER_PRODUCT, device=None):
+        if codec_str != "Flat":
+            raise RuntimeError(f"VideoIndex: only the 'Flat' codec exists on this path (got {codec_str!r})")
+        self.dim = int(dim)
+        self.index = DeviceIndex(self.dim, metric, device)
+        self.device = self.index.device
+        self.videos: list = []
+        self._r_off = np.zeros(1, dtype=np.int64)
+
+    def add(self, db: Sequence):
+        if not db:
+            return
+        for vf in db:
+            if vf.feature.shape[1] != self.dim:
+                raise AssertionError(f"add: expected [n, {self.dim}] features, got {tuple(vf.feature.shape)}")
+        self.index.add(_search._cat(db, self.device, "vi_add"))
+        self.videos.extend(db)
+        self._r_off = _offsets(self.videos)
+
+    # -- device results ------------------------------------------------------------------------
+    def _frame_pairs(self, queries: Sequence, global_k: int, threshold: Optional[float] = None):
+        q = _search._cat(queries, self.device, "vi_q")
+        if global_k < 0:
+            # vsc/index.py:167-177: per-row kNN, every (row, neighbour) pair is a hit
+            logging.warning("Using local k for KNN search. Warning: this is against the VSC rules, since predictions "
+                            "for a query-ref pair are not independent of other references.")
+            k = min(-global_k, max(self.index.ntotal, 1))
+            D, I = self.index.search(q, k)
+            qi = torch.arange(q.shape[0], device=self.device).repeat_interleave(k)
+            return D.reshape(-1), qi, I.reshape(-1)
+        return self.index.global_search(q, global_k, threshold)
+
+    def search(self, queries: Sequence, global_k: int) -> list:
+        """-> List[PairMatches], one per (query video, ref video) with at least one retrieved frame pair, in order
+        of first appearance in the best-first hit list (vsc/index.py:96-140)."""
+        PairMatch, PairMatches, _ = _result_types()
+        sc, qi, ri = self._frame_pairs(queries, global_k)
+        sc, qi, ri = sc.cpu().numpy(), qi.cpu().numpy(), ri.cpu().numpy()
+        q_off = _offsets(queries)
+        qv = np.searchsorted(q_off, qi, side="right") - 1
+        rv = np.searchsorted(self._r_off, ri, side="right") - 1
+        pair_nns: dict = {}
+        for j in range(sc.shape[0]):
+            qvid, rvid = queries[qv[j]], self.videos[rv[j]]
+            match = PairMatch(query_timestamps=_timestamps(qvid.timestamps, qi[j] - q_off[qv[j]]),
+                              ref_timestamps=_timestamps(rvid.timestamps, ri[j] - self._r_off[rv[j]]),
+                              score=sc[j])
+            pair_nns.setdefault((qvid.video_id, rvid.video_id), []).append(match)
+        return [PairMatches(qid, rid, matches) for (qid, rid), matches in pair_nns.items()]
+
+    def video_pairs(self, queries: Sequence, global_k: int = 0, threshold: Optional[float] = None):
+        """(score f32 [m], query video index i64 [m], ref video index i64 [m]) numpy arrays: every video pair that
+        owns at least one retrieved frame pair, scored by its best one, best first."""
+        if global_k < 0:
+            raise RuntimeError("video_pairs: the kNN mode (global_k < 0) goes through search()")
+        self._frame_pairs(queries, global_k, threshold)
+        sc, qv, rv = self.index.global_video_pairs(torch.from_numpy(_offsets(queries)), torch.from_numpy(self._r_off))
+        return sc.cpu().numpy(), qv.cpu().numpy(), rv.cpu().numpy()
+
+
+class MaxScoreAggregation:
+    """vsc/candidates.py:24-26."""
+
+    def aggregate(self, match) -> float:
+        return np.max([m.score for m in match.matches])
+
+    def score(self, match):
+        _, _, CandidatePair = _result_types()
+        return CandidatePair(query_id=match.query_id, ref_id=match.ref_id, score=self.aggregate(match))
+
+
+class CandidateGeneration:
+    """vsc/candidates.py:29-40.  With ``MaxScoreAggregation`` (the only aggregation the reference ships) the
+    per-video-pair maximum and the final sort run on the device; any other aggregation object gets the
+    reference's generic path over ``VideoIndex.search``."""
+
+    def __init__(self, references: Sequence, aggregation, device=None):
+        self.aggregation = aggregation
+        dim = int(references[0].feature.shape[1])
+        self.index = VideoIndex(dim, device=device)
+        self.index.add(references)
+
+    def query(self, queries: Sequence, global_k: int) -> list:
+        _, _, CandidatePair = _result_types()
+        if isinstance(self.aggregation, MaxScoreAggregation) and global_k >= 0:
+            sc, qv, rv = self.index.video_pairs(queries, global_k)
+            refs = self.index.videos
+            return [CandidatePair(query_id=queries[qv[j]].video_id, ref_id=refs[rv[j]].video_id, score=sc[j])
+                    for j in range(sc.shape[0])]
+        matches = self.index.search(queries, global_k=global_k)
+        candidates = [self.aggregation.score(m) for m in matches]
+        return sorted(candidates, key=lambda c: c.score, reverse=True)
+
+
+def threshold_candidates(index: VideoIndex, queries: Sequence, threshold: float) -> List[Tuple[str, str, float]]:
+    """``search_res_list`` of M/infer/infer_matching.py:229-256: (query_id, ref_id, best frame-pair score) for every
+    video pair with a frame pair strictly above ``threshold`` (``SEARCH_THRESHOLD``), best first."""
+    sc, qv, rv = index.video_pairs(queries, 0, threshold)
+    return [(queries[qv[j]].video_id, index.videos[rv[j]].video_id, sc[j]) for j in range(sc.shape[0])]

@@ -1,0 +1,629 @@
+// Global (cross-query) candidate search on the device: the `global_k` best (query row, bank row) pairs over ALL
+// queries, and their reduction to (query video, reference video) candidates.
+//
+// Replaces, behind one C-ABI call each:
+//   * vsc/index.py:142-165 `_global_threshold_knn_search` + vsc/exhaustive_search.py:206-292
+//     `range_search_max_results` / :178-203 `apply_maxres` / :149-161 `threshold_radius_nres` -- the adaptive-radius
+//     range search whose result handling is Python loops and numpy partitions on the host;
+//   * vsc/index.py:119-140 (regrouping hits by video pair) + vsc/candidates.py:24-40 (MaxScoreAggregation, sort);
+//   * M/infer/infer_matching.py:229-256 (per-video search + CPU range_search(thr) + dict max-reduce + sort).
+//
+// Algorithm (same idea as the reference's: keep <= 2K survivors, raise the radius when the table overflows):
+//   per query block: dense tensor-core score block S (score_block) -> `gt_emit_kernel` appends every pair better
+//   than the current radius (minus the tensor-core error margin) to a survivor buffer.  When the buffer would
+//   overflow, an exact 3-level radix select (11+11+10 bits of the order-preserving key, shared-memory histograms)
+//   over {buffer, block} finds the K-th best value, which becomes the new radius; the buffer is compacted and the
+//   block emitted again.  At the end every survivor is rescored in exact fp32 (exact.cuh: the one summation order of
+//   all search paths), sorted by (score, query row, bank row) with a stable LSD radix sort (sort.cu) and cut to K.
+//   The result is therefore the exact fp32 global top-K, not an approximation of it.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "exact.cuh"
+#include "host_util.h"
+#include "index_internal.h"
+#include "kernels.h"
+
+namespace vscb200 {
+size_t radix_sort_scratch_bytes(int64_t n);
+int radix_sort_pairs(uint64_t* k0, uint64_t* v0, uint64_t* k1, uint64_t* v1, int64_t n, int bit_lo, int bit_hi,
+                     void* scratch, int* result_in_alt, cudaStream_t stream);
+}  // namespace vscb200
+
+using namespace vscb200;
+
+namespace {
+
+constexpr int kGtThreads = 256;
+constexpr int kGtChunk = 4096;            // columns of one row handled per work item
+constexpr float kTcMargin = 1.5e-5f;      // tensor-core score error bound relative to |q||r| (select.cu range_hit)
+
+// order-preserving key, larger = better (IP: larger score; L2: smaller distance)
+__host__ __device__ __forceinline__ uint32_t better_key(float v, bool keep_max) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(v);
+#else
+  uint32_t b;
+  memcpy(&b, &v, 4);
+#endif
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return keep_max ? b : ~b;
+}
+__host__ __device__ __forceinline__ float key_value(uint32_t key, bool keep_max) {
+  uint32_t b = keep_max ? key : ~key;
+  b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+
+struct GtBlock {
+  const float* S; int64_t ldS; int64_t nb; int64_t n;     // score block [nb, n]
+  int64_t q0;                                             // global query row of block row 0
+  const float* qn;                                        // [nq_total] squared query norms
+  const float* rn_max;                                    // device scalar: max squared bank norm
+  float radius; int has_radius; int keep_max;
+};
+
+// a pair survives when it is better than the radius by more than the scoring error could hide
+__device__ __forceinline__ float row_threshold(const GtBlock& a, int64_t row) {
+  if (!a.has_radius) return a.keep_max ? -INFINITY : INFINITY;
+  const float m = 2.f * kTcMargin * sqrtf(a.qn[a.q0 + row] * *a.rn_max) * (a.keep_max ? 1.f : 2.f);
+  return a.keep_max ? a.radius - m : a.radius + m;
+}
+__device__ __forceinline__ bool better(float v, float thr, int keep_max) { return keep_max ? v > thr : v < thr; }
+
+// ---- radix-select histograms over {block entries better than the radius} U {buffer} --------------------------
+// level 0: digit = key >> 21; level 1: (key >> 21) == prefix, digit = (key >> 10) & 2047;
+// level 2: (key >> 10) == prefix, digit = key & 1023
+__device__ __forceinline__ void hist_add(uint32_t* h, uint32_t key, int level, uint32_t prefix, bool pass) {
+  uint32_t digit;
+  if (level == 0) digit = key >> 21;
+  else if (level == 1) { pass = pass && (key >> 21) == prefix; digit = (key >> 10) & 2047u; }
+  else { pass = pass && (key >> 10) == prefix; digit = key & 1023u; }
+  const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+  if (pass) {
+    const uint32_t peers = __match_any_sync(mask, digit);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&h[digit], __popc(peers));
+  }
+}
+
+__global__ void __launch_bounds__(kGtThreads)
+gt_hist_kernel(GtBlock a, const float* __restrict__ bufv, int64_t nbuf, int level, uint32_t prefix,
+               unsigned long long* __restrict__ hist) {
+  __shared__ uint32_t h[2048];
+  for (int i = threadIdx.x; i < 2048; i += kGtThreads) h[i] = 0;
+  __syncthreads();
+  const int64_t chunks = (a.n + kGtChunk - 1) / kGtChunk;
+  const int64_t work = a.nb * chunks;
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int64_t row = w / chunks, c0 = (w % chunks) * kGtChunk;
+    const float thr = row_threshold(a, row);
+    const float* p = a.S + row * a.ldS + c0;
+    const int cnt = a.n - c0 < kGtChunk ? static_cast<int>(a.n - c0) : kGtChunk;
+    for (int j0 = 0; j0 < cnt; j0 += kGtThreads * 4) {
+      const int j = j0 + threadIdx.x * 4;
+      float v[4];
+      bool ok[4];
+      if (j + 3 < cnt) {
+        const float4 t = *reinterpret_cast<const float4*>(p + j);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        ok[0] = ok[1] = ok[2] = ok[3] = true;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ok[u] = j + u < cnt; v[u] = ok[u] ? p[j + u] : 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        hist_add(h, better_key(v[u], a.keep_max), level, prefix, ok[u] && better(v[u], thr, a.keep_max));
+    }
+  }
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kGtThreads; i0 < nbuf; i0 += static_cast<int64_t>(gridDim.x) * kGtThreads) {
+    const int64_t i = i0 + threadIdx.x;
+    const bool ok = i < nbuf;
+    hist_add(h, better_key(ok ? bufv[i] : 0.f, a.keep_max), level, prefix, ok);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += kGtThreads)
+    if (h[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(h[i]));
+}
+
+// ---- emit: append the survivors of one score block (warp-aggregated) -----------------------------------------
+// The counter keeps counting past `cap`, so the host sees by how much a block overflowed.
+__global__ void __launch_bounds__(kGtThreads)
+gt_emit_kernel(GtBlock a, int64_t ntotal, float* __restrict__ bufv, uint64_t* __restrict__ bufp,
+               unsigned long long* __restrict__ counter, unsigned long long cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunks = (a.n + kGtChunk - 1) / kGtChunk;
+  const int64_t work = a.nb * chunks;
+  for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
+    const int64_t row = w / chunks, c0 = (w % chunks) * kGtChunk;
+    const float thr = row_threshold(a, row);
+    const float* p = a.S + row * a.ldS + c0;
+    const uint64_t pbase = static_cast<uint64_t>(a.q0 + row) * static_cast<uint64_t>(ntotal) + static_cast<uint64_t>(c0);
+    const int cnt = a.n - c0 < kGtChunk ? static_cast<int>(a.n - c0) : kGtChunk;
+    for (int j0 = 0; j0 < cnt; j0 += kGtThreads * 4) {
+      const int j = j0 + threadIdx.x * 4;
+      float v[4];
+      bool hit[4];
+      if (j + 3 < cnt) {
+        const float4 t = *reinterpret_cast<const float4*>(p + j);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hit[u] = better(v[u], thr, a.keep_max);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = j + u < cnt ? p[j + u] : 0.f;
+          hit[u] = j + u < cnt && better(v[u], thr, a.keep_max);
+        }
+      }
+      const int mine = int(hit[0]) + int(hit[1]) + int(hit[2]) + int(hit[3]);
+      if (__ballot_sync(0xffffffffu, mine > 0) == 0u) continue;
+      int incl = mine;                                   // warp inclusive scan of the per-thread hit counts
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(counter, static_cast<unsigned long long>(total));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      unsigned long long pos = base + static_cast<unsigned long long>(incl - mine);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (hit[u]) {
+          if (pos < cap) { bufv[pos] = v[u]; bufp[pos] = pbase + static_cast<uint64_t>(j + u); }
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
+// ---- compaction of the survivor buffer against a raised radius -----------------------------------------------
+__global__ void __launch_bounds__(kGtThreads)
+gt_compact_kernel(const float* __restrict__ inv, const uint64_t* __restrict__ inp, int64_t n, int64_t ntotal,
+                  const float* __restrict__ qn, const float* __restrict__ rn_max, float radius, int keep_max,
+                  float* __restrict__ outv, uint64_t* __restrict__ outp, unsigned long long* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kGtThreads; i0 < n; i0 += static_cast<int64_t>(gridDim.x) * kGtThreads) {
+    const int64_t i = i0 + threadIdx.x;
+    bool keep = false;
+    float v = 0.f;
+    uint64_t p = 0;
+    if (i < n) {
+      v = inv[i];
+      p = inp[i];
+      const float m = 2.f * kTcMargin * sqrtf(qn[p / static_cast<uint64_t>(ntotal)] * *rn_max) * (keep_max ? 1.f : 2.f);
+      keep = keep_max ? v > radius - m : v < radius + m;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (!bal) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, static_cast<unsigned long long>(__popc(bal)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+      outv[pos] = v;
+      outp[pos] = p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float ws[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, x[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = ws[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) *out = m;
+  }
+}
+
+// ---- exact rescoring + sort keys ---------------------------------------------------------------------------
+// one warp per survivor; key_p = pair id (tie order), key_s = order key of the exact score, ascending = best first.
+// fixed_thr: pairs that fail the caller's threshold on the exact score get the worst key and are counted.
+__global__ void __launch_bounds__(kGtThreads)
+gt_rescore_kernel(const uint64_t* __restrict__ bufp, int64_t n, const float* __restrict__ Q, const float* __restrict__ bank,
+                  int d, int64_t ntotal, int keep_max, int use_thresh, float thresh, uint64_t* __restrict__ key_p,
+                  uint64_t* __restrict__ key_s, unsigned long long* __restrict__ n_fail) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kGtThreads) >> 5;
+  for (int64_t i = warp0; i < n; i += nwarps) {
+    const uint64_t p = bufp[i];
+    const uint64_t qi = p / static_cast<uint64_t>(ntotal), ri = p % static_cast<uint64_t>(ntotal);
+    const float* const rp[1] = {bank + ri * d};
+    float acc[1];
+    exact_rows_warp<1>(Q + qi * d, rp, d, lane, !keep_max, acc);
+    if (lane == 0) {
+      uint32_t k = ~better_key(acc[0], keep_max);       // ascending = best first
+      if (use_thresh && !(keep_max ? acc[0] > thresh : acc[0] < thresh)) {
+        k = 0xffffffffu;
+        atomicAdd(n_fail, 1ull);
+      }
+      key_p[i] = p;
+      key_s[i] = k;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGtThreads)
+gt_output_kernel(const uint64_t* __restrict__ key_s, const uint64_t* __restrict__ key_p, int64_t n, int64_t ntotal,
+                 int64_t id_offset, int keep_max, float* __restrict__ score, int64_t* __restrict__ qrow,
+                 int64_t* __restrict__ brow) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t p = key_p[i];
+  score[i] = key_value(~static_cast<uint32_t>(key_s[i]), keep_max);
+  qrow[i] = static_cast<int64_t>(p / static_cast<uint64_t>(ntotal));
+  brow[i] = static_cast<int64_t>(p % static_cast<uint64_t>(ntotal)) + id_offset;
+}
+
+// ---- video-pair reduction -----------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t segment_of(const int64_t* __restrict__ off, int64_t nseg, int64_t row) {
+  int64_t lo = 0, hi = nseg;             // largest s with off[s] <= row
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= row) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// the input is sorted best first, so the smallest index of a (query video, ref video) key is its best pair
+__global__ void __launch_bounds__(kGtThreads)
+vp_insert_kernel(const int64_t* __restrict__ qrow, const int64_t* __restrict__ brow, int64_t n, int64_t id_offset,
+                 const int64_t* __restrict__ q_off, int64_t nqv, const int64_t* __restrict__ r_off, int64_t nrv,
+                 unsigned long long* __restrict__ tkey, uint32_t* __restrict__ tmin, uint64_t mask) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (i >= n) return;
+  const int64_t qv = segment_of(q_off, nqv, qrow[i]);
+  const int64_t rv = segment_of(r_off, nrv, brow[i] - id_offset);
+  const unsigned long long key = static_cast<unsigned long long>(qv) * static_cast<unsigned long long>(nrv) +
+                                 static_cast<unsigned long long>(rv);
+  uint64_t slot = mix64(key) & mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(&tkey[slot], ~0ull, key);
+    if (prev == ~0ull || prev == key) {
+      atomicMin(&tmin[slot], static_cast<uint32_t>(i));
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(kGtThreads)
+vp_extract_kernel(const unsigned long long* __restrict__ tkey, const uint32_t* __restrict__ tmin, uint64_t slots,
+                  uint64_t* __restrict__ first_idx, uint64_t* __restrict__ keys, unsigned long long* __restrict__ counter) {
+  const uint64_t s = static_cast<uint64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (s >= slots || tkey[s] == ~0ull) return;
+  const unsigned long long pos = atomicAdd(counter, 1ull);
+  first_idx[pos] = tmin[s];
+  keys[pos] = tkey[s];
+}
+
+__global__ void __launch_bounds__(kGtThreads)
+vp_output_kernel(const uint64_t* __restrict__ first_idx, const uint64_t* __restrict__ keys, int64_t m, int64_t nrv,
+                 const float* __restrict__ g_score, float* __restrict__ score, int64_t* __restrict__ qv,
+                 int64_t* __restrict__ rv) {
+  const int64_t j = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (j >= m) return;
+  score[j] = g_score[first_idx[j]];
+  qv[j] = static_cast<int64_t>(keys[j] / static_cast<uint64_t>(nrv));
+  rv[j] = static_cast<int64_t>(keys[j] % static_cast<uint64_t>(nrv));
+}
+
+int bits_for(uint64_t n) {   // bits needed to represent values < n
+  int b = 0;
+  while (b < 64 && (n > (1ull << b))) ++b;
+  return std::max(b, 1);
+}
+
+struct Scratch {               // pool blocks released on every exit path
+  std::vector<void*> blocks;
+  cudaStream_t s;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  ~Scratch() { for (void* b : blocks) pool_free(b, s); }
+  template <typename Tp>
+  int get(Tp** p, size_t bytes) {
+    void* v = nullptr;
+    int rc = pool_alloc(&v, std::max<size_t>(bytes, 256), s);
+    if (rc) return rc;
+    blocks.push_back(v);
+    *p = static_cast<Tp*>(v);
+    return VSCB200_OK;
+  }
+  void drop(void* p) {
+    if (!p) return;
+    for (auto& b : blocks) if (b == p) { pool_free(b, s); b = nullptr; }
+  }
+};
+
+int grid_for(int64_t work) {
+  const int64_t g = std::min<int64_t>(std::max<int64_t>(work, 1), static_cast<int64_t>(device_sm_count()) * 8);
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+extern "C" {
+
+int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, int64_t global_k, int use_thresh,
+                                float thresh, int64_t* n_found, void* stream) {
+  VSCB_REQUIRE(ix && n_found && (nq == 0 || q), "index_global_search: null argument");
+  VSCB_REQUIRE(nq >= 0, "index_global_search: negative query count");
+  VSCB_REQUIRE(global_k > 0 || use_thresh, "index_global_search: need global_k > 0 or a threshold");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = flush_pending(ix, s);
+  if (rc) return rc;
+  *n_found = 0;
+  ix->g_n = 0;
+  ix->vp_n = 0;
+  const int64_t n = ix->ntotal;
+  if (nq == 0 || n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(static_cast<double>(nq) * static_cast<double>(n) < 9.0e18, "index_global_search: nq * ntotal overflows");
+  const bool keep_max = ix->metric == VSCB200_METRIC_INNER_PRODUCT;
+  const bool limited = global_k > 0;
+  const uint64_t total_pairs = static_cast<uint64_t>(nq) * static_cast<uint64_t>(n);
+  const uint64_t K = limited ? std::min<uint64_t>(static_cast<uint64_t>(global_k), total_pairs) : total_pairs;
+
+  Scratch sc(s);
+  // squared norms of ALL query rows (error margins) and the largest bank norm
+  float *qn_all = nullptr, *rn_max = nullptr;
+  if ((rc = sc.get(&qn_all, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+  if ((rc = sc.get(&rn_max, sizeof(float)))) return rc;
+  if ((rc = row_sqnorm(q, nq, ix->d, qn_all, s))) return rc;
+  max_reduce_kernel<<<1, 1024, 0, s>>>(ix->rnorm, n, rn_max);
+  count_launch();
+
+  // survivor buffers (ping-pong for compaction); capacity 2K like the reference's max_results
+  uint64_t cap = limited ? std::min<uint64_t>(2 * K + 4096, total_pairs) : std::min<uint64_t>(total_pairs, 1u << 20);
+  float* bufv[2] = {nullptr, nullptr};
+  uint64_t* bufp[2] = {nullptr, nullptr};
+  auto alloc_bufs = [&](uint64_t c, float** v, uint64_t** p) {
+    int r = sc.get(v, c * sizeof(float));
+    if (r) return r;
+    return sc.get(p, c * sizeof(uint64_t));
+  };
+  if ((rc = alloc_bufs(cap, &bufv[0], &bufp[0]))) return rc;
+  unsigned long long *counter = nullptr, *hist = nullptr;
+  if ((rc = sc.get(&counter, sizeof(unsigned long long)))) return rc;
+  if ((rc = sc.get(&hist, 2048 * sizeof(unsigned long long)))) return rc;
+  VSCB_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+
+  const int64_t blk = block_rows(ix, nq);
+  const int64_t ldS = (n + 3) & ~3ll;
+  if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s))) return rc;
+
+  unsigned long long count = 0;     // host mirror of the buffer fill
+  float radius = use_thresh ? thresh : 0.f;
+  bool has_radius = use_thresh != 0;
+  std::vector<unsigned long long> hh(2048);
+
+  auto read_counter = [&](unsigned long long* out) {
+    VSCB_CUDA_OK(cudaMemcpyAsync(out, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    VSCB_CUDA_OK(cudaStreamSynchronize(s));
+    return static_cast<int>(VSCB200_OK);
+  };
+  auto set_counter = [&](unsigned long long v) {
+    VSCB_CUDA_OK(cudaMemcpyAsync(counter, &v, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    VSCB_CUDA_OK(cudaStreamSynchronize(s));      // v lives on this frame
+    return static_cast<int>(VSCB200_OK);
+  };
+
+  for (int64_t q0 = 0; q0 < nq; q0 += blk) {
+    const int64_t nb = std::min(blk, nq - q0);
+    if ((rc = score_block(ix, q + q0 * ix->d, nb, ix->ws, ldS, s))) return rc;
+    GtBlock a{ix->ws, ldS, nb, n, q0, qn_all, rn_max, radius, has_radius ? 1 : 0, keep_max ? 1 : 0};
+    const int64_t work = nb * ((n + kGtChunk - 1) / kGtChunk);
+    const int grid = grid_for(work);
+    const uint64_t blk_pairs = static_cast<uint64_t>(nb) * static_cast<uint64_t>(n);
+    unsigned long long after = 0;
+    bool emitted = false;
+    if (has_radius || count + blk_pairs <= cap) {
+      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
+      count_launch();
+      if ((rc = read_counter(&after))) return rc;
+      emitted = after <= cap;
+    } else {
+      after = count + blk_pairs;     // no radius yet: everything would be emitted
+    }
+    if (!emitted && limited) {
+      // raise the radius: exact K-th best value over {buffer, block entries better than the radius}
+      uint32_t prefix = 0;
+      uint64_t want = K;
+      for (int level = 0; level < 3; ++level) {
+        VSCB_CUDA_OK(cudaMemsetAsync(hist, 0, 2048 * sizeof(unsigned long long), s));
+        gt_hist_kernel<<<grid, kGtThreads, 0, s>>>(a, bufv[0], static_cast<int64_t>(count), level, prefix, hist);
+        count_launch();
+        VSCB_CUDA_OK(cudaMemcpyAsync(hh.data(), hist, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        VSCB_CUDA_OK(cudaStreamSynchronize(s));
+        const int nd = level == 2 ? 1024 : 2048;
+        int dgt = nd - 1;
+        uint64_t cum = 0;
+        for (; dgt > 0; --dgt) {
+          if (cum + hh[dgt] >= want) break;
+          cum += hh[dgt];
+        }
+        want -= cum;
+        prefix = level == 2 ? ((prefix << 10) | static_cast<uint32_t>(dgt)) : ((prefix << 11) | static_cast<uint32_t>(dgt));
+      }
+      const float kth = key_value(prefix, keep_max);
+      if (!has_radius || (keep_max ? kth > radius : kth < radius)) radius = kth;
+      has_radius = true;
+      a.radius = radius;
+      a.has_radius = 1;
+      // compact what the buffer held before this block, then emit the block again
+      if (!bufv[1] && (rc = alloc_bufs(cap, &bufv[1], &bufp[1]))) return rc;
+      if ((rc = set_counter(0))) return rc;
+      if (count) {
+        gt_compact_kernel<<<grid_for((static_cast<int64_t>(count) + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
+            bufv[0], bufp[0], static_cast<int64_t>(count), n, qn_all, rn_max, radius, keep_max ? 1 : 0, bufv[1], bufp[1], counter);
+        count_launch();
+        std::swap(bufv[0], bufv[1]);
+        std::swap(bufp[0], bufp[1]);
+      }
+      if ((rc = read_counter(&count))) return rc;
+      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
+      count_launch();
+      if ((rc = read_counter(&after))) return rc;
+      emitted = after <= cap;
+    }
+    while (!emitted) {
+      // unlimited (threshold) mode, or more ties at the radius than the buffer holds: grow and emit again
+      const uint64_t ncap = std::min<uint64_t>(total_pairs, std::max<uint64_t>(after + after / 4, cap * 2));
+      float* nv = nullptr;
+      uint64_t* np = nullptr;
+      if ((rc = alloc_bufs(ncap, &nv, &np))) return rc;
+      if (count) {
+        VSCB_CUDA_OK(cudaMemcpyAsync(nv, bufv[0], count * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        VSCB_CUDA_OK(cudaMemcpyAsync(np, bufp[0], count * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+      }
+      sc.drop(bufv[0]); sc.drop(bufp[0]); sc.drop(bufv[1]); sc.drop(bufp[1]);
+      bufv[0] = nv; bufp[0] = np; bufv[1] = nullptr; bufp[1] = nullptr;
+      cap = ncap;
+      if ((rc = set_counter(count))) return rc;
+      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
+      count_launch();
+      if ((rc = read_counter(&after))) return rc;
+      emitted = after <= cap;
+    }
+    count = after;
+  }
+
+  if (count == 0) return VSCB200_OK;
+  // exact scores + sort keys; the alternate survivor buffer is no longer needed
+  sc.drop(bufv[1]); sc.drop(bufp[1]);
+  const int64_t m = static_cast<int64_t>(count);
+  uint64_t *kp = nullptr, *ks = nullptr, *kp2 = nullptr, *ks2 = nullptr;
+  void* sort_ws = nullptr;
+  if ((rc = sc.get(&kp, m * sizeof(uint64_t))) || (rc = sc.get(&ks, m * sizeof(uint64_t))) ||
+      (rc = sc.get(&kp2, m * sizeof(uint64_t))) || (rc = sc.get(&ks2, m * sizeof(uint64_t))) ||
+      (rc = sc.get(&sort_ws, radix_sort_scratch_bytes(m))))
+    return rc;
+  if ((rc = set_counter(0))) return rc;
+  gt_rescore_kernel<<<grid_for((m + 7) / 8), kGtThreads, 0, s>>>(bufp[0], m, q, ix->bank, ix->d, n, keep_max ? 1 : 0,
+                                                                 use_thresh, thresh, kp, ks, counter);
+  count_launch();
+  // (1) by pair id, (2) stably by score key: best first, ties in (query row, bank row) order
+  int alt = 0;
+  if ((rc = radix_sort_pairs(kp, ks, kp2, ks2, m, 0, bits_for(total_pairs), sort_ws, &alt, s))) return rc;
+  uint64_t *p_sorted = alt ? kp2 : kp, *s_by_p = alt ? ks2 : ks;
+  uint64_t *p_other = alt ? kp : kp2, *s_other = alt ? ks : ks2;
+  if ((rc = radix_sort_pairs(s_by_p, p_sorted, s_other, p_other, m, 0, 32, sort_ws, &alt, s))) return rc;
+  const uint64_t* fs = alt ? s_other : s_by_p;
+  const uint64_t* fp = alt ? p_other : p_sorted;
+  unsigned long long n_fail = 0;
+  if ((rc = read_counter(&n_fail))) return rc;
+  int64_t keep = m - static_cast<int64_t>(n_fail);
+  if (limited) keep = std::min<int64_t>(keep, static_cast<int64_t>(K));
+  if (keep > 0) {
+    if ((rc = grow(&ix->g_score, &ix->g_score_bytes, keep * sizeof(float), s))) return rc;
+    if ((rc = grow(&ix->g_q, &ix->g_q_bytes, keep * sizeof(int64_t), s))) return rc;
+    if ((rc = grow(&ix->g_r, &ix->g_r_bytes, keep * sizeof(int64_t), s))) return rc;
+    gt_output_kernel<<<static_cast<unsigned>((keep + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
+        fs, fp, keep, n, ix->id_offset, keep_max ? 1 : 0, ix->g_score, ix->g_q, ix->g_r);
+    count_launch();
+  }
+  VSCB_CUDA_OK(cudaGetLastError());
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  ix->g_n = keep;
+  *n_found = keep;
+  return VSCB200_OK;
+}
+
+int vscb200_index_global_results(vscb200_index* ix, float* scores, int64_t* qrows, int64_t* brows, void* stream) {
+  VSCB_REQUIRE(ix, "index_global_results: null index");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ix->g_n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(scores && qrows && brows, "index_global_results: null output");
+  VSCB_CUDA_OK(cudaMemcpyAsync(scores, ix->g_score, ix->g_n * sizeof(float), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaMemcpyAsync(qrows, ix->g_q, ix->g_n * sizeof(int64_t), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaMemcpyAsync(brows, ix->g_r, ix->g_n * sizeof(int64_t), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  return VSCB200_OK;
+}
+
+int vscb200_index_global_video_pairs(vscb200_index* ix, const int64_t* q_offsets, int64_t nqv, const int64_t* r_offsets,
+                                     int64_t nrv, int64_t* n_pairs, void* stream) {
+  VSCB_REQUIRE(ix && n_pairs && q_offsets && r_offsets && nqv > 0 && nrv > 0, "index_global_video_pairs: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  *n_pairs = 0;
+  ix->vp_n = 0;
+  const int64_t n = ix->g_n;
+  if (n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(n < (1ll << 31), "index_global_video_pairs: too many frame pairs");
+  Scratch sc(s);
+  uint64_t slots = 1024;
+  while (slots < static_cast<uint64_t>(n) * 2) slots <<= 1;
+  unsigned long long *tkey = nullptr, *counter = nullptr;
+  uint32_t* tmin = nullptr;
+  uint64_t *fi = nullptr, *kk = nullptr, *fi2 = nullptr, *kk2 = nullptr;
+  void* sort_ws = nullptr;
+  int rc;
+  if ((rc = sc.get(&tkey, slots * sizeof(unsigned long long))) || (rc = sc.get(&tmin, slots * sizeof(uint32_t))) ||
+      (rc = sc.get(&counter, sizeof(unsigned long long))) || (rc = sc.get(&fi, n * sizeof(uint64_t))) ||
+      (rc = sc.get(&kk, n * sizeof(uint64_t))) || (rc = sc.get(&fi2, n * sizeof(uint64_t))) ||
+      (rc = sc.get(&kk2, n * sizeof(uint64_t))) || (rc = sc.get(&sort_ws, radix_sort_scratch_bytes(n))))
+    return rc;
+  VSCB_CUDA_OK(cudaMemsetAsync(tkey, 0xff, slots * sizeof(unsigned long long), s));
+  VSCB_CUDA_OK(cudaMemsetAsync(tmin, 0xff, slots * sizeof(uint32_t), s));
+  VSCB_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+  const unsigned g = static_cast<unsigned>((n + kGtThreads - 1) / kGtThreads);
+  vp_insert_kernel<<<g, kGtThreads, 0, s>>>(ix->g_q, ix->g_r, n, ix->id_offset, q_offsets, nqv, r_offsets, nrv, tkey, tmin,
+                                            slots - 1);
+  vp_extract_kernel<<<static_cast<unsigned>((slots + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(tkey, tmin, slots, fi,
+                                                                                                        kk, counter);
+  count_launch(2);
+  unsigned long long m = 0;
+  VSCB_CUDA_OK(cudaMemcpyAsync(&m, counter, sizeof(m), cudaMemcpyDeviceToHost, s));
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  int alt = 0;
+  if ((rc = radix_sort_pairs(fi, kk, fi2, kk2, static_cast<int64_t>(m), 0, bits_for(static_cast<uint64_t>(n)), sort_ws, &alt, s)))
+    return rc;
+  if ((rc = grow(&ix->vp_score, &ix->vp_score_bytes, m * sizeof(float), s))) return rc;
+  if ((rc = grow(&ix->vp_q, &ix->vp_q_bytes, m * sizeof(int64_t), s))) return rc;
+  if ((rc = grow(&ix->vp_r, &ix->vp_r_bytes, m * sizeof(int64_t), s))) return rc;
+  vp_output_kernel<<<static_cast<unsigned>((m + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
+      alt ? fi2 : fi, alt ? kk2 : kk, static_cast<int64_t>(m), nrv, ix->g_score, ix->vp_score, ix->vp_q, ix->vp_r);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  ix->vp_n = static_cast<int64_t>(m);
+  *n_pairs = ix->vp_n;
+  return VSCB200_OK;
+}
+
+int vscb200_index_video_pair_results(vscb200_index* ix, float* scores, int64_t* qv, int64_t* rv, void* stream) {
+  VSCB_REQUIRE(ix, "index_video_pair_results: null index");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (ix->vp_n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(scores && qv && rv, "index_video_pair_results: null output");
+  VSCB_CUDA_OK(cudaMemcpyAsync(scores, ix->vp_score, ix->vp_n * sizeof(float), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaMemcpyAsync(qv, ix->vp_q, ix->vp_n * sizeof(int64_t), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaMemcpyAsync(rv, ix->vp_r, ix->vp_n * sizeof(int64_t), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  return VSCB200_OK;
+}
+
+}  // extern "C"

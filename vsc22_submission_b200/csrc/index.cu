@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "host_util.h"
+#include "index_internal.h"
 #include "kernels.h"
 
 using namespace vscb200;
@@ -25,61 +26,13 @@ int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl
                   const float* qn, const float* rn, int slabs, float* cand_d, int32_t* cand_i, cudaStream_t stream);
 }  // namespace vscb200
 
-struct vscb200_index {
-  int d = 0, metric = 0;
-  int64_t ntotal = 0;        // rows resident on the device
-  int64_t capacity = 0;
-  float* bank = nullptr;     // [capacity, d]
-  float* rnorm = nullptr;    // [capacity] squared norms (L2 metric only)
-  int dp = 0;                // d rounded up to 8: row length of the bf16 operand planes
-  uint16_t* bank_hi = nullptr;   // [capacity, dp] bf16(x)
-  uint16_t* bank_lo = nullptr;   // [capacity, dp] bf16(x - hi)
-  uint16_t* q_planes = nullptr; size_t q_planes_bytes = 0;   // hi | lo planes of the current query block
-  std::vector<float> pending;   // host rows appended by add_host, uploaded lazily in one copy
-  int64_t id_offset = 0;
-  float* ws = nullptr;       // score workspace
-  size_t ws_bytes = 0;
-  // staging for the host-buffer API
-  float* q_stage = nullptr; size_t q_stage_bytes = 0;
-  float* D_stage = nullptr; size_t D_stage_bytes = 0;
-  int64_t* I_stage = nullptr; size_t I_stage_bytes = 0;
-  float* qnorm = nullptr; size_t qnorm_bytes = 0;
-  unsigned long long* counts = nullptr; size_t counts_bytes = 0;
-  float* Dtmp = nullptr; size_t Dtmp_bytes = 0;       // survivors of the tensor-core pass (k + slack per row)
-  int64_t* Itmp = nullptr; size_t Itmp_bytes = 0;
-  float* cand_d = nullptr; size_t cand_d_bytes = 0;   // fused top-k epilogue candidates [nq, slabs*2*kFK]
-  int32_t* cand_i = nullptr; size_t cand_i_bytes = 0;
-  int no_fused = 0;
-  int no_stream = 0;
-  float* gmax = nullptr; size_t gmax_bytes = 0;       // streaming search: per (32-row group, query) maxima
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t last_stream = nullptr;   // stream of the most recent call (orders the final frees)
-  int force_simt = 0;
-};
-
-namespace {
+namespace vscb200 {
 
 size_t ws_budget_bytes() {
-  static size_t v = 0;
-  if (!v) {
-    const char* e = getenv("VSCB200_WS_MB");
-    v = (e ? static_cast<size_t>(atoll(e)) : 2048) << 20;
-    if (v < (1u << 20)) v = 1u << 20;
-  }
+  const char* e = getenv("VSCB200_WS_MB");     // read per call: tests shrink it to force many query blocks
+  size_t v = (e ? static_cast<size_t>(atoll(e)) : 2048) << 20;
+  if (v < (1u << 20)) v = 1u << 20;
   return v;
-}
-
-template <typename Tp>
-int grow(Tp** p, size_t* have, size_t need, cudaStream_t s) {
-  if (*have >= need) return VSCB200_OK;
-  if (*p) pool_free(*p, s);
-  *p = nullptr;
-  *have = 0;
-  size_t want = std::max(need, static_cast<size_t>(256));
-  int rc = pool_alloc(reinterpret_cast<void**>(p), want, s);
-  if (rc) return rc;
-  *have = want;
-  return VSCB200_OK;
 }
 
 int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
@@ -186,7 +139,7 @@ int own_stream(vscb200_index* ix, cudaStream_t* s) {
   return VSCB200_OK;
 }
 
-}  // namespace
+}  // namespace vscb200
 
 extern "C" {
 
@@ -214,7 +167,8 @@ void vscb200_index_destroy(vscb200_index* ix) {
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
   void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
-                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax};
+                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax,
+                    ix->g_score, ix->g_q, ix->g_r, ix->vp_score, ix->vp_q, ix->vp_r};
   if (ix->own_stream && s == ix->own_stream) {
     cudaStreamSynchronize(s);     // own stream is destroyed below: drain it, then free un-ordered
     s = nullptr;

@@ -91,6 +91,45 @@ class DeviceIndex:
                                                            _stream(self.device)), "index.search")
         return D, I
 
+    def global_search(self, q: torch.Tensor, global_k: int = 0, threshold: Optional[float] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """The ``global_k`` best (query row, bank row) pairs over ALL query rows -- the result of
+        ``VideoIndex._global_threshold_knn_search`` (vsc/index.py:142-165) -- and/or every pair strictly better
+        than ``threshold`` (infer_matching.py:229-247).  Returns (scores f32 [n], query rows i64 [n], bank rows
+        i64 [n]) on the device, best first, ties by (query row, bank row); scores are exact fp32."""
+        q = _f32_cuda(q, "DeviceIndex.global_search")
+        if q.dim() != 2 or q.shape[1] != self.d:
+            raise AssertionError(f"global_search: expected [n, {self.d}], got {tuple(q.shape)}")
+        n = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vscb200_index_global_search(
+                self._ptr, _p(q), q.shape[0], int(global_k), 0 if threshold is None else 1,
+                float(0.0 if threshold is None else threshold), C.byref(n), _stream(self.device)), "index.global_search")
+            sc = torch.empty(n.value, dtype=torch.float32, device=self.device)
+            qi = torch.empty(n.value, dtype=torch.int64, device=self.device)
+            ri = torch.empty(n.value, dtype=torch.int64, device=self.device)
+            _lib.check(_lib.lib().vscb200_index_global_results(self._ptr, _p(sc), _p(qi), _p(ri), _stream(self.device)),
+                       "index.global_results")
+        return sc, qi, ri
+
+    def global_video_pairs(self, q_offsets: torch.Tensor, r_offsets: torch.Tensor
+                           ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Reduce the pairs of the last ``global_search`` to (query video, ref video) candidates scored by their
+        best frame pair, best first (vsc/candidates.py:24-40).  ``*_offsets``: int64 [n_videos + 1] first rows."""
+        qo = q_offsets.to(self.device, torch.int64).contiguous()
+        ro = r_offsets.to(self.device, torch.int64).contiguous()
+        m = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vscb200_index_global_video_pairs(
+                self._ptr, _p(qo), qo.numel() - 1, _p(ro), ro.numel() - 1, C.byref(m), _stream(self.device)),
+                "index.global_video_pairs")
+            sc = torch.empty(m.value, dtype=torch.float32, device=self.device)
+            qv = torch.empty(m.value, dtype=torch.int64, device=self.device)
+            rv = torch.empty(m.value, dtype=torch.int64, device=self.device)
+            _lib.check(_lib.lib().vscb200_index_video_pair_results(self._ptr, _p(sc), _p(qv), _p(rv),
+                                                                   _stream(self.device)), "index.video_pair_results")
+        return sc, qv, rv
+
     def scores(self, q: torch.Tensor) -> torch.Tensor:
         """Dense [nq, ntotal] score matrix (localization.py:32-35 form)."""
         q = _f32_cuda(q, "DeviceIndex.scores")
