@@ -33,6 +33,7 @@ N_FRAMES = 10_000          # configs[1]: 10k synthetic frames
 BATCH = 512                # encoder plan chunk (max_frames): the 10k-frame job is walked in chunks of 512 frames
                            # (measured: 256 -> 22.2k, 384 -> 22.7k, 512 -> 23.1k, 768 -> 23.1k frames/s; tools/sweep_batch.py)
 SIM_NQ, SIM_NR, SIM_NZ, SIM_D, SIM_K = 10_000, 40_000, 40_000, 512, 10   # configs[2]
+SIM_NQ_C, SIM_NR_C = 10_000, 40_000                                     # candidate generation on the same shapes
 
 
 def load_traffic(kernel: str):
@@ -378,6 +379,7 @@ def bench_sim(args, world, rank, peaks):
     e2e = None
     stream = None
     dense = None
+    cand = None
     if world == 1:
         import dataclasses
 
@@ -411,6 +413,7 @@ def bench_sim(args, world, rank, peaks):
                "idx_agree_with_device_path": float((Ih == I.cpu().numpy()).mean())}
         stream = bench_sim_stream(peaks)
         dense = bench_sim_dense(peaks)
+        cand = bench_candidates(peaks)
     flops = 2.0 * SIM_D * pairs / world            # per GPU
     bytes_alg = (SIM_NQ + SIM_NR + SIM_NZ) * SIM_D * 4 + SIM_NQ * SIM_K * 12
     sc = prof["scores"]
@@ -424,7 +427,7 @@ def bench_sim(args, world, rank, peaks):
     roof["note"] = ("fp32-equivalent scores = 3 bf16 MMAs per product (hi.hi + lo.hi + hi.lo): the kernel's ceiling is "
                     "1/3 of the bf16 peak; config 3 as stated is tensor-bound, the HBM-bound form is 'stream'")
     return {"metric": "sim-pairs/sec", "value": value, "unit": "sim-pairs/sec", "ms_per_step": ms, "e2e": e2e,
-            "stream": stream, "dense": dense,
+            "stream": stream, "dense": dense, "candidates": cand,
             "gpu_launches": int(launches), "roofline": roof, "dtype": "f32",
             "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
                                    "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
@@ -517,6 +520,86 @@ def bench_sim_dense(peaks, n=40_000, iters=3):
                          "note": "3 bf16 MMAs per product: tensor ceiling 1/3"}}
 
 
+def bench_candidates(peaks, nq=SIM_NQ_C, nr=SIM_NR_C, rows_q=40, rows_r=50, iters=3):
+    """Video-level candidate generation (sscd_baseline.py:87-101): the global top-K frame
+    pairs over ALL query rows (K = 1200 per query video, vsc/index.py:142-165) reduced to (query video, ref video)
+    candidates -- device-resident, then through the reference-facing mirror with per-video host arrays."""
+    import dataclasses
+
+    import numpy as np
+    import torch
+
+    from vsc22_submission_b200 import candidates, search
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(8)
+    unit = lambda n: torch.nn.functional.normalize(torch.randn((n, SIM_D), generator=g, device=dev))
+    Q, R = unit(nq), unit(nr)
+    K = 1200 * (nq // rows_q)
+    ix = search.DeviceIndex(SIM_D)
+    ix.add(R)
+    qo, ro = torch.arange(0, nq + 1, rows_q), torch.arange(0, nr + 1, rows_r)
+    ix.global_search(Q, K)
+    ts, tv = [], []
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        s, qi, ri = ix.global_search(Q, K)
+        e1.record()
+        sc, qv, rv = ix.global_video_pairs(qo, ro)
+        e2.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1)); tv.append(e1.elapsed_time(e2))
+    ms, ms_v = min(ts), min(tv)
+
+    @dataclasses.dataclass
+    class VF:
+        video_id: str
+        feature: np.ndarray
+        timestamps: np.ndarray = None
+
+    Qh, Rh = Q.cpu().numpy(), R.cpu().numpy()
+    qv_l = [VF(f"Q{i}", Qh[i:i + rows_q]) for i in range(0, nq, rows_q)]
+    rv_l = [VF(f"R{i}", Rh[i:i + rows_r]) for i in range(0, nr, rows_r)]
+
+    def host_step():
+        cg = candidates.CandidateGeneration(rv_l, candidates.MaxScoreAggregation())
+        return cg.query(qv_l, global_k=K)
+    host_step()
+    t0 = time.perf_counter()
+    cands = host_step()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    del ix
+    torch.cuda.empty_cache()
+    return {"workload": f"global top-{K} frame pairs of {nq} x {nr} x {SIM_D} (1200 per query video of {rows_q} rows) -> "
+                        f"(query video, ref video) candidates by best frame pair, sorted",
+            "global_search_ms": ms, "video_pairs_ms": ms_v, "pairs_per_sec": nq * nr / ((ms + ms_v) / 1e3),
+            "frame_pairs_kept": int(s.numel()), "candidates": int(sc.numel()),
+            "e2e": {"ms": e2e_ms, "pairs_per_sec": nq * nr / (e2e_ms / 1e3), "candidates": len(cands),
+                    "h2d_bytes": int((nq + nr) * SIM_D * 4), "d2h_bytes": int(sc.numel() * 20),
+                    "api": "candidates.CandidateGeneration(refs, MaxScoreAggregation()).query(queries, global_k) on "
+                           "per-video host arrays (index build included)"},
+            "roofline": {"bound": "tensor", "tensor_frac": 2.0 * nq * nr * SIM_D / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
+                         "note": "score block by the split-bf16 kernel (ceiling 1/3) + one HBM pass of the block per "
+                                 "radix-select level / emit"}}
+
+
+def cpu_baseline_candidates(nq=1000, nr=SIM_NR_C, rows_q=40, rows_r=50):
+    """oracle port of CandidateGeneration on a bounded sample (1k of the 10k query rows, full bank)."""
+    import numpy as np
+
+    from oracle import candidates_np, faiss_np
+    faiss_np.set_accumulate("f32")
+    rng = np.random.default_rng(8)
+    unit = lambda n: (lambda x: x / np.linalg.norm(x, axis=1, keepdims=True))(rng.standard_normal((n, SIM_D)).astype(np.float32))
+    Q, R = unit(nq), unit(nr)
+    t0 = time.perf_counter()
+    c = candidates_np.candidates(Q, R, [rows_q] * (nq // rows_q), [rows_r] * (nr // rows_r), 1200 * (nq // rows_q))
+    dt = time.perf_counter() - t0
+    return {"value": nq * nr / dt, "unit": "sim-pairs/sec", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{nq} of {SIM_NQ_C} query rows x {nr} bank rows, global_k = 1200 per video ({len(c)} candidates), {dt:.1f} s"}
+
+
 def cpu_baseline_sim():
     import numpy as np
 
@@ -607,7 +690,8 @@ def main():
         if enc_res is None:
             line.update(metric="sim-pairs/sec", unit="sim-pairs/sec", value=sim["value"], ms_per_step=sim["ms_per_step"],
                         e2e=sim["e2e"], gpu_launches=sim["gpu_launches"], roofline=sim["roofline"], dtype="f32",
-                        config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"))
+                        config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"),
+                        candidates=sim.get("candidates"))
         else:
             line["sim"] = sim
     if rank == 0 and world == 1 and args.workload == "both":
@@ -629,6 +713,9 @@ def main():
             line["parity"] = {"encoder_rel_l2_max_vs_fp32_oracle": rel, "frames": 4, "tolerance": 2e-2}
         if args.workload in ("both", "sim"):
             cb = cpu_baseline_sim()
+            tgt = line["sim"] if "sim" in line else line
+            if tgt.get("candidates"):
+                tgt["candidates"]["cpu_baseline"] = cpu_baseline_candidates()
             if "sim" in line:
                 line["sim"]["cpu_baseline"] = cb
             else:
