@@ -165,9 +165,9 @@ class CandidateGeneration:
         _, _, CandidatePair = _result_types()
         if isinstance(self.aggregation, MaxScoreAggregation) and global_k >= 0:
             sc, qv, rv = self.index.video_pairs(queries, global_k)
-            refs = self.index.videos
-            return [CandidatePair(query_id=queries[qv[j]].video_id, ref_id=refs[rv[j]].video_id, score=sc[j])
-                    for j in range(sc.shape[0])]
+            qids, rids = [q.video_id for q in queries], [r.video_id for r in self.index.videos]
+            return [CandidatePair(query_id=qids[a], ref_id=rids[b], score=s)
+                    for a, b, s in zip(qv.tolist(), rv.tolist(), list(sc))]      # scores stay numpy float32 scalars
         matches = self.index.search(queries, global_k=global_k)
         candidates = [self.aggregation.score(m) for m in matches]
         return sorted(candidates, key=lambda c: c.score, reverse=True)
@@ -177,4 +177,5 @@ def threshold_candidates(index: VideoIndex, queries: Sequence, threshold: float)
     """``search_res_list`` of M/infer/infer_matching.py:229-256: (query_id, ref_id, best frame-pair score) for every
     video pair with a frame pair strictly above ``threshold`` (``SEARCH_THRESHOLD``), best first."""
     sc, qv, rv = index.video_pairs(queries, 0, threshold)
-    return [(queries[qv[j]].video_id, index.videos[rv[j]].video_id, sc[j]) for j in range(sc.shape[0])]
+    qids, rids = [q.video_id for q in queries], [r.video_id for r in index.videos]
+    return [(qids[a], rids[b], s) for a, b, s in zip(qv.tolist(), rv.tolist(), list(sc))]
