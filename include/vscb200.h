@@ -209,6 +209,19 @@ int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_l
                       const int64_t* s_off_dev, const int64_t* row_off_dev, int k, float* topv_dev, int32_t* topi_dev,
                       void* stream);
 
+/* Temporal-network alignment of every candidate pair (vcsl/vta.py:244-363 `tn`, run by localization.py:38-76 through a
+ * 16-process pool): input = the per-row top-k of vscb200_pair_topk (same k, row_off, lengths); output = up to
+ * max_path + 1 boxes [q_min, r_min, q_max, r_max] per pair in boxes_dev [n_pairs, max_path + 1, 4] and their number in
+ * n_boxes_dev [n_pairs].  max_q_len >= every q_len (sizes the per-warp scratch).  k <= 8, tn_max_step <= 16. */
+int vscb200_tn_align(const float* topv_dev, const int32_t* topi_dev, int k, int64_t n_pairs, const int32_t* q_len_dev,
+                     const int32_t* r_len_dev, const int64_t* row_off_dev, int max_q_len, int tn_max_step, int max_path,
+                     double min_sim, double min_length, double max_iou, int32_t* boxes_dev, int32_t* n_boxes_dev,
+                     void* stream);
+/* VCSLLocalizationMaxSim.score (localization.py:87-90): sims[x1:x2, y1:y2].max() - bias for every box */
+int vscb200_tn_box_scores(const float* sims_dev, const int64_t* s_off_dev, const int32_t* r_len_dev, int64_t n_pairs,
+                          const int32_t* boxes_dev, const int32_t* n_boxes_dev, int box_cap, float bias,
+                          float* box_score_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Building blocks exported for unit tests and micro-benchmarks.
  * ---------------------------------------------------------------------------------------------- */

@@ -5,11 +5,16 @@ Mirrors ``LocalizationWithMetadata.similarity`` / ``VCSLLocalization.similarity`
 ``queries[c.query_id].feature @ refs[c.ref_id].feature.T + similarity_bias``; in addition the per-row top-k that
 ``vcsl.vta.tn`` computes first (vta.py:262-265).  The reference does one numpy matmul per pair inside a 16-process
 pool; here every video's descriptors are uploaded once and all pairs are computed by one launch.
+
+``VCSLLocalization`` / ``VCSLLocalizationMaxSim`` / ``VCSLLocalizationCandidateScore`` (localization.py:38-95, as
+constructed by sscd_baseline.py:113-131 with ``model_type="TN"``) run the whole of ``localize_all`` on the device: the
+similarity matrices, their per-row top-k, the temporal-network alignment ``vcsl.vta.tn`` (vta.py:244-363; one warp per
+pair, csrc/tn_align.cu) and the MaxSim box scores; the host only turns the boxes into ``Match`` tuples.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, NamedTuple, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -88,3 +93,103 @@ class PairSimilarity:
             out.append((f"{c.query_id}-{c.ref_id}", host[s_off[i]:s_off[i + 1]].reshape(ql[i], rl[i]),
                         hi[rows, :top].astype(np.int64), hv[rows, :top]))
         return out
+
+
+class _Match(NamedTuple):                # vsc/metrics.py:182-191
+    query_id: str
+    ref_id: str
+    score: float
+    query_start: float
+    query_end: float
+    ref_start: float
+    ref_end: float
+
+
+def _match_type():
+    try:
+        from vsc.metrics import Match
+        return Match
+    except Exception:
+        return _Match
+
+
+def _timestamps(ts: np.ndarray, idx: int):
+    """VideoMetadata.get_timestamps (vsc/index.py:26-30)."""
+    t = ts[idx]
+    if ts.ndim == 1:
+        return (t, t)
+    return (t[0], t[1])
+
+
+class VCSLLocalization(PairSimilarity):
+    """``VCSLLocalization(queries, refs, model_type, similarity_bias=0.0, **kwargs)`` (localization.py:38-84) for
+    ``model_type == "TN"``; ``kwargs`` are ``TnVtaModel``'s (vta.py:499-518): tn_max_step, tn_top_k, max_path, min_sim,
+    min_length, max_iou (``concurrency`` is accepted and ignored: there is no process pool)."""
+
+    def __init__(self, queries: Sequence, refs: Sequence, model_type: str = "TN", similarity_bias: float = 0.0,
+                 concurrency: int = 4, version: str = "v1", tn_max_step: int = 10, tn_top_k: int = 5, max_path: int = 10,
+                 min_sim: float = 0.2, min_length: float = 5, max_iou: float = 0.3, device="cuda"):
+        if model_type != "TN":
+            raise ValueError(f"VCSLLocalization: only the temporal network ('TN') runs on the device, got {model_type!r}")
+        super().__init__(queries, refs, similarity_bias, device)
+        self.similarity_bias = float(similarity_bias)
+        self.queries = {m.video_id: m for m in queries}
+        self.refs = {m.video_id: m for m in refs}
+        self.tn = dict(tn_max_step=int(tn_max_step), tn_top_k=int(tn_top_k), max_path=int(max_path),
+                       min_sim=float(min_sim), min_length=float(min_length), max_iou=float(max_iou))
+
+    def align(self, candidates: Sequence):
+        """-> (boxes int32 [n, max_path + 1, 4], n_boxes int32 [n], MaxSim box scores f32 [n, max_path + 1]) numpy;
+        ``boxes[i, :n_boxes[i]]`` is what ``self.model.forward_sim(sims)[i][1]`` holds in the reference."""
+        cap = self.tn["max_path"] + 1
+        if not candidates:
+            return np.zeros((0, cap, 4), np.int32), np.zeros((0,), np.int32), np.zeros((0, cap), np.float32)
+        k = self.tn["tn_top_k"]
+        sims, s_off, row_off, ql, rl, topv, topi = self._device_run(candidates, k)
+        dev, n = self.device, len(candidates)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+        d_ql, d_rl, d_row, d_so = t(ql, np.int32), t(rl, np.int32), t(row_off[:-1], np.int64), t(s_off[:-1], np.int64)
+        boxes = torch.zeros((n, cap, 4), dtype=torch.int32, device=dev)
+        nb = torch.zeros((n,), dtype=torch.int32, device=dev)
+        score = torch.zeros((n, cap), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(_lib.lib().vscb200_tn_align(_p(topv), _p(topi), k, n, _p(d_ql), _p(d_rl), _p(d_row), int(ql.max()),
+                                                   self.tn["tn_max_step"], self.tn["max_path"], self.tn["min_sim"],
+                                                   self.tn["min_length"], self.tn["max_iou"], _p(boxes), _p(nb), stream),
+                       "tn_align")
+            _lib.check(_lib.lib().vscb200_tn_box_scores(_p(sims), _p(d_so), _p(d_rl), n, _p(boxes), _p(nb), cap,
+                                                        self.similarity_bias, _p(score), stream), "tn_box_scores")
+        return boxes.cpu().numpy(), nb.cpu().numpy(), score.cpu().numpy()
+
+    def localize_all(self, candidates: Sequence) -> list:
+        Match = _match_type()
+        boxes, nb, box_scores = self.align(candidates)
+        matches = []
+        for i, c in enumerate(candidates):
+            query, ref = self.queries[c.query_id], self.refs[c.ref_id]
+            for b in range(int(nb[i])):
+                x1, y1, x2, y2 = (int(v) for v in boxes[i, b])
+                match = Match(query_id=c.query_id, ref_id=c.ref_id,
+                              query_start=_timestamps(query.timestamps, x1)[0], query_end=_timestamps(query.timestamps, x2)[1],
+                              ref_start=_timestamps(ref.timestamps, y1)[0], ref_end=_timestamps(ref.timestamps, y2)[1],
+                              score=0.0)
+                matches.append(match._replace(score=self.score(c, match, (x1, y1, x2, y2), box_scores[i, b])))
+        return matches
+
+    def localize(self, candidate) -> list:
+        return self.localize_all([candidate])
+
+    def score(self, candidate, match, box, max_sim) -> float:
+        """``max_sim``: sims[x1:x2, y1:y2].max() - similarity_bias of this box, computed on the device."""
+        return 1.0
+
+
+class VCSLLocalizationMaxSim(VCSLLocalization):        # localization.py:87-90
+    def score(self, candidate, match, box, max_sim) -> float:
+        return max_sim
+
+
+class VCSLLocalizationCandidateScore(VCSLLocalization):   # localization.py:93-95
+    def score(self, candidate, match, box, max_sim) -> float:
+        return candidate.score
