@@ -380,6 +380,7 @@ def bench_sim(args, world, rank, peaks):
     stream = None
     dense = None
     cand = None
+    loc = None
     if world == 1:
         import dataclasses
 
@@ -414,6 +415,7 @@ def bench_sim(args, world, rank, peaks):
         stream = bench_sim_stream(peaks)
         dense = bench_sim_dense(peaks)
         cand = bench_candidates(peaks)
+        loc = bench_localization()
     flops = 2.0 * SIM_D * pairs / world            # per GPU
     bytes_alg = (SIM_NQ + SIM_NR + SIM_NZ) * SIM_D * 4 + SIM_NQ * SIM_K * 12
     sc = prof["scores"]
@@ -427,7 +429,7 @@ def bench_sim(args, world, rank, peaks):
     roof["note"] = ("fp32-equivalent scores = 3 bf16 MMAs per product (hi.hi + lo.hi + hi.lo): the kernel's ceiling is "
                     "1/3 of the bf16 peak; config 3 as stated is tensor-bound, the HBM-bound form is 'stream'")
     return {"metric": "sim-pairs/sec", "value": value, "unit": "sim-pairs/sec", "ms_per_step": ms, "e2e": e2e,
-            "stream": stream, "dense": dense, "candidates": cand,
+            "stream": stream, "dense": dense, "candidates": cand, "localization": loc,
             "gpu_launches": int(launches), "roofline": roof, "dtype": "f32",
             "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
                                    "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
@@ -584,6 +586,69 @@ def bench_candidates(peaks, nq=SIM_NQ_C, nr=SIM_NR_C, rows_q=40, rows_r=50, iter
                                  "radix-select level / emit"}}
 
 
+def bench_localization(n_q=2000, n_r=8000, per_q=5):
+    """SURVEY.md 8f row f1 (sscd_baseline.py:107-152): for 5 candidates per query video, the frame-similarity matrix
+    (+0.5 bias), its per-row top-5 and the temporal-network alignment vcsl.vta.tn(tn_max_step=5, min_length=4) with MaxSim
+    scoring -- the reference runs this in a 16-process pool over networkx; here one device pass for all pairs."""
+    import dataclasses
+
+    import numpy as np
+    import torch
+
+    from oracle import tn_np
+    from vsc22_submission_b200.localization import VCSLLocalizationMaxSim
+
+    @dataclasses.dataclass
+    class VF:
+        video_id: str
+        feature: np.ndarray
+        timestamps: np.ndarray
+
+    @dataclasses.dataclass
+    class Cand:
+        query_id: str
+        ref_id: str
+        score: float = 0.0
+
+    rng = np.random.default_rng(0)
+    unit = lambda x: (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    mk = lambda pre, i, f: VF(f"{pre}{i}", f, np.arange(len(f), dtype=np.float32))
+    refs = [mk("R", i, unit(rng.standard_normal((int(rng.integers(20, 80)), SIM_D)))) for i in range(n_r)]
+    queries = []
+    for i in range(n_q):
+        n = int(rng.integers(10, 60))
+        f = rng.standard_normal((n, SIM_D))
+        src = refs[i].feature
+        L = min(n, len(src), 25)
+        f[:L] = src[:L] + 0.3 * rng.standard_normal((L, SIM_D)) / np.sqrt(SIM_D)      # a copied segment per query
+        queries.append(mk("Q", i, unit(f)))
+    cands = [Cand(f"Q{i}", f"R{(i + j * 7) % n_r}") for i in range(n_q) for j in range(per_q)]
+    loc = VCSLLocalizationMaxSim(queries, refs, model_type="TN", tn_max_step=5, min_length=4, similarity_bias=0.5)
+    loc.align(cands[:64])
+    ts, te = [], []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        boxes, nb, _ = loc.align(cands)
+        t1 = time.perf_counter()
+        matches = loc.localize_all(cands)
+        t2 = time.perf_counter()
+        ts.append(t1 - t0); te.append(t2 - t1)
+    sims = loc.similarities(cands[:300])
+    t0 = time.perf_counter()
+    same = sum(tn_np.tn(s, tn_max_step=5, min_length=4) == boxes[i, :nb[i]].tolist() for i, (_, s) in enumerate(sims))
+    cpu = 300 / (time.perf_counter() - t0)
+    torch.cuda.empty_cache()
+    return {"workload": f"{len(cands)} candidate pairs ({per_q} per query video; 10-60 x 20-80 frames x {SIM_D}): sims + top-5 + "
+                        "temporal network + MaxSim scores",
+            "align_ms": min(ts) * 1e3, "pairs_per_sec": len(cands) / min(ts), "boxes": int(nb.sum()),
+            "e2e": {"ms": min(te) * 1e3, "pairs_per_sec": len(cands) / min(te), "matches": len(matches),
+                    "api": "localization.VCSLLocalizationMaxSim(...).localize_all(candidates) -> Match tuples"},
+            "cpu_baseline": {"value": cpu, "unit": "pairs/sec", "cores": 1, "kind": "port",
+                             "sample": "oracle tn on 300 of the pairs (similarity matrices taken from the device)"},
+            "parity": {"pairs_checked": 300, "boxes_identical": int(same)}}
+
+
 def cpu_baseline_candidates(nq=1000, nr=SIM_NR_C, rows_q=40, rows_r=50):
     """oracle port of CandidateGeneration on a bounded sample (1k of the 10k query rows, full bank)."""
     import numpy as np
@@ -691,7 +756,7 @@ def main():
             line.update(metric="sim-pairs/sec", unit="sim-pairs/sec", value=sim["value"], ms_per_step=sim["ms_per_step"],
                         e2e=sim["e2e"], gpu_launches=sim["gpu_launches"], roofline=sim["roofline"], dtype="f32",
                         config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"),
-                        candidates=sim.get("candidates"))
+                        candidates=sim.get("candidates"), localization=sim.get("localization"))
         else:
             line["sim"] = sim
     if rank == 0 and world == 1 and args.workload == "both":

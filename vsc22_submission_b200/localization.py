@@ -162,19 +162,45 @@ class VCSLLocalization(PairSimilarity):
                                                         self.similarity_bias, _p(score), stream), "tn_box_scores")
         return boxes.cpu().numpy(), nb.cpu().numpy(), score.cpu().numpy()
 
+    def _ts_arrays(self, videos, index):
+        """(start, end) timestamp of every packed row, in pack order (VideoMetadata.get_timestamps, index.py:26-30)."""
+        st = [np.asarray(v.timestamps) if np.asarray(v.timestamps).ndim == 1 else np.asarray(v.timestamps)[:, 0] for v in videos]
+        en = [np.asarray(v.timestamps) if np.asarray(v.timestamps).ndim == 1 else np.asarray(v.timestamps)[:, 1] for v in videos]
+        return np.concatenate(st), np.concatenate(en)
+
     def localize_all(self, candidates: Sequence) -> list:
         Match = _match_type()
         boxes, nb, box_scores = self.align(candidates)
+        if not len(candidates) or not int(nb.sum()):
+            return []
+        if not hasattr(self, "_q_ts"):
+            self._q_ts = self._ts_arrays(list(self.queries.values()), self.q_index)
+            self._r_ts = self._ts_arrays(list(self.refs.values()), self.r_index)
+        sel = np.arange(boxes.shape[1])[None, :] < nb[:, None]
+        ci = np.nonzero(sel)[0]                                   # candidate of every box, candidate-major order
+        bx = boxes[sel].astype(np.int64)
+        qoff = np.array([self.q_index[c.query_id][0] for c in candidates], dtype=np.int64)[ci]
+        roff = np.array([self.r_index[c.ref_id][0] for c in candidates], dtype=np.int64)[ci]
+        qs, qe = self._q_ts[0][qoff + bx[:, 0]], self._q_ts[1][qoff + bx[:, 2]]
+        rs, re = self._r_ts[0][roff + bx[:, 1]], self._r_ts[1][roff + bx[:, 3]]
+        ms = box_scores[sel]
+        fast = {VCSLLocalization.score: 0, VCSLLocalizationMaxSim.score: 1, VCSLLocalizationCandidateScore.score: 2}
+        mode = fast.get(type(self).score, -1)
         matches = []
-        for i, c in enumerate(candidates):
-            query, ref = self.queries[c.query_id], self.refs[c.ref_id]
-            for b in range(int(nb[i])):
-                x1, y1, x2, y2 = (int(v) for v in boxes[i, b])
-                match = Match(query_id=c.query_id, ref_id=c.ref_id,
-                              query_start=_timestamps(query.timestamps, x1)[0], query_end=_timestamps(query.timestamps, x2)[1],
-                              ref_start=_timestamps(ref.timestamps, y1)[0], ref_end=_timestamps(ref.timestamps, y2)[1],
+        for j, (i, a, b, c_, d_, m) in enumerate(zip(ci.tolist(), qs, qe, rs, re, ms)):
+            c = candidates[i]
+            if mode == 0:
+                sc = 1.0
+            elif mode == 1:
+                sc = m
+            elif mode == 2:
+                sc = c.score
+            else:
+                match = Match(query_id=c.query_id, ref_id=c.ref_id, query_start=a, query_end=b, ref_start=c_, ref_end=d_,
                               score=0.0)
-                matches.append(match._replace(score=self.score(c, match, (x1, y1, x2, y2), box_scores[i, b])))
+                sc = self.score(c, match, tuple(int(v) for v in bx[j]), m)
+            matches.append(Match(query_id=c.query_id, ref_id=c.ref_id, query_start=a, query_end=b, ref_start=c_,
+                                 ref_end=d_, score=sc))
         return matches
 
     def localize(self, candidate) -> list:
