@@ -127,3 +127,45 @@ def test_long_videos_and_many_pairs():
     for i in list(range(0, 1500, 30)) + list(range(7, 1500, 97)):       # the planted pairs and a sample of the rest
         assert boxes[i, :nb[i]].tolist() == tn_np.tn(sims[i][1], tn_max_step=5, min_length=4), i
     assert int((nb[::30] > 0).sum()) >= 40
+
+
+def test_config1_pipeline_matches_reference_golden(golden_dir, tmp_path):
+    """SURVEY 8d config 1 on the device: pipeline.run (= sscd_baseline.main, eval.sh arguments) on the fixture's features
+    reproduces the candidates.csv / matches.csv the UNMODIFIED reference wrote for them (tests/golden/make_golden.py
+    make_pipeline), without and with score normalisation."""
+    import os
+
+    import pandas as pd
+    from vsc22_submission_b200 import pipeline
+    g = np.load(os.path.join(golden_dir, "pipeline_small.npz"))
+
+    def videos(prefix, base, arr, lens):
+        out, i = [], 0
+        for n, ln in enumerate(lens):
+            ln = int(ln)
+            ts = np.stack([np.arange(ln), np.arange(ln) + 1], 1).astype(np.float32)
+            out.append(VF(f"{prefix}{base + n:06d}", arr[i:i + ln], ts))
+            i += ln
+        return out
+
+    queries, refs = videos("Q", 100000, g["q"], g["q_len"]), videos("R", 200000, g["r"], g["r_len"])
+    noise = videos("R", 300000, g["z"], g["z_len"])
+    for tag, sn in (("plain", None), ("sn", noise)):
+        out = str(tmp_path / tag)
+        cf, mf = pipeline.run(queries, refs, out, score_norm_refs=sn, overwrite=True)
+        cand, mt = pd.read_csv(cf), pd.read_csv(mf)
+        assert list(cand.columns) == ["query_id", "ref_id", "score"]
+        assert list(mt.columns) == ["query_id", "ref_id", "query_start", "query_end", "ref_start", "ref_end", "score"]
+        ws = g[f"{tag}_cand_s"]
+        np.testing.assert_allclose(cand.score.to_numpy(), ws, rtol=0, atol=2e-6)
+        same = (cand.query_id.to_numpy(str) == g[f"{tag}_cand_q"]) & (cand.ref_id.to_numpy(str) == g[f"{tag}_cand_r"])
+        near = np.zeros(len(ws), bool)
+        close = np.abs(np.diff(ws)) <= 1e-6
+        near[1:] |= close
+        near[:-1] |= close
+        assert (same | near).all() and same[:40].all()
+        assert list(mt.query_id) == list(g[f"{tag}_match_q"]) and list(mt.ref_id) == list(g[f"{tag}_match_r"])
+        np.testing.assert_array_equal(mt[["query_start", "query_end", "ref_start", "ref_end"]].to_numpy(), g[f"{tag}_match_box"])
+        np.testing.assert_allclose(mt.score.to_numpy(), g[f"{tag}_match_s"], rtol=0, atol=5e-6)
+    with pytest.raises(Exception, match="overwrite"):
+        pipeline.run(queries, refs, str(tmp_path / "plain"))

@@ -161,16 +161,20 @@ class CandidateGeneration:
         self.index = VideoIndex(dim, device=device)
         self.index.add(references)
 
-    def query(self, queries: Sequence, global_k: int) -> list:
+    def query(self, queries: Sequence, global_k: int, limit: Optional[int] = None) -> list:
+        """``limit`` (not in the reference): build result objects for the first ``limit`` candidates only -- the caller
+        of sscd_baseline.py:98-100 slices the list right away, and a Python object per candidate is the expensive part."""
         _, _, CandidatePair = _result_types()
         if isinstance(self.aggregation, MaxScoreAggregation) and global_k >= 0:
             sc, qv, rv = self.index.video_pairs(queries, global_k)
+            if limit is not None:
+                sc, qv, rv = sc[:limit], qv[:limit], rv[:limit]
             qids, rids = [q.video_id for q in queries], [r.video_id for r in self.index.videos]
             return [CandidatePair(query_id=qids[a], ref_id=rids[b], score=s)
                     for a, b, s in zip(qv.tolist(), rv.tolist(), list(sc))]      # scores stay numpy float32 scalars
         matches = self.index.search(queries, global_k=global_k)
         candidates = [self.aggregation.score(m) for m in matches]
-        return sorted(candidates, key=lambda c: c.score, reverse=True)
+        return sorted(candidates, key=lambda c: c.score, reverse=True)[:limit]
 
 
 def threshold_candidates(index: VideoIndex, queries: Sequence, threshold: float) -> List[Tuple[str, str, float]]:
