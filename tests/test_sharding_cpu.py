@@ -40,8 +40,16 @@ def _worker(rank, world, port, out_dir):
     Dm, Im = sharding.merge_partial_topk(torch.from_numpy(D), torch.from_numpy(I), 12)
     lvd = sharding.global_low_var_dim(torch.from_numpy(R[a:b]))
     desc = sharding.gather_descriptors(torch.from_numpy(R[a:b]), len(R))
+    # global candidate search: each rank's top-40 pairs over its shard (the oracle stands in for the per-rank GPU
+    # search), merged to the global top-40; rank 1 also contributes fewer than 40 pairs in threshold mode
+    from oracle import candidates_np
+    gs, gq, gr = candidates_np.global_topk_pairs(Q, R[a:b], 40)
+    ms, mq, mr = sharding.merge_partial_global_topk(torch.from_numpy(gs.copy()), torch.from_numpy(gq), torch.from_numpy(gr + a), 40)
+    ts, tq, tr = candidates_np.threshold_pairs(Q, R[a:b], 12.0)
+    us, uq, ur = sharding.merge_partial_global_topk(torch.from_numpy(ts.copy()), torch.from_numpy(tq), torch.from_numpy(tr + a), 0)
     if rank == 0:
-        np.savez(os.path.join(out_dir, "merged.npz"), D=Dm.numpy(), I=Im.numpy(), lvd=lvd, desc=desc.numpy(), R=R, Q=Q)
+        np.savez(os.path.join(out_dir, "merged.npz"), D=Dm.numpy(), I=Im.numpy(), lvd=lvd, desc=desc.numpy(), R=R, Q=Q,
+                 ms=ms.numpy(), mq=mq.numpy(), mr=mr.numpy(), us=us.numpy(), uq=uq.numpy(), ur=ur.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,6 +78,14 @@ def test_two_rank_bank_sharding_matches_single_index(tmp_path):
     assert g["I"][0, 0] == 10 and g["I"][0, 1] == 500           # tie across shards resolved to the lower id
     assert int(g["lvd"]) == score_norm_np.low_var_dim(g["R"].astype(np.float64))
     np.testing.assert_array_equal(g["desc"], g["R"])
+    from oracle import candidates_np
+    for got, want in (((g["ms"], g["mq"], g["mr"]), candidates_np.global_topk_pairs(g["Q"], g["R"], 40)),
+                      ((g["us"], g["uq"], g["ur"]), candidates_np.threshold_pairs(g["Q"], g["R"], 12.0))):
+        assert len(want[0]) > 3
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+    j = int(np.flatnonzero((g["mq"] == 0) & (g["mr"] == 10))[0])    # the cross-shard exact tie keeps (q row, bank row) order
+    assert (g["mq"][j + 1], g["mr"][j + 1]) == (0, 500) and g["ms"][j] == g["ms"][j + 1]
 
 
 def test_merge_handles_padding_single_process():

@@ -7,6 +7,10 @@
   vsc/exhaustive_search.py:232-234 ``co.shard = False``); every rank searches its shard with GLOBAL
   row ids (``DeviceIndex.set_id_offset``) and ONE all-gather of the ``[nq, k]`` partial results
   followed by a k-way merge gives the global top-k.
+* Global candidate search (``DeviceIndex.global_search``): every rank finds the global_k best (query row, bank row)
+  pairs against ITS bank shard (global bank ids through ``set_id_offset``); one all-gather of the padded
+  ``[global_k]`` partial lists and a merge by (score, query row, bank row) gives the exact global list
+  (``merge_partial_global_topk``) -- the union of per-shard top-K always contains the global top-K.
 * Score-norm prep: column moments are all-reduced once per bank (``global_low_var_dim``).
 
 Works with NCCL (CUDA tensors) and gloo (CPU tensors: the world_size-2 tests in
@@ -46,6 +50,33 @@ def merge_partial_topk(D: torch.Tensor, I: torch.Tensor, k: int, keep_max: bool 
     key, D, I = torch.gather(key, 1, order), torch.gather(D, 1, order), torch.gather(I, 1, order)
     order = torch.argsort(key, dim=1, descending=keep_max, stable=True)[:, :k]
     return torch.gather(D, 1, order), torch.gather(I, 1, order)
+
+
+def merge_partial_global_topk(scores: torch.Tensor, qrows: torch.Tensor, brows: torch.Tensor, global_k: int,
+                              keep_max: bool = True, group: Optional[dist.ProcessGroup] = None
+                              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather every rank's partial global-search result (variable length <= global_k; bank rows are GLOBAL ids) and
+    keep the ``global_k`` best pairs overall (all of them when ``global_k <= 0``, threshold mode): best first, ties by
+    (query row, bank row) -- the order ``DeviceIndex.global_search`` produces on one GPU."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        n = torch.tensor([scores.numel()], dtype=torch.int64, device=scores.device)
+        ns = [torch.empty_like(n) for _ in range(world)]
+        dist.all_gather(ns, n, group=group)
+        cap = max(int(max(x.item() for x in ns)), 1)
+        pad = lambda t, fill: torch.cat([t, torch.full((cap - t.numel(),), fill, dtype=t.dtype, device=t.device)])
+        parts = []
+        for t, fill in ((scores, 0.0), (qrows, -1), (brows, -1)):
+            outs = [torch.empty(cap, dtype=t.dtype, device=t.device) for _ in range(world)]
+            dist.all_gather(outs, pad(t.contiguous(), fill), group=group)
+            parts.append(torch.cat([o[: int(m.item())] for o, m in zip(outs, ns)]))
+        scores, qrows, brows = parts
+    order = torch.argsort(brows, stable=True)
+    order = order[torch.argsort(qrows[order], stable=True)]
+    order = order[torch.argsort(scores[order], descending=keep_max, stable=True)]
+    if global_k > 0:
+        order = order[:global_k]
+    return scores[order], qrows[order], brows[order]
 
 
 def global_low_var_dim(z_shard: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> int:
