@@ -209,6 +209,17 @@ int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_l
                       const int64_t* s_off_dev, const int64_t* row_off_dev, int k, float* topv_dev, int32_t* topi_dev,
                       void* stream);
 
+/* Matching-track candidate features: M/infer/src/utils.py:18-47 / :50-73 + the zero-padded
+ * similarity images of M/infer/src/dataset.py:103-144.  sims_dev: the blocks written by vscb200_pair_sims (whole query
+ * video x reference).  seg_len[p] = query_video_len_map[qid]: when the query holds several seg_len-frame copies, the one
+ * with the best mean of its 10 largest row maxima is kept.  images_dev [n_pairs, 1 or 2, H, W]: the kept block cropped /
+ * zero-padded to H x W and (with_transpose) its transpose (ref x query); info_dev [n_pairs, 4] = (segment, rows kept,
+ * h, w).  rowmax_scratch_dev: [sum q_len] floats. */
+int vscb200_pair_segment_images(const float* sims_dev, int64_t n_pairs, const int32_t* q_len_dev, const int32_t* r_len_dev,
+                                const int64_t* s_off_dev, const int64_t* row_off_dev, const int32_t* seg_len_dev,
+                                float* rowmax_scratch_dev, int H, int W, int with_transpose, float* images_dev,
+                                int32_t* info_dev, void* stream);
+
 /* Temporal-network alignment of every candidate pair (vcsl/vta.py:244-363 `tn`, run by localization.py:38-76 through a
  * 16-process pool): input = the per-row top-k of vscb200_pair_topk (same k, row_off, lengths); output = up to
  * max_path + 1 boxes [q_min, r_min, q_max, r_max] per pair in boxes_dev [n_pairs, max_path + 1, 4] and their number in

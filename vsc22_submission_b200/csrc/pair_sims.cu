@@ -114,6 +114,111 @@ pair_topk_kernel(const float* __restrict__ S, PairDesc pd, const int64_t* __rest
   }
 }
 
+// ---- matching-track candidate features ----------------------------------------------------
+// M/infer/src/utils.py:18-47 / :50-73: a query video may hold several `seg_len`-frame copies of itself (one per detected
+// sub-image); the copy whose rows match the reference best -- mean of the 10 largest row maxima, utils.py:33-41 -- is kept,
+// and its similarity block (and the transposed block, utils.py:44-46) is zero-padded / cropped to an H x W image
+// (M/infer/src/dataset.py:103-144).  One CTA per pair: row maxima -> per-segment score -> argmax -> images.
+constexpr int kSegTop = 10;
+
+// numpy's float32 pairwise add.reduce over a[0..m) for m <= 10 (8 partial sums, combined as a tree, then the tail)
+__device__ __forceinline__ float numpy_sum_f32(const float* a, int m) {
+  if (m < 8) {
+    float r = 0.f;          // -0.0 start in numpy; identical for the sums that occur here
+    for (int i = 0; i < m; ++i) r = __fadd_rn(r, a[i]);
+    return r;
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])),
+                        __fadd_rn(__fadd_rn(a[4], a[5]), __fadd_rn(a[6], a[7])));
+  for (int i = 8; i < m; ++i) res = __fadd_rn(res, a[i]);
+  return res;
+}
+
+__global__ void __launch_bounds__(256)
+pair_segment_images_kernel(const float* __restrict__ S, PairDesc pd, const int64_t* __restrict__ row_off,
+                           const int32_t* __restrict__ seg_len, float* __restrict__ rowmax, int H, int W, int with_transpose,
+                           float* __restrict__ images, int32_t* __restrict__ info) {
+  __shared__ float seg_score[256];
+  __shared__ int best_seg;
+  const int64_t pair = blockIdx.x;
+  const int nq = pd.q_len[pair], nr = pd.r_len[pair];
+  const float* s = S + pd.s_off[pair];
+  float* rm = rowmax + row_off[pair];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = seg_len[pair] > 0 ? seg_len[pair] : nq;
+  const int nseg = min((nq + sl - 1) / sl, 256);          // seg_score[] capacity; real inputs hold a handful of copies
+  if (nseg > 1) {
+    for (int row = warp; row < nq; row += 8) {
+      float m = -INFINITY;
+      for (int c = lane; c < nr; c += 32) m = fmaxf(m, s[static_cast<int64_t>(row) * nr + c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) rm[row] = m;
+    }
+    __syncthreads();
+    for (int sg = warp; sg < nseg; sg += 8) {
+      const int a = sg * sl, b = min(nq, a + sl);
+      // the (up to) 10 largest row maxima of the segment, found largest first
+      float topv[kSegTop];
+      float prev_v = INFINITY;
+      int prev_i = -1, m = 0;
+      for (int rnk = 0; rnk < kSegTop && rnk < b - a; ++rnk) {
+        float bv = -INFINITY;
+        int bi = 0x7FFFFFFF;
+        for (int c = a + lane; c < b; c += 32) {
+          const float v = rm[c];
+          const bool after = v < prev_v || (v == prev_v && c > prev_i);
+          if (after && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        topv[rnk] = bv;
+        prev_v = bv;
+        prev_i = bi;
+        ++m;
+      }
+      if (lane == 0) {
+        float asc[kSegTop];
+        for (int i = 0; i < m; ++i) asc[i] = topv[m - 1 - i];          // maxs.sort(); maxs[-10:]
+        seg_score[sg] = __fdiv_rn(numpy_sum_f32(asc, m), static_cast<float>(m));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int bs = 0;
+      for (int sg = 1; sg < nseg && sg < 256; ++sg)
+        if (seg_score[sg] > seg_score[bs]) bs = sg;                     // np.argmax: first maximum
+      best_seg = bs;
+    }
+  } else if (threadIdx.x == 0) {
+    best_seg = 0;
+  }
+  __syncthreads();
+  const int start = best_seg * sl, len = min(nq, start + sl) - start;
+  const int n_img = with_transpose ? 2 : 1;
+  float* img = images + pair * n_img * static_cast<int64_t>(H) * W;
+  const int h = min(len, H), w = min(nr, W);
+  for (int e = threadIdx.x; e < H * W; e += 256) {
+    const int i = e / W, j = e % W;
+    img[e] = (i < h && j < w) ? s[static_cast<int64_t>(start + i) * nr + j] : 0.f;
+  }
+  if (with_transpose) {
+    float* imt = img + static_cast<int64_t>(H) * W;
+    const int ht = min(nr, H), wt = min(len, W);
+    for (int e = threadIdx.x; e < H * W; e += 256) {
+      const int i = e / W, j = e % W;                                   // (ref frame, query frame)
+      imt[e] = (i < ht && j < wt) ? s[static_cast<int64_t>(start + j) * nr + i] : 0.f;
+    }
+  }
+  if (threadIdx.x == 0) {
+    info[pair * 4 + 0] = best_seg; info[pair * 4 + 1] = len; info[pair * 4 + 2] = h; info[pair * 4 + 3] = w;
+  }
+}
+
 }  // namespace vscb200
 
 using namespace vscb200;
@@ -146,6 +251,25 @@ int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_l
   PairDesc pd{nullptr, q_len_dev, nullptr, r_len_dev, s_off_dev};
   ProfScope prof(kProfSelect, s, 0.0);
   pair_topk_kernel<<<dim3(static_cast<unsigned>(n_pairs), 4), 256, 0, s>>>(sims_dev, pd, row_off_dev, k, topv_dev, topi_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+int vscb200_pair_segment_images(const float* sims_dev, int64_t n_pairs, const int32_t* q_len_dev, const int32_t* r_len_dev,
+                                const int64_t* s_off_dev, const int64_t* row_off_dev, const int32_t* seg_len_dev,
+                                float* rowmax_scratch_dev, int H, int W, int with_transpose, float* images_dev,
+                                int32_t* info_dev, void* stream_v) {
+  VSCB_REQUIRE(n_pairs >= 0 && H >= 1 && W >= 1, "pair_segment_images: bad shape");
+  if (n_pairs == 0) return VSCB200_OK;
+  VSCB_REQUIRE(sims_dev && q_len_dev && r_len_dev && s_off_dev && row_off_dev && seg_len_dev && rowmax_scratch_dev &&
+               images_dev && info_dev, "pair_segment_images: null argument");
+  VSCB_REQUIRE(n_pairs < (1ll << 31), "pair_segment_images: too many pairs in one call");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_v);
+  PairDesc pd{nullptr, q_len_dev, nullptr, r_len_dev, s_off_dev};
+  pair_segment_images_kernel<<<static_cast<unsigned>(n_pairs), 256, 0, s>>>(sims_dev, pd, row_off_dev, seg_len_dev,
+                                                                          rowmax_scratch_dev, H, W, with_transpose ? 1 : 0,
+                                                                          images_dev, info_dev);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
