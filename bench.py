@@ -256,6 +256,54 @@ def bench_swin(args):
             "config": {"workload": "SwinV2-B 256x256 window 16 (config_v106.py), random init, bf16 operands, 1 GPU"}}
 
 
+def bench_ingest(n=512, h=360, w=640, out=224):
+    """SURVEY.md 8f row f4 (after JPEG decode): Resize(bicubic) + ToTensor + Normalize of D/infer/src/transform.py:20-43 for
+    decoded 360 x 640 frames -- device kernels (uint8 frames uploaded from pinned memory inside the timed region) next to
+    Pillow + numpy on one host core (what each DataLoader worker of the reference runs)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from vsc22_submission_b200 import ingest
+    rng = np.random.default_rng(0)
+    frames = torch.from_numpy(rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)).pin_memory()
+    pre = ingest.sscd_transform(out, out)
+    dev_frames = frames.cuda()
+    pre(dev_frames[:8])
+    torch.cuda.synchronize()
+    td, te = [], []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = pre(dev_frames)
+        e1.record()
+        torch.cuda.synchronize()
+        td.append(e0.elapsed_time(e1))
+        t0 = time.perf_counter()
+        y2 = pre(frames)
+        torch.cuda.synchronize()
+        te.append((time.perf_counter() - t0) * 1e3)
+    sample = 48
+    mean, std = np.array(ingest.IMAGENET_MEAN, np.float32)[:, None, None], np.array(ingest.IMAGENET_STD, np.float32)[:, None, None]
+    t0 = time.perf_counter()
+    for i in range(sample):
+        im = np.asarray(Image.fromarray(frames[i].numpy()).resize((out, out), Image.BICUBIC))
+        ref = (im.transpose(2, 0, 1).astype(np.float32) / np.float32(255) - mean) / std
+    cpu = sample / (time.perf_counter() - t0)
+    same = bool(np.array_equal(ref, y[sample - 1].cpu().numpy()))
+    bytes_alg = n * (h * w * 3 + out * out * 3 * 4)
+    del dev_frames, y, y2
+    torch.cuda.empty_cache()
+    return {"workload": f"{n} decoded {h}x{w} RGB frames -> bicubic {out}x{out} + ToTensor + Normalize (float32 NCHW)",
+            "frames_per_sec": n / (min(td) / 1e3), "ms": min(td),
+            "hbm_frac_algorithmic": bytes_alg / (min(td) / 1e3) / 1e9 / load_peaks()["hbm_gbs"],
+            "e2e": {"frames_per_sec": n / (min(te) / 1e3), "ms": min(te), "h2d_bytes": n * h * w * 3,
+                    "api": "ingest.sscd_transform(224, 224)(pinned uint8 frames)"},
+            "cpu_baseline": {"value": cpu, "unit": "frames/sec", "cores": 1, "kind": "reference",
+                             "sample": f"{sample} frames through Pillow Image.resize(BICUBIC) + numpy ToTensor/Normalize"},
+            "parity": {"bit_identical_to_pillow": same}}
+
+
 def h2d_bandwidth_gbs():
     """Pinned host -> device copy rate of this box (the ceiling of every e2e number that ships fp32 frames)."""
     import torch
@@ -761,6 +809,7 @@ def main():
             line["sim"] = sim
     if rank == 0 and world == 1 and args.workload == "both":
         line["swin"] = bench_swin(args)
+        line["ingest"] = bench_ingest()
         line["h2d_pinned_gbs"] = h2d_bandwidth_gbs()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g = torch.Generator().manual_seed(1)

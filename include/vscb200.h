@@ -209,6 +209,13 @@ int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_l
                       const int64_t* s_off_dev, const int64_t* row_off_dev, int k, float* topv_dev, int32_t* topi_dev,
                       void* stream);
 
+/* Frame preprocessing (after JPEG decode): Pillow's antialiased bicubic `Image.resize` + torchvision
+ * ToTensor + Normalize of D/infer/src/transform.py:20-43, bit-exact.  frames_dev: [n, H, W, 3] uint8 RGB (device);
+ * mean3 / std3: host float[3]; mid_scratch_dev: n*H*out_w*3 bytes (may be NULL when W == out_w);
+ * out_dev: [n, 3, out_h, out_w] float32 -- the tensor the encoder's forward takes. */
+int vscb200_resize_normalize(const uint8_t* frames_dev, int64_t n, int H, int W, int out_h, int out_w, const float* mean3,
+                             const float* std3, uint8_t* mid_scratch_dev, float* out_dev, void* stream);
+
 /* Matching-track candidate features: M/infer/src/utils.py:18-47 / :50-73 + the zero-padded
  * similarity images of M/infer/src/dataset.py:103-144.  sims_dev: the blocks written by vscb200_pair_sims (whole query
  * video x reference).  seg_len[p] = query_video_len_map[qid]: when the query holds several seg_len-frame copies, the one
