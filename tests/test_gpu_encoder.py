@@ -180,3 +180,29 @@ def test_encoder_vit_b16_full_config(torch):
     outb = enc(big).cpu().numpy()
     np.testing.assert_allclose(outb[:3], out, rtol=0, atol=1e-5)
     np.testing.assert_allclose(outb[129], out[129 % 3], rtol=0, atol=1e-5)
+
+
+def test_extractor_mirrors_with_the_b200_encoder():
+    """extractor.extract_vsc_feat / single_infer over a real encoder plan: same descriptors as
+    calling the module batch by batch the way D/infer/src/extractor.py:13-30 does."""
+    import torch
+    from oracle import vit_ref
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VitSpec
+    from vsc22_submission_b200.extractor import extract_vsc_feat, single_infer
+    kw = dict(img=64, patch=16, width=128, layers=2, heads=2, tail="gem_linear", out_dim=64)
+    enc = B200ViTEncoder(VitSpec(**kw), vit_ref.init_weights(vit_ref.VitSpec(**kw), seed=0), max_frames=8).cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    loader = []
+    for b, lens in enumerate([(3, 7), (1, 2), (9, 4)]):          # 9 + 4 frames > max_frames: chunked inside the plan
+        S = max(lens)
+        frames = torch.zeros(len(lens), S, 3, 64, 64)
+        for i, n in enumerate(lens):
+            frames[i, :n] = torch.randn(n, 3, 64, 64, generator=g).clamp(-1, 1)
+        mask = (frames.reshape(len(lens), S, -1).sum(-1) != 0).long()
+        loader.append((frames, mask, (f"R{b}0", f"R{b}1")))
+    vids, feat, ts = extract_vsc_feat(enc, loader, torch.device("cuda"))
+    want = torch.cat([enc(fr.cuda()[m.bool().cuda()]) for fr, m, _ in loader]).cpu().numpy()
+    np.testing.assert_array_equal(feat, want)
+    assert len(vids) == feat.shape[0] == ts.shape[0] == 26 and vids[:3] == ["R00"] * 3 and ts[:4].tolist() == [0, 1, 2, 0]
+    x = loader[2][0][0].cuda()
+    np.testing.assert_array_equal(single_infer(enc, x), enc(x).cpu().numpy())
