@@ -149,13 +149,20 @@ gt_emit_kernel(GtBlock a, int64_t ntotal, float* __restrict__ bufv, uint64_t* __
     const float* p = a.S + row * a.ldS + c0;
     const uint64_t pbase = static_cast<uint64_t>(a.q0 + row) * static_cast<uint64_t>(ntotal) + static_cast<uint64_t>(c0);
     const int cnt = a.n - c0 < kGtChunk ? static_cast<int>(a.n - c0) : kGtChunk;
-    for (int j0 = 0; j0 < cnt; j0 += kGtThreads * 4) {
-      const int j = j0 + threadIdx.x * 4;
-      float v[4];
+    // one work item = 4096 columns = 4 float4 per thread: all loads are issued before any is consumed
+    float4 ld[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = (u * kGtThreads + threadIdx.x) * 4;
+      ld[u] = j + 3 < cnt ? *reinterpret_cast<const float4*>(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u4 = 0; u4 < 4; ++u4) {
+      const int j = (u4 * kGtThreads + threadIdx.x) * 4;
+      if (u4 * kGtThreads * 4 >= cnt) break;
+      float v[4] = {ld[u4].x, ld[u4].y, ld[u4].z, ld[u4].w};
       bool hit[4];
       if (j + 3 < cnt) {
-        const float4 t = *reinterpret_cast<const float4*>(p + j);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 #pragma unroll
         for (int u = 0; u < 4; ++u) hit[u] = better(v[u], thr, a.keep_max);
       } else {
@@ -186,6 +193,20 @@ gt_emit_kernel(GtBlock a, int64_t ntotal, float* __restrict__ bufv, uint64_t* __
         }
       }
     }
+  }
+}
+
+// ---- bootstrap sample: every 64th score of the block (column offset rotated per row), for a first radius estimate
+constexpr int kGtSampleStride = 64;
+__global__ void __launch_bounds__(kGtThreads)
+gt_sample_kernel(const float* __restrict__ S, int64_t ldS, int64_t nb, int64_t n, int64_t per_row, int keep_max,
+                 float* __restrict__ out) {
+  const int64_t total = nb * per_row;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * kGtThreads) {
+    const int64_t row = i / per_row, t = i % per_row;
+    const int64_t col = (row * 17) % kGtSampleStride + t * kGtSampleStride;
+    out[i] = col < n ? S[row * ldS + col] : (keep_max ? -INFINITY : INFINITY);
   }
 }
 
@@ -396,8 +417,12 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   max_reduce_kernel<<<1, 1024, 0, s>>>(ix->rnorm, n, rn_max);
   count_launch();
 
-  // survivor buffers (ping-pong for compaction); capacity 2K like the reference's max_results
-  uint64_t cap = limited ? std::min<uint64_t>(2 * K + 4096, total_pairs) : std::min<uint64_t>(total_pairs, 1u << 20);
+  // survivor buffers (ping-pong for compaction).  Logical bound 2K like the reference's max_results: above it the
+  // radius is raised to the K-th best survivor; the physical capacity is larger so that a block emitted under a loose
+  // (bootstrap) radius still fits.
+  const uint64_t logical_cap = limited ? std::min<uint64_t>(2 * K + 4096, total_pairs) : ~0ull;
+  uint64_t cap = limited ? std::min<uint64_t>(total_pairs, std::max<uint64_t>(logical_cap, std::min<uint64_t>(16 * K + (1u << 20), 1u << 27)))
+                         : std::min<uint64_t>(total_pairs, 1u << 20);
   float* bufv[2] = {nullptr, nullptr};
   uint64_t* bufp[2] = {nullptr, nullptr};
   auto alloc_bufs = [&](uint64_t c, float** v, uint64_t** p) {
@@ -414,6 +439,8 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (n + 3) & ~3ll;
   if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s))) return rc;
+  const int64_t per_row = (n + kGtSampleStride - 1) / kGtSampleStride;
+  float* sample = nullptr;
 
   unsigned long long count = 0;     // host mirror of the buffer fill
   float radius = use_thresh ? thresh : 0.f;
@@ -430,6 +457,49 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     VSCB_CUDA_OK(cudaStreamSynchronize(s));      // v lives on this frame
     return static_cast<int>(VSCB200_OK);
   };
+  // exact `want`-th best value over {entries of block `a` better than its radius} U {vals[0:nvals)}: 3-level radix select
+  auto select_kth = [&](const GtBlock& a, const float* vals, int64_t nvals, uint64_t want, float* kth) {
+    const int64_t work = a.nb * ((a.n + kGtChunk - 1) / kGtChunk);
+    const int grid = grid_for(std::max<int64_t>(work, (nvals + kGtThreads - 1) / kGtThreads));
+    uint32_t prefix = 0;
+    for (int level = 0; level < 3; ++level) {
+      VSCB_CUDA_OK(cudaMemsetAsync(hist, 0, 2048 * sizeof(unsigned long long), s));
+      gt_hist_kernel<<<grid, kGtThreads, 0, s>>>(a, vals, nvals, level, prefix, hist);
+      count_launch();
+      VSCB_CUDA_OK(cudaMemcpyAsync(hh.data(), hist, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+      VSCB_CUDA_OK(cudaStreamSynchronize(s));
+      const int nd = level == 2 ? 1024 : 2048;
+      int dgt = nd - 1;
+      uint64_t cum = 0;
+      for (; dgt > 0; --dgt) {
+        if (cum + hh[dgt] >= want) break;
+        cum += hh[dgt];
+      }
+      want -= cum;
+      prefix = level == 2 ? ((prefix << 10) | static_cast<uint32_t>(dgt)) : ((prefix << 11) | static_cast<uint32_t>(dgt));
+    }
+    *kth = key_value(prefix, keep_max);
+    return static_cast<int>(VSCB200_OK);
+  };
+  // keep the buffer entries that can still be among the K best under `radius`; updates count
+  auto compact = [&]() {
+    if (!bufv[1] && alloc_bufs(cap, &bufv[1], &bufp[1])) return static_cast<int>(VSCB200_ERR_NOMEM);
+    int r = set_counter(0);
+    if (r) return r;
+    if (count) {
+      gt_compact_kernel<<<grid_for((static_cast<int64_t>(count) + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
+          bufv[0], bufp[0], static_cast<int64_t>(count), n, qn_all, rn_max, radius, keep_max ? 1 : 0, bufv[1], bufp[1], counter);
+      count_launch();
+      std::swap(bufv[0], bufv[1]);
+      std::swap(bufp[0], bufp[1]);
+    }
+    return read_counter(&count);
+  };
+  auto raise_radius = [&](float kth) {
+    if (!has_radius || (keep_max ? kth > radius : kth < radius)) radius = kth;
+    has_radius = true;
+  };
+  const GtBlock no_block{nullptr, 0, 0, n, 0, qn_all, rn_max, 0.f, 0, keep_max ? 1 : 0};
 
   for (int64_t q0 = 0; q0 < nq; q0 += blk) {
     const int64_t nb = std::min(blk, nq - q0);
@@ -439,51 +509,58 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     const int grid = grid_for(work);
     const uint64_t blk_pairs = static_cast<uint64_t>(nb) * static_cast<uint64_t>(n);
     unsigned long long after = 0;
-    bool emitted = false;
-    if (has_radius || count + blk_pairs <= cap) {
+    bool emitted = false, tentative = false;
+    float r_hat = 0.f;
+    if (!has_radius && count + blk_pairs > cap) {
+      // No radius yet and the block does not fit: estimate one from a 1/64 sample of the block -- the value that about
+      // 4K entries of the block should exceed -- emit under it, then VERIFY below (the K-th best survivor must not be
+      // worse than the estimate, otherwise pairs between the two were never emitted and the exact select runs instead).
+      const int64_t ns = nb * per_row;
+      const uint64_t want_s = (4 * K) / kGtSampleStride;
+      if (want_s >= 16 && static_cast<uint64_t>(ns) > 4 * want_s) {
+        if (!sample && (rc = sc.get(&sample, static_cast<size_t>(blk) * per_row * sizeof(float)))) return rc;
+        gt_sample_kernel<<<grid_for((ns + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(ix->ws, ldS, nb, n, per_row,
+                                                                                          keep_max ? 1 : 0, sample);
+        count_launch();
+        if ((rc = select_kth(no_block, sample, ns, want_s, &r_hat))) return rc;
+        a.radius = r_hat;
+        a.has_radius = 1;
+        tentative = true;
+      }
+    }
+    if (a.has_radius || count + blk_pairs <= cap) {
       gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
       count_launch();
       if ((rc = read_counter(&after))) return rc;
       emitted = after <= cap;
+      if (emitted && tentative) {
+        float kth = 0.f;
+        const bool enough = after >= K;
+        if (enough && (rc = select_kth(no_block, bufv[0], static_cast<int64_t>(after), K, &kth))) return rc;
+        if (enough && (keep_max ? kth >= r_hat : kth <= r_hat)) {
+          count = after;                     // every pair at least as good as kth was emitted: kth is exact
+          raise_radius(kth);
+          if ((rc = compact())) return rc;
+          after = count;
+        } else {
+          emitted = false;                   // estimate too tight: forget this emission, take the exact path
+          if ((rc = set_counter(count))) return rc;
+          a.radius = radius;
+          a.has_radius = has_radius ? 1 : 0;
+          after = count + blk_pairs;
+        }
+      }
     } else {
-      after = count + blk_pairs;     // no radius yet: everything would be emitted
+      after = count + blk_pairs;             // no radius at all: everything would be emitted
     }
     if (!emitted && limited) {
       // raise the radius: exact K-th best value over {buffer, block entries better than the radius}
-      uint32_t prefix = 0;
-      uint64_t want = K;
-      for (int level = 0; level < 3; ++level) {
-        VSCB_CUDA_OK(cudaMemsetAsync(hist, 0, 2048 * sizeof(unsigned long long), s));
-        gt_hist_kernel<<<grid, kGtThreads, 0, s>>>(a, bufv[0], static_cast<int64_t>(count), level, prefix, hist);
-        count_launch();
-        VSCB_CUDA_OK(cudaMemcpyAsync(hh.data(), hist, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        VSCB_CUDA_OK(cudaStreamSynchronize(s));
-        const int nd = level == 2 ? 1024 : 2048;
-        int dgt = nd - 1;
-        uint64_t cum = 0;
-        for (; dgt > 0; --dgt) {
-          if (cum + hh[dgt] >= want) break;
-          cum += hh[dgt];
-        }
-        want -= cum;
-        prefix = level == 2 ? ((prefix << 10) | static_cast<uint32_t>(dgt)) : ((prefix << 11) | static_cast<uint32_t>(dgt));
-      }
-      const float kth = key_value(prefix, keep_max);
-      if (!has_radius || (keep_max ? kth > radius : kth < radius)) radius = kth;
-      has_radius = true;
+      float kth = 0.f;
+      if ((rc = select_kth(a, bufv[0], static_cast<int64_t>(count), K, &kth))) return rc;
+      raise_radius(kth);
       a.radius = radius;
       a.has_radius = 1;
-      // compact what the buffer held before this block, then emit the block again
-      if (!bufv[1] && (rc = alloc_bufs(cap, &bufv[1], &bufp[1]))) return rc;
-      if ((rc = set_counter(0))) return rc;
-      if (count) {
-        gt_compact_kernel<<<grid_for((static_cast<int64_t>(count) + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
-            bufv[0], bufp[0], static_cast<int64_t>(count), n, qn_all, rn_max, radius, keep_max ? 1 : 0, bufv[1], bufp[1], counter);
-        count_launch();
-        std::swap(bufv[0], bufv[1]);
-        std::swap(bufp[0], bufp[1]);
-      }
-      if ((rc = read_counter(&count))) return rc;
+      if ((rc = compact())) return rc;       // what the buffer held before this block
       gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
       count_launch();
       if ((rc = read_counter(&after))) return rc;
@@ -509,6 +586,13 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
       emitted = after <= cap;
     }
     count = after;
+    if (limited && count > logical_cap) {
+      // more than 2K survivors: the K-th best of them is the new radius (apply_maxres, exhaustive_search.py:178-203)
+      float kth = 0.f;
+      if ((rc = select_kth(no_block, bufv[0], static_cast<int64_t>(count), K, &kth))) return rc;
+      raise_radius(kth);
+      if ((rc = compact())) return rc;
+    }
   }
 
   if (count == 0) return VSCB200_OK;

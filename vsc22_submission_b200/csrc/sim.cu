@@ -176,6 +176,18 @@ __global__ void col_moments_kernel(const float* __restrict__ x, int64_t n, int d
   }
 }
 
+// first minimum of the column variance (numpy var(axis=0).argmin()); d is a few hundred: one thread
+__global__ void var_argmin_kernel(const double* __restrict__ sums, int64_t n, int d, int* __restrict__ out) {
+  int best = 0;
+  double best_var = 0;
+  for (int c = 0; c < d; ++c) {
+    const double mean = sums[c] / n;
+    const double var = __dsub_rn(sums[d + c] / n, __dmul_rn(mean, mean));     // no FMA contraction: the host formula
+    if (c == 0 || var < best_var) { best = c; best_var = var; }
+  }
+  *out = best;
+}
+
 }  // namespace vscb200
 
 extern "C" {
@@ -200,31 +212,32 @@ int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, voi
   using namespace vscb200;
   VSCB_REQUIRE(n > 0 && d > 0 && dim_host, "low_var_dim: empty input");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // scratch from the caching pool (no cudaMalloc / cudaFree -- each is a device-wide synchronisation -- per call);
+  // the argmin runs on the device, 4 bytes come back through a page-locked word
   double* sums = nullptr;
-  VSCB_CUDA_OK(cudaMalloc(&sums, sizeof(double) * 2 * d));
-  VSCB_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream));
+  int rc = pool_alloc(reinterpret_cast<void**>(&sums), sizeof(double) * 2 * d + sizeof(int), stream);
+  if (rc) return rc;
+  int* best_dev = reinterpret_cast<int*>(sums + 2 * d);
+  static thread_local int* best_pinned = nullptr;
+  if (!best_pinned && cudaMallocHost(&best_pinned, sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    pool_free(sums, stream);
+    set_last_error("low_var_dim: cudaMallocHost failed");
+    return VSCB200_ERR_NOMEM;
+  }
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream);
   dim3 grid((d + 31) / 32, static_cast<unsigned>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048)));
   col_moments_kernel<<<grid, dim3(32, 8), 0, stream>>>(x_dev, n, d, sums);
-  count_launch();
-  std::string err;
-  double* h = static_cast<double*>(malloc(sizeof(double) * 2 * d));
-  cudaError_t e = cudaMemcpyAsync(h, sums, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, stream);
+  var_argmin_kernel<<<1, 1, 0, stream>>>(sums, n, d, best_dev);
+  count_launch(2);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(best_pinned, best_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  cudaFree(sums);
+  pool_free(sums, stream);
   if (e != cudaSuccess) {
-    free(h);
     set_last_error(std::string("low_var_dim: ") + cudaGetErrorString(e));
     return VSCB200_ERR_CUDA;
   }
-  int best = 0;
-  double best_var = 0;
-  for (int c = 0; c < d; ++c) {
-    const double mean = h[c] / n;
-    const double var = h[d + c] / n - mean * mean;
-    if (c == 0 || var < best_var) { best = c; best_var = var; }
-  }
-  free(h);
-  *dim_host = best;
+  *dim_host = *best_pinned;
   return VSCB200_OK;
 }
 }
