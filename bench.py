@@ -358,7 +358,7 @@ def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
     import torch
 
     from vsc22_submission_b200 import search
-    lvd = search.low_var_dim(Z_shard) if world == 1 else _global_low_var_dim(Z_shard)
+    lvd = search.low_var_dim_device(Z_shard) if world == 1 else _global_low_var_dim(Z_shard)
     z_t = search.sn_transform(Z_shard, lvd, True, fill=0.0)
     q_0 = search.sn_transform(Q, lvd, True, fill=0.0)
     zi = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)

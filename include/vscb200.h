@@ -113,6 +113,12 @@ int vscb200_index_video_pair_results(vscb200_index* ix, float* scores, int64_t* 
  * or, when bias_dev != NULL, bias_dev[row] (queries, :96-97).  x: [n, d] -> out: [n, d]. */
 int vscb200_sn_transform(const float* x_dev, int64_t n, int d, int drop_dim, int l2_normalize, float fill,
                          const float* bias_dev, float* out_dev, void* stream);
+/* the same with the dropped column read from device memory (*drop_dim_dev written by vscb200_low_var_dim_dev earlier in
+ * the stream): the whole score-normalisation chain is enqueued without a host round trip.  Output has d columns. */
+int vscb200_sn_transform_dev(const float* x_dev, int64_t n, int d, const int* drop_dim_dev, int l2_normalize, float fill,
+                             const float* bias_dev, float* out_dev, void* stream);
+/* column variance argmin left in device memory (*dim_dev, int32), no synchronisation */
+int vscb200_low_var_dim_dev(const float* x_dev, int64_t n, int d, int* dim_dev, void* stream);
 /* column variance argmin of a [n, d] matrix (score_normalization.py:72), result to *dim_host */
 int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, void* stream);
 /* bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96) */

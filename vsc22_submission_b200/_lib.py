@@ -66,6 +66,8 @@ SIGNATURES = {
     "vscb200_index_global_video_pairs": (_i, [_p, _p, _i64, _p, _i64, C.POINTER(_i64), _p]),
     "vscb200_index_video_pair_results": (_i, [_p, _p, _p, _p, _p]),
     "vscb200_sn_transform": (_i, [_p, _i64, _i, _i, _i, _f, _p, _p, _p]),
+    "vscb200_sn_transform_dev": (_i, [_p, _i64, _i, _p, _i, _f, _p, _p, _p]),
+    "vscb200_low_var_dim_dev": (_i, [_p, _i64, _i, _p, _p]),
     "vscb200_low_var_dim": (_i, [_p, _i64, _i, C.POINTER(_i), _p]),
     "vscb200_sn_bias": (_i, [_p, _i64, _i, _i, _f, _p, _p]),
     "vscb200_vit_create": (_i, [C.POINTER(VitSpecC), _i, C.POINTER(_p)]),

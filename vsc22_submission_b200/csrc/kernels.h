@@ -34,7 +34,7 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
                 const float* qn, const float* rn, cudaStream_t stream);
 int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
 int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
-                 float* out, cudaStream_t stream);
+                 float* out, cudaStream_t stream, const int* drop_dim_dev = nullptr);
 // row r = S + r*ldS, element i of a row at [i*es] (es = 1: dense rows; es > 1: a column of a row-major matrix)
 int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
               int64_t id_offset, cudaStream_t stream, int64_t es = 1);

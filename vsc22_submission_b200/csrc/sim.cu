@@ -106,11 +106,15 @@ int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream
 // ------------------------------------------------------------------ score-normalisation prologue
 // out[row] = [ l2norm(x[row] without column drop_dim) , last ]   (score_normalization.py:73-83,96-101)
 // sklearn.normalize semantics: zero rows stay zero.  Norm accumulated in fp32 like sklearn (float32 in).
+// drop_dim_dev != nullptr: the dropped column is read from device memory (written by var_argmin_kernel earlier in the
+// stream), so the whole score-normalisation chain is enqueued without a host round trip.
 __global__ void sn_transform_kernel(const float* __restrict__ x, int64_t n, int d, int drop_dim, int l2_normalize,
-                                    float fill, const float* __restrict__ bias, float* __restrict__ out) {
+                                    float fill, const float* __restrict__ bias, float* __restrict__ out,
+                                    const int* __restrict__ drop_dim_dev) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
+  if (drop_dim_dev) drop_dim = *drop_dim_dev;
   const float* xr = x + row * d;
   float s = 0.f;
   for (int c = lane; c < d; c += 32) {
@@ -138,11 +142,11 @@ __global__ void sn_transform_kernel(const float* __restrict__ x, int64_t n, int 
 }
 
 int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
-                 float* out, cudaStream_t stream) {
+                 float* out, cudaStream_t stream, const int* drop_dim_dev) {
   if (n == 0) return VSCB200_OK;
   VSCB_REQUIRE(drop_dim < d, "sn_transform: drop_dim out of range");
   sn_transform_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, drop_dim, l2_normalize,
-                                                                                      fill, bias, out);
+                                                                                      fill, bias, out, drop_dim_dev);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -194,7 +198,36 @@ extern "C" {
 int vscb200_sn_transform(const float* x_dev, int64_t n, int d, int drop_dim, int l2_normalize, float fill,
                          const float* bias_dev, float* out_dev, void* stream) {
   return vscb200::sn_transform(x_dev, n, d, drop_dim, l2_normalize, fill, bias_dev, out_dev,
-                               static_cast<cudaStream_t>(stream));
+                               static_cast<cudaStream_t>(stream), nullptr);
+}
+
+int vscb200_sn_transform_dev(const float* x_dev, int64_t n, int d, const int* drop_dim_dev, int l2_normalize, float fill,
+                             const float* bias_dev, float* out_dev, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(drop_dim_dev, "sn_transform_dev: null drop_dim_dev");
+  return vscb200::sn_transform(x_dev, n, d, 0, l2_normalize, fill, bias_dev, out_dev, static_cast<cudaStream_t>(stream),
+                               drop_dim_dev);
+}
+
+int vscb200_low_var_dim_dev(const float* x_dev, int64_t n, int d, int* dim_dev, void* stream_v) {
+  using namespace vscb200;
+  VSCB_REQUIRE(n > 0 && d > 0 && dim_dev, "low_var_dim_dev: empty input");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  double* sums = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&sums), sizeof(double) * 2 * d, stream);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream);
+  dim3 grid((d + 31) / 32, static_cast<unsigned>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048)));
+  col_moments_kernel<<<grid, dim3(32, 8), 0, stream>>>(x_dev, n, d, sums);
+  var_argmin_kernel<<<1, 1, 0, stream>>>(sums, n, d, dim_dev);
+  count_launch(2);
+  pool_free(sums, stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error(std::string("low_var_dim_dev: ") + cudaGetErrorString(e));
+    return VSCB200_ERR_CUDA;
+  }
+  return VSCB200_OK;
 }
 
 int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream) {

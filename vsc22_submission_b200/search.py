@@ -154,12 +154,30 @@ def low_var_dim(noise: torch.Tensor) -> int:
     return int(out.value)
 
 
-def sn_transform(x: torch.Tensor, drop_dim: int, l2_normalize: bool, fill: float = 0.0,
+def low_var_dim_device(noise: torch.Tensor) -> torch.Tensor:
+    """``low_var_dim`` left on the device (int32 tensor [1]) -- no host synchronisation; feed it to ``sn_transform``."""
+    noise = _f32_cuda(noise, "low_var_dim_device")
+    out = torch.empty((1,), dtype=torch.int32, device=noise.device)
+    with torch.cuda.device(noise.device):
+        _lib.check(_lib.lib().vscb200_low_var_dim_dev(_p(noise), noise.shape[0], noise.shape[1], _p(out),
+                                                      _stream(noise.device)), "low_var_dim_dev")
+    return out
+
+
+def sn_transform(x: torch.Tensor, drop_dim, l2_normalize: bool, fill: float = 0.0,
                  bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[l2norm(delete(x, drop_dim)), last] in one pass (score_normalization.py:73-83, 96-101).
-    drop_dim < 0: nothing dropped, output gains a column."""
+    drop_dim < 0: nothing dropped, output gains a column.  ``drop_dim`` may be the device tensor of
+    ``low_var_dim_device`` (a column is always dropped then)."""
     x = _f32_cuda(x, "sn_transform")
     n, d = x.shape
+    if isinstance(drop_dim, torch.Tensor):
+        out = torch.empty((n, d), dtype=torch.float32, device=x.device)
+        if n:
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.lib().vscb200_sn_transform_dev(_p(x), n, d, _p(drop_dim), int(bool(l2_normalize)), float(fill),
+                                                               _p(bias), _p(out), _stream(x.device)), "sn_transform_dev")
+        return out
     dout = d if 0 <= drop_dim < d else d + 1
     out = torch.empty((n, dout), dtype=torch.float32, device=x.device)
     if n:
@@ -194,7 +212,7 @@ def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch
     """Array form of score_normalize: -> (q' , r' or None, low_var_dim)."""
     lvd = -1
     if replace_dim:
-        lvd = low_var_dim(z) if low_var_dim_ is None else int(low_var_dim_)
+        lvd = low_var_dim_device(z) if low_var_dim_ is None else int(low_var_dim_)    # stays on the device: no sync
     # the noise search ignores the appended column (0 on both sides)
     z_t = sn_transform(z, lvd, l2_normalize, fill=0.0)
     q_0 = sn_transform(q, lvd, l2_normalize, fill=0.0)
