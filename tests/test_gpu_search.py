@@ -328,3 +328,7 @@ def test_query_and_ref_score_normalize_match_oracle():
     got_r = np.concatenate([v.feature for v in search.ref_score_normalize(r, z)])
     ref_r, _ = score_norm_np.ref_score_normalize(ra, za)
     np.testing.assert_allclose(got_r, ref_r, rtol=2e-5, atol=2e-6)
+    # matching-track signature (M/infer/infer_matching.py:213): (queries, refs, low_var_dim, beta=1.5, nk=10), no gate
+    got_m = np.concatenate([v.feature for v in search.query_score_normalize(q, z, 7, beta=1.5, nk=10)])
+    ref_m = score_norm_np.query_score_normalize(qa, za, np.zeros(90, bool), low_var_dim_=7, beta=1.5, nk=10)
+    np.testing.assert_allclose(got_m, ref_m, rtol=2e-5, atol=2e-5)

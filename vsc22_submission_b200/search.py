@@ -284,15 +284,22 @@ def score_normalize(queries, refs, score_norm_refs, l2_normalize: bool = True, r
     return _split(queries, _to_host(q_t, "qo")), _split(refs, _to_host(r_t, "ro"))
 
 
-def query_score_normalize(queries, score_norm_refs, video_scores: dict, score_threshold: float = 0.001,
+def query_score_normalize(queries, score_norm_refs, video_scores=None, score_threshold: float = 0.001,
                           low_var_dim: int = 0, l2_normalize: bool = True, replace_dim: bool = True,
                           beta: float = 1.0, nk: int = 1, device="cuda"):
-    """score_normalization.py:107-148 (video-score gate: bias = -100 below the threshold, :142-143)."""
+    """Descriptor track: score_normalization.py:107-148 ``(queries, score_norm_refs, video_scores, score_threshold,
+    low_var_dim, ...)`` with the video-score gate (bias = -100 below the threshold, :142-143).
+    Matching track: M/infer/vsc/baseline/score_normalization.py:107-145 ``(queries, score_norm_refs, low_var_dim, ...)``
+    -- no gate; recognised by the third argument being an integer (infer_matching.py:213)."""
+    if video_scores is not None and not isinstance(video_scores, dict):
+        low_var_dim, video_scores = int(video_scores), None
     dev = torch.device(device)
-    gated = np.concatenate([np.full(q.feature.shape[0], video_scores[q.video_id] < score_threshold) for q in queries])
+    gated = None
+    if video_scores is not None:
+        gated = torch.from_numpy(np.concatenate([np.full(q.feature.shape[0], video_scores[q.video_id] < score_threshold)
+                                                 for q in queries]))
     q_t, _, _ = score_normalize_tensors(_cat(queries, dev, "q"), None, _cat(score_norm_refs, dev, "z"), l2_normalize,
-                                        replace_dim, beta, nk, low_var_dim_=low_var_dim,
-                                        gated_rows=torch.from_numpy(gated))
+                                        replace_dim, beta, nk, low_var_dim_=low_var_dim, gated_rows=gated)
     return _split(queries, _to_host(q_t, "qo"))
 
 
