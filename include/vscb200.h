@@ -199,6 +199,10 @@ int vscb200_swin_out_dim(const vscb200_swin* m);
  * ---------------------------------------------------------------------------------------------- */
 int vscb200_ensemble_pca(const float* const* parts_dev, const int* dims, int n_parts, int64_t n, const float* mean_dev,
                          const float* components_dev, int out_dim, float* out_dev, void* stream);
+/* Near-duplicate frame filter of ONE query video (extract_query_feats.py:190-200): keep_dev[i] = 0 for every frame
+ * removed by the greedy sweep over frames in descending mean-similarity order (threshold FRAME_THRESHOLD = 0.975 in the
+ * reference).  feat_dev: [n, d] float32 (rows are normalised inside), n <= 4096. */
+int vscb200_near_dup_keep(const float* feat_dev, int64_t n, int d, double threshold, uint8_t* keep_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Candidate-pair frame-similarity matrices: `np.matmul(a, b.T)` (+ similarity_bias) of

@@ -332,3 +332,31 @@ def test_query_and_ref_score_normalize_match_oracle():
     got_m = np.concatenate([v.feature for v in search.query_score_normalize(q, z, 7, beta=1.5, nk=10)])
     ref_m = score_norm_np.query_score_normalize(qa, za, np.zeros(90, bool), low_var_dim_=7, beta=1.5, nk=10)
     np.testing.assert_allclose(got_m, ref_m, rtol=2e-5, atol=2e-5)
+
+
+def test_near_duplicate_frame_filter_and_query_tail():
+    """ensemble.near_dup_keep / query_tail (extract_query_feats.py:169-204) against the oracle (pinned to the reference's
+    own source lines in tests/test_oracle_near_dup.py)."""
+    import torch
+    from oracle import near_dup_np, pca_np
+    from test_oracle_near_dup import videos
+    from vsc22_submission_b200.ensemble import B200PCA, near_dup_keep, query_tail
+    vids = videos()
+    for x in vids[:-1]:
+        keep = near_dup_keep(torch.from_numpy(x).cuda()).cpu().numpy()
+        assert np.flatnonzero(keep).tolist() == near_dup_np.keep_indices(x)
+    keep = np.flatnonzero(near_dup_keep(torch.from_numpy(vids[-1]).cuda()).cpu().numpy())
+    assert len(keep) == 3 and len({k // 5 for k in keep}) == 3            # exact duplicates: one frame per group survives
+    assert near_dup_keep(torch.zeros((0, 8), device="cuda")).shape == (0,)
+    rng = np.random.default_rng(8)
+    parts = [rng.standard_normal((40, 64)).astype(np.float32) * (i + 1) for i in range(4)]
+    for p in parts:
+        p[10:14] = p[9] + 0.01 * rng.standard_normal((4, 64)).astype(np.float32)   # a static shot
+    mean = (rng.standard_normal(256) * 0.01).astype(np.float32)
+    comp = np.linalg.qr(rng.standard_normal((256, 32)))[0].T.astype(np.float32)
+    feats, idx = query_tail(B200PCA(mean, comp), [torch.from_numpy(p).cuda() for p in parts])
+    cat = np.concatenate([p / np.linalg.norm(p, axis=1, keepdims=True) for p in parts], axis=1)
+    want_idx = near_dup_np.keep_indices(cat)
+    assert idx.cpu().tolist() == want_idx and len(want_idx) < 40
+    ref = pca_np.ensemble_pca([p[want_idx] for p in parts], mean, comp)
+    assert np.abs(feats.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())

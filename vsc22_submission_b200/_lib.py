@@ -83,6 +83,7 @@ SIGNATURES = {
     "vscb200_swin_forward_host": (_i, [_p, _p, _i64, _p]),
     "vscb200_swin_out_dim": (_i, [_p]),
     "vscb200_ensemble_pca": (_i, [_p, _p, _i, _i64, _p, _p, _i, _p, _p]),
+    "vscb200_near_dup_keep": (_i, [_p, _i64, _i, C.c_double, _p, _p]),
     "vscb200_pair_sims": (_i, [_p, _p, _i, _i64, _p, _p, _p, _p, _p, _f, _p, _p]),
     "vscb200_pair_topk": (_i, [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p]),
     "vscb200_pair_segment_images": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),

@@ -39,9 +39,91 @@ ensemble_center_kernel(EnsParts parts, const float* __restrict__ mean, float* __
   }
 }
 
+// ---- near-duplicate frame filter of one query video (extract_query_feats.py:190-200, infer_matching.py query side) -------
+// feat = rows / ||row||; sim = feat feat^T - I (float64 from float32 products, as numpy promotes it); frames are visited
+// by descending column mean of sim; a visited frame that is still alive removes every frame whose similarity to it
+// exceeds the threshold.  One CTA: means -> ranks -> the greedy sweep (sequential in the visiting order by definition).
+__global__ void __launch_bounds__(256)
+row_normalize_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* src = x + row * d;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) { const float v = src[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = sqrtf(ss);
+  for (int c = lane; c < d; c += 32) out[row * d + c] = src[c] / nrm;
+}
+
+constexpr int kDupMaxFrames = 4096;
+
+__global__ void __launch_bounds__(1024)
+near_dup_kernel(const float* __restrict__ sim, int n, double thr, double* __restrict__ mean, int* __restrict__ order,
+                uint8_t* __restrict__ keep) {
+  __shared__ uint8_t removed[kDupMaxFrames];
+  __shared__ int alive;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += static_cast<double>(sim[static_cast<int64_t>(i) * n + j]) - (i == j ? 1.0 : 0.0);
+    mean[j] = sum / n;
+    removed[j] = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double mi = mean[i];
+    int pos = 0;                                   // argsort()[::-1]: descending, equal values by descending index
+    for (int j = 0; j < n; ++j) pos += (mean[j] > mi || (mean[j] == mi && j > i)) ? 1 : 0;
+    order[pos] = i;
+  }
+  __syncthreads();
+  for (int p = 0; p < n; ++p) {
+    const int i = order[p];
+    if (threadIdx.x == 0) alive = removed[i] ? 0 : 1;
+    __syncthreads();
+    if (alive) {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double v = static_cast<double>(sim[static_cast<int64_t>(i) * n + j]) - (i == j ? 1.0 : 0.0);
+        if (v > thr) removed[j] = 1;
+      }
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) keep[j] = removed[j] ? 0 : 1;
+}
+
 }  // namespace vscb200
 
 using namespace vscb200;
+
+extern "C" int vscb200_near_dup_keep(const float* feat_dev, int64_t n, int d, double threshold, uint8_t* keep_dev,
+                                     void* stream_v) {
+  VSCB_REQUIRE(n >= 0 && d > 0, "near_dup_keep: bad shape");
+  if (n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(feat_dev && keep_dev, "near_dup_keep: null argument");
+  VSCB_REQUIRE(n <= kDupMaxFrames, "near_dup_keep: more than 4096 frames in one video");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_v);
+  float* fn = nullptr;
+  const size_t bytes = static_cast<size_t>(n) * d * sizeof(float) + static_cast<size_t>(n) * n * sizeof(float) +
+                       static_cast<size_t>(n) * (sizeof(double) + sizeof(int)) + 64;
+  int rc = pool_alloc(reinterpret_cast<void**>(&fn), bytes, s);
+  if (rc) return rc;
+  float* sim = fn + n * d;
+  double* mean = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sim + n * n) + 15) & ~uintptr_t(15));
+  int* order = reinterpret_cast<int*>(mean + n);
+  row_normalize_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(feat_dev, n, d, fn);
+  count_launch();
+  rc = scores_simt(fn, fn, sim, n, n, d, n, false, nullptr, nullptr, s);
+  if (rc == VSCB200_OK) {
+    near_dup_kernel<<<1, 1024, 0, s>>>(sim, static_cast<int>(n), threshold, mean, order, keep_dev);
+    count_launch();
+  }
+  pool_free(fn, s);
+  if (rc) return rc;
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
 
 extern "C" int vscb200_ensemble_pca(const float* const* parts_dev, const int* dims, int n_parts, int64_t n,
                                     const float* mean_dev, const float* components_dev, int out_dim, float* out_dev,

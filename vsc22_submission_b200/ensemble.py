@@ -64,3 +64,28 @@ class B200PCA:
     def transform_parts_host(self, parts: Sequence[np.ndarray]) -> np.ndarray:
         dev = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).to(self.device) for p in parts]
         return self._run(dev).cpu().numpy()
+
+
+def near_dup_keep(features: torch.Tensor, threshold: float = 0.975) -> torch.Tensor:
+    """Near-duplicate frame filter of one query video (D/infer/extract_query_feats.py:190-200, ``FRAME_THRESHOLD``):
+    bool CUDA mask [n] of the frames that survive -- ``to_keep_idx`` of the reference as a mask."""
+    if not isinstance(features, torch.Tensor) or not features.is_cuda:
+        raise RuntimeError("near_dup_keep: expected a CUDA tensor (no CPU fallback)")
+    x = features.contiguous().float()
+    keep = torch.empty((x.shape[0],), dtype=torch.uint8, device=x.device)
+    if x.shape[0]:
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(_lib.lib().vscb200_near_dup_keep(C.c_void_p(x.data_ptr()), x.shape[0], x.shape[1], float(threshold),
+                                                        C.c_void_p(keep.data_ptr()), C.c_void_p(stream)), "near_dup_keep")
+    return keep.bool()
+
+
+def query_tail(pca: B200PCA, parts: Sequence[torch.Tensor], frame_threshold: float = 0.975):
+    """The descriptor tail of ``Main.process`` for a query video that passed the video-score gate
+    (extract_query_feats.py:169-204): per-model normalize -> concat -> drop near-duplicate frames -> PCA.
+    Returns (features [n_kept, n_components] CUDA, kept frame indices int64 CUDA)."""
+    normed = [torch.nn.functional.normalize(p.float(), dim=1) for p in parts]         # sklearn normalize per model
+    keep = near_dup_keep(torch.cat(normed, dim=1), frame_threshold)
+    idx = torch.nonzero(keep).flatten()
+    return pca.transform_parts([p[idx] for p in parts]), idx
