@@ -135,12 +135,16 @@ gt_hist_kernel(GtBlock a, const float* __restrict__ bufv, int64_t nbuf, int leve
     if (h[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(h[i]));
 }
 
-// ---- emit: append the survivors of one score block (warp-aggregated) -----------------------------------------
+// ---- emit: append the survivors of one score block -----------------------------------------------------------
+// One atomicAdd on the global counter per CTA and work item (4096 scores): under a loose bootstrap radius a block emits
+// ~10^6 survivors, and per-warp atomics on the one counter address (~1 per ns) were the whole cost of the pass.
 // The counter keeps counting past `cap`, so the host sees by how much a block overflowed.
 __global__ void __launch_bounds__(kGtThreads)
 gt_emit_kernel(GtBlock a, int64_t ntotal, float* __restrict__ bufv, uint64_t* __restrict__ bufp,
                unsigned long long* __restrict__ counter, unsigned long long cap) {
-  const int lane = threadIdx.x & 31;
+  __shared__ int warp_cnt[kGtThreads / 32];
+  __shared__ unsigned long long cta_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t chunks = (a.n + kGtChunk - 1) / kGtChunk;
   const int64_t work = a.nb * chunks;
   for (int64_t w = blockIdx.x; w < work; w += gridDim.x) {
@@ -150,62 +154,65 @@ gt_emit_kernel(GtBlock a, int64_t ntotal, float* __restrict__ bufv, uint64_t* __
     const uint64_t pbase = static_cast<uint64_t>(a.q0 + row) * static_cast<uint64_t>(ntotal) + static_cast<uint64_t>(c0);
     const int cnt = a.n - c0 < kGtChunk ? static_cast<int>(a.n - c0) : kGtChunk;
     // one work item = 4096 columns = 4 float4 per thread: all loads are issued before any is consumed
-    float4 ld[4];
+    float v[16];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = (u * kGtThreads + threadIdx.x) * 4;
-      ld[u] = j + 3 < cnt ? *reinterpret_cast<const float4*>(p + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u4 = 0; u4 < 4; ++u4) {
-      const int j = (u4 * kGtThreads + threadIdx.x) * 4;
-      if (u4 * kGtThreads * 4 >= cnt) break;
-      float v[4] = {ld[u4].x, ld[u4].y, ld[u4].z, ld[u4].w};
-      bool hit[4];
       if (j + 3 < cnt) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) hit[u] = better(v[u], thr, a.keep_max);
+        const float4 t = *reinterpret_cast<const float4*>(p + j);
+        v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
       } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v[u] = j + u < cnt ? p[j + u] : 0.f;
-          hit[u] = j + u < cnt && better(v[u], thr, a.keep_max);
-        }
+        for (int e = 0; e < 4; ++e) v[4 * u + e] = j + e < cnt ? p[j + e] : (a.keep_max ? -INFINITY : INFINITY);
       }
-      const int mine = int(hit[0]) + int(hit[1]) + int(hit[2]) + int(hit[3]);
-      if (__ballot_sync(0xffffffffu, mine > 0) == 0u) continue;
-      int incl = mine;                                   // warp inclusive scan of the per-thread hit counts
+    }
+    uint32_t hits = 0;                                   // bit 4u+e: element e of load u survives
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(counter, static_cast<unsigned long long>(total));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      unsigned long long pos = base + static_cast<unsigned long long>(incl - mine);
+    for (int e = 0; e < 16; ++e) hits |= better(v[e], thr, a.keep_max) ? (1u << e) : 0u;
+    const int mine = __popc(hits);
+    int incl = mine;                                     // warp inclusive scan of the per-thread survivor counts
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (hit[u]) {
-          if (pos < cap) { bufv[pos] = v[u]; bufp[pos] = pbase + static_cast<uint64_t>(j + u); }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_cnt[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int total = 0;
+#pragma unroll
+      for (int i = 0; i < kGtThreads / 32; ++i) { const int c = warp_cnt[i]; warp_cnt[i] = total; total += c; }
+      cta_base = total ? atomicAdd(counter, static_cast<unsigned long long>(total)) : 0ull;
+    }
+    __syncthreads();
+    if (mine) {
+      unsigned long long pos = cta_base + static_cast<unsigned long long>(warp_cnt[warp] + incl - mine);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (hits & (1u << e)) {
+          const int j = ((e >> 2) * kGtThreads + threadIdx.x) * 4 + (e & 3);
+          if (pos < cap) { bufv[pos] = v[e]; bufp[pos] = pbase + static_cast<uint64_t>(j); }
           ++pos;
         }
       }
     }
+    __syncthreads();                                     // warp_cnt / cta_base are reused by the next work item
   }
 }
 
-// ---- bootstrap sample: every 64th score of the block (column offset rotated per row), for a first radius estimate
+// ---- bootstrap sample: 1/64 of the block's scores for a first radius estimate -- runs of 64 consecutive scores (256 B:
+// whole sectors) out of every 4096, the run's position inside its 4096 rotated from row to row
 constexpr int kGtSampleStride = 64;
+constexpr int kGtSampleRun = 64;
 __global__ void __launch_bounds__(kGtThreads)
 gt_sample_kernel(const float* __restrict__ S, int64_t ldS, int64_t nb, int64_t n, int64_t per_row, int keep_max,
                  float* __restrict__ out) {
   const int64_t total = nb * per_row;
+  constexpr int64_t span = static_cast<int64_t>(kGtSampleStride) * kGtSampleRun;      // 4096
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * kGtThreads) {
     const int64_t row = i / per_row, t = i % per_row;
-    const int64_t col = (row * 17) % kGtSampleStride + t * kGtSampleStride;
+    const int64_t col = (t / kGtSampleRun) * span + (row * kGtSampleRun) % span + t % kGtSampleRun;
     out[i] = col < n ? S[row * ldS + col] : (keep_max ? -INFINITY : INFINITY);
   }
 }
@@ -439,7 +446,7 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (n + 3) & ~3ll;
   if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s))) return rc;
-  const int64_t per_row = (n + kGtSampleStride - 1) / kGtSampleStride;
+  const int64_t per_row = ((n + kGtSampleStride * kGtSampleRun - 1) / (kGtSampleStride * kGtSampleRun)) * kGtSampleRun;
   float* sample = nullptr;
 
   unsigned long long count = 0;     // host mirror of the buffer fill
