@@ -429,48 +429,6 @@ def bench_sim(args, world, rank, peaks):
     host_probe = {"torch_empty_us": (t1 - t0) / 200 * 1e6, "tiny_launch_us": (t2 - t1) / 200 * 1e6}
     _lib.prof_collect()
     n0 = _lib.launch_count()
-    def _diag(tag):
-        from vsc22_submission_b200 import search as S
-        st = torch.cuda.memory_stats()
-        free_b, total_b = torch.cuda.mem_get_info()
-        print(f"DIAG {tag} mem reserved={torch.cuda.memory_reserved() >> 20}MB allocated={torch.cuda.memory_allocated() >> 20}MB "
-              f"dev_free={free_b >> 20}MB retries={st.get('num_alloc_retries')} segments={st.get('segment.all.current')} "
-              f"device_allocs={st.get('num_device_alloc')} device_frees={st.get('num_device_free')}", file=sys.stderr)
-        ts = []
-        keepalive = []
-        for _ in range(4):
-            t0 = time.perf_counter()
-            keepalive.append(torch.empty(100 << 20, dtype=torch.uint8, device=dev))
-            ts.append(round((time.perf_counter() - t0) * 1e6))
-        del keepalive
-        print(f"DIAG {tag} fresh 100MB torch.empty us: {ts}", file=sys.stderr)
-        for rep in range(2):
-            marks = []
-            def tick(name):
-                marks.append((name, time.perf_counter()))
-            flush.zero_()
-            torch.cuda.synchronize()
-            e0.record()
-            tick("start")
-            lvd = S.low_var_dim_device(Z_s); tick("lvd")
-            z_t = S.sn_transform(Z_s, lvd, True, fill=0.0); tick("sn_z")
-            q_0 = S.sn_transform(Q, lvd, True, fill=0.0); tick("sn_q")
-            zi = S.DeviceIndex(SIM_D, S.METRIC_INNER_PRODUCT); tick("create")
-            zi.add(z_t); tick("add")
-            Dz, _ = zi.search(q_0, 1); tick("search1")
-            bias = S.bias_from_topk(Dz, 1.2, 1); tick("bias")
-            q_t = S.sn_transform(Q, lvd, True, bias=bias); tick("sn_q2")
-            r_t = S.sn_transform(R_s, lvd, True, fill=1.0); tick("sn_r")
-            ri = S.DeviceIndex(SIM_D, S.METRIC_INNER_PRODUCT); tick("create2")
-            ri.add(r_t); tick("add2")
-            D2, I2 = ri.search(q_t, SIM_K); tick("search10")
-            del zi, ri; tick("del")
-            e1.record()
-            torch.cuda.synchronize(); tick("sync")
-            print(f"DIAG {tag} gpu={e0.elapsed_time(e1):.2f}ms " +
-                  " ".join(f"{n}={1e6 * (t - marks[i][1]):.0f}us" for i, (n, t) in enumerate(marks[1:])), file=sys.stderr)
-    if os.environ.get("VSCB200_BENCH_DIAG"):
-        _diag("pre")
     total, host_issue, step_ms = 0.0, 0.0, []
     for _ in range(args.steps):
         flush.zero_()
@@ -483,8 +441,6 @@ def bench_sim(args, world, rank, peaks):
         torch.cuda.synchronize()
         total += e0.elapsed_time(e1)
         step_ms.append(round(e0.elapsed_time(e1), 3))
-    if os.environ.get("VSCB200_BENCH_DIAG"):
-        _diag("post")
     barrier_sync(world)
     ms = max_over_ranks(total, world) / args.steps
     launches = _lib.launch_count() - n0

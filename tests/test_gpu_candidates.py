@@ -65,6 +65,8 @@ def _global(ix, q, k=0, thr=None):
     (300, 5000, 64, 700, 1, 1),         # same under L2 (smaller = better)
     (1500, 20000, 512, 30000, 0, 16),   # 8 blocks, K > rows: many survivors per row
     (257, 4099, 20, 1, 0, 1),           # K = 1, ragged sizes, d not a multiple of 8
+    (2000, 20000, 64, 7, 0, None),      # tiny K on one 40 M-pair block: radius bootstrapped from the 1/64 sample
+    (2000, 20000, 64, 7, 1, None),
 ])
 def test_global_topk_matches_oracle(monkeypatch, nq, nr, d, k, metric, ws_mb):
     import torch

@@ -523,8 +523,8 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
       // 4K entries of the block should exceed -- emit under it, then VERIFY below (the K-th best survivor must not be
       // worse than the estimate, otherwise pairs between the two were never emitted and the exact select runs instead).
       const int64_t ns = nb * per_row;
-      const uint64_t want_s = (4 * K) / kGtSampleStride;
-      if (want_s >= 16 && static_cast<uint64_t>(ns) > 4 * want_s) {
+      const uint64_t want_s = std::max<uint64_t>((4 * K) / kGtSampleStride, 16);     // >= ~1000 pairs even for a tiny K
+      if (static_cast<uint64_t>(ns) > 4 * want_s) {
         if (!sample && (rc = sc.get(&sample, static_cast<size_t>(blk) * per_row * sizeof(float)))) return rc;
         gt_sample_kernel<<<grid_for((ns + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(ix->ws, ldS, nb, n, per_row,
                                                                                           keep_max ? 1 : 0, sample);
