@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "host_util.h"
@@ -92,15 +93,66 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
   return VSCB200_OK;
 }
 
-int flush_pending(vscb200_index* ix, cudaStream_t s) {
-  ix->last_stream = s;
-  if (ix->pending.empty()) return VSCB200_OK;
-  const int64_t n = static_cast<int64_t>(ix->pending.size()) / ix->d;
-  int rc = append_rows(ix, ix->pending.data(), n, cudaMemcpyHostToDevice, s);
-  if (rc) return rc;
-  VSCB_CUDA_OK(cudaStreamSynchronize(s));   // the host vector is released next
-  std::vector<float>().swap(ix->pending);
+// ---- host rows on their way to the device ------------------------------------------------------------------------
+// The reference adds one video (~30 rows) at a time (vsc/index.py:87-94).  Rows are packed into one of two process-wide
+// page-locked 8 MB slots; a full slot (or the next search / add on this index) is uploaded asynchronously on the index's
+// own stream while the host fills the other slot -- no growing host vector, no pageable copies, no launch per video.
+namespace {
+struct StageSlot { float* p = nullptr; cudaEvent_t ev = nullptr; };
+constexpr size_t kStageBytes = 8u << 20;
+std::mutex g_stage_mu;
+StageSlot g_stage[2];
+int g_stage_cur = 0;
+vscb200_index* g_stage_owner = nullptr;      // the index whose rows sit in the current slot
+int64_t g_stage_rows = 0;
+
+int stage_init() {
+  for (StageSlot& sl : g_stage) {
+    if (!sl.p) {
+      VSCB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&sl.p), kStageBytes));
+      VSCB_CUDA_OK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    }
+  }
   return VSCB200_OK;
+}
+
+// all work on an index is ordered, whatever stream each call arrives on
+int order_stream(vscb200_index* ix, cudaStream_t s) {
+  if (ix->has_stream && ix->last_stream != s) {
+    if (!ix->order_ev) VSCB_CUDA_OK(cudaEventCreateWithFlags(&ix->order_ev, cudaEventDisableTiming));
+    VSCB_CUDA_OK(cudaEventRecord(ix->order_ev, ix->last_stream));
+    VSCB_CUDA_OK(cudaStreamWaitEvent(s, ix->order_ev, 0));
+  }
+  ix->last_stream = s;
+  ix->has_stream = true;
+  return VSCB200_OK;
+}
+
+// g_stage_mu held: upload the rows staged for `ix` on its own stream and move on to the other slot
+int stage_submit(vscb200_index* ix) {
+  if (g_stage_owner != ix || g_stage_rows == 0) return VSCB200_OK;
+  cudaStream_t s;
+  int rc = own_stream(ix, &s);
+  if (rc) return rc;
+  if ((rc = order_stream(ix, s))) return rc;
+  StageSlot& sl = g_stage[g_stage_cur];
+  const int64_t rows = g_stage_rows;
+  g_stage_rows = 0;
+  g_stage_owner = nullptr;
+  g_stage_cur ^= 1;
+  if ((rc = append_rows(ix, sl.p, rows, cudaMemcpyHostToDevice, s))) return rc;
+  VSCB_CUDA_OK(cudaEventRecord(sl.ev, s));        // the slot is free again once this copy has run
+  return VSCB200_OK;
+}
+}  // namespace
+
+int flush_pending(vscb200_index* ix, cudaStream_t s) {
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    int rc = stage_submit(ix);
+    if (rc) return rc;
+  }
+  return order_stream(ix, s);
 }
 
 int64_t block_rows(const vscb200_index* ix, int64_t nq) {
@@ -164,6 +216,10 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
 
 void vscb200_index_destroy(vscb200_index* ix) {
   if (!ix) return;
+  {
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (g_stage_owner == ix) { g_stage_owner = nullptr; g_stage_rows = 0; }      // rows never searched: dropped
+  }
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
   void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
@@ -175,6 +231,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   }
   for (void* b : blocks) pool_free(b, s);
   if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+  if (ix->order_ev) cudaEventDestroy(ix->order_ev);
   delete ix;
 }
 
@@ -190,21 +247,41 @@ int vscb200_index_add(vscb200_index* ix, const float* x_dev, int64_t n, void* st
 int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n) {
   VSCB_REQUIRE(ix && (n == 0 || x_host), "index_add_host: null argument");
   VSCB_REQUIRE(n >= 0, "index_add_host: negative row count");
-  // The reference adds one video (~30 rows) at a time (vsc/index.py:87-94): rows are staged on the
-  // host and uploaded in ONE copy at the next search.
-  ix->pending.insert(ix->pending.end(), x_host, x_host + n * ix->d);
+  const size_t row_bytes = static_cast<size_t>(ix->d) * sizeof(float);
+  VSCB_REQUIRE(row_bytes <= kStageBytes, "index_add_host: descriptor dimension too large");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  int rc = stage_init();
+  if (rc) return rc;
+  if (g_stage_owner && g_stage_owner != ix && (rc = stage_submit(g_stage_owner))) return rc;
+  const int64_t cap_rows = static_cast<int64_t>(kStageBytes / row_bytes);
+  while (n > 0) {
+    StageSlot& sl = g_stage[g_stage_cur];
+    if (g_stage_rows == 0) {
+      VSCB_CUDA_OK(cudaEventSynchronize(sl.ev));      // the slot's previous upload has left the host buffer
+      g_stage_owner = ix;
+    }
+    const int64_t take = std::min(n, cap_rows - g_stage_rows);
+    memcpy(sl.p + g_stage_rows * ix->d, x_host, static_cast<size_t>(take) * row_bytes);
+    g_stage_rows += take;
+    x_host += take * ix->d;
+    n -= take;
+    if (g_stage_rows == cap_rows && (rc = stage_submit(ix))) return rc;
+  }
   return VSCB200_OK;
 }
 
 int vscb200_index_reset(vscb200_index* ix) {
   VSCB_REQUIRE(ix, "index_reset: null index");
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  if (g_stage_owner == ix) { g_stage_owner = nullptr; g_stage_rows = 0; }
   ix->ntotal = 0;
-  std::vector<float>().swap(ix->pending);
   return VSCB200_OK;
 }
 
 int64_t vscb200_index_ntotal(const vscb200_index* ix) {
-  return ix ? ix->ntotal + static_cast<int64_t>(ix->pending.size()) / ix->d : 0;
+  if (!ix) return 0;
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  return ix->ntotal + (g_stage_owner == ix ? g_stage_rows : 0);
 }
 int vscb200_index_dim(const vscb200_index* ix) { return ix ? ix->d : 0; }
 int vscb200_index_metric(const vscb200_index* ix) { return ix ? ix->metric : 0; }

@@ -18,7 +18,8 @@ struct vscb200_index {
   uint16_t* bank_hi = nullptr;   // [capacity, dp] bf16(x)
   uint16_t* bank_lo = nullptr;   // [capacity, dp] bf16(x - hi)
   uint16_t* q_planes = nullptr; size_t q_planes_bytes = 0;   // hi | lo planes of the current query block
-  std::vector<float> pending;   // host rows appended by add_host, uploaded lazily in one copy
+  cudaEvent_t order_ev = nullptr;   // orders this index's work when consecutive calls arrive on different streams
+  bool has_stream = false;
   int64_t id_offset = 0;
   float* ws = nullptr;       // score workspace
   size_t ws_bytes = 0;
