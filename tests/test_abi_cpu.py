@@ -45,8 +45,13 @@ def test_argument_validation_without_gpu(lib):
     assert lib.vscb200_index_create(8, 0, C.byref(h)) == 0
     assert lib.vscb200_index_dim(h) == 8 and lib.vscb200_index_metric(h) == 0 and lib.vscb200_index_ntotal(h) == 0
     x = np.zeros((5, 8), np.float32)
-    assert lib.vscb200_index_add_host(h, x.ctypes.data_as(C.c_void_p), 5) == 0     # staged on the host
-    assert lib.vscb200_index_ntotal(h) == 5
+    import torch
+    rc = lib.vscb200_index_add_host(h, x.ctypes.data_as(C.c_void_p), 5)            # rows go to a page-locked staging slot
+    if torch.cuda.is_available():
+        assert rc == 0 and lib.vscb200_index_ntotal(h) == 5
+    else:                                           # no device: the product path fails loudly, it has no host fallback
+        assert rc == 2 and b"cudaHostAlloc" in lib.vscb200_last_error() and lib.vscb200_index_ntotal(h) == 0
+    assert lib.vscb200_index_add_host(h, None, 5) == 1                              # null rows
     assert lib.vscb200_index_search(h, None, 3, 0, None, None, None) == 1           # null pointers / bad k
     assert lib.vscb200_index_reset(h) == 0 and lib.vscb200_index_ntotal(h) == 0
     lib.vscb200_index_destroy(h)

@@ -98,7 +98,12 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
 // page-locked 8 MB slots; a full slot (or the next search / add on this index) is uploaded asynchronously on the index's
 // own stream while the host fills the other slot -- no growing host vector, no pageable copies, no launch per video.
 namespace {
-struct StageSlot { float* p = nullptr; cudaEvent_t ev = nullptr; };
+constexpr int kStageMaxDevices = 16;
+struct StageSlot {
+  float* p = nullptr;
+  cudaEvent_t ev[kStageMaxDevices] = {};     // per device: events belong to the device of the stream they are recorded on
+  int last_dev = -1;                         // device whose upload used the slot last
+};
 constexpr size_t kStageBytes = 8u << 20;
 std::mutex g_stage_mu;
 StageSlot g_stage[2];
@@ -106,13 +111,15 @@ int g_stage_cur = 0;
 vscb200_index* g_stage_owner = nullptr;      // the index whose rows sit in the current slot
 int64_t g_stage_rows = 0;
 
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int stage_init() {
-  for (StageSlot& sl : g_stage) {
-    if (!sl.p) {
-      VSCB_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&sl.p), kStageBytes));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
-    }
-  }
+  for (StageSlot& sl : g_stage)
+    if (!sl.p) VSCB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&sl.p), kStageBytes, cudaHostAllocPortable));
   return VSCB200_OK;
 }
 
@@ -131,6 +138,7 @@ int order_stream(vscb200_index* ix, cudaStream_t s) {
 // g_stage_mu held: upload the rows staged for `ix` on its own stream and move on to the other slot
 int stage_submit(vscb200_index* ix) {
   if (g_stage_owner != ix || g_stage_rows == 0) return VSCB200_OK;
+  DeviceGuard guard(ix->device);
   cudaStream_t s;
   int rc = own_stream(ix, &s);
   if (rc) return rc;
@@ -141,7 +149,10 @@ int stage_submit(vscb200_index* ix) {
   g_stage_owner = nullptr;
   g_stage_cur ^= 1;
   if ((rc = append_rows(ix, sl.p, rows, cudaMemcpyHostToDevice, s))) return rc;
-  VSCB_CUDA_OK(cudaEventRecord(sl.ev, s));        // the slot is free again once this copy has run
+  const int dev = ix->device;
+  if (!sl.ev[dev]) VSCB_CUDA_OK(cudaEventCreateWithFlags(&sl.ev[dev], cudaEventDisableTiming));
+  VSCB_CUDA_OK(cudaEventRecord(sl.ev[dev], s));   // the slot is free again once this copy has run
+  sl.last_dev = dev;
   return VSCB200_OK;
 }
 }  // namespace
@@ -202,6 +213,8 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
                "index_create: metric must be METRIC_INNER_PRODUCT or METRIC_L2");
   vscb200_index* ix = new vscb200_index();
   ix->d = d;
+  cudaGetDevice(&ix->device);
+  VSCB_REQUIRE(ix->device >= 0 && ix->device < 16, "index_create: device ordinal out of range");
   ix->dp = (d + 7) & ~7;
   ix->metric = metric;
   const char* e = getenv("VSCB200_FORCE_SIMT");
@@ -257,7 +270,7 @@ int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n) {
   while (n > 0) {
     StageSlot& sl = g_stage[g_stage_cur];
     if (g_stage_rows == 0) {
-      VSCB_CUDA_OK(cudaEventSynchronize(sl.ev));      // the slot's previous upload has left the host buffer
+      if (sl.last_dev >= 0) VSCB_CUDA_OK(cudaEventSynchronize(sl.ev[sl.last_dev]));   // its previous upload has left the host buffer
       g_stage_owner = ix;
     }
     const int64_t take = std::min(n, cap_rows - g_stage_rows);

@@ -10,6 +10,7 @@
 
 struct vscb200_index {
   int d = 0, metric = 0;
+  int device = 0;            // CUDA device the index lives on (current device at create)
   int64_t ntotal = 0;        // rows resident on the device
   int64_t capacity = 0;
   float* bank = nullptr;     // [capacity, d]

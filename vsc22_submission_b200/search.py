@@ -228,6 +228,7 @@ def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch
 # the reference's function signatures (lists of VideoFeature-like objects, numpy features)
 # ------------------------------------------------------------------------------------------------
 _PINNED = {}      # staging buffers (page-locked host memory), reused across calls: name -> uint8 tensor
+_PINNED_EV = {}   # name -> event recorded after the last upload from that buffer
 
 
 def _pinned(name: str, nbytes: int) -> torch.Tensor:
@@ -263,7 +264,9 @@ def _cat(features: Sequence, device, name: str = "cat") -> torch.Tensor:
     rows = sum(lens)
     d = int(features[0].feature.shape[1])
     stage = _pinned(name, rows * d * 4)[: rows * d * 4].view(torch.float32).view(rows, d)
-    torch.cuda.current_stream(device).synchronize()      # the previous upload from this buffer has drained
+    ev = _PINNED_EV.get(name)
+    if ev is not None:
+        ev.synchronize()                                  # the previous upload from THIS buffer has drained
     out = stage.numpy()
     offs = np.concatenate([[0], np.cumsum(lens)])
     n = len(features)
@@ -275,7 +278,11 @@ def _cat(features: Sequence, device, name: str = "cat") -> torch.Tensor:
                 out[offs[i]:offs[i + 1]] = features[i].feature
         return run
     _parallel([job(a, min(n, a + per)) for a in range(0, n, per)])
-    return stage.to(device, non_blocking=True)
+    dev_t = stage.to(device, non_blocking=True)           # overlaps with the host packing of the next list
+    ev = _PINNED_EV.get(name) or torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    _PINNED_EV[name] = ev
+    return dev_t
 
 
 def _to_host(t: torch.Tensor, name: str) -> np.ndarray:
