@@ -348,6 +348,9 @@ def test_near_duplicate_frame_filter_and_query_tail():
     keep = np.flatnonzero(near_dup_keep(torch.from_numpy(vids[-1]).cuda()).cpu().numpy())
     assert len(keep) == 3 and len({k // 5 for k in keep}) == 3            # exact duplicates: one frame per group survives
     assert near_dup_keep(torch.zeros((0, 8), device="cuda")).shape == (0,)
+    z = vids[2].copy()
+    z[3] = 0.0                                           # an all-zero descriptor: NaN similarities, must not crash
+    assert near_dup_keep(torch.from_numpy(z).cuda()).shape == (len(z),)
     rng = np.random.default_rng(8)
     parts = [rng.standard_normal((40, 64)).astype(np.float32) * (i + 1) for i in range(4)]
     for p in parts:

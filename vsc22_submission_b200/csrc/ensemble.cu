@@ -72,9 +72,14 @@ near_dup_kernel(const float* __restrict__ sim, int n, double thr, double* __rest
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double mi = mean[i];
-    int pos = 0;                                   // argsort()[::-1]: descending, equal values by descending index
-    for (int j = 0; j < n; ++j) pos += (mean[j] > mi || (mean[j] == mi && j > i)) ? 1 : 0;
+    // argsort()[::-1]: descending, equal values by descending index.  A NaN mean (an all-zero descriptor row) ranks
+    // as -inf so that the ranks stay a permutation.
+    const double mi = mean[i] == mean[i] ? mean[i] : -INFINITY;
+    int pos = 0;
+    for (int j = 0; j < n; ++j) {
+      const double mj = mean[j] == mean[j] ? mean[j] : -INFINITY;
+      pos += (mj > mi || (mj == mi && j > i)) ? 1 : 0;
+    }
     order[pos] = i;
   }
   __syncthreads();
