@@ -427,8 +427,8 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   // survivor buffers (ping-pong for compaction).  Logical bound 2K like the reference's max_results: above it the
   // radius is raised to the K-th best survivor; the physical capacity is larger so that a block emitted under a loose
   // (bootstrap) radius still fits.
-  const uint64_t logical_cap = limited ? std::min<uint64_t>(2 * K + 4096, total_pairs) : ~0ull;
-  uint64_t cap = limited ? std::min<uint64_t>(total_pairs, std::max<uint64_t>(logical_cap, std::min<uint64_t>(16 * K + (1u << 20), 1u << 27)))
+  const uint64_t logical_cap = limited ? (K > (1ull << 60) ? total_pairs : std::min<uint64_t>(2 * K + 4096, total_pairs)) : ~0ull;
+  uint64_t cap = limited ? std::min<uint64_t>(total_pairs, std::max<uint64_t>(logical_cap, (K > (1ull << 32) ? (1ull << 27) : std::min<uint64_t>(16 * K + (1u << 20), 1u << 27))))
                          : std::min<uint64_t>(total_pairs, 1u << 20);
   float* bufv[2] = {nullptr, nullptr};
   uint64_t* bufp[2] = {nullptr, nullptr};
