@@ -131,6 +131,13 @@ int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, f
  * ---------------------------------------------------------------------------------------------- */
 typedef struct vscb200_vit vscb200_vit;
 
+/* Arithmetic of the encoders' matrix products.  BF16: operands rounded to bf16 (fp32 accumulation, residual stream,
+ * LayerNorm, softmax) -- the throughput mode, equal to the matched-precision oracle within 1e-3.  FP32: every operand
+ * carried as two bf16 planes (hi + lo, 16 mantissa bits), three tcgen05 MMAs per product, attention in fp32 -- equal to
+ * the reference's fp32 modules within 1e-3 (the reference runs them without autocast: D/infer/src/extractor.py:25). */
+#define VSCB200_PRECISION_BF16 0
+#define VSCB200_PRECISION_FP32 1
+
 #define VSCB200_ACT_QUICK_GELU 0 /* clip.py:22-25 */
 #define VSCB200_ACT_GELU 1       /* timm Mlp (erf) */
 #define VSCB200_TAIL_TOKENS 0          /* [n, T, W]  (clip.py:158; caller slices [:,0]) */
@@ -147,6 +154,7 @@ typedef struct vscb200_vit_spec {
   int gem_hidden;
   float ln_eps;
   float gem_p;
+  int precision; /* VSCB200_PRECISION_* */
 } vscb200_vit_spec;
 
 int vscb200_vit_create(const vscb200_vit_spec* spec, int max_frames, vscb200_vit** out);
@@ -166,7 +174,8 @@ int64_t vscb200_vit_out_elems_per_frame(const vscb200_vit* m);
  * (A) Swin-V2 frame encoder.  Replaces the TorchScript module `swinv2_v1xx` called at
  *     D/infer/src/extractor.py:25 / D/infer/extract_query_feats.py:148 (architecture:
  *     D/train/train_v106/vsc/baseline/model_factory/backbones/swinv2.py:502-633, config_v106.py:8-24).
- *     head_dim is 32 in every stage (heads[i] * 32 == embed << i), window side 4 / 8 / 16.
+ *     head_dim is 32 in every stage (heads[i] * 32 == embed << i); window sides 4 / 8 / 16 run on the tcgen05 window
+ *     attention, any other side dividing the token map (24: SwinV2-L@384) on the fp32 kernel.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct vscb200_swin vscb200_swin;
 
@@ -179,6 +188,7 @@ typedef struct vscb200_swin_spec {
   int out_dim;
   float ln_eps;
   float gem_p;
+  int precision; /* VSCB200_PRECISION_* */
 } vscb200_swin_spec;
 
 int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_swin** out);
@@ -260,12 +270,22 @@ int vscb200_tn_box_scores(const float* sims_dev, const int64_t* s_off_dev, const
  * K % 8 == 0, N % 8 == 0; act: -1 none, VSCB200_ACT_*. */
 int vscb200_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* C, int64_t M, int N, int K,
                       int64_t lda, int64_t ldw, int64_t ldc, int epilogue, int act, void* stream);
+/* the split-bf16 (fp32-equivalent) form: A and W as hi / lo bf16 planes; a bf16 output leaves as two planes too */
+int vscb200_gemm_split(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const float* bias, void* C,
+                       void* C_lo, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int epilogue, int act,
+                       void* stream);
 int vscb200_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width,
                       float eps, int out_bf16, void* stream);
 /* qkv: [n*T, 3W] bf16 (q|k|v, heads contiguous 64-wide) -> out [n*T, W] bf16; head_dim 64 */
 int vscb200_attention(const void* qkv_bf16, void* out_bf16, int n_frames, int T, int heads, int head_dim,
                       void* stream);
 int vscb200_cast_f32_bf16(const float* x, void* y_bf16, int64_t count, void* stream);
+/* x fp32 [count] -> hi = bf16(x), lo = bf16(x - hi) */
+int vscb200_split_f32_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t count, void* stream);
+/* fp32 attention over n_segs segments of N consecutive rows (ViT frames), head_dim 32 / 64, q.k scaled by head_dim^-0.5;
+ * qkv [n_segs*N, 3*heads*head_dim] as hi (+ lo, may be NULL) planes -> out hi (+ lo) [n_segs*N, heads*head_dim] */
+int vscb200_attention_fp32(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo, int64_t n_segs, int N,
+                           int heads, int head_dim, void* stream);
 
 #ifdef __cplusplus
 }

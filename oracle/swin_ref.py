@@ -67,6 +67,8 @@ class SwinSpec:
 
 
 SWINV2_B_256 = SwinSpec()                                   # config_v106.py (swinv2_v106 / v107 / v115 checkpoints)
+SWINV2_L_384 = SwinSpec(img=384, patch=4, embed=192, depths=(2, 2, 18, 2), heads=(6, 12, 24, 48), window=24,
+                        pretrained_windows=(12, 12, 12, 6), out_dim=512)     # BASELINE configs[3]
 
 
 def param_shapes(spec: SwinSpec) -> "OrderedDict[str, tuple]":
@@ -180,26 +182,48 @@ def _unwindows(xw, ws, H, W):   # inverse (window_reverse :54-69)
     return xw.view(B, H // ws, W // ws, ws, ws, -1).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
 
 
-def window_attention(w, p: str, xw: torch.Tensor, nH: int, bias: torch.Tensor, mask):
-    """swinv2.py:147-185."""
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.bfloat16().float()
+
+
+def window_attention(w, p: str, xw: torch.Tensor, nH: int, bias: torch.Tensor, mask, r=lambda t: t, matched=False):
+    """swinv2.py:147-185.  ``matched``: operand rounding points of the CUDA encoder (see ``forward``)."""
     B_, N, C = xw.shape
     qkv_bias = torch.cat((w[p + "q_bias"], torch.zeros_like(w[p + "v_bias"]), w[p + "v_bias"]))
-    qkv = F.linear(xw, w[p + "qkv.weight"], qkv_bias).reshape(B_, N, 3, nH, -1).permute(2, 0, 3, 1, 4)
+    qkv = F.linear(r(xw), r(w[p + "qkv.weight"]), qkv_bias).reshape(B_, N, 3, nH, -1).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
-    attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
-    attn = attn * torch.clamp(w[p + "logit_scale"], max=math.log(1.0 / 0.01)).exp()
+    scale = torch.clamp(w[p + "logit_scale"], max=math.log(1.0 / 0.01)).exp()
+    if not matched:
+        attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)
+        attn = attn * scale
+    else:      # the scale rides on q before the bf16 rounding (QKV-projection epilogue of the CUDA encoder)
+        attn = r(F.normalize(q, dim=-1) * scale) @ r(F.normalize(k, dim=-1)).transpose(-2, -1)
+        v = r(v)
     attn = attn + bias.unsqueeze(0)
     if mask is not None:
         nW = mask.shape[0]
         attn = (attn.view(B_ // nW, nW, nH, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, nH, N, N)
-    attn = attn.softmax(dim=-1)
-    out = (attn @ v).transpose(1, 2).reshape(B_, N, C)
-    return F.linear(out, w[p + "proj.weight"], w[p + "proj.bias"])
+    if not matched:
+        attn = attn.softmax(dim=-1)
+        out = (attn @ v).transpose(1, 2).reshape(B_, N, C)
+    else:      # un-normalised probabilities are the bf16 operand; the row sum stays fp32
+        pr = torch.exp(attn - attn.amax(dim=-1, keepdim=True))
+        out = ((r(pr) @ v) / pr.sum(dim=-1, keepdim=True)).transpose(1, 2).reshape(B_, N, C)
+    return F.linear(r(out), r(w[p + "proj.weight"]), w[p + "proj.bias"])
 
 
-def forward(spec: SwinSpec, w: Dict[str, torch.Tensor], frames: torch.Tensor, return_tokens: bool = False):
+@torch.no_grad()
+def forward(spec: SwinSpec, w: Dict[str, torch.Tensor], frames: torch.Tensor, return_tokens: bool = False,
+            precision: str = "fp32"):
+    """``precision="fp32"``: the reference's arithmetic, bit for bit.  ``precision="bf16"``: the matched-precision oracle --
+    every matrix-product operand (patch pixels, weight matrices, projection inputs, normalised q (with its logit scale) / k,
+    v, un-normalised softmax probabilities, attention output, activated MLP hidden) rounded to bf16 where the CUDA encoder
+    rounds it; accumulators, biases, CPB bias table, residual stream, LayerNorm, softmax statistics and the tail fp32."""
+    assert precision in ("fp32", "bf16")
+    matched = precision == "bf16"
+    r = _bf16 if matched else (lambda t: t)
     eps = spec.ln_eps
-    x = F.conv2d(frames.float(), w["patch_embed.proj.weight"], w["patch_embed.proj.bias"], stride=spec.patch)
+    x = F.conv2d(r(frames.float()), r(w["patch_embed.proj.weight"]), w["patch_embed.proj.bias"], stride=spec.patch)
     x = x.flatten(2).transpose(1, 2)
     x = F.layer_norm(x, x.shape[-1:], w["patch_embed.norm.weight"], w["patch_embed.norm.bias"], eps)
     B = x.shape[0]
@@ -214,18 +238,18 @@ def forward(spec: SwinSpec, w: Dict[str, torch.Tensor], frames: torch.Tensor, re
             h = x.view(B, res, res, C)
             if shift:
                 h = torch.roll(h, shifts=(-shift, -shift), dims=(1, 2))
-            a = window_attention(w, p + "attn.", _windows(h, ws), nH, bias, mask)
+            a = window_attention(w, p + "attn.", _windows(h, ws), nH, bias, mask, r, matched)
             h = _unwindows(a, ws, res, res)
             if shift:
                 h = torch.roll(h, shifts=(shift, shift), dims=(1, 2))
             x = x + F.layer_norm(h.reshape(B, res * res, C), (C,), w[p + "norm1.weight"], w[p + "norm1.bias"], eps)
-            m = F.linear(F.gelu(F.linear(x, w[p + "mlp.fc1.weight"], w[p + "mlp.fc1.bias"])),
-                         w[p + "mlp.fc2.weight"], w[p + "mlp.fc2.bias"])
+            m = F.linear(r(F.gelu(F.linear(r(x), r(w[p + "mlp.fc1.weight"]), w[p + "mlp.fc1.bias"]))),
+                         r(w[p + "mlp.fc2.weight"]), w[p + "mlp.fc2.bias"])
             x = x + F.layer_norm(m, (C,), w[p + "norm2.weight"], w[p + "norm2.bias"], eps)
         if i + 1 < len(spec.depths):
             h = x.view(B, res, res, C)
             h = torch.cat([h[:, 0::2, 0::2], h[:, 1::2, 0::2], h[:, 0::2, 1::2], h[:, 1::2, 1::2]], -1)
-            h = F.linear(h.reshape(B, -1, 4 * C), w[f"layers.{i}.downsample.reduction.weight"])
+            h = F.linear(r(h.reshape(B, -1, 4 * C)), r(w[f"layers.{i}.downsample.reduction.weight"]))
             x = F.layer_norm(h, (2 * C,), w[f"layers.{i}.downsample.norm.weight"], w[f"layers.{i}.downsample.norm.bias"], eps)
     x = F.layer_norm(x, x.shape[-1:], w["norm.weight"], w["norm.bias"], eps)
     if return_tokens:

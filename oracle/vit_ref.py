@@ -73,6 +73,7 @@ class VitSpec:
 
 CLIP_B16_224 = VitSpec(224, 16, 768, 12, 12, tail="gem_linear")          # BASELINE config 2
 CLIP_L14_224 = VitSpec(224, 14, 1024, 24, 16, tail="tokens")             # shipped CLIP ViT-L/14
+CLIP_L16_384 = VitSpec(384, 16, 1024, 24, 16, tail="tokens")             # BASELINE configs[3] (T = 577)
 TIMM_B32_384 = VitSpec(384, 32, 768, 12, 12, patch_bias=True, pre_norm=False, act="gelu",
                        ln_eps=1e-6, tail="gem_conv_linear")              # vit_v68
 
@@ -153,14 +154,28 @@ def gem_tokens(x, p=3.0, eps=1e-6):
     return x.clamp(min=eps).pow(p).mean(dim=1).pow(1.0 / p)
 
 
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.bfloat16().float()
+
+
 @torch.no_grad()
 def forward(spec: VitSpec, w: Dict[str, torch.Tensor], frames: torch.Tensor,
-            return_tokens: bool = False) -> torch.Tensor:
-    """frames [N,3,H,W] float32 -> [N,T,W] (tail 'tokens') or [N,out_dim]."""
+            return_tokens: bool = False, precision: str = "fp32") -> torch.Tensor:
+    """frames [N,3,H,W] float32 -> [N,T,W] (tail 'tokens') or [N,out_dim].
+
+    ``precision="fp32"``: the reference's arithmetic (every op fp32).
+    ``precision="bf16"``: the MATCHED-PRECISION oracle (SURVEY.md 8d "vs oracle in matching precision"): every
+    matrix-product OPERAND is rounded to bf16 at the point where the CUDA encoder rounds it -- the patch pixels and every
+    weight matrix, the LayerNorm outputs that feed a projection, q / k / v, the un-normalised softmax probabilities
+    (the row sum stays fp32), the attention output, the activated MLP hidden -- while accumulation, biases, the residual
+    stream, LayerNorm statistics, softmax and the GeM / Linear tail stay fp32, exactly like the reference under
+    ``torch.autocast(bfloat16)`` would keep them."""
+    assert precision in ("fp32", "bf16")
+    r = _bf16 if precision == "bf16" else (lambda t: t)
     x = frames.float()
     N = x.shape[0]
     W, H, dh = spec.width, spec.heads, spec.head_dim
-    x = F.conv2d(x, w["patch_w"], w.get("patch_b"), stride=spec.patch)      # clip.py:143
+    x = F.conv2d(r(x), r(w["patch_w"]), w.get("patch_b"), stride=spec.patch)  # clip.py:143
     x = x.reshape(N, W, -1).permute(0, 2, 1)                                # :144-145
     x = torch.cat([w["cls"].expand(N, 1, W), x], dim=1)                     # :146-150
     x = x + w["pos"]                                                        # :151
@@ -170,21 +185,26 @@ def forward(spec: VitSpec, w: Dict[str, torch.Tensor], frames: torch.Tensor,
     for l in range(spec.layers):
         p = f"l{l}."
         h = F.layer_norm(x, (W,), w[p + "ln1_w"], w[p + "ln1_b"], spec.ln_eps)
-        qkv = F.linear(h, w[p + "qkv_w"], w[p + "qkv_b"]).reshape(N, T, 3, H, dh)
+        qkv = r(F.linear(r(h), r(w[p + "qkv_w"]), w[p + "qkv_b"])).reshape(N, T, 3, H, dh)
         q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))      # [N,H,T,dh]
-        att = torch.softmax((q * dh ** -0.5) @ k.transpose(-1, -2), dim=-1)
-        o = (att @ v).permute(0, 2, 1, 3).reshape(N, T, W)
-        x = x + F.linear(o, w[p + "proj_w"], w[p + "proj_b"])               # clip.py:48
+        if precision == "fp32":
+            att = torch.softmax((q * dh ** -0.5) @ k.transpose(-1, -2), dim=-1)
+            o = (att @ v).permute(0, 2, 1, 3).reshape(N, T, W)
+        else:
+            s_ = (q @ k.transpose(-1, -2)) * dh ** -0.5
+            pr = torch.exp(s_ - s_.amax(dim=-1, keepdim=True))
+            o = ((r(pr) @ v) / pr.sum(dim=-1, keepdim=True)).permute(0, 2, 1, 3).reshape(N, T, W)
+        x = x + F.linear(r(o), r(w[p + "proj_w"]), w[p + "proj_b"])         # clip.py:48
         h = F.layer_norm(x, (W,), w[p + "ln2_w"], w[p + "ln2_b"], spec.ln_eps)
-        h = _act(F.linear(h, w[p + "fc1_w"], w[p + "fc1_b"]), spec.act)
-        x = x + F.linear(h, w[p + "fc2_w"], w[p + "fc2_b"])                 # clip.py:49
+        h = _act(F.linear(r(h), r(w[p + "fc1_w"]), w[p + "fc1_b"]), spec.act)
+        x = x + F.linear(r(h), r(w[p + "fc2_w"]), w[p + "fc2_b"])           # clip.py:49
     x = F.layer_norm(x, (W,), w["ln_post_w"], w["ln_post_b"], spec.ln_eps)  # :158
     if spec.tail == "tokens" or return_tokens:
         return x
     if spec.tail == "gem_linear":
         return F.linear(gem_tokens(x, spec.gem_p), w["head_w"], w["head_b"])
     if spec.tail == "gem_conv_linear":                                      # sscd.py:30-40, :86
-        y = F.linear(x, w["gem_conv_w"], w["gem_conv_b"])                   # Conv1d k=1 over tokens
+        y = F.linear(r(x), r(w["gem_conv_w"]), w["gem_conv_b"])             # Conv1d k=1 over tokens
         g = y.clamp(min=1e-6).pow(spec.gem_p).mean(dim=1).pow(1.0 / spec.gem_p)
         return F.linear(g, w["head_w"], w["head_b"])
     raise ValueError(spec.tail)

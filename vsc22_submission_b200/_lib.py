@@ -22,13 +22,17 @@ EPI_BF16, EPI_F32, EPI_RESIDUAL_F32 = 0, 1, 2
 
 class VitSpecC(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("img", "patch", "width", "layers", "heads", "patch_bias", "pre_norm", "act",
-                                       "tail", "out_dim", "gem_hidden")] + [("ln_eps", C.c_float), ("gem_p", C.c_float)]
+                                       "tail", "out_dim", "gem_hidden")] + [("ln_eps", C.c_float), ("gem_p", C.c_float),
+                                                                           ("precision", C.c_int)]
 
 
 class SwinSpecC(C.Structure):
     _fields_ = [("img", C.c_int), ("patch", C.c_int), ("embed", C.c_int), ("n_stages", C.c_int), ("depths", C.c_int * 4),
                 ("heads", C.c_int * 4), ("window", C.c_int), ("pretrained_windows", C.c_int * 4), ("out_dim", C.c_int),
-                ("ln_eps", C.c_float), ("gem_p", C.c_float)]
+                ("ln_eps", C.c_float), ("gem_p", C.c_float), ("precision", C.c_int)]
+
+
+PRECISION = {"bf16": 0, "fp32": 1}
 
 
 class Vscb200Error(RuntimeError):
@@ -91,6 +95,9 @@ SIGNATURES = {
     "vscb200_tn_align": (_i, [_p, _p, _i, _i64, _p, _p, _p, _i, _i, _i, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
     "vscb200_tn_box_scores": (_i, [_p, _p, _p, _i64, _p, _p, _i, _f, _p, _p]),
     "vscb200_gemm_bf16": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
+    "vscb200_gemm_split": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _p]),
+    "vscb200_split_f32_bf16": (_i, [_p, _p, _p, _i64, _p]),
+    "vscb200_attention_fp32": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),
     "vscb200_layernorm": (_i, [_p, _p, _p, _p, _i64, _i, _f, _i, _p]),
     "vscb200_attention": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vscb200_cast_f32_bf16": (_i, [_p, _p, _i64, _p]),

@@ -10,6 +10,11 @@
 // static persistent tile schedule (tile = blockIdx.x + i*gridDim.x, N-blocks fastest so that
 // concurrently resident CTAs share A tiles through L2 while W stays L2 resident).
 //
+// kSplit (the encoders' fp32-equivalent mode): both operands arrive as two bf16 planes, x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi), and every K step issues three MMAs  hi.hi + lo.hi + hi.lo  into the same fp32 accumulator (the
+// dropped lo.lo term is <= 2^-18 |a.w| per product) -- 16 mantissa bits per operand instead of 8.  bf16 outputs leave
+// as two planes as well (a second tensor map).  128 x 128 tiles, one CTA per tile, 3-stage ring of {Ah, Al, Wh, Wl}.
+//
 // This is the dense-projection engine of the ViT encoder (reference: every nn.Linear /
 // nn.MultiheadAttention projection of D/train/train_vid_score/video/clip.py:33-39,45-49 and the
 // conv patch-embed :105,143 as an im2row GEMM), replacing the cuBLAS calls of torch 1.11.
@@ -24,7 +29,6 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
-constexpr int kEpiWarpStage = 8192;
 
 struct GemmParams {
   const float* bias;
@@ -49,13 +53,17 @@ struct GemmParams {
 
 constexpr int VSCB_EPI_PATCH_F32 = 3;
 
-template <int BN, int kCluster>
+template <int BN, int kCluster, bool kSplit>
 struct GemmCfg {
-  static constexpr int kStages = (kCluster == 2) ? 5 : ((BN == 256) ? 3 : 5);
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = (BN / kCluster) * kBK * 2;   // pair mode: each CTA stages half of the W tile
+  static constexpr int kStages = kSplit ? 3 : ((kCluster == 2) ? 5 : ((BN == 256) ? 3 : 5));
+  static constexpr int kATile = kBM * kBK * 2;
+  static constexpr int kBTile = (BN / kCluster) * kBK * 2;        // pair mode: each CTA stages half of the W tile
+  static constexpr int kABytes = kATile * (kSplit ? 2 : 1);       // split mode: hi plane tile, then lo plane tile
+  static constexpr int kBBytes = kBTile * (kSplit ? 2 : 1);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStageBytes = kEpiWarps * kEpiWarpStage;   // per-warp epilogue boxes (2 x 4 KB, double-buffered)
+  static constexpr int kEpiBoxes = kSplit ? 1 : 2;                // 4 KB epilogue boxes per warp (double-buffered unless split)
+  static constexpr int kEpiWarpBytes = 4096 * kEpiBoxes;
+  static constexpr int kStageBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kSmemBytes =
       kStages * (kABytes + kBBytes) + kStageBytes + 256 /*barriers*/ + 1024 /*align slack*/;
 };
@@ -66,10 +74,13 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 
+template <bool kPrecise>
 __device__ __forceinline__ float apply_act(float x, int act) {
   // QuickGELU x*sigmoid(1.702x) = 0.5x*tanh(0.851x) + 0.5x : ONE MUFU op per element (ex2 + rcp would be
   // two, and the epilogue of the K=768 fc1 GEMM is MUFU-paced).  tanh.approx error 2^-11 << bf16 output ulp.
+  // kPrecise (fp32-equivalent mode): the reference's formula with expf.
   if (act == VSCB200_ACT_QUICK_GELU) {
+    if (kPrecise) return x / (1.0f + expf(-1.702f * x));
     const float h = 0.5f * x;
     return fmaf(h, tanh_approx(0.851f * x), h);
   }
@@ -85,11 +96,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // rank 0's full barrier; stages and accumulators are released to both CTAs by multicast tcgen05.commit;
 // each CTA drains its own 128 accumulator lanes and the peer's epilogue warps arrive remotely on rank
 // 0's TMEM-empty barrier.
-template <int BN, int kCluster>
+template <int BN, int kCluster, bool kSplit>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, GemmParams p) {
-  using Cfg = GemmCfg<BN, kCluster>;
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmC2, GemmParams p) {
+  static_assert(!kSplit || kCluster == 1, "the split-bf16 mode runs one CTA per tile");
+  using Cfg = GemmCfg<BN, kCluster, kSplit>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -111,6 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
+    if (kSplit) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); prefetch_tmap(&tmC2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -163,6 +177,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes);
             tma_load_2d(sA + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
             tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
+            if (kSplit) {
+              tma_load_2d(sA + stage * Cfg::kABytes + Cfg::kATile, &tmA2, &full_bar[stage], kb * kBK, m_blk * kBM, kEvictNormal);
+              tma_load_2d(sB + stage * Cfg::kBBytes + Cfg::kBTile, &tmB2, &full_bar[stage], kb * kBK, n_blk * BN, kEvictLast);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -189,6 +207,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // +32 bytes per K=16 step inside the 128B swizzle row: +2 in the (addr>>4) field
             if (kCluster > 1) umma_bf16_ss_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kSplit) {       // + lo.hi + hi.lo (the lo tiles follow their hi tiles inside the stage)
+              const uint64_t a_lo = a_desc + (Cfg::kATile >> 4), b_lo = b_desc + (Cfg::kBTile >> 4);
+              umma_bf16_ss(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1u);
+              umma_bf16_ss(d_tmem, a_desc + 2 * k, b_lo + 2 * k, idesc, 1u);
+            }
           }
           if (kCluster > 1) umma_commit_cg2_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
           else umma_commit(&empty_bar[stage]);
@@ -203,7 +226,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 4;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;           // column half of the tile
-    uint8_t* wstage = stage_all + ew * kEpiWarpStage;   // two 4 KB boxes (1024-byte aligned), or one 32x32 fp32 tile
+    uint8_t* wstage = stage_all + ew * Cfg::kEpiWarpBytes;   // 4 KB boxes (1024-byte aligned), or one 32x32 fp32 tile
     constexpr int kChunks = BN / 2 / 32;
     const bool tma_epi = p.epilogue != VSCB_EPI_PATCH_F32;
     const bool out_bf16 = p.epilogue == VSCB200_EPI_BF16;
@@ -228,10 +251,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int col0 = half * (BN / 2) + c * 32;
           const int gcol = n_blk * BN + col0;
           if (gcol >= p.N || row_base >= p.M) continue;   // warp-uniform
-          uint8_t* box = wstage + (box_no & 1u) * 4096u;
+          uint8_t* box = wstage + (Cfg::kEpiBoxes > 1 ? (box_no & 1u) * 4096u : 0u);
           ++box_no;
-          if (lane == 0) tma_store_wait_read<1>();        // the store that last read this buffer has drained
+          if (lane == 0) tma_store_wait_read<Cfg::kEpiBoxes - 1>();        // the store that last read this buffer has drained
           __syncwarp();
+          uint32_t lo_pk[kSplit ? 32 : 1];                // split mode, bf16 output: the lo plane of this thread's 64 columns
           for (int sub = 0; sub < step; ++sub) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + col0 + sub * 32, v);
@@ -262,12 +286,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if (qk_norm) { o.x *= rnorm; o.y *= rnorm; o.z *= rnorm; o.w *= rnorm; }
               if (p.act >= 0) {
-                o.x = apply_act(o.x, p.act); o.y = apply_act(o.y, p.act);
-                o.z = apply_act(o.z, p.act); o.w = apply_act(o.w, p.act);
+                o.x = apply_act<kSplit>(o.x, p.act); o.y = apply_act<kSplit>(o.y, p.act);
+                o.z = apply_act<kSplit>(o.z, p.act); o.w = apply_act<kSplit>(o.w, p.act);
               }
               if (out_bf16) {
                 v[2 * q] = pack_bf16x2(o.x, o.y);
                 v[2 * q + 1] = pack_bf16x2(o.z, o.w);
+                if (kSplit) {
+                  lo_pk[sub * 16 + 2 * q] = pack_bf16x2(o.x - __uint_as_float(v[2 * q] << 16),
+                                                        o.y - __uint_as_float(v[2 * q] & 0xFFFF0000u));
+                  lo_pk[sub * 16 + 2 * q + 1] = pack_bf16x2(o.z - __uint_as_float(v[2 * q + 1] << 16),
+                                                            o.w - __uint_as_float(v[2 * q + 1] & 0xFFFF0000u));
+                }
               } else {
                 *reinterpret_cast<float4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
               }
@@ -285,6 +315,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.epilogue == VSCB200_EPI_RESIDUAL_F32) tma_reduce_add_2d(&tmC, box, gcol, static_cast<int>(row_base));
             else tma_store_2d(&tmC, box, gcol, static_cast<int>(row_base));
             tma_store_commit();
+          }
+          if (kSplit && out_bf16) {                       // the lo plane through the same box, once the hi store has read it
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_uint4(lo_pk[4 * q], lo_pk[4 * q + 1], lo_pk[4 * q + 2], lo_pk[4 * q + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC2, box, gcol, static_cast<int>(row_base));
+              tma_store_commit();
+            }
           }
         }
       } else {
@@ -346,11 +390,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int BN, int kCluster>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, kCluster>;
-  VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+struct GemmMaps {
+  CUtensorMap A, B, C, A2, B2, C2;     // *2: the lo planes (split mode); copies of the hi maps otherwise
+};
+
+template <int BN, int kCluster, bool kSplit>
+static int launch_gemm(const GemmMaps& tm, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, kCluster, kSplit>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "gemm: shared memory budget");
+  VSCB_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_kernel<BN, kCluster, kSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
   const int sched_tiles = ((p.tiles_m + kCluster - 1) / kCluster) * p.tiles_n;     // (pair) tiles
   const int max_groups = device_sm_count() / kCluster;
@@ -370,7 +418,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster>, tmA, tmB, tmC, p));
+  VSCB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, kCluster, kSplit>, tm.A, tm.B, tm.C, tm.A2, tm.B2, tm.C2, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -378,7 +426,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
               int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
-              bool reverse, int qk_norm_cols, const float* qscale) {
+              bool reverse, int qk_norm_cols, const float* qscale, const void* A_lo, const void* W_lo, void* C_lo) {
   VSCB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
   VSCB_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K/lda/ldw must be multiples of 8 (16-byte TMA strides)");
   VSCB_REQUIRE(N % 8 == 0 && ldc % 8 == 0, "gemm: N/ldc must be multiples of 8");
@@ -387,19 +435,30 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
                "gemm: operands must be 16-byte aligned");
   VSCB_REQUIRE(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue");
   VSCB_REQUIRE(epilogue != VSCB_EPI_PATCH_F32 || (pos != nullptr && patch_P > 0), "gemm: patch epilogue needs pos/P");
-  const int BN = (N >= 256 || N > 128) ? 256 : 128;
+  const bool split = A_lo != nullptr || W_lo != nullptr;
+  VSCB_REQUIRE(!split || (A_lo != nullptr && W_lo != nullptr && (epilogue != VSCB200_EPI_BF16 || C_lo != nullptr)),
+               "gemm: the split-bf16 mode needs the lo planes of A and W (and of a bf16 output)");
+  VSCB_REQUIRE(!split || ((reinterpret_cast<uintptr_t>(A_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(W_lo) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(C_lo) & 15) == 0), "gemm: lo planes must be 16-byte aligned");
+  const int BN = split ? 128 : ((N >= 256 || N > 128) ? 256 : 128);
   const int tiles_m_all = static_cast<int>((M + kBM - 1) / kBM);
   static const int force_cluster = [] { const char* e = getenv("VSCB200_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
   const int tiles_n_all = (N + BN - 1) / BN;
-  const bool pair = force_cluster ? (force_cluster == 2 && tiles_m_all >= 2)
-                                  : (BN == 256 && tiles_m_all >= 2 &&
-                                     static_cast<int64_t>(tiles_m_all) * tiles_n_all >= 2 * device_sm_count());
-  CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, kBM, kBK, true);
+  const bool pair = split ? false
+                          : force_cluster ? (force_cluster == 2 && tiles_m_all >= 2)
+                                          : (BN == 256 && tiles_m_all >= 2 &&
+                                             static_cast<int64_t>(tiles_m_all) * tiles_n_all >= 2 * device_sm_count());
+  GemmMaps tm;
+  int rc = make_tmap_2d(&tm.A, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, kBM, kBK, true);
   if (rc) return rc;
   // in pair mode each CTA's TMA box is its half of the W tile (BN/2 rows)
-  rc = make_tmap_2d(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, pair ? BN / 2 : BN, kBK, true);
+  rc = make_tmap_2d(&tm.B, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, pair ? BN / 2 : BN, kBK, true);
   if (rc) return rc;
+  tm.A2 = tm.A; tm.B2 = tm.B;
+  if (split) {
+    if ((rc = make_tmap_2d(&tm.A2, A_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, lda, kBM, kBK, true))) return rc;
+    if ((rc = make_tmap_2d(&tm.B2, W_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldw, BN, kBK, true))) return rc;
+  }
   GemmParams p;
   p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.epilogue = epilogue; p.act = act;
   p.pos = pos; p.patch_P = patch_P; p.reverse = reverse ? 1 : 0;
@@ -409,15 +468,19 @@ int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t 
   p.tiles_m = static_cast<int>((M + kBM - 1) / kBM);
   p.tiles_n = (N + BN - 1) / BN;
   // output tensor map: 32-row boxes of 128 B (64 bf16 / 32 fp32 columns); unused by the patch-embed epilogue
-  CUtensorMap tmC = tmA;
+  tm.C = tm.A;
   if (epilogue == VSCB200_EPI_BF16) {
-    rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldc, 32, 64, true);
+    rc = make_tmap_2d(&tm.C, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldc, 32, 64, true);
   } else if (epilogue != VSCB_EPI_PATCH_F32) {
-    rc = make_tmap_2d(&tmC, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldc, 32, 32, true);
+    rc = make_tmap_2d(&tm.C, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldc, 32, 32, true);
   }
   if (rc) return rc;
-  if (pair) return BN == 256 ? launch_gemm<256, 2>(tmA, tmB, tmC, p, stream) : launch_gemm<128, 2>(tmA, tmB, tmC, p, stream);
-  return BN == 256 ? launch_gemm<256, 1>(tmA, tmB, tmC, p, stream) : launch_gemm<128, 1>(tmA, tmB, tmC, p, stream);
+  tm.C2 = tm.C;
+  if (split && epilogue == VSCB200_EPI_BF16 &&
+      (rc = make_tmap_2d(&tm.C2, C_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, ldc, 32, 64, true))) return rc;
+  if (split) return launch_gemm<128, 1, true>(tm, p, stream);
+  if (pair) return BN == 256 ? launch_gemm<256, 2, false>(tm, p, stream) : launch_gemm<128, 2, false>(tm, p, stream);
+  return BN == 256 ? launch_gemm<256, 1, false>(tm, p, stream) : launch_gemm<128, 1, false>(tm, p, stream);
 }
 
 }  // namespace vscb200
@@ -429,5 +492,17 @@ extern "C" int vscb200_gemm_bf16(const void* A, const void* W, const float* bias
     return VSCB200_ERR_INVALID;
   }
   return vscb200::gemm_bf16(A, W, bias, C, M, N, K, lda, ldw, ldc, epilogue, act, static_cast<cudaStream_t>(stream),
-                            nullptr, 0, false, 0, nullptr);
+                            nullptr, 0, false, 0, nullptr, nullptr, nullptr, nullptr);
+}
+
+// Split-bf16 (fp32-equivalent) form: operands as hi / lo bf16 planes; a bf16 output leaves as two planes too.
+extern "C" int vscb200_gemm_split(const void* A_hi, const void* A_lo, const void* W_hi, const void* W_lo, const float* bias,
+                                  void* C, void* C_lo, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc,
+                                  int epilogue, int act, void* stream) {
+  if (epilogue < 0 || epilogue > 2) {
+    vscb200::set_last_error("vscb200_gemm_split: epilogue must be VSCB200_EPI_{BF16,F32,RESIDUAL_F32}");
+    return VSCB200_ERR_INVALID;
+  }
+  return vscb200::gemm_bf16(A_hi, W_hi, bias, C, M, N, K, lda, ldw, ldc, epilogue, act, static_cast<cudaStream_t>(stream),
+                            nullptr, 0, false, 0, nullptr, A_lo, W_lo, C_lo);
 }

@@ -15,13 +15,20 @@ constexpr int VSCB_EPI_PATCH_F32_ID = 3;
 
 int gemm_bf16(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda,
               int64_t ldw, int64_t ldc, int epilogue, int act, cudaStream_t stream, const float* pos, int patch_P,
-              bool reverse = false, int qk_norm_cols = 0, const float* qscale = nullptr);
+              bool reverse = false, int qk_norm_cols = 0, const float* qscale = nullptr, const void* A_lo = nullptr,
+              const void* W_lo = nullptr, void* C_lo = nullptr);
 int attention(const void* qkv, void* out, int n_frames, int T, int heads, int head_dim, cudaStream_t stream,
               bool reverse = false);
+// lo_off / y_lo: fp32-equivalent mode -- the bf16 output is written as two planes (hi at y, the rounding residual
+// bf16(v - hi) at y + lo_off elements); 0 / nullptr: single plane
 int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,
-              int out_bf16, cudaStream_t stream, bool reverse = false);
-int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream);
-int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream);
+              int out_bf16, cudaStream_t stream, bool reverse = false, int64_t lo_off = 0);
+int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream, void* y_lo = nullptr);
+int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream, int64_t lo_off = 0);
+// attention_fp32.cu: fp32 attention over segments of N consecutive rows (hi + lo planes when *_lo_off != 0)
+int attention_fp32(const void* qkv, int64_t qkv_lo_off, void* out, int64_t out_lo_off, int64_t n_segs, int N, int heads,
+                   int head_dim, float scale, const float* tables, int ws, int res, int shift, int nWx, int nW_per_frame,
+                   cudaStream_t stream);
 int cls_rows(const float* cls, const float* pos, float* x, int64_t n, int T, int W, cudaStream_t stream);
 int gem_head(const float* y, const float* gamma, const float* beta, const float* head_w, const float* head_b,
              float* out, int64_t n, int T, int C, int out_dim, float eps, float p, bool fuse_ln,

@@ -311,4 +311,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// lo plane of a split-bf16 pair: bf16(x - hi) for the two values packed in `hi` (first value in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2_lo(float a, float b, uint32_t hi) {
+  return pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+}
+
 }  // namespace vscb200

@@ -11,6 +11,9 @@
 //   per stage end: 2x2 gather -> reduction GEMM (no bias) -> LN                       (PatchMerging :353-368)
 //   tail: LN -> GeM(p) over the tokens -> Linear                                      (:630-632, :664-665)
 // Residual stream, LayerNorm, softmax and accumulators fp32; GEMM / attention operands bf16.
+// spec.precision == VSCB200_PRECISION_FP32: bf16 operand buffers hold (hi, lo) plane pairs, projections run the
+// split-bf16 GEMM, window attention runs in fp32 (attention_fp32.cu) -- as in vit.cu.  Window sides other than 4 / 8 / 16
+// (24: SwinV2-L@384, BASELINE configs[3]) use the fp32 attention kernel in both modes.
 #include <stdlib.h>
 #include <string.h>
 
@@ -24,12 +27,13 @@
 using namespace vscb200;
 
 namespace vscb200 {
-int window_gather_bf16(const float* x, void* h, int64_t n, int res, int ws, int shift, int C, cudaStream_t stream);
+int window_gather_bf16(const float* x, void* h, int64_t n, int res, int ws, int shift, int C, cudaStream_t stream,
+                       int64_t lo_off = 0);
 // h_next != nullptr: the updated rows are also written as bf16 in the row order of the next consumer (ws_next x ws_next
 // windows shifted by shift_next; ws_next == res, shift 0: token order)
 int ln_residual_scatter(const float* y, const float* gamma, const float* beta, float* x, int64_t n, int res, int ws, int shift,
-                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next);
-int patch_merge_gather(const float* x, void* out, int64_t n, int res, int C, cudaStream_t stream);
+                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next, int64_t lo_off = 0);
+int patch_merge_gather(const float* x, void* out, int64_t n, int res, int C, cudaStream_t stream, int64_t lo_off = 0);
 int cpb_table(const float* w0, const float* b0, const float* w2, float* table, int ws, int pretrained_ws, int heads,
               cudaStream_t stream);
 int swin_prep(const float* logit_scale, const float* q_bias, const float* v_bias, float* qscale, float* qkv_bias, int heads,
@@ -75,6 +79,8 @@ struct vscb200_swin {
   cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   bool finalized = false;
+  bool exact = false;        // fp32-equivalent mode: bf16 buffers are (hi, lo) plane pairs
+  int planes = 1;
   std::vector<void*> allocs;
   std::map<std::string, bool> loaded;
 };
@@ -91,6 +97,26 @@ int sw_alloc(vscb200_swin* m, Tp** p, size_t bytes) {
   }
   m->allocs.push_back(q);
   *p = reinterpret_cast<Tp*>(q);
+  return VSCB200_OK;
+}
+
+inline void* lo_plane(const vscb200_swin* m, void* hi, int64_t elems) {
+  return m->exact ? static_cast<void*>(static_cast<uint16_t*>(hi) + elems) : nullptr;
+}
+
+int host_staging(vscb200_swin* m) {
+  const int64_t in_per = 3LL * m->spec.img * m->spec.img, out_per = m->spec.out_dim;
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
+    VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+    VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
+  }
   return VSCB200_OK;
 }
 
@@ -118,9 +144,14 @@ int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_s
                "swin_create: img must be a multiple of an even patch size");
   VSCB_REQUIRE(spec->embed % 64 == 0, "swin_create: embed dim must be a multiple of 64 (head pairs of 2 x 32)");
   VSCB_REQUIRE(max_frames > 0 && spec->out_dim > 0, "swin_create: max_frames / out_dim must be positive");
+  VSCB_REQUIRE(spec->precision == VSCB200_PRECISION_BF16 || spec->precision == VSCB200_PRECISION_FP32,
+               "swin_create: precision must be VSCB200_PRECISION_BF16 or VSCB200_PRECISION_FP32");
   vscb200_swin* m = new vscb200_swin();
   m->spec = *spec;
   m->max_frames = max_frames;
+  m->exact = spec->precision == VSCB200_PRECISION_FP32;
+  m->planes = m->exact ? 2 : 1;
+  const size_t P2 = 2 * static_cast<size_t>(m->planes);      // bytes per bf16 operand element (both planes)
   m->Kraw = 3 * spec->patch * spec->patch;
   m->Kp = (m->Kraw + 63) / 64 * 64;
   const int res0 = spec->img / spec->patch;
@@ -134,9 +165,9 @@ int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_s
     st.ws = spec->window < st.res ? spec->window : st.res;
     st.heads = spec->heads[i];
     st.pretrained_ws = spec->pretrained_windows[i];
-    if (!(st.heads * 32 == st.C && (st.ws == 4 || st.ws == 8 || st.ws == 16) && st.res % st.ws == 0 && st.C <= 1024 &&
-          (res0 % (1 << i)) == 0 && spec->depths[i] > 0)) {
-      set_last_error("swin_create: every stage needs head_dim 32, a window side of 4/8/16 dividing the token map, width <= 1024");
+    if (!(st.heads * 32 == st.C && st.ws >= 2 && st.ws <= 32 && st.res % st.ws == 0 && st.C <= 2048 && (st.C <= 1024 || st.C % 256 == 0) &&
+          (res0 % (1 << i)) == 0 && spec->depths[i] > 0 && (st.res <= spec->window || spec->window % 2 == 0))) {
+      set_last_error("swin_create: every stage needs head_dim 32, a window side in [2, 32] dividing the token map (even when shifted), width <= 2048");
       vscb200_swin_destroy(m);
       return VSCB200_ERR_INVALID;
     }
@@ -147,22 +178,23 @@ int vscb200_swin_create(const vscb200_swin_spec* spec, int max_frames, vscb200_s
       A(b.norm1_w, C * 4); A(b.norm1_b, C * 4); A(b.norm2_w, C * 4); A(b.norm2_b, C * 4);
       A(b.logit_scale, st.heads * 4); A(b.cpb0_w, 512 * 2 * 4); A(b.cpb0_b, 512 * 4); A(b.cpb2_w, st.heads * 512 * 4);
       A(b.q_bias, C * 4); A(b.v_bias, C * 4); A(b.proj_b, C * 4); A(b.fc1_b, 4 * C * 4); A(b.fc2_b, C * 4);
-      A(b.qkv_w, 3 * C * C * 2); A(b.proj_w, C * C * 2); A(b.fc1_w, 4 * C * C * 2); A(b.fc2_w, 4 * C * C * 2);
+      A(b.qkv_w, 3 * C * C * P2); A(b.proj_w, C * C * P2); A(b.fc1_w, 4 * C * C * P2); A(b.fc2_w, 4 * C * C * P2);
       A(b.table, static_cast<size_t>(st.heads) * ts * ts * 4); A(b.qscale, st.heads * 4); A(b.qkv_bias, 3 * C * 4);
     }
     if (i + 1 < spec->n_stages) {
-      A(st.red_w, 2 * C * 4 * C * 2); A(st.red_norm_w, 2 * C * 4); A(st.red_norm_b, 2 * C * 4);
+      A(st.red_w, 2 * C * 4 * C * P2); A(st.red_norm_w, 2 * C * 4); A(st.red_norm_b, 2 * C * 4);
     }
   }
   m->Cf = spec->embed << (spec->n_stages - 1);
-  A(m->patch_w, static_cast<size_t>(spec->embed) * m->Kp * 2);
+  A(m->patch_w, static_cast<size_t>(spec->embed) * m->Kp * P2);
   A(m->patch_b, spec->embed * 4); A(m->patch_norm_w, spec->embed * 4); A(m->patch_norm_b, spec->embed * 4);
   A(m->norm_w, m->Cf * 4); A(m->norm_b, m->Cf * 4);
   A(m->head_w, static_cast<size_t>(spec->out_dim) * m->Cf * 4); A(m->head_b, spec->out_dim * 4);
   const size_t M0 = static_cast<size_t>(max_frames) * res0 * res0, C0 = spec->embed;
-  A(m->x, M0 * C0 * 4); A(m->y, M0 * C0 * 4); A(m->h, M0 * C0 * 2); A(m->qkv, M0 * 3 * C0 * 2); A(m->ao, M0 * C0 * 2);
-  A(m->u, M0 * 4 * C0 * 2); A(m->patches, M0 * m->Kp * 2);
+  A(m->x, M0 * C0 * 4); A(m->y, M0 * C0 * 4); A(m->h, M0 * C0 * P2); A(m->qkv, M0 * 3 * C0 * P2); A(m->ao, M0 * C0 * P2);
+  A(m->u, M0 * 4 * C0 * P2); A(m->patches, M0 * m->Kp * P2);
 #undef A
+  if ((rc = host_staging(m))) { vscb200_swin_destroy(m); return rc; }
   *out = m;
   return VSCB200_OK;
 }
@@ -240,7 +272,7 @@ int vscb200_swin_set_param(vscb200_swin* m, const char* name_c, const float* w, 
     return VSCB200_ERR_INVALID;
   }
   if (t.bf16) {
-    int rc = cast_f32_bf16_padded(w, t.dst, t.rows, t.cols, t.ld, stream);
+    int rc = cast_f32_bf16_padded(w, t.dst, t.rows, t.cols, t.ld, stream, lo_plane(m, t.dst, t.rows * t.ld));
     if (rc) return rc;
   } else {
     VSCB_CUDA_OK(cudaMemcpyAsync(t.dst, w, count * 4, cudaMemcpyDeviceToDevice, stream));
@@ -257,11 +289,16 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
   R(finalize(m, s));
   const int res0 = sp.img / sp.patch;
   const float eps = sp.ln_eps;
+  // plane strides (elements) of the operand buffers: fixed by the plan's capacity (stage 0 sizes); 0 in the bf16 mode
+  const int64_t M0cap = static_cast<int64_t>(m->max_frames) * res0 * res0;
+  const int64_t h_lo = m->exact ? M0cap * sp.embed : 0, qkv_lo = 3 * h_lo, u_lo = 4 * h_lo, pat_lo = m->exact ? M0cap * m->Kp : 0;
+  auto lo = [&](void* hi, int64_t off) -> void* { return off ? static_cast<void*>(static_cast<uint16_t*>(hi) + off) : nullptr; };
+  auto wlo = [&](void* w, int64_t rows, int64_t ld) -> const void* { return lo_plane(m, w, rows * ld); };
   {
     const int64_t M0 = static_cast<int64_t>(n) * res0 * res0;
-    R(im2row(frames, m->patches, n, sp.img, sp.patch, m->Kp, s));
+    R(im2row(frames, m->patches, n, sp.img, sp.patch, m->Kp, s, pat_lo));
     R(gemm_bf16(m->patches, m->patch_w, m->patch_b, m->x, M0, sp.embed, m->Kp, m->Kp, m->Kp, sp.embed, VSCB200_EPI_F32, -1, s,
-                nullptr, 0));
+                nullptr, 0, false, 0, nullptr, lo(m->patches, pat_lo), wlo(m->patch_w, sp.embed, m->Kp), nullptr));
     R(layernorm(m->x, m->patch_norm_w, m->patch_norm_b, m->x, M0, sp.embed, eps, 0, s));
   }
   for (size_t i = 0; i < m->stages.size(); ++i) {
@@ -269,27 +306,38 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
     const int C = st.C, res = st.res, ws = st.ws;
     const int64_t M = static_cast<int64_t>(n) * res * res;
     const int nWx = res / ws, nW = nWx * nWx;
+    const bool tc_attn = !m->exact && (ws == 4 || ws == 8 || ws == 16);
     for (size_t j = 0; j < st.blocks.size(); ++j) {
       const SwinBlockW& b = st.blocks[j];
       const int shift = (res > sp.window && (j & 1)) ? sp.window / 2 : 0;     // swinv2.py:223-226, 411
       // ---- (shifted) window attention branch.  Only the first block of a stage gathers its input rows itself: every
       //      later block finds them written, in its own window order, by the previous block's res-post-norm kernel.
-      if (j == 0) R(window_gather_bf16(m->x, m->h, n, res, ws, shift, C, s));
+      if (j == 0) R(window_gather_bf16(m->x, m->h, n, res, ws, shift, C, s, h_lo));
       R(gemm_bf16(m->h, b.qkv_w, b.qkv_bias, m->qkv, M, 3 * C, C, C, C, 3 * C, VSCB200_EPI_BF16, -1, s, nullptr, 0, false,
-                  2 * C, b.qscale));
-      R(swin_attention(m->qkv, m->ao, b.table, static_cast<int64_t>(n) * nW, nW, nWx, ws, shift, st.heads, s));
-      R(gemm_bf16(m->ao, b.proj_w, b.proj_b, m->y, M, C, C, C, C, C, VSCB200_EPI_F32, -1, s, nullptr, 0));
-      R(ln_residual_scatter(m->y, b.norm1_w, b.norm1_b, m->x, n, res, ws, shift, C, eps, s, m->h, res, 0));   // h: MLP input
+                  2 * C, b.qscale, lo(m->h, h_lo), wlo(b.qkv_w, 3 * C, C), lo(m->qkv, qkv_lo)));
+      if (tc_attn) {
+        R(swin_attention(m->qkv, m->ao, b.table, static_cast<int64_t>(n) * nW, nW, nWx, ws, shift, st.heads, s));
+      } else {
+        R(attention_fp32(m->qkv, qkv_lo, m->ao, h_lo, static_cast<int64_t>(n) * nW, ws * ws, st.heads, 32, 1.0f, b.table, ws, res,
+                         shift, nWx, nW, s));
+      }
+      R(gemm_bf16(m->ao, b.proj_w, b.proj_b, m->y, M, C, C, C, C, C, VSCB200_EPI_F32, -1, s, nullptr, 0, false, 0, nullptr,
+                  lo(m->ao, h_lo), wlo(b.proj_w, C, C), nullptr));
+      R(ln_residual_scatter(m->y, b.norm1_w, b.norm1_b, m->x, n, res, ws, shift, C, eps, s, m->h, res, 0, h_lo));   // h: MLP input
       // ---- MLP branch (token order: identity map)
-      R(gemm_bf16(m->h, b.fc1_w, b.fc1_b, m->u, M, 4 * C, C, C, C, 4 * C, VSCB200_EPI_BF16, VSCB200_ACT_GELU, s, nullptr, 0));
-      R(gemm_bf16(m->u, b.fc2_w, b.fc2_b, m->y, M, C, 4 * C, 4 * C, 4 * C, C, VSCB200_EPI_F32, -1, s, nullptr, 0));
+      R(gemm_bf16(m->h, b.fc1_w, b.fc1_b, m->u, M, 4 * C, C, C, C, 4 * C, VSCB200_EPI_BF16, VSCB200_ACT_GELU, s, nullptr, 0, false,
+                  0, nullptr, lo(m->h, h_lo), wlo(b.fc1_w, 4 * C, C), lo(m->u, u_lo)));
+      R(gemm_bf16(m->u, b.fc2_w, b.fc2_b, m->y, M, C, 4 * C, 4 * C, 4 * C, C, VSCB200_EPI_F32, -1, s, nullptr, 0, false, 0, nullptr,
+                  lo(m->u, u_lo), wlo(b.fc2_w, C, 4 * C), nullptr));
       const bool more = j + 1 < st.blocks.size();
       const int next_shift = (res > sp.window && ((j + 1) & 1)) ? sp.window / 2 : 0;
-      R(ln_residual_scatter(m->y, b.norm2_w, b.norm2_b, m->x, n, res, res, 0, C, eps, s, more ? m->h : nullptr, ws, next_shift));
+      R(ln_residual_scatter(m->y, b.norm2_w, b.norm2_b, m->x, n, res, res, 0, C, eps, s, more ? m->h : nullptr, ws, next_shift,
+                            h_lo));
     }
     if (i + 1 < m->stages.size()) {
-      R(patch_merge_gather(m->x, m->h, n, res, C, s));
-      R(gemm_bf16(m->h, st.red_w, nullptr, m->y, M / 4, 2 * C, 4 * C, 4 * C, 4 * C, 2 * C, VSCB200_EPI_F32, -1, s, nullptr, 0));
+      R(patch_merge_gather(m->x, m->h, n, res, C, s, h_lo));
+      R(gemm_bf16(m->h, st.red_w, nullptr, m->y, M / 4, 2 * C, 4 * C, 4 * C, 4 * C, 2 * C, VSCB200_EPI_F32, -1, s, nullptr, 0, false,
+                  0, nullptr, lo(m->h, h_lo), wlo(st.red_w, 2 * C, 4 * C), nullptr));
       R(layernorm(m->y, st.red_norm_w, st.red_norm_b, m->x, M / 4, 2 * C, eps, 0, s));
     }
   }
@@ -318,19 +366,6 @@ int vscb200_swin_forward_host(vscb200_swin* m, const float* frames_host, int64_t
   // of chunk i; descriptors land in page-locked buffers and are handed to the caller one chunk later.
   VSCB_REQUIRE(m && (n == 0 || (frames_host && out_host)), "swin_forward_host: null argument");
   const int64_t in_per = 3LL * m->spec.img * m->spec.img, out_per = m->spec.out_dim;
-  if (!m->own_stream) {
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-      VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
-      VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
-      VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
-    }
-  }
   int64_t chunk = 0, last_f0 = 0;
   int last_nc = 0, last_b = 0;
   for (int64_t f0 = 0; f0 < n; f0 += m->max_frames, ++chunk) {

@@ -37,7 +37,8 @@ __device__ __forceinline__ int token_to_win_row(const WinMap& m, int tok) {
 }
 
 __global__ void __launch_bounds__(256)
-window_gather_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h, int64_t rows, int C, WinMap m) {
+window_gather_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h, int64_t rows, int C, WinMap m,
+                          int64_t lo_off) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -46,40 +47,46 @@ window_gather_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict
   const int tok = win_row_to_token(m, static_cast<int>(row % L));
   const float4* src = reinterpret_cast<const float4*>(x + (frame * L + tok) * C);
   uint2* dst = reinterpret_cast<uint2*>(h + row * C);
+  uint2* dst_lo = reinterpret_cast<uint2*>(h + lo_off + row * C);
   for (int c = lane; c < (C >> 2); c += 32) {
     const float4 v = src[c];
-    dst[c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    const uint2 hi = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    dst[c] = hi;
+    if (lo_off) dst_lo[c] = make_uint2(pack_bf16x2_lo(v.x, v.y, hi.x), pack_bf16x2_lo(v.z, v.w, hi.y));
   }
 }
 
-int window_gather_bf16(const float* x, void* h, int64_t n, int res, int ws, int shift, int C, cudaStream_t stream) {
+int window_gather_bf16(const float* x, void* h, int64_t n, int res, int ws, int shift, int C, cudaStream_t stream,
+                       int64_t lo_off) {
   VSCB_REQUIRE(C % 4 == 0 && res % ws == 0, "window_gather: C % 4 and res % ws must be 0");
   const int64_t rows = n * res * res;
   if (rows == 0) return VSCB200_OK;
   WinMap m{res, ws, shift, res / ws};
   ProfScope prof(kProfVitOther, stream, static_cast<double>(rows) * C * 6);
   window_gather_bf16_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(h),
-                                                                                       rows, C, m);
+                                                                                       rows, C, m, lo_off);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
 
-constexpr int kSwLnMaxVec = 8;    // float4 per lane -> C <= 1024
+constexpr int kSwLnMaxVec = 8;    // float4 per lane -> C <= 1024 (kSwLnWideVec: <= 2048, SwinV2-L's 1536-wide last stage)
+constexpr int kSwLnWideVec = 16;
 
+template <int kVec>
 __global__ void __launch_bounds__(256)
 ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                            float* __restrict__ x, int64_t rows, int C, float eps, WinMap m, __nv_bfloat16* __restrict__ h_next,
-                           WinMap m_next) {
+                           WinMap m_next, int64_t lo_off) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = C >> 2;
   const float4* yr = reinterpret_cast<const float4*>(y + row * C);
-  float4 v[kSwLnMaxVec];
+  float4 v[kVec];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSwLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       v[i] = yr[c];
@@ -91,7 +98,7 @@ ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict_
   const float mean = sum / C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kSwLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -109,7 +116,7 @@ ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict_
   // (token order for the MLP, the next block's shifted-window order for its QKV projection) -- no gather/cast pass
   uint2* hr = h_next ? reinterpret_cast<uint2*>(h_next + (frame * L + token_to_win_row(m_next, tok)) * C) : nullptr;
 #pragma unroll
-  for (int i = 0; i < kSwLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -120,21 +127,30 @@ ln_residual_scatter_kernel(const float* __restrict__ y, const float* __restrict_
       r.z += (v[i].z - mean) * rstd * gm.z + bt.z;
       r.w += (v[i].w - mean) * rstd * gm.w + bt.w;
       xr[c] = r;
-      if (hr) hr[c] = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+      if (hr) {
+        const uint2 hi = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+        hr[c] = hi;
+        if (lo_off) (hr + (lo_off >> 2))[c] = make_uint2(pack_bf16x2_lo(r.x, r.y, hi.x), pack_bf16x2_lo(r.z, r.w, hi.y));
+      }
     }
   }
 }
 
 int ln_residual_scatter(const float* y, const float* gamma, const float* beta, float* x, int64_t n, int res, int ws, int shift,
-                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next) {
-  VSCB_REQUIRE(C % 4 == 0 && C <= 128 * kSwLnMaxVec && res % ws == 0, "ln_residual_scatter: C must be a multiple of 4, <= 1024");
+                        int C, float eps, cudaStream_t stream, void* h_next, int ws_next, int shift_next, int64_t lo_off) {
+  VSCB_REQUIRE(C % 4 == 0 && C <= 128 * kSwLnWideVec && res % ws == 0, "ln_residual_scatter: C must be a multiple of 4, <= 2048");
+  VSCB_REQUIRE(lo_off % 4 == 0, "ln_residual_scatter: lo plane offset must be a multiple of 4 elements");
   const int64_t rows = n * res * res;
   if (rows == 0) return VSCB200_OK;
   WinMap m{res, ws, shift, res / ws};
   ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * C * 12);
   WinMap mn{res, ws_next > 0 ? ws_next : res, shift_next, ws_next > 0 ? res / ws_next : 1};
-  ln_residual_scatter_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-      y, gamma, beta, x, rows, C, eps, m, reinterpret_cast<__nv_bfloat16*>(h_next), mn);
+  if (C <= 128 * kSwLnMaxVec)
+    ln_residual_scatter_kernel<kSwLnMaxVec><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+        y, gamma, beta, x, rows, C, eps, m, reinterpret_cast<__nv_bfloat16*>(h_next), mn, lo_off);
+  else
+    ln_residual_scatter_kernel<kSwLnWideVec><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+        y, gamma, beta, x, rows, C, eps, m, reinterpret_cast<__nv_bfloat16*>(h_next), mn, lo_off);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -142,7 +158,8 @@ int ln_residual_scatter(const float* y, const float* gamma, const float* beta, f
 
 // out row (frame, y2, x2) = [x(2y2, 2x2) | x(2y2+1, 2x2) | x(2y2, 2x2+1) | x(2y2+1, 2x2+1)]
 __global__ void __launch_bounds__(256)
-patch_merge_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int res, int C) {
+patch_merge_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int res, int C,
+                          int64_t lo_off) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -157,18 +174,20 @@ patch_merge_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict
     const float4* src = reinterpret_cast<const float4*>(x + ((frame * res + yy) * res + xx) * C);
     for (int c = lane; c < (C >> 2); c += 32) {
       const float4 v = src[c];
-      dst[part * (C >> 2) + c] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      const uint2 hi = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      dst[part * (C >> 2) + c] = hi;
+      if (lo_off) (dst + (lo_off >> 2))[part * (C >> 2) + c] = make_uint2(pack_bf16x2_lo(v.x, v.y, hi.x), pack_bf16x2_lo(v.z, v.w, hi.y));
     }
   }
 }
 
-int patch_merge_gather(const float* x, void* out, int64_t n, int res, int C, cudaStream_t stream) {
+int patch_merge_gather(const float* x, void* out, int64_t n, int res, int C, cudaStream_t stream, int64_t lo_off) {
   VSCB_REQUIRE(C % 4 == 0 && res % 2 == 0, "patch_merge: C % 4 and even resolution required");
   const int64_t rows = n * (res / 2) * (res / 2);
   if (rows == 0) return VSCB200_OK;
   ProfScope prof(kProfVitOther, stream, static_cast<double>(rows) * 4 * C * 6);
   patch_merge_gather_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out),
-                                                                                      rows, res, C);
+                                                                                      rows, res, C, lo_off);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;

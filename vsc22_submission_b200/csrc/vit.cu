@@ -6,7 +6,10 @@
 //   L x { LN1 -> QKV GEMM -> fused MHSA -> proj GEMM (+residual) -> LN2 -> fc1 GEMM (+act) -> fc2 GEMM (+residual) }
 //   -> tail: ln_post tokens | ln_post+GeM+Linear (fused) | ln_post -> conv1x1 GEMM -> GeM+Linear.
 // Residual stream, LayerNorm statistics, softmax, GeM and all accumulators are fp32; GEMM operands bf16.
-// No allocation after create(): the workspace is sized for max_frames.
+// spec.precision == VSCB200_PRECISION_FP32: every bf16 operand buffer (weights and activations) holds two planes, hi at
+// the base and lo = bf16(x - hi) `lo_off` elements behind it; the projections run the split-bf16 GEMM and attention runs
+// in fp32 (attention_fp32.cu).
+// No allocation after create(): the workspace and the host-API staging are sized for max_frames.
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,6 +53,8 @@ struct vscb200_vit {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   std::map<std::string, bool> loaded;
+  bool exact = false;        // fp32-equivalent mode: bf16 buffers are (hi, lo) plane pairs
+  int planes = 1;
 };
 
 namespace {
@@ -71,6 +76,27 @@ int64_t out_elems(const vscb200_vit* m) {
   return m->spec.tail == VSCB200_TAIL_TOKENS ? static_cast<int64_t>(m->T) * m->W : m->spec.out_dim;
 }
 
+// lo plane of a bf16 buffer of `elems` elements per plane (nullptr in the bf16 mode)
+inline void* lo_plane(const vscb200_vit* m, void* hi, int64_t elems) {
+  return m->exact ? static_cast<void*>(static_cast<uint16_t*>(hi) + elems) : nullptr;
+}
+
+int host_staging(vscb200_vit* m) {
+  const int64_t in_per = 3LL * m->spec.img * m->spec.img, out_per = out_elems(m);
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
+  VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
+    VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+    VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
+    VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
+  }
+  return VSCB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -84,9 +110,13 @@ int vscb200_vit_create(const vscb200_vit_spec* spec, int max_frames, vscb200_vit
   VSCB_REQUIRE(spec->layers > 0 && max_frames > 0, "vit_create: layers/max_frames must be positive");
   VSCB_REQUIRE(spec->tail >= 0 && spec->tail <= 2, "vit_create: unknown tail");
   VSCB_REQUIRE(spec->tail == VSCB200_TAIL_TOKENS || spec->out_dim > 0, "vit_create: out_dim must be positive");
+  VSCB_REQUIRE(spec->precision == VSCB200_PRECISION_BF16 || spec->precision == VSCB200_PRECISION_FP32,
+               "vit_create: precision must be VSCB200_PRECISION_BF16 or VSCB200_PRECISION_FP32");
   vscb200_vit* m = new vscb200_vit();
   m->spec = *spec;
   m->max_frames = max_frames;
+  m->exact = spec->precision == VSCB200_PRECISION_FP32;
+  m->planes = m->exact ? 2 : 1;
   const int g = spec->img / spec->patch;
   m->P = g * g;
   m->T = m->P + 1;
@@ -98,7 +128,8 @@ int vscb200_vit_create(const vscb200_vit_spec* spec, int max_frames, vscb200_vit
   const size_t M = static_cast<size_t>(max_frames) * m->T;
   int rc = 0;
 #define A(ptr, bytes) if ((rc = dev_alloc(m, &(ptr), (bytes)))) { vscb200_vit_destroy(m); return rc; }
-  A(m->patch_w, static_cast<size_t>(W) * m->Kp * 2);
+  const size_t P2 = 2 * static_cast<size_t>(m->planes);      // bytes per bf16 operand element (both planes)
+  A(m->patch_w, static_cast<size_t>(W) * m->Kp * P2);
   A(m->patch_b, W * 4);
   A(m->cls, W * 4);
   A(m->pos, static_cast<size_t>(m->T) * W * 4);
@@ -107,26 +138,27 @@ int vscb200_vit_create(const vscb200_vit_spec* spec, int max_frames, vscb200_vit
   for (auto& l : m->layers) {
     A(l.ln1_w, W * 4); A(l.ln1_b, W * 4); A(l.ln2_w, W * 4); A(l.ln2_b, W * 4);
     A(l.qkv_b, 3 * W * 4); A(l.proj_b, W * 4); A(l.fc1_b, 4 * W * 4); A(l.fc2_b, W * 4);
-    A(l.qkv_w, static_cast<size_t>(3) * W * W * 2); A(l.proj_w, static_cast<size_t>(W) * W * 2);
-    A(l.fc1_w, static_cast<size_t>(4) * W * W * 2); A(l.fc2_w, static_cast<size_t>(4) * W * W * 2);
+    A(l.qkv_w, static_cast<size_t>(3) * W * W * P2); A(l.proj_w, static_cast<size_t>(W) * W * P2);
+    A(l.fc1_w, static_cast<size_t>(4) * W * W * P2); A(l.fc2_w, static_cast<size_t>(4) * W * W * P2);
   }
   if (spec->tail == VSCB200_TAIL_GEM_LINEAR) {
     A(m->head_w, static_cast<size_t>(spec->out_dim) * W * 4); A(m->head_b, spec->out_dim * 4);
   } else if (spec->tail == VSCB200_TAIL_GEM_CONV_LINEAR) {
     VSCB_REQUIRE(spec->gem_hidden > 0 && spec->gem_hidden % 8 == 0, "vit_create: gem_hidden must be a multiple of 8");
-    A(m->gem_conv_w, static_cast<size_t>(spec->gem_hidden) * W * 2); A(m->gem_conv_b, spec->gem_hidden * 4);
+    A(m->gem_conv_w, static_cast<size_t>(spec->gem_hidden) * W * P2); A(m->gem_conv_b, spec->gem_hidden * 4);
     A(m->head_w, static_cast<size_t>(spec->out_dim) * spec->gem_hidden * 4); A(m->head_b, spec->out_dim * 4);
     A(m->y, M * spec->gem_hidden * 4);
   }
   A(m->x, M * W * 4);
-  A(m->h, M * W * 2);
-  A(m->qkv, M * 3 * W * 2);
-  A(m->ao, M * W * 2);
-  A(m->u, M * 4 * W * 2);
-  A(m->patches, static_cast<size_t>(max_frames) * m->P * m->Kp * 2);
+  A(m->h, M * W * P2);
+  A(m->qkv, M * 3 * W * P2);
+  A(m->ao, M * W * P2);
+  A(m->u, M * 4 * W * P2);
+  A(m->patches, static_cast<size_t>(max_frames) * m->P * m->Kp * P2);
 #undef A
   // zero-initialised optional parameters (patch bias absent in the CLIP flavour)
   cudaMemset(m->patch_b, 0, W * 4);
+  if ((rc = host_staging(m))) { vscb200_vit_destroy(m); return rc; }
   *out = m;
   return VSCB200_OK;
 }
@@ -197,7 +229,7 @@ int vscb200_vit_set_param(vscb200_vit* m, const char* name_c, const float* w, in
     return VSCB200_ERR_INVALID;
   }
   if (t.bf16) {
-    int rc = cast_f32_bf16_padded(w, t.dst, t.rows, t.cols, t.ld, stream);
+    int rc = cast_f32_bf16_padded(w, t.dst, t.rows, t.cols, t.ld, stream, lo_plane(m, t.dst, t.rows * t.ld));
     if (rc) return rc;
   } else {
     VSCB_CUDA_OK(cudaMemcpyAsync(t.dst, w, count * 4, cudaMemcpyDeviceToDevice, stream));
@@ -210,11 +242,18 @@ static int forward_chunk(vscb200_vit* m, const float* frames, int n, float* out,
   const vscb200_vit_spec& sp = m->spec;
   const int W = m->W, T = m->T, P = m->P;
   const int64_t M = static_cast<int64_t>(n) * T;
+  // plane strides (elements) of the operand buffers, fixed by the plan's capacity; 0 in the bf16 mode
+  const int64_t Mcap = static_cast<int64_t>(m->max_frames) * T;
+  const int64_t h_lo = m->exact ? Mcap * W : 0, qkv_lo = m->exact ? Mcap * 3 * W : 0, u_lo = m->exact ? Mcap * 4 * W : 0;
+  const int64_t pat_lo = m->exact ? static_cast<int64_t>(m->max_frames) * P * m->Kp : 0;
+  auto lo = [&](void* hi, int64_t off) -> void* { return off ? static_cast<void*>(static_cast<uint16_t*>(hi) + off) : nullptr; };
+  auto wlo = [&](void* w, int64_t rows, int64_t ld) -> const void* { return lo_plane(m, w, rows * ld); };
   int rc;
 #define R(call) if ((rc = (call))) return rc
-  R(im2row(frames, m->patches, n, sp.img, sp.patch, m->Kp, s));
+  R(im2row(frames, m->patches, n, sp.img, sp.patch, m->Kp, s, pat_lo));
   R(gemm_bf16(m->patches, m->patch_w, sp.patch_bias ? m->patch_b : nullptr, m->x, static_cast<int64_t>(n) * P, W, m->Kp,
-              m->Kp, m->Kp, W, VSCB_EPI_PATCH_F32_ID, -1, s, m->pos, P));
+              m->Kp, m->Kp, W, VSCB_EPI_PATCH_F32_ID, -1, s, m->pos, P, false, 0, nullptr, lo(m->patches, pat_lo),
+              wlo(m->patch_w, W, m->Kp), nullptr));
   R(cls_rows(m->cls, m->pos, m->x, n, T, W, s));
   if (sp.pre_norm) R(layernorm(m->x, m->ln_pre_w, m->ln_pre_b, m->x, M, W, sp.ln_eps, 0, s));
   // zig-zag walk (kernels.h): every kernel consumes its input starting from the rows its producer wrote last
@@ -222,13 +261,22 @@ static int forward_chunk(vscb200_vit* m, const float* frames, int n, float* out,
   bool rev = false;
   auto dir = [&]() { const bool r = rev; if (zigzag) rev = !rev; return r; };
   for (const LayerW& l : m->layers) {
-    R(layernorm(m->x, l.ln1_w, l.ln1_b, m->h, M, W, sp.ln_eps, 1, s, dir()));
-    R(gemm_bf16(m->h, l.qkv_w, l.qkv_b, m->qkv, M, 3 * W, W, W, W, 3 * W, VSCB200_EPI_BF16, -1, s, nullptr, 0, dir()));
-    R(attention(m->qkv, m->ao, n, T, sp.heads, 64, s, dir()));
-    R(gemm_bf16(m->ao, l.proj_w, l.proj_b, m->x, M, W, W, W, W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir()));
-    R(layernorm(m->x, l.ln2_w, l.ln2_b, m->h, M, W, sp.ln_eps, 1, s, dir()));
-    R(gemm_bf16(m->h, l.fc1_w, l.fc1_b, m->u, M, 4 * W, W, W, W, 4 * W, VSCB200_EPI_BF16, sp.act, s, nullptr, 0, dir()));
-    R(gemm_bf16(m->u, l.fc2_w, l.fc2_b, m->x, M, W, 4 * W, 4 * W, 4 * W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir()));
+    R(layernorm(m->x, l.ln1_w, l.ln1_b, m->h, M, W, sp.ln_eps, 1, s, dir(), h_lo));
+    R(gemm_bf16(m->h, l.qkv_w, l.qkv_b, m->qkv, M, 3 * W, W, W, W, 3 * W, VSCB200_EPI_BF16, -1, s, nullptr, 0, dir(), 0, nullptr,
+                lo(m->h, h_lo), wlo(l.qkv_w, 3 * W, W), lo(m->qkv, qkv_lo)));
+    if (m->exact) {
+      dir();
+      R(attention_fp32(m->qkv, qkv_lo, m->ao, h_lo, n, T, sp.heads, 64, 0.125f, nullptr, 0, 0, 0, 0, 0, s));
+    } else {
+      R(attention(m->qkv, m->ao, n, T, sp.heads, 64, s, dir()));
+    }
+    R(gemm_bf16(m->ao, l.proj_w, l.proj_b, m->x, M, W, W, W, W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir(), 0, nullptr,
+                lo(m->ao, h_lo), wlo(l.proj_w, W, W), nullptr));
+    R(layernorm(m->x, l.ln2_w, l.ln2_b, m->h, M, W, sp.ln_eps, 1, s, dir(), h_lo));
+    R(gemm_bf16(m->h, l.fc1_w, l.fc1_b, m->u, M, 4 * W, W, W, W, 4 * W, VSCB200_EPI_BF16, sp.act, s, nullptr, 0, dir(), 0, nullptr,
+                lo(m->h, h_lo), wlo(l.fc1_w, 4 * W, W), lo(m->u, u_lo)));
+    R(gemm_bf16(m->u, l.fc2_w, l.fc2_b, m->x, M, W, 4 * W, 4 * W, 4 * W, W, VSCB200_EPI_RESIDUAL_F32, -1, s, nullptr, 0, dir(), 0,
+                nullptr, lo(m->u, u_lo), wlo(l.fc2_w, W, 4 * W), nullptr));
   }
   if (sp.tail == VSCB200_TAIL_TOKENS) {
     R(layernorm(m->x, m->ln_post_w, m->ln_post_b, out, M, W, sp.ln_eps, 0, s));
@@ -236,9 +284,9 @@ static int forward_chunk(vscb200_vit* m, const float* frames, int n, float* out,
     R(gem_head(m->x, m->ln_post_w, m->ln_post_b, m->head_w, m->head_b, out, n, T, W, sp.out_dim, sp.ln_eps, sp.gem_p,
                true, s));
   } else {
-    R(layernorm(m->x, m->ln_post_w, m->ln_post_b, m->h, M, W, sp.ln_eps, 1, s));
+    R(layernorm(m->x, m->ln_post_w, m->ln_post_b, m->h, M, W, sp.ln_eps, 1, s, false, h_lo));
     R(gemm_bf16(m->h, m->gem_conv_w, m->gem_conv_b, m->y, M, sp.gem_hidden, W, W, W, sp.gem_hidden, VSCB200_EPI_F32, -1,
-                s, nullptr, 0));
+                s, nullptr, 0, false, 0, nullptr, lo(m->h, h_lo), wlo(m->gem_conv_w, sp.gem_hidden, W), nullptr));
     R(gem_head(m->y, nullptr, nullptr, m->head_w, m->head_b, out, n, T, sp.gem_hidden, sp.out_dim, sp.ln_eps,
                sp.gem_p, false, s));
   }
@@ -265,19 +313,6 @@ int vscb200_vit_forward_host(vscb200_vit* m, const float* frames_host, int64_t n
   // buffers; with pageable memory the copies serialise but the result is the same.
   VSCB_REQUIRE(m && (n == 0 || (frames_host && out_host)), "vit_forward_host: null argument");
   const int64_t in_per = 3LL * m->spec.img * m->spec.img, out_per = out_elems(m);
-  if (!m->own_stream) {
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->in_stream, cudaStreamNonBlocking));
-    VSCB_CUDA_OK(cudaStreamCreateWithFlags(&m->out_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; ++b) {
-      VSCB_CUDA_OK(cudaMalloc(&m->frames_stage2[b], static_cast<size_t>(m->max_frames) * in_per * 4));
-      VSCB_CUDA_OK(cudaMalloc(&m->out_stage2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
-      VSCB_CUDA_OK(cudaMallocHost(&m->out_pinned2[b], static_cast<size_t>(m->max_frames) * out_per * 4));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
-      VSCB_CUDA_OK(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
-    }
-  }
   int64_t chunk = 0, last_f0 = 0;
   int last_nc = 0, last_b = 0;
   for (int64_t f0 = 0; f0 < n; f0 += m->max_frames, ++chunk) {

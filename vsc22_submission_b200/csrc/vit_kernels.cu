@@ -8,12 +8,13 @@
 namespace vscb200 {
 
 // ------------------------------------------------------------------ LayerNorm: one warp per row
-constexpr int kLnMaxVec = 8;   // float4 per lane -> width <= 1024
+constexpr int kLnMaxVec = 8;   // float4 per lane -> width <= 1024 (kLnWideVec: <= 2048, SwinV2-L's 1536-wide last stage)
+constexpr int kLnWideVec = 16;
 
-template <bool kOutBf16>
+template <bool kOutBf16, int kVec>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 void* __restrict__ y, int64_t rows, int width, float eps, int reverse) {
+                 void* __restrict__ y, int64_t rows, int width, float eps, int reverse, int64_t lo_off) {
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -22,10 +23,10 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   if (row >= rows) return;
   const int nvec = width >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + row * width);
-  float4 v[kLnMaxVec];
+  float4 v[kVec];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       v[i] = xr[c];
@@ -37,7 +38,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   const float mean = sum / width;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -48,7 +49,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / width + eps);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < kVec; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -61,6 +62,9 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
       if (kOutBf16) {
         uint2 o2 = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
         reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * width)[c] = o2;
+        if (lo_off)       // fp32-equivalent mode: second bf16 plane with the rounding residual
+          reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + lo_off + row * width)[c] =
+              make_uint2(pack_bf16x2_lo(r.x, r.y, o2.x), pack_bf16x2_lo(r.z, r.w, o2.y));
       } else {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * width)[c] = r;
       }
@@ -69,16 +73,23 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 int layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width, float eps,
-              int out_bf16, cudaStream_t stream, bool reverse) {
-  VSCB_REQUIRE(width % 4 == 0 && width <= 128 * kLnMaxVec, "layernorm: width must be a multiple of 4 and <= 1024");
+              int out_bf16, cudaStream_t stream, bool reverse, int64_t lo_off) {
+  VSCB_REQUIRE(width % 4 == 0 && width <= 128 * kLnWideVec, "layernorm: width must be a multiple of 4 and <= 2048");
+  const bool wide = width > 128 * kLnMaxVec;
   if (rows == 0) return VSCB200_OK;
   const int rows_per_block = 8;
   const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
   ProfScope prof(kProfLayerNorm, stream, static_cast<double>(rows) * width * (out_bf16 ? 6 : 8));
-  if (out_bf16)
-    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<true>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0));
+  const int rv = reverse ? 1 : 0;
+  const int64_t no_lo = 0;
+  if (out_bf16 && !wide)
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<true, kLnMaxVec>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, rv, lo_off));
+  else if (out_bf16)
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<true, kLnWideVec>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, rv, lo_off));
+  else if (!wide)
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<false, kLnMaxVec>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, rv, no_lo));
   else
-    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<false>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, reverse ? 1 : 0));
+    VSCB_CUDA_OK(launch_pdl(layernorm_kernel<false, kLnWideVec>, dim3(grid), dim3(256), 0, stream, x, gamma, beta, y, rows, width, eps, rv, no_lo));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -86,19 +97,22 @@ int layernorm(const float* x, const float* gamma, const float* beta, void* y, in
 
 // ------------------------------------------------------------------ fp32 -> bf16 (weights, with row padding)
 __global__ void cast_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t rows, int cols,
-                                int ld_out) {
+                                int ld_out, __nv_bfloat16* __restrict__ y_lo) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * ld_out) return;
   const int64_t r = i / ld_out;
   const int c = static_cast<int>(i % ld_out);
-  y[i] = __float2bfloat16_rn(c < cols ? x[r * cols + c] : 0.f);
+  const float v = c < cols ? x[r * cols + c] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  y[i] = h;
+  if (y_lo) y_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream) {
+int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld_out, cudaStream_t stream, void* y_lo) {
   const int64_t n = rows * ld_out;
   if (n == 0) return VSCB200_OK;
   cast_pad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, ld_out);
+      x, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, ld_out, reinterpret_cast<__nv_bfloat16*>(y_lo));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -108,7 +122,7 @@ int cast_f32_bf16_padded(const float* x, void* y, int64_t rows, int cols, int ld
 // frames [n,3,H,H] fp32 NCHW -> patches [n*P, Kp] bf16, column k = c*p*p + i*p + j (the flattening of
 // conv1.weight [W,3,p,p], clip.py:105), zero padded to Kp.
 __global__ void im2row_kernel(const float* __restrict__ frames, __nv_bfloat16* __restrict__ patches, int64_t n,
-                              int img, int patch, int Kp) {
+                              int img, int patch, int Kp, int64_t lo_off) {
   const int grid = img / patch;
   const int P = grid * grid;
   const int kpairs = Kp >> 1;
@@ -127,13 +141,16 @@ __global__ void im2row_kernel(const float* __restrict__ frames, __nv_bfloat16* _
     const float* src = frames + ((f * 3 + c) * img + (py * patch + i)) * static_cast<int64_t>(img) + px * patch + j;
     v = *reinterpret_cast<const float2*>(src);
   }
-  reinterpret_cast<uint32_t*>(patches)[idx] = pack_bf16x2(v.x, v.y);
+  const uint32_t hi = pack_bf16x2(v.x, v.y);
+  reinterpret_cast<uint32_t*>(patches)[idx] = hi;
+  if (lo_off) reinterpret_cast<uint32_t*>(patches + lo_off)[idx] = pack_bf16x2_lo(v.x, v.y, hi);
 }
 
 // Fast path (patch % 4 == 0, no K padding): one thread per 4 consecutive pixels of an image row -- a 128-bit
 // coalesced read of the frame, one 8-byte store into the patch row (4 threads fill a 32-byte sector).
 __global__ void __launch_bounds__(256)
-im2row_vec4_kernel(const float4* __restrict__ frames, uint2* __restrict__ patches, int64_t total, int img, int patch) {
+im2row_vec4_kernel(const float4* __restrict__ frames, uint2* __restrict__ patches, int64_t total, int img, int patch,
+                   int64_t lo_off4) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int q = img >> 2;                                   // float4 per image row
@@ -148,18 +165,21 @@ im2row_vec4_kernel(const float4* __restrict__ frames, uint2* __restrict__ patche
   const int K = 3 * patch * patch;
   const int64_t dst = ((f * grid + py) * grid + px) * K + (c * patch + i) * patch + j;     // bf16 elements
   const float4 v = ldg_nc_f4(frames + idx);
-  patches[dst >> 2] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  const uint2 hi = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  patches[dst >> 2] = hi;
+  if (lo_off4) patches[lo_off4 + (dst >> 2)] = make_uint2(pack_bf16x2_lo(v.x, v.y, hi.x), pack_bf16x2_lo(v.z, v.w, hi.y));
 }
 
-int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream) {
+int im2row(const float* frames, void* patches, int64_t n, int img, int patch, int Kp, cudaStream_t stream, int64_t lo_off) {
   VSCB_REQUIRE(patch % 2 == 0 && img % patch == 0 && Kp % 2 == 0, "im2row: patch must be even and divide img");
+  VSCB_REQUIRE(lo_off % 4 == 0, "im2row: lo plane offset must be a multiple of 4 elements");
   const int P = (img / patch) * (img / patch);
   if (n == 0) return VSCB200_OK;
   if (patch % 4 == 0 && Kp == 3 * patch * patch && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
     const int64_t total4 = n * 3 * img * (img / 4);
     ProfScope prof(kProfVitOther, stream, static_cast<double>(total4) * 24);
     im2row_vec4_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const float4*>(frames), reinterpret_cast<uint2*>(patches), total4, img, patch);
+        reinterpret_cast<const float4*>(frames), reinterpret_cast<uint2*>(patches), total4, img, patch, lo_off / 4);
     count_launch();
     VSCB_CUDA_OK(cudaGetLastError());
     return VSCB200_OK;
@@ -167,7 +187,7 @@ int im2row(const float* frames, void* patches, int64_t n, int img, int patch, in
   const int64_t total = n * P * (Kp / 2);
   ProfScope prof(kProfVitOther, stream, static_cast<double>(total) * 2 * 6);
   im2row_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-      frames, reinterpret_cast<__nv_bfloat16*>(patches), n, img, patch, Kp);
+      frames, reinterpret_cast<__nv_bfloat16*>(patches), n, img, patch, Kp, lo_off);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -195,7 +215,7 @@ int cls_rows(const float* cls, const float* pos, float* x, int64_t n, int T, int
 // g[c] = (mean_t clamp(y[t,c], 1e-6)^p)^(1/p) ; out[o] = head_b[o] + sum_c head_w[o,c] * g[c].
 constexpr int kTailThreads = 256;
 
-template <bool kLN>
+template <bool kLN, int kVec>
 __global__ void __launch_bounds__(kTailThreads)
 gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ pooled, int T, int C, float eps, float p) {
@@ -209,15 +229,15 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
   if (kLN) {
     // one warp per token row; lane owns columns lane*4 + 128*i
     const int nvec = C >> 2;
-    float4 acc[kLnMaxVec];
+    float4 acc[kVec];
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kVec; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = warp; t < T; t += nwarp) {
       const float4* xr = reinterpret_cast<const float4*>(yf + static_cast<int64_t>(t) * C);
-      float4 v[kLnMaxVec];
+      float4 v[kVec];
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < kLnMaxVec; ++i) {
+      for (int i = 0; i < kVec; ++i) {
         const int c = lane + 32 * i;
         if (c < nvec) { v[i] = xr[c]; sum += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
       }
@@ -226,7 +246,7 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
       const float mean = sum / C;
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < kLnMaxVec; ++i) {
+      for (int i = 0; i < kVec; ++i) {
         const int c = lane + 32 * i;
         if (c < nvec) {
           const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -237,7 +257,7 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = rsqrtf(sq / C + eps);
 #pragma unroll
-      for (int i = 0; i < kLnMaxVec; ++i) {
+      for (int i = 0; i < kVec; ++i) {
         const int c = lane + 32 * i;
         if (c < nvec) {
           const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
@@ -254,7 +274,7 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
       }
     }
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
+    for (int i = 0; i < kVec; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         atomicAdd(&tail_smem[4 * c + 0], acc[i].x);
@@ -321,7 +341,7 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
              float* out, int64_t n, int T, int C, int out_dim, float eps, float p, bool fuse_ln,
              cudaStream_t stream) {
   if (n == 0) return VSCB200_OK;
-  VSCB_REQUIRE(!fuse_ln || (C % 4 == 0 && C <= 128 * kLnMaxVec), "gem_head: fused LN needs width % 4 == 0 and <= 1024");
+  VSCB_REQUIRE(!fuse_ln || (C % 4 == 0 && C <= 128 * kLnWideVec), "gem_head: fused LN needs width % 4 == 0 and <= 2048");
   const size_t smem = static_cast<size_t>(C) * sizeof(float);
   const size_t hl_smem_bytes = static_cast<size_t>(kHlFrames) * C * sizeof(float);
   VSCB_REQUIRE(hl_smem_bytes <= 200 * 1024, "gem_head: width too large for the head kernel");
@@ -330,10 +350,12 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
   int rc = pool_alloc(reinterpret_cast<void**>(&pooled), static_cast<size_t>(n) * C * sizeof(float), stream);
   if (rc) return rc;
   ProfScope prof(kProfVitOther, stream, static_cast<double>(n) * T * C * 4);
-  if (fuse_ln)
-    gem_head_kernel<true><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
+  if (fuse_ln && C <= 128 * kLnMaxVec)
+    gem_head_kernel<true, kLnMaxVec><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
+  else if (fuse_ln)
+    gem_head_kernel<true, kLnWideVec><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
   else
-    gem_head_kernel<false><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
+    gem_head_kernel<false, kLnMaxVec><<<static_cast<unsigned>(n), kTailThreads, smem, stream>>>(y, gamma, beta, pooled, T, C, eps, p);
   count_launch();
   dim3 grid(static_cast<unsigned>((n + kHlFrames - 1) / kHlFrames), static_cast<unsigned>((out_dim + kHlOuts - 1) / kHlOuts));
   head_linear_kernel<<<grid, 256, hl_smem_bytes, stream>>>(pooled, head_w, head_b, out, n, C,
@@ -349,9 +371,12 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
 extern "C" {
 int vscb200_layernorm(const float* x, const float* gamma, const float* beta, void* y, int64_t rows, int width,
                       float eps, int out_bf16, void* stream) {
-  return vscb200::layernorm(x, gamma, beta, y, rows, width, eps, out_bf16, static_cast<cudaStream_t>(stream), false);
+  return vscb200::layernorm(x, gamma, beta, y, rows, width, eps, out_bf16, static_cast<cudaStream_t>(stream), false, 0);
+}
+int vscb200_split_f32_bf16(const float* x, void* hi_bf16, void* lo_bf16, int64_t count, void* stream) {
+  return vscb200::cast_f32_bf16_padded(x, hi_bf16, count, 1, 1, static_cast<cudaStream_t>(stream), lo_bf16);
 }
 int vscb200_cast_f32_bf16(const float* x, void* y_bf16, int64_t count, void* stream) {
-  return vscb200::cast_f32_bf16_padded(x, y_bf16, count, 1, 1, static_cast<cudaStream_t>(stream));
+  return vscb200::cast_f32_bf16_padded(x, y_bf16, count, 1, 1, static_cast<cudaStream_t>(stream), nullptr);
 }
 }

@@ -40,6 +40,10 @@ class VitSpec:
     out_dim: int = 512
     gem_p: float = 3.0
     gem_hidden: int = 2048
+    # "bf16": tensor-core operands rounded to bf16 (throughput mode; == the matched-precision oracle within 1e-3);
+    # "fp32": fp32-equivalent arithmetic (split-bf16 tcgen05 GEMMs, fp32 attention; == the reference's fp32 module
+    #         within 1e-3 -- the reference calls its encoders without autocast, D/infer/src/extractor.py:25)
+    precision: str = "bf16"
 
     @property
     def tokens(self) -> int:
@@ -62,12 +66,14 @@ class VitSpec:
             act={"quick_gelu": _lib.ACT_QUICK_GELU, "gelu": _lib.ACT_GELU}[self.act],
             tail={"tokens": _lib.TAIL_TOKENS, "gem_linear": _lib.TAIL_GEM_LINEAR,
                   "gem_conv_linear": _lib.TAIL_GEM_CONV_LINEAR}[self.tail],
-            out_dim=self.out_dim, gem_hidden=self.gem_hidden, ln_eps=self.ln_eps, gem_p=self.gem_p)
+            out_dim=self.out_dim, gem_hidden=self.gem_hidden, ln_eps=self.ln_eps, gem_p=self.gem_p,
+            precision=_lib.PRECISION[self.precision])
 
 
 # Named configurations on the reference's inference path / in BASELINE.json
 VIT_B16_224_GEM = VitSpec(224, 16, 768, 12, 12, tail="gem_linear")                    # BASELINE config 2
 CLIP_L14_224 = VitSpec(224, 14, 1024, 24, 16, tail="tokens")                          # extract_query_feats.py:77
+VIT_L16_384 = VitSpec(384, 16, 1024, 24, 16, tail="tokens")                           # BASELINE configs[3] "ViT-L ... 384^2" (T = 577)
 VIT_V68 = VitSpec(384, 32, 768, 12, 12, patch_bias=True, pre_norm=False, act="gelu", ln_eps=1e-6,
                   tail="gem_conv_linear")                                              # infer_ref.sh vit_v68
 

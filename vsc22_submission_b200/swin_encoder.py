@@ -35,6 +35,7 @@ class SwinSpec:
     out_dim: int = 512
     gem_p: float = 3.0
     ln_eps: float = 1e-5
+    precision: str = "bf16"        # "bf16" | "fp32" (fp32-equivalent arithmetic), see encoder.VitSpec.precision
 
     def stage(self, i: int):
         res = self.img // self.patch // (2 ** i)
@@ -55,10 +56,13 @@ class SwinSpec:
         return _lib.SwinSpecC(img=self.img, patch=self.patch, embed=self.embed, n_stages=len(self.depths),
                               depths=pad(self.depths), heads=pad(self.heads), window=self.window,
                               pretrained_windows=pad(self.pretrained_windows), out_dim=self.out_dim,
-                              ln_eps=self.ln_eps, gem_p=self.gem_p)
+                              ln_eps=self.ln_eps, gem_p=self.gem_p, precision=_lib.PRECISION[self.precision])
 
 
 SWINV2_B_256 = SwinSpec()          # config_v106.py: swinv2_v106 / v107 / v115
+# BASELINE configs[3] "Swin-L ... 384^2": SwinV2-L, 24 x 24 windows (576 tokens), pre-trained at window 12
+SWINV2_L_384 = SwinSpec(img=384, patch=4, embed=192, depths=(2, 2, 18, 2), heads=(6, 12, 24, 48), window=24,
+                        pretrained_windows=(12, 12, 12, 6), out_dim=512)
 
 
 def param_names(spec: SwinSpec) -> List[str]:
