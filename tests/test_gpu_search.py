@@ -363,3 +363,50 @@ def test_near_duplicate_frame_filter_and_query_tail():
     assert idx.cpu().tolist() == want_idx and len(want_idx) < 40
     ref = pca_np.ensemble_pca([p[want_idx] for p in parts], mean, comp)
     assert np.abs(feats.cpu().numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_single_pass_search_equals_split_path_and_oracle(faiss, monkeypatch):
+    """k <= 10 on a large bank: selection on ONE bf16 MMA per product + error margin + exact rescoring (sim_tc1.cu) must
+    return exactly what the split-bf16 (3 MMAs) path and the fp32 oracle return -- also where the margin is crowded:
+    300 bank rows within 2e-3 of a query (survivor overflow -> exhaustive fp32 fallback for that query)."""
+    from oracle import faiss_np
+    rng = np.random.default_rng(31)
+    d = 256
+    unit = lambda x: (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+    xb = unit(rng.standard_normal((50000, d)))
+    xq = unit(rng.standard_normal((700, d)))
+    xb[20000:20300] = unit(xq[5] + 2e-3 * rng.standard_normal((300, d)))        # crowded margin for query 5
+    xb[41000:41012] = unit(xq[9] + 1e-2 * rng.standard_normal((12, d)))         # a dozen close rows for query 9
+    res = {}
+    for passes in ("1", "3"):
+        monkeypatch.setenv("VSCB200_SIM_PASSES", passes)
+        for metric in (faiss.METRIC_INNER_PRODUCT, faiss.METRIC_L2):
+            ix = faiss.IndexFlat(d, metric)
+            ix.add(xb)
+            res[passes, metric] = ix.search(xq, 10)
+    for metric in (faiss.METRIC_INNER_PRODUCT, faiss.METRIC_L2):
+        (D1, I1), (D3, I3) = res["1", metric], res["3", metric]
+        np.testing.assert_array_equal(I1, I3)
+        np.testing.assert_array_equal(D1, D3)          # both report the one exact fp32 summation order
+        o = faiss_np.IndexFlat(d, metric)
+        o.add(xb)
+        Do, Io = o.search(xq, 10)
+        ok, frac = tie_aware_equal(I1, D1, Io, Do)
+        assert ok and frac > 0.995, frac
+        assert np.abs(D1 - Do).max() <= 1e-5
+
+
+def test_single_pass_search_ragged_shapes(faiss):
+    """Bank / query counts that are not multiples of the 256-wide pair tiles, several query blocks, k = 1."""
+    from oracle import faiss_np
+    rng = np.random.default_rng(32)
+    for (nb, nq, d, k) in [(2049, 129, 64, 1), (70001, 1000, 512, 10), (5000, 513, 96, 7)]:
+        xb = rng.standard_normal((nb, d)).astype(np.float32)
+        xq = rng.standard_normal((nq, d)).astype(np.float32)
+        a, b = faiss.IndexFlat(d, faiss.METRIC_INNER_PRODUCT), faiss_np.IndexFlat(d, faiss.METRIC_INNER_PRODUCT)
+        a.add(xb); b.add(xb)
+        D, I = a.search(xq, k)
+        Do, Io = b.search(xq, k)
+        ok, frac = tie_aware_equal(I, D, Io, Do)
+        assert ok and frac > 0.999, (nb, nq, d, k, frac)
+        assert np.abs(D - Do).max() <= 1e-3 * np.abs(Do).max()

@@ -83,7 +83,12 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
   if (rc) return rc;
   float* dst = ix->bank + ix->ntotal * ix->d;
   VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
-  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);   // L2 transform + range-search error margins
+  if (!ix->rmax2_bits && (rc = pool_alloc(reinterpret_cast<void**>(&ix->rmax2_bits), sizeof(unsigned int), s))) return rc;
+  if (ix->rmax2_reset) {
+    VSCB_CUDA_OK(cudaMemsetAsync(ix->rmax2_bits, 0, sizeof(unsigned int), s));
+    ix->rmax2_reset = false;
+  }
+  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s, ix->rmax2_bits);   // L2 transform + search error margins
   if (rc) return rc;
   if (!ix->force_simt) {
     rc = split_planes(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->bank_lo + ix->ntotal * ix->dp, n, ix->d, ix->dp, s);
@@ -223,6 +228,8 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
   ix->no_fused = (nf && atoi(nf)) ? 1 : 0;
   const char* ns = getenv("VSCB200_NO_STREAM_SEARCH");
   ix->no_stream = (ns && atoi(ns)) ? 1 : 0;
+  const char* sp = getenv("VSCB200_SIM_PASSES");     // 3: the split-bf16 fused top-k (cross-validation / A-B timing)
+  ix->sim_passes = (sp && atoi(sp) == 3) ? 3 : 1;
   *out = ix;
   return VSCB200_OK;
 }
@@ -235,7 +242,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   }
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
-  void* blocks[] = {ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
+  void* blocks[] = {ix->rmax2_bits, ix->flags, ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
                     ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax,
                     ix->g_score, ix->g_q, ix->g_r, ix->vp_score, ix->vp_q, ix->vp_r};
   if (ix->own_stream && s == ix->own_stream) {
@@ -288,6 +295,7 @@ int vscb200_index_reset(vscb200_index* ix) {
   std::lock_guard<std::mutex> lk(g_stage_mu);
   if (g_stage_owner == ix) { g_stage_owner = nullptr; g_stage_rows = 0; }
   ix->ntotal = 0;
+  ix->rmax2_reset = true;
   return VSCB200_OK;
 }
 
@@ -344,8 +352,32 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
     return group_rescore(q, ix->bank, ix->d, !keep_max, ix->ntotal, ix->Itmp, nullptr, nullptr, 0, kg, nq, k, D, I,
                          ix->id_offset, s);
   }
-  // Small k on a large bank: top-k fused into the scoring kernel's epilogue (no score block in HBM), then a
-  // per-query merge + exact rescoring of the survivors.
+  // Small k on a large bank, single pass: approximate scores from ONE bf16 MMA per product select, per query, every
+  // bank row within a proven error margin of the k-th best; the survivors are rescored in exact fp32 (sim_tc1.cu).
+  if (!ix->force_simt && !ix->no_fused && ix->sim_passes == 1 && k + 6 <= sim1_list_len() && ix->ntotal >= 2048 &&
+      ix->ntotal < (1ll << 31) && ix->d % 4 == 0) {
+    const int fk = sim1_list_len();
+    for (int64_t q0 = 0; q0 < nq; q0 += (1 << 20)) {
+      const int64_t nb = std::min<int64_t>(1 << 20, nq - q0);
+      const int slabs = sim1_slabs(nb, ix->ntotal);
+      const size_t ncand = static_cast<size_t>(slabs) * 2 * fk;
+      if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nb) * ncand * sizeof(float), s))) return rc;
+      if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nb) * ncand * sizeof(int32_t), s))) return rc;
+      if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nb) * sizeof(float), s))) return rc;
+      if ((rc = grow(&ix->flags, &ix->flags_bytes, static_cast<size_t>(nb + 1) * sizeof(int), s))) return rc;
+      const float* qb = q + q0 * ix->d;
+      const size_t plane = static_cast<size_t>(nb) * ix->dp;
+      if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
+      if ((rc = q_hi_norm(qb, ix->q_planes, ix->qnorm, nb, ix->d, ix->dp, s))) return rc;
+      VSCB_CUDA_OK(cudaMemsetAsync(ix->flags + nb, 0, sizeof(int), s));
+      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, slabs, ix->cand_d,
+                          ix->cand_i, s))) return rc;
+      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slabs, k, ix->qnorm,
+                             ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->flags + nb, s))) return rc;
+    }
+    return VSCB200_OK;
+  }
+  // The same with fp32-equivalent scores (three MMAs per product), kept for cross-validation (VSCB200_SIM_PASSES=3).
   const int kFusedSlack = 6;
   if (!ix->force_simt && !ix->no_fused && k + kFusedSlack <= fused_topk_list_len() && ix->ntotal >= 2048 &&
       ix->ntotal < (1ll << 31)) {

@@ -81,7 +81,8 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
 }
 
 // ------------------------------------------------------------------ squared row norms (warp per row)
-__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
+__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out,
+                                  unsigned int* __restrict__ max_bits) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -92,12 +93,17 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d,
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[row] = s;
+  if (lane == 0) {
+    out[row] = s;
+    if (max_bits) atomicMax(max_bits, __float_as_uint(s));      // s >= 0: float order == unsigned order of the bits
+  }
 }
 
-int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream) {
+// max_bits != nullptr: also maintains the running maximum of the squared norms (as float bits) -- the |r| bound of the
+// single-pass search margin (sim_tc1.cu)
+int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream, unsigned int* max_bits) {
   if (n == 0) return VSCB200_OK;
-  row_sqnorm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, out);
+  row_sqnorm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, out, max_bits);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
