@@ -78,6 +78,10 @@ int vscb200_index_search(vscb200_index* ix, const float* q_dev, int64_t nq, int 
                          void* stream);
 int vscb200_index_search_host(vscb200_index* ix, const float* q_host, int64_t nq, int k, float* D_host,
                               int64_t* I_host);
+/* index.reconstruct_n(i0, n) -> rows [i0, i0+n) as float32 into host memory or the memory of any device; complete on return */
+int vscb200_index_reconstruct_n(vscb200_index* ix, int64_t i0, int64_t n, float* out);
+/* diagnostic: how many queries of the last small-k batch search needed the exhaustive fp32 fallback (-1: none ran) */
+int64_t vscb200_index_last_fallbacks(vscb200_index* ix);
 
 /* index.range_search(x, thresh) -> (lims, D, I) -- exhaustive_search.py:74,126,246,
  * infer_matching.py:235.  Strict '>' (IP) / '<' (L2).  lims: [nq+1] uint64 (host); D/I are allocated
@@ -121,6 +125,20 @@ int vscb200_sn_transform_dev(const float* x_dev, int64_t n, int d, const int* dr
 int vscb200_low_var_dim_dev(const float* x_dev, int64_t n, int d, int* dim_dev, void* stream);
 /* column variance argmin of a [n, d] matrix (score_normalization.py:72), result to *dim_host */
 int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, void* stream);
+/* Row-sharded banks: the two passes of the column variance separately, so that the [d] vectors can be
+ * all-reduced between them.  out[c] = sum_r x[r,c] (sum_in_dev == NULL) or sum_r (x[r,c] - sum_in_dev[c]*inv_n)^2.
+ * Fixed reduction order (deterministic).  vscb200_var_argmin_dev: first minimum of ss_dev[0..d) -> *dim_dev. */
+int vscb200_col_sums(const float* x_dev, int64_t n, int d, const double* sum_in_dev, double inv_n, double* out_dev,
+                     void* stream);
+int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stream);
+/* Exchange format of partial top-k results between bank shards: one 64-bit key per entry,
+ * (order-preserving score bits << 32) | ~id (0 = padding; ids < 2^32), so ONE all-gather moves scores and ids.
+ * vscb200_topk_merge: keys_dev [parts][nq][kin] (the all-gather layout) -> the kout best per query, best first, ties to
+ * the lower id (faiss order). */
+int vscb200_topk_pack(const float* D_dev, const int64_t* I_dev, int64_t nq, int k, int keep_max, uint64_t* keys_dev,
+                      void* stream);
+int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin, int kout, int keep_max, float* D_dev,
+                       int64_t* I_dev, void* stream);
 /* bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96) */
 int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream);
 

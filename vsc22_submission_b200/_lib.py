@@ -62,6 +62,8 @@ SIGNATURES = {
     "vscb200_index_set_id_offset": (_i, [_p, _i64]),
     "vscb200_index_search": (_i, [_p, _p, _i64, _i, _p, _p, _p]),
     "vscb200_index_search_host": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "vscb200_index_last_fallbacks": (_i64, [_p]),
+    "vscb200_index_reconstruct_n": (_i, [_p, _i64, _i64, _p]),
     "vscb200_index_range_search_host": (_i, [_p, _p, _i64, _f, _p, C.POINTER(_p), C.POINTER(_p)]),
     "vscb200_free": (None, [_p]),
     "vscb200_index_scores": (_i, [_p, _p, _i64, _p, _i64, _p]),
@@ -74,6 +76,10 @@ SIGNATURES = {
     "vscb200_low_var_dim_dev": (_i, [_p, _i64, _i, _p, _p]),
     "vscb200_low_var_dim": (_i, [_p, _i64, _i, C.POINTER(_i), _p]),
     "vscb200_sn_bias": (_i, [_p, _i64, _i, _i, _f, _p, _p]),
+    "vscb200_col_sums": (_i, [_p, _i64, _i, _p, C.c_double, _p, _p]),
+    "vscb200_var_argmin_dev": (_i, [_p, _i, _p, _p]),
+    "vscb200_topk_pack": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    "vscb200_topk_merge": (_i, [_p, _i, _i64, _i, _i, _i, _p, _p, _p]),
     "vscb200_vit_create": (_i, [C.POINTER(VitSpecC), _i, C.POINTER(_p)]),
     "vscb200_vit_destroy": (None, [_p]),
     "vscb200_vit_set_param": (_i, [_p, C.c_char_p, _p, _i64, _p]),

@@ -58,13 +58,15 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  static std::atomic<int> sms[64];                 // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
   }
-  return sms;
+  return v;
 }
 
 // ---------------------------------------------------------------- caching allocator
@@ -125,8 +127,16 @@ void pool_free(void* p, cudaStream_t stream) {
     if (g_pool_live[i].p == p) {
       PoolBlock b = g_pool_live[i];
       g_pool_live.erase(g_pool_live.begin() + i);
-      if (!b.ev) cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
-      if (b.ev) cudaEventRecord(b.ev, stream);
+      // The guarding event belongs to the block's device, which need not be the caller's current one (an index
+      // destroyed from a Python finaliser while another GPU is current): switch for the create / record, and if the
+      // record fails (`stream` of a different device) order the reuse by draining the stream instead.
+      DeviceGuard guard(b.device);
+      if (!b.ev && cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) b.ev = nullptr;
+      if (!b.ev || cudaEventRecord(b.ev, stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(stream);
+        if (b.ev) { cudaEventDestroy(b.ev); b.ev = nullptr; }
+      }
       g_pool_free.push_back(b);
       return;
     }

@@ -40,7 +40,19 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
                  uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 
-int device_sm_count();
+int device_sm_count();     // of the current device (cached per device)
+
+// Switch to `dev` for the lifetime of the guard (several GPUs driven by one process: faiss_compat.index_cpu_to_all_gpus)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 bool pdl_enabled();     // VSCB200_PDL=1: launch with programmatic stream serialization (measured: no gain, off by default)
 
 // <<<>>> with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the

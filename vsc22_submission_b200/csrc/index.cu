@@ -83,12 +83,14 @@ int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kin
   if (rc) return rc;
   float* dst = ix->bank + ix->ntotal * ix->d;
   VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
-  if (!ix->rmax2_bits && (rc = pool_alloc(reinterpret_cast<void**>(&ix->rmax2_bits), sizeof(unsigned int), s))) return rc;
+  if (!ix->rmax2_bits && (rc = pool_alloc(reinterpret_cast<void**>(&ix->rmax2_bits), 2 * sizeof(unsigned int), s))) return rc;
   if (ix->rmax2_reset) {
-    VSCB_CUDA_OK(cudaMemsetAsync(ix->rmax2_bits, 0, sizeof(unsigned int), s));
+    VSCB_CUDA_OK(cudaMemsetAsync(ix->rmax2_bits, 0, 2 * sizeof(unsigned int), s));
     ix->rmax2_reset = false;
   }
-  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s, ix->rmax2_bits);   // L2 transform + search error margins
+  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);   // L2 transform + range-search error margins
+  if (rc) return rc;
+  if (!ix->force_simt) rc = bank_norm_max(dst, n, ix->d, ix->rmax2_bits, s);   // margin of the single-pass search
   if (rc) return rc;
   if (!ix->force_simt) {
     rc = split_planes(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->bank_lo + ix->ntotal * ix->dp, n, ix->d, ix->dp, s);
@@ -115,12 +117,6 @@ StageSlot g_stage[2];
 int g_stage_cur = 0;
 vscb200_index* g_stage_owner = nullptr;      // the index whose rows sit in the current slot
 int64_t g_stage_rows = 0;
-
-struct DeviceGuard {
-  int prev = 0;
-  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev != prev) cudaSetDevice(dev); else prev = -1; }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
 int stage_init() {
   for (StageSlot& sl : g_stage)
@@ -236,6 +232,7 @@ int vscb200_index_create(int d, int metric, vscb200_index** out) {
 
 void vscb200_index_destroy(vscb200_index* ix) {
   if (!ix) return;
+  DeviceGuard guard(ix->device);          // may run from a finaliser while another device is current
   {
     std::lock_guard<std::mutex> lk(g_stage_mu);
     if (g_stage_owner == ix) { g_stage_owner = nullptr; g_stage_rows = 0; }      // rows never searched: dropped
@@ -359,21 +356,23 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
     const int fk = sim1_list_len();
     for (int64_t q0 = 0; q0 < nq; q0 += (1 << 20)) {
       const int64_t nb = std::min<int64_t>(1 << 20, nq - q0);
-      const int slabs = sim1_slabs(nb, ix->ntotal);
-      const size_t ncand = static_cast<size_t>(slabs) * 2 * fk;
+      int pairs = 0, slots = 0;
+      sim1_plan(nb, ix->ntotal, &pairs, &slots);
+      const size_t ncand = static_cast<size_t>(slots) * 2 * fk;
       if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nb) * ncand * sizeof(float), s))) return rc;
       if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nb) * ncand * sizeof(int32_t), s))) return rc;
-      if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nb) * sizeof(float), s))) return rc;
+      if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(2 * nb) * sizeof(float), s))) return rc;
       if ((rc = grow(&ix->flags, &ix->flags_bytes, static_cast<size_t>(nb + 1) * sizeof(int), s))) return rc;
       const float* qb = q + q0 * ix->d;
       const size_t plane = static_cast<size_t>(nb) * ix->dp;
       if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
-      if ((rc = q_hi_norm(qb, ix->q_planes, ix->qnorm, nb, ix->d, ix->dp, s))) return rc;
+      if ((rc = q_hi_norm(qb, ix->q_planes, ix->qnorm, ix->qnorm + nb, nb, ix->d, ix->dp, s))) return rc;
       VSCB_CUDA_OK(cudaMemsetAsync(ix->flags + nb, 0, sizeof(int), s));
-      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, slabs, ix->cand_d,
-                          ix->cand_i, s))) return rc;
-      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slabs, k, ix->qnorm,
-                             ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->flags + nb, s))) return rc;
+      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, pairs, slots,
+                          ix->cand_d, ix->cand_i, s))) return rc;
+      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slots, k, ix->qnorm,
+                             ix->qnorm + nb, ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->flags + nb, s))) return rc;
+      ix->last_flag_count = ix->flags + nb;
     }
     return VSCB200_OK;
   }
@@ -432,10 +431,40 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   return VSCB200_OK;
 }
 
+/* index.reconstruct_n(i0, n): rows [i0, i0 + n) of the bank as float32.  `out` may be host memory or memory of ANY device
+ * (unified addressing): this is how faiss_compat.index_cpu_to_all_gpus distributes a bank over the GPUs of one process.
+ * The copy runs on the index's own stream (on the index's device) and has completed when the call returns. */
+int vscb200_index_reconstruct_n(vscb200_index* ix, int64_t i0, int64_t n, float* out) {
+  VSCB_REQUIRE(ix && (n == 0 || out), "index_reconstruct_n: null argument");
+  DeviceGuard guard(ix->device);
+  cudaStream_t s;
+  int rc = own_stream(ix, &s);
+  if (rc) return rc;
+  if ((rc = flush_pending(ix, s))) return rc;
+  VSCB_REQUIRE(i0 >= 0 && n >= 0 && i0 + n <= ix->ntotal, "index_reconstruct_n: row range out of bounds");
+  if (n == 0) return VSCB200_OK;
+  VSCB_CUDA_OK(cudaMemcpyAsync(out, ix->bank + i0 * ix->d, static_cast<size_t>(n) * ix->d * sizeof(float), cudaMemcpyDefault, s));
+  VSCB_CUDA_OK(cudaStreamSynchronize(s));
+  return VSCB200_OK;
+}
+
+int64_t vscb200_index_last_fallbacks(vscb200_index* ix) {
+  // diagnostic: queries of the last single-pass search (its last 2^20-row block) that took the exhaustive fallback
+  if (!ix || !ix->last_flag_count) return -1;
+  int n = 0;
+  if (cudaStreamSynchronize(ix->last_stream) != cudaSuccess ||
+      cudaMemcpy(&n, ix->last_flag_count, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
 int vscb200_index_search_host(vscb200_index* ix, const float* q_host, int64_t nq, int k, float* D_host,
                               int64_t* I_host) {
   VSCB_REQUIRE(ix && (nq == 0 || (q_host && D_host && I_host)), "index_search_host: null argument");
   if (nq == 0) return VSCB200_OK;
+  DeviceGuard guard(ix->device);
   cudaStream_t s;
   int rc = own_stream(ix, &s);
   if (rc) return rc;
@@ -475,6 +504,7 @@ int vscb200_index_range_search_host(vscb200_index* ix, const float* q_host, int6
   *D_out = nullptr;
   *I_out = nullptr;
   lims_host[0] = 0;
+  DeviceGuard guard(ix->device);
   cudaStream_t s;
   int rc = own_stream(ix, &s);
   if (rc) return rc;

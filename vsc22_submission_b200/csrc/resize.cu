@@ -14,6 +14,7 @@
 
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -41,12 +42,14 @@ struct CoeffTable {
 };
 
 std::mutex g_mu;
-std::map<std::pair<int, int>, CoeffTable> g_tables;
+std::map<std::tuple<int, int, int>, CoeffTable> g_tables;      // (device, input size, output size): the tables live in device memory
 
 // precompute_coeffs + normalize_coeffs_8bpc (Resample.c) for the full-image box
 int get_table(int in_size, int out_size, CoeffTable* out, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_tables.find({in_size, out_size});
+  int dev = 0;
+  VSCB_CUDA_OK(cudaGetDevice(&dev));
+  auto it = g_tables.find(std::make_tuple(dev, in_size, out_size));
   if (it != g_tables.end()) { *out = it->second; return VSCB200_OK; }
   const double scale = static_cast<double>(in_size) / out_size;
   const double filterscale = scale < 1.0 ? 1.0 : scale;
@@ -82,7 +85,7 @@ int get_table(int in_size, int out_size, CoeffTable* out, cudaStream_t s) {
   VSCB_CUDA_OK(cudaMemcpyAsync(t.bounds, bounds.data(), bounds.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VSCB_CUDA_OK(cudaMemcpyAsync(t.weights, kk.data(), kk.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VSCB_CUDA_OK(cudaStreamSynchronize(s));       // the host vectors die with this frame
-  g_tables[{in_size, out_size}] = t;
+  g_tables[std::make_tuple(dev, in_size, out_size)] = t;
   *out = t;
   return VSCB200_OK;
 }

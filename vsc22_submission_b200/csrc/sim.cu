@@ -81,8 +81,7 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
 }
 
 // ------------------------------------------------------------------ squared row norms (warp per row)
-__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out,
-                                  unsigned int* __restrict__ max_bits) {
+__global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d, float* __restrict__ out) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -93,17 +92,12 @@ __global__ void row_sqnorm_kernel(const float* __restrict__ x, int64_t n, int d,
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) {
-    out[row] = s;
-    if (max_bits) atomicMax(max_bits, __float_as_uint(s));      // s >= 0: float order == unsigned order of the bits
-  }
+  if (lane == 0) out[row] = s;
 }
 
-// max_bits != nullptr: also maintains the running maximum of the squared norms (as float bits) -- the |r| bound of the
-// single-pass search margin (sim_tc1.cu)
-int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream, unsigned int* max_bits) {
+int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream) {
   if (n == 0) return VSCB200_OK;
-  row_sqnorm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, out, max_bits);
+  row_sqnorm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, n, d, out);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -168,34 +162,80 @@ __global__ void sn_bias_kernel(const float* __restrict__ D, int64_t nq, int k, i
   bias[row] = -beta * (s / nk);
 }
 
-// column sums and sums of squares in double (var.argmin, score_normalization.py:72)
-__global__ void col_moments_kernel(const float* __restrict__ x, int64_t n, int d, double* __restrict__ sums) {
-  // grid.x = column blocks of 32, grid.y = row slabs; block = 32 x 8
+// Column statistics for `sn_features.var(axis=0).argmin()` (score_normalization.py:72), two passes in double with a
+// FIXED reduction order (no atomics): pass 1 column sums, pass 2 sums of squared deviations from the mean.  Row-sharded
+// banks all-reduce the [d] vector between the passes (sharding.py).  partial[slab][c]: grid.y row slabs; block 32 x 8.
+__global__ void col_partial_kernel(const float* __restrict__ x, int64_t n, int d, const double* __restrict__ sum_in,
+                                   double inv_n, double* __restrict__ partial) {
+  __shared__ double red[8][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
-  double s = 0.0, s2 = 0.0;
+  double s = 0.0;
   if (c < d) {
+    const double mean = sum_in ? sum_in[c] * inv_n : 0.0;
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      const double v = x[r * d + c];
-      s += v;
-      s2 += v * v;
+      const double v = static_cast<double>(x[r * d + c]) - mean;
+      s += sum_in ? v * v : v;
     }
-    atomicAdd(&sums[c], s);
-    atomicAdd(&sums[d + c], s2);
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    double t = red[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][threadIdx.x];
+    partial[static_cast<int64_t>(blockIdx.y) * d + c] = t;
   }
 }
 
-// first minimum of the column variance (numpy var(axis=0).argmin()); d is a few hundred: one thread
-__global__ void var_argmin_kernel(const double* __restrict__ sums, int64_t n, int d, int* __restrict__ out) {
+__global__ void col_finish_kernel(const double* __restrict__ partial, int slabs, int d, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double t = 0.0;
+  for (int sl = 0; sl < slabs; ++sl) t += partial[static_cast<int64_t>(sl) * d + c];
+  out[c] = t;
+}
+
+// out[c] = sum_r x[r, c]                         (sum_in == nullptr)
+//        = sum_r (x[r, c] - sum_in[c] * inv_n)^2 (sum_in != nullptr)
+int col_sums(const float* x, int64_t n, int d, const double* sum_in, double inv_n, double* out, cudaStream_t stream) {
+  const int slabs = static_cast<int>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048));
+  double* partial = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&partial), sizeof(double) * static_cast<size_t>(slabs) * d, stream);
+  if (rc) return rc;
+  if (n > 0) {
+    col_partial_kernel<<<dim3((d + 31) / 32, slabs), dim3(32, 8), 0, stream>>>(x, n, d, sum_in, inv_n, partial);
+    col_finish_kernel<<<(d + 127) / 128, 128, 0, stream>>>(partial, slabs, d, out);
+    count_launch(2);
+  } else {
+    cudaMemsetAsync(out, 0, sizeof(double) * d, stream);
+  }
+  pool_free(partial, stream);
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+// first minimum (numpy argmin) of the column variances; the common factor 1/n does not change it.  d is a few hundred.
+__global__ void var_argmin_kernel(const double* __restrict__ ss, int d, int* __restrict__ out) {
   int best = 0;
   double best_var = 0;
   for (int c = 0; c < d; ++c) {
-    const double mean = sums[c] / n;
-    const double var = __dsub_rn(sums[d + c] / n, __dmul_rn(mean, mean));     // no FMA contraction: the host formula
+    const double var = ss[c];
     if (c == 0 || var < best_var) { best = c; best_var = var; }
   }
   *out = best;
+}
+
+// both passes + argmin for a bank that lives on one device; scratch: 2 d doubles
+int low_var_dim_local(const float* x, int64_t n, int d, double* scratch, int* dim_dev, cudaStream_t stream) {
+  int rc = col_sums(x, n, d, nullptr, 0.0, scratch, stream);
+  if (rc) return rc;
+  if ((rc = col_sums(x, n, d, scratch, 1.0 / static_cast<double>(n), scratch + d, stream))) return rc;
+  var_argmin_kernel<<<1, 1, 0, stream>>>(scratch + d, d, dim_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
 }
 
 }  // namespace vscb200
@@ -219,20 +259,27 @@ int vscb200_low_var_dim_dev(const float* x_dev, int64_t n, int d, int* dim_dev, 
   using namespace vscb200;
   VSCB_REQUIRE(n > 0 && d > 0 && dim_dev, "low_var_dim_dev: empty input");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  double* sums = nullptr;
-  int rc = pool_alloc(reinterpret_cast<void**>(&sums), sizeof(double) * 2 * d, stream);
+  double* scratch = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&scratch), sizeof(double) * 2 * d, stream);
   if (rc) return rc;
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream);
-  dim3 grid((d + 31) / 32, static_cast<unsigned>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048)));
-  col_moments_kernel<<<grid, dim3(32, 8), 0, stream>>>(x_dev, n, d, sums);
-  var_argmin_kernel<<<1, 1, 0, stream>>>(sums, n, d, dim_dev);
-  count_launch(2);
-  pool_free(sums, stream);
-  if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_last_error(std::string("low_var_dim_dev: ") + cudaGetErrorString(e));
-    return VSCB200_ERR_CUDA;
-  }
+  rc = low_var_dim_local(x_dev, n, d, scratch, dim_dev, stream);
+  pool_free(scratch, stream);
+  return rc;
+}
+
+int vscb200_col_sums(const float* x_dev, int64_t n, int d, const double* sum_in_dev, double inv_n, double* out_dev,
+                     void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(n >= 0 && d > 0 && out_dev && (n == 0 || x_dev), "col_sums: bad argument");
+  return col_sums(x_dev, n, d, sum_in_dev, inv_n, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(ss_dev && d > 0 && dim_dev, "var_argmin_dev: bad argument");
+  var_argmin_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(ss_dev, d, dim_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
 
@@ -264,11 +311,11 @@ int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, voi
     set_last_error("low_var_dim: cudaMallocHost failed");
     return VSCB200_ERR_NOMEM;
   }
-  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, stream);
-  dim3 grid((d + 31) / 32, static_cast<unsigned>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048)));
-  col_moments_kernel<<<grid, dim3(32, 8), 0, stream>>>(x_dev, n, d, sums);
-  var_argmin_kernel<<<1, 1, 0, stream>>>(sums, n, d, best_dev);
-  count_launch(2);
+  cudaError_t e = cudaSuccess;
+  if ((rc = low_var_dim_local(x_dev, n, d, sums, best_dev, stream))) {
+    pool_free(sums, stream);
+    return rc;
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(best_pinned, best_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   pool_free(sums, stream);

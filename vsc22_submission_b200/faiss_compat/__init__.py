@@ -147,18 +147,115 @@ class GpuMultipleClonerOptions:
 
 
 class GpuIndexView(IndexFlat):
-    """What index_cpu_to_all_gpus returns.  The bank already lives in HBM, so the 'clone' is a view
-    sharing the device copy (faiss would replicate it per GPU, exhaustive_search.py:232-234)."""
+    """What index_cpu_to_all_gpus returns on a one-GPU box.  The bank already lives in HBM, so the 'clone' is a view
+    sharing the device copy (faiss would copy it, exhaustive_search.py:232-234)."""
 
     def __init__(self, base: IndexFlat):  # noqa: super().__init__ deliberately not called
         self.d, self.metric_type, self.is_trained = base.d, base.metric_type, True
         self._h = base._h
 
 
+class MultiGpuIndex:
+    """What index_cpu_to_all_gpus returns when several GPUs are visible: ONE process driving all of them, like faiss
+    (vsc/index.py:171, vsc/exhaustive_search.py:229-234, score_normalization.py:88-89, infer_matching.py:225-226).
+
+    ``co.shard = True``   the bank rows are split into contiguous shards, one per GPU, searched with global row ids; the
+                          per-GPU ``[nq, k]`` results travel to GPU 0 as packed 64-bit keys (peer copies over NVLink) and
+                          are merged k-way by a device kernel (csrc/merge.cu) -- faiss ``IndexShards``.
+    ``co.shard = False``  (faiss's and the reference's default) every GPU holds the whole bank and takes a contiguous
+                          slice of the query rows -- faiss ``IndexReplicas``; no merge.
+
+    Either way the results are those of the single index, bit for bit: every reported score comes from the same exact
+    fp32 summation (csrc/exact.cuh).  The snapshot is taken when the function is called (the reference never adds to
+    the GPU index afterwards); ``add`` therefore raises."""
+
+    def __init__(self, base: IndexFlat, devices, shard: bool):
+        import torch
+        from .. import search, sharding
+        self._torch, self._search = torch, search
+        self.d, self.metric_type, self.is_trained = base.d, base.metric_type, True
+        self.shard = bool(shard)
+        self.devices = [torch.device("cuda", int(i)) for i in devices]
+        n = base.ntotal
+        self._ntotal = n
+        self.subs, self.spans = [], []
+        for j, dev in enumerate(self.devices):
+            a, b = sharding.shard_range(n, len(self.devices), j) if self.shard else (0, n)
+            sub = search.DeviceIndex(self.d, self.metric_type, dev)
+            if b > a:
+                rows = torch.empty((b - a, self.d), dtype=torch.float32, device=dev)
+                torch.cuda.current_stream(dev).synchronize()        # `rows` is allocated before the foreign-stream copy lands
+                # the copy engine moves the rows from the base index's GPU to GPU j (unified addressing)
+                _lib.check(_lib.lib().vscb200_index_reconstruct_n(base._h.ptr, a, b - a, C.c_void_p(rows.data_ptr())),
+                           "index.reconstruct_n")
+                sub.add(rows)
+            sub.set_id_offset(a)
+            self.subs.append(sub)
+            self.spans.append((a, b))
+
+    @property
+    def ntotal(self):
+        return self._ntotal
+
+    def add(self, x):
+        raise RuntimeError("MultiGpuIndex is a snapshot of the CPU-side index: add to that index and clone again")
+
+    def reset(self):
+        for sub in self.subs:
+            sub.reset()
+        self._ntotal = 0
+
+    def search(self, x, k):
+        torch = self._torch
+        x = _f32_2d(x, self.d, "search")
+        k = int(k)
+        if k <= 0:
+            raise AssertionError("search: k must be positive")
+        nq = x.shape[0]
+        keep_max = self.metric_type == METRIC_INNER_PRODUCT
+        if nq == 0:
+            return np.empty((0, k), np.float32), np.empty((0, k), np.int64)
+        xt = torch.from_numpy(x)
+        if not self.shard:
+            # replicas: GPU j answers a contiguous slice of the queries; all slices are enqueued before the first result
+            # is read back, so the GPUs work concurrently
+            from .. import sharding
+            parts = []
+            for j, (dev, sub) in enumerate(zip(self.devices, self.subs)):
+                a, b = sharding.shard_range(nq, len(self.devices), j)
+                if b > a:
+                    parts.append(sub.search(xt[a:b].to(dev, non_blocking=True), k))
+            D = np.concatenate([p[0].cpu().numpy() for p in parts], axis=0)
+            I = np.concatenate([p[1].cpu().numpy() for p in parts], axis=0)
+            return D, I
+        # shards: every GPU searches its rows for all queries; packed partial results -> GPU 0 -> k-way merge kernel
+        dev0 = self.devices[0]
+        keys = torch.empty((len(self.devices), nq, k), dtype=torch.int64, device=dev0)
+        done = []
+        for j, (dev, sub) in enumerate(zip(self.devices, self.subs)):
+            Dj, Ij = sub.search(xt.to(dev, non_blocking=True), k)
+            kj = self._search.pack_topk(Dj, Ij, keep_max)
+            with torch.cuda.device(dev):
+                keys[j].copy_(kj, non_blocking=True)            # peer copy, ordered on GPU j's stream
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+            done.append(ev)
+        with torch.cuda.device(dev0):
+            for ev in done:
+                torch.cuda.current_stream(dev0).wait_event(ev)
+            D, I = self._search.merge_packed_topk(keys, k, keep_max)
+            return D.cpu().numpy(), I.cpu().numpy()
+
+
 def index_cpu_to_all_gpus(index, co=None, ngpu=-1):
-    if get_num_gpus() == 0:
+    """faiss.index_cpu_to_all_gpus: where the work is spread over the GPUs of the box."""
+    avail = get_num_gpus()
+    if avail == 0:
         raise RuntimeError("index_cpu_to_all_gpus: no CUDA device")
-    return GpuIndexView(index)
+    n = avail if ngpu is None or ngpu < 0 else min(int(ngpu), avail)
+    if n <= 1 or not isinstance(index, IndexFlat) or isinstance(index, MultiGpuIndex):
+        return GpuIndexView(index) if isinstance(index, IndexFlat) else index
+    return MultiGpuIndex(index, range(n), bool(co.shard) if co is not None else False)
 
 
 def index_cpu_to_gpu(res, device, index, options=None):

@@ -142,6 +142,53 @@ class DeviceIndex:
 
 
 # ------------------------------------------------------------------------------------------------
+# exchange format of partial top-k results between bank shards (csrc/merge.cu)
+# ------------------------------------------------------------------------------------------------
+def pack_topk(D: torch.Tensor, I: torch.Tensor, keep_max: bool = True) -> torch.Tensor:
+    """(D f32 [nq,k], I i64 [nq,k]) -> int64 [nq,k] keys ``(order-preserving score bits << 32) | ~id`` (0 = padding):
+    scores and ids travel in ONE all-gather and a larger key (as uint64) is a better result, ties to the lower id."""
+    D, I = _f32_cuda(D, "pack_topk"), I.contiguous()
+    keys = torch.empty(D.shape, dtype=torch.int64, device=D.device)
+    if D.numel():
+        with torch.cuda.device(D.device):
+            _lib.check(_lib.lib().vscb200_topk_pack(_p(D), _p(I), D.shape[0], D.shape[1], int(bool(keep_max)), _p(keys),
+                                                    _stream(D.device)), "topk_pack")
+    return keys
+
+
+def merge_packed_topk(keys: torch.Tensor, k: int, keep_max: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """keys int64 [parts, nq, kin] (the all-gather layout) -> the k best per query (D f32 [nq,k], I i64 [nq,k])."""
+    assert keys.dim() == 3 and keys.dtype == torch.int64 and keys.is_cuda
+    keys = keys.contiguous()
+    parts, nq, kin = keys.shape
+    D = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    if nq:
+        with torch.cuda.device(keys.device):
+            _lib.check(_lib.lib().vscb200_topk_merge(_p(keys), parts, nq, kin, int(k), int(bool(keep_max)), _p(D), _p(I),
+                                                     _stream(keys.device)), "topk_merge")
+    return D, I
+
+
+def col_sums(x: torch.Tensor, sum_in: Optional[torch.Tensor] = None, inv_n: float = 0.0) -> torch.Tensor:
+    """float64 [d]: column sums of x, or (``sum_in`` given) sums of squared deviations from ``sum_in * inv_n``."""
+    x = _f32_cuda(x, "col_sums")
+    out = torch.empty((x.shape[1],), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vscb200_col_sums(_p(x), x.shape[0], x.shape[1], _p(sum_in), float(inv_n), _p(out),
+                                               _stream(x.device)), "col_sums")
+    return out
+
+
+def var_argmin_device(ss: torch.Tensor) -> torch.Tensor:
+    """First minimum of a float64 [d] vector, left on the device (int32 [1])."""
+    out = torch.empty((1,), dtype=torch.int32, device=ss.device)
+    with torch.cuda.device(ss.device):
+        _lib.check(_lib.lib().vscb200_var_argmin_dev(_p(ss), ss.numel(), _p(out), _stream(ss.device)), "var_argmin_dev")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # score normalisation on device tensors
 # ------------------------------------------------------------------------------------------------
 def low_var_dim(noise: torch.Tensor) -> int:

@@ -5,8 +5,8 @@
   dist.barrier, D/infer/extract_ref_feats.py:33-36).
 * Similarity: the reference bank is sharded by rows (the reference replicates it instead,
   vsc/exhaustive_search.py:232-234 ``co.shard = False``); every rank searches its shard with GLOBAL
-  row ids (``DeviceIndex.set_id_offset``) and ONE all-gather of the ``[nq, k]`` partial results
-  followed by a k-way merge gives the global top-k.
+  row ids (``DeviceIndex.set_id_offset``); the ``[nq, k]`` partial results travel as ONE 64-bit key per entry
+  (score bits | ~id) in ONE all-gather and a device kernel merges them k-way (csrc/merge.cu).
 * Global candidate search (``DeviceIndex.global_search``): every rank finds the global_k best (query row, bank row)
   pairs against ITS bank shard (global bank ids through ``set_id_offset``); one all-gather of the padded
   ``[global_k]`` partial lists and a merge by (score, query row, bank row) gives the exact global list
@@ -31,25 +31,57 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def _pack_cpu(D: torch.Tensor, I: torch.Tensor, keep_max: bool) -> torch.Tensor:
+    """The key format of csrc/merge.cu on CPU tensors (host logic of the gloo tests): (score bits << 32) | ~id."""
+    u = D.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    okey = torch.where(u >= 0x80000000, (~u) & 0xFFFFFFFF, u | 0x80000000)
+    if not keep_max:
+        okey = (~okey) & 0xFFFFFFFF
+    keys = (okey << 32) | ((~I) & 0xFFFFFFFF)
+    return torch.where(I < 0, torch.zeros_like(keys), keys)
+
+
+def _merge_cpu(keys: torch.Tensor, k: int, keep_max: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    parts, nq, kin = keys.shape
+    flat = keys.permute(1, 0, 2).reshape(nq, parts * kin)
+    # unsigned 64-bit order on signed storage: flip the sign bit
+    order = torch.argsort(flat ^ (-0x8000000000000000), dim=1, descending=True, stable=True)[:, :k]
+    best = torch.gather(flat, 1, order)
+    okey = (best >> 32) & 0xFFFFFFFF
+    if not keep_max:
+        okey = (~okey) & 0xFFFFFFFF
+    u = torch.where(okey >= 0x80000000, okey ^ 0x80000000, (~okey) & 0xFFFFFFFF)
+    D = (u.to(torch.int64) - ((u >= 0x80000000).to(torch.int64) << 32)).to(torch.int32).view(torch.float32)
+    I = (~best) & 0xFFFFFFFF
+    pad = best == 0
+    fmax = torch.finfo(torch.float32).max
+    D = torch.where(pad, torch.full_like(D, -fmax if keep_max else fmax), D)
+    return D, torch.where(pad, torch.full_like(I, -1), I)
+
+
 def merge_partial_topk(D: torch.Tensor, I: torch.Tensor, k: int, keep_max: bool = True,
                        group: Optional[dist.ProcessGroup] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather every rank's partial (D [nq, k_r], I [nq, k_r] with global ids, -1 = padding) and
-    merge to the global best-k per row: best-first, ties to the lower id (faiss semantics)."""
+    """Every rank's partial (D [nq, k_r], I [nq, k_r] with GLOBAL ids < 2^32, -1 = padding) -> the global best-k per row,
+    best first, ties to the lower id (faiss semantics).  Scores and ids are packed into one 64-bit key per entry, so the
+    exchange is a SINGLE all-gather of [nq, k_r] words; the k-way merge runs in a device kernel (csrc/merge.cu)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if D.is_cuda:
+        from . import search
+        keys = search.pack_topk(D, I, keep_max)
+        if world > 1:
+            gathered = torch.empty((world,) + tuple(keys.shape), dtype=torch.int64, device=keys.device)
+            dist.all_gather_into_tensor(gathered, keys, group=group)
+        else:
+            gathered = keys.unsqueeze(0)
+        return search.merge_packed_topk(gathered, k, keep_max)
+    keys = _pack_cpu(D, I, keep_max)            # CPU tensors: gloo, world_size-2 tests of the host logic
     if world > 1:
-        Ds = [torch.empty_like(D) for _ in range(world)]
-        Is = [torch.empty_like(I) for _ in range(world)]
-        dist.all_gather(Ds, D.contiguous(), group=group)
-        dist.all_gather(Is, I.contiguous(), group=group)
-        D, I = torch.cat(Ds, dim=1), torch.cat(Is, dim=1)
-    # order by (score best-first, id ascending); padding entries (id -1) go last
-    bad = I < 0
-    key = torch.where(bad, torch.full_like(D, float("-inf") if keep_max else float("inf")), D)
-    idkey = torch.where(bad, torch.full_like(I, torch.iinfo(torch.int64).max), I)
-    order = torch.argsort(idkey, dim=1, stable=True)
-    key, D, I = torch.gather(key, 1, order), torch.gather(D, 1, order), torch.gather(I, 1, order)
-    order = torch.argsort(key, dim=1, descending=keep_max, stable=True)[:, :k]
-    return torch.gather(D, 1, order), torch.gather(I, 1, order)
+        parts = [torch.empty_like(keys) for _ in range(world)]
+        dist.all_gather(parts, keys, group=group)
+        keys = torch.stack(parts)
+    else:
+        keys = keys.unsqueeze(0)
+    return _merge_cpu(keys, k, keep_max)
 
 
 def merge_partial_global_topk(scores: torch.Tensor, qrows: torch.Tensor, brows: torch.Tensor, global_k: int,
@@ -79,15 +111,35 @@ def merge_partial_global_topk(scores: torch.Tensor, qrows: torch.Tensor, brows: 
     return scores[order], qrows[order], brows[order]
 
 
-def global_low_var_dim(z_shard: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> int:
-    """argmin of the column variance of the row-sharded noise bank (score_normalization.py:72)."""
+def global_low_var_dim(z_shard: torch.Tensor, n_total: Optional[int] = None, group: Optional[dist.ProcessGroup] = None):
+    """argmin of the column variance of the row-sharded noise bank (score_normalization.py:72): two passes (column sums,
+    then squared deviations from the global mean) with one all-reduce of a float64 [d] vector after each.  CUDA shards:
+    device kernels with a fixed reduction order, the result stays on the device (int32 [1] tensor, no host sync) -- feed
+    it to ``search.sn_transform``.  ``n_total``: rows over all shards (default: all-reduced too).  CPU tensors (gloo
+    tests): the same two passes in torch, returns an int."""
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    if n_total is None:
+        n = torch.tensor([z_shard.shape[0]], dtype=torch.float64, device=z_shard.device)
+        if sharded:
+            dist.all_reduce(n, group=group)
+        n_total = int(n.item())
+    if z_shard.is_cuda:
+        from . import search
+        sums = search.col_sums(z_shard)
+        if sharded:
+            dist.all_reduce(sums, group=group)
+        ss = search.col_sums(z_shard, sums, 1.0 / n_total)
+        if sharded:
+            dist.all_reduce(ss, group=group)
+        return search.var_argmin_device(ss)
     z = z_shard.double()
-    mom = torch.stack([z.sum(0), (z * z).sum(0), torch.full((z.shape[1],), float(z.shape[0]), dtype=torch.float64,
-                                                             device=z.device)])
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(mom, group=group)
-    mean = mom[0] / mom[2]
-    return int((mom[1] / mom[2] - mean * mean).argmin().item())
+    sums = z.sum(0)
+    if sharded:
+        dist.all_reduce(sums, group=group)
+    ss = ((z - sums / n_total) ** 2).sum(0)
+    if sharded:
+        dist.all_reduce(ss, group=group)
+    return int(ss.argmin().item())
 
 
 def gather_descriptors(local: torch.Tensor, n_total: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
