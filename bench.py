@@ -38,12 +38,15 @@ SIM_NQ_C, SIM_NR_C = 10_000, 40_000                                     # candid
 
 def load_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
-    capture (profiles/r01_traffic.json; a number measured under the profiler, never a timing)."""
-    p = os.path.join(REPO, "profiles", "r01_traffic.json")
-    try:
-        return json.load(open(p)).get(kernel)
-    except Exception:
-        return None
+    captures (profiles/r02_traffic.json, else round 1's; numbers measured under the profiler, never timings)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            v = json.load(open(os.path.join(REPO, "profiles", name))).get(kernel)
+        except Exception:
+            v = None
+        if v is not None:
+            return v
+    return None
 
 
 def load_peaks():
@@ -225,7 +228,11 @@ def bench_encoder(args, world, rank, peaks):
 
 def bench_swin(args):
     """Second encoder family on the reference's path (swinv2_v106/107/115: SwinV2-B 256x256, config_v106.py:8-24):
-    device-resident frames, 1024 synthetic frames per step, plan chunk 256; parity of 2 frames vs the fp32 oracle."""
+    device-resident frames, 1024 synthetic frames per step, plan chunk 256, in both arithmetic modes; parity of 8 frames:
+    the bf16 mode against the matched-precision oracle (and the fp32 figure beside it), the fp32-equivalent mode against
+    the fp32 oracle, which reproduces the reference class bit for bit -- the 1e-3 contract."""
+    import dataclasses
+
     import numpy as np
     import torch
 
@@ -233,27 +240,38 @@ def bench_swin(args):
     from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SWINV2_B_256, random_weights
     dev = torch.device("cuda", torch.cuda.current_device())
     w = random_weights(SWINV2_B_256, seed=0)
-    enc = B200SwinEncoder(SWINV2_B_256, w, max_frames=256).to(dev).eval()
     n = 1024
     frames = torch.randn((n, 3, 256, 256), generator=torch.Generator(device=dev).manual_seed(7), device=dev).clamp_(-1, 1)
-    for _ in range(2):
-        out = enc(frames)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = enc(frames)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    ref = swin_ref.forward(swin_ref.SWINV2_B_256, w, frames[:2].cpu()).numpy()
-    got = out[:2].cpu().numpy()
-    rel = float((np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
-    fps = n / (ms / 1e3)
-    return {"metric": "frame-descriptors/sec", "value": fps, "ms_per_step": ms, "frames_per_step": n,
-            "tflops": fps * SWINV2_B_256.flops_per_frame() / 1e12, "flops_per_frame": SWINV2_B_256.flops_per_frame(),
-            "parity_rel_l2_max_vs_fp32_oracle": rel,
-            "config": {"workload": "SwinV2-B 256x256 window 16 (config_v106.py), random init, bf16 operands, 1 GPU"}}
+    x8 = frames[:8].cpu()
+    refs = {p: swin_ref.forward(swin_ref.SWINV2_B_256, w, x8, precision=p).numpy() for p in ("fp32", "bf16")}
+    rel = lambda a, b: float((np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)).max())
+    out = {}
+    for mode in ("bf16", "fp32"):
+        enc = B200SwinEncoder(dataclasses.replace(SWINV2_B_256, precision=mode), w, max_frames=256).to(dev).eval()
+        for _ in range(2):
+            y = enc(frames)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = enc(frames)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        got = y[:8].cpu().numpy()
+        fps = n / (ms / 1e3)
+        out[mode] = {"value": fps, "ms_per_step": ms, "tflops": fps * SWINV2_B_256.flops_per_frame() / 1e12,
+                     "parity_rel_l2_max_vs_fp32_oracle": rel(got, refs["fp32"]),
+                     "parity_rel_l2_max_vs_matched_precision_oracle": rel(got, refs["bf16"]) if mode == "bf16" else None}
+        del enc, y
+        torch.cuda.empty_cache()
+    return {"metric": "frame-descriptors/sec", "value": out["bf16"]["value"], "ms_per_step": out["bf16"]["ms_per_step"],
+            "frames_per_step": n, "tflops": out["bf16"]["tflops"], "flops_per_frame": SWINV2_B_256.flops_per_frame(),
+            "parity_rel_l2_max_vs_fp32_oracle": out["bf16"]["parity_rel_l2_max_vs_fp32_oracle"],
+            "modes": out, "parity_tolerance": 1e-3, "parity_frames": 8,
+            "parity_contract": "fp32-equivalent mode <= 1e-3 vs the fp32 oracle (== the reference class); the bf16 mode sits on "
+                               "the bf16-operand floor of this 24-block res-post-norm network",
+            "config": {"workload": "SwinV2-B 256x256 window 16 (config_v106.py), random init, 1 GPU"}}
 
 
 def bench_ingest(n=512, h=360, w=640, out=224):
@@ -358,7 +376,7 @@ def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
     import torch
 
     from vsc22_submission_b200 import search
-    lvd = search.low_var_dim_device(Z_shard) if world == 1 else _global_low_var_dim(Z_shard)
+    lvd = search.low_var_dim_device(Z_shard) if world == 1 else _global_low_var_dim(Z_shard, world)
     z_t = search.sn_transform(Z_shard, lvd, True, fill=0.0)
     q_0 = search.sn_transform(Q, lvd, True, fill=0.0)
     zi = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
@@ -379,14 +397,17 @@ def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
 
 
 def _merge_topk(D, I, k):
-    """One all-gather of the [nq, k] partial results per rank, then a k-way merge."""
+    """ONE all-gather of the [nq, k] partial results per rank (score and id packed into a 64-bit key), then the k-way merge
+    kernel (csrc/merge.cu)."""
     from vsc22_submission_b200 import sharding
     return sharding.merge_partial_topk(D, I, k)
 
 
-def _global_low_var_dim(Z_shard):
+def _global_low_var_dim(Z_shard, world):
+    """Column statistics of the row-sharded noise bank: device kernels + two all-reduces of a float64 [d] vector; the
+    dropped dimension stays on the device (no host synchronisation inside the step)."""
     from vsc22_submission_b200 import sharding
-    return sharding.global_low_var_dim(Z_shard)
+    return sharding.global_low_var_dim(Z_shard, n_total=Z_shard.shape[0] * world)
 
 
 def bench_sim(args, world, rank, peaks):
@@ -448,6 +469,7 @@ def bench_sim(args, world, rank, peaks):
     prof = _lib.prof_collect()
     pairs = SIM_NQ * (SIM_NR + SIM_NZ) * world
     value = pairs / (ms / 1e3)
+    sim_parity = sim_parity_check(Q, R_s, Z_s, D, I, world, rank) if world > 1 else None
     # e2e through the reference-facing API: lists of per-video host feature arrays through score_normalize
     # (score_normalization.py:33-104), the normalised features added video by video to a faiss-style index
     # (vsc/index.py:87-94) and one search over all query rows -- host buffers in, host results out
@@ -496,22 +518,48 @@ def bench_sim(args, world, rank, peaks):
     sc = prof["scores"]
     roof = {"bound": "tensor", "kernel": "similarity scores kernel (both banks)",
             "achieved": (sc["work"] / (sc["ms"] / 1e3) / 1e12) if sc["ms"] > 0 else 0.0, "peak": peaks["bf16_tflops"],
-            "unit": "TFLOP/s", "peak_source": f"{peaks['source']} bf16_tflops (burst)", "traffic": load_traffic("sim3_kernel"),
+            "unit": "TFLOP/s", "peak_source": f"{peaks['source']} bf16_tflops (burst)", "traffic": load_traffic("sim1_topk_kernel"),
             "whole_step_tensor_frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
             "whole_step_hbm_frac": bytes_alg / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
             "kernel_ms": {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["note"] = ("fp32-equivalent scores = 3 bf16 MMAs per product (hi.hi + lo.hi + hi.lo): the kernel's ceiling is "
-                    "1/3 of the bf16 peak; config 3 as stated is tensor-bound, the HBM-bound form is 'stream'")
+    roof["note"] = ("selection on ONE bf16 MMA per product (sim1_topk_kernel, CTA pairs) with a proven error margin; the "
+                    "survivors are rescored in exact fp32, so reported scores and indices are those of an fp32 brute force; "
+                    "config 3 as stated is tensor-bound, the HBM-bound form is 'stream'")
+    roof["kernel"] = "sim1_topk_kernel (single bf16 pass, both banks)"
     return {"metric": "sim-pairs/sec", "value": value, "unit": "sim-pairs/sec", "ms_per_step": ms,
             "host_issue_ms_per_step": host_issue * 1e3 / args.steps, "host_probe": host_probe, "step_ms": step_ms, "e2e": e2e,
             "stream": stream, "dense": dense, "candidates": cand, "localization": loc,
-            "gpu_launches": int(launches), "roofline": roof, "dtype": "f32",
+            "gpu_launches": int(launches), "roofline": roof, "dtype": "f32", "parity": sim_parity,
             "config": {"workload": "configs[2]: 10k query x 40k ref 512-D cosine sim + score-norm (40k noise bank, "
                                    "beta=1.2, nk=1) + top-10", "nq": SIM_NQ, "nr": SIM_NR, "nz": SIM_NZ, "d": SIM_D,
                        "k": SIM_K, "l2_flush": "256 MiB write between steps",
                        "scaling": "weak (every rank holds a 40k + 40k row bank shard; global banks = world x that)",
                        "sharding": "bank rows over ranks + all-gather of partial top-k" if world > 1 else "single GPU"}}
+
+
+def sim_parity_check(Q, R_s, Z_s, D, I, world, rank, sample=64):
+    """N > 1: the merged top-k of a 64-query sample against a brute force over the GATHERED banks on rank 0 (fp64 scores
+    of the score-normalised descriptors; the all-gather here is test plumbing, outside every timed region)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import score_norm_np
+    R_all = [torch.empty_like(R_s) for _ in range(world)]
+    Z_all = [torch.empty_like(Z_s) for _ in range(world)]
+    dist.all_gather(R_all, R_s)
+    dist.all_gather(Z_all, Z_s)
+    if rank != 0:
+        return None
+    Rg, Zg = torch.cat(R_all).cpu().numpy(), torch.cat(Z_all).cpu().numpy()
+    q = Q[:sample].cpu().numpy()
+    q2, r2, _ = score_norm_np.score_normalize(q, Rg, Zg, beta=1.2, nk=1)
+    S = q2.astype("float64") @ r2.astype("float64").T
+    order = (-S).argsort(axis=1, kind="stable")[:, :SIM_K]
+    ref_d = S[[[i] for i in range(sample)], order]
+    got_i, got_d = I[:sample].cpu().numpy(), D[:sample].cpu().numpy()
+    return {"queries_checked": sample, "bank_rows": int(Rg.shape[0]), "noise_rows": int(Zg.shape[0]),
+            "topk_index_agreement": float((got_i == order).mean()),
+            "max_abs_score_err": float(abs(got_d - ref_d).max()), "checker": "oracle/score_norm_np.py + fp64 brute force"}
 
 
 def bench_sim_stream(peaks, nq=40, nr=1_000_000, k=10, iters=10):
@@ -844,16 +892,41 @@ def main():
         g = torch.Generator().manual_seed(1)
         if args.workload in ("both", "encoder"):
             line["cpu_baseline"] = cpu_baseline_encoder(lambda n: torch.randn((n, 3, 224, 224), generator=g).clamp_(-1, 1))
-            # parity beside the timing: first frames of the job vs the oracle on the same weights
+            # parity beside the timing: the first 32 frames of the job vs the oracle on the same weights, at the north-star
+            # tolerance (1e-3 relative L2 per frame): the benched bf16 mode against the fp32 oracle AND the matched-precision
+            # oracle, and the fp32-equivalent mode (split-bf16 GEMMs, fp32 attention) with its own throughput
+            import dataclasses
+
             from oracle import vit_ref
-            from vsc22_submission_b200.encoder import VIT_B16_224_GEM, random_weights
+            from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_B16_224_GEM, random_weights
             w = random_weights(VIT_B16_224_GEM, seed=0)
             gd = torch.Generator(device="cuda").manual_seed(1)
-            x = torch.randn((1000, 3, 224, 224), generator=gd, device="cuda").clamp_(-1, 1)[:4].cpu()
-            ref = vit_ref.forward(vit_ref.CLIP_B16_224, w, x)
-            got = enc_res["out"][:4].cpu()
-            rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
-            line["parity"] = {"encoder_rel_l2_max_vs_fp32_oracle": rel, "frames": 4, "tolerance": 2e-2}
+            xd = torch.randn((1000, 3, 224, 224), generator=gd, device="cuda").clamp_(-1, 1)
+            x = xd[:32].cpu()
+            rel = lambda a, b: ((a - b).norm(dim=1) / b.norm(dim=1)).max().item()
+            ref32 = vit_ref.forward(vit_ref.CLIP_B16_224, w, x)
+            ref16 = vit_ref.forward(vit_ref.CLIP_B16_224, w, x, precision="bf16")
+            got = enc_res["out"][:32].cpu()
+            enc32 = B200ViTEncoder(dataclasses.replace(VIT_B16_224_GEM, precision="fp32"), w, max_frames=256).cuda().eval()
+            got32 = enc32(xd[:32]).cpu()
+            for _ in range(2):
+                enc32(xd)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            enc32(xd)
+            f1.record()
+            torch.cuda.synchronize()
+            fps32 = 1000 / (f0.elapsed_time(f1) / 1e3)
+            line["parity"] = {"encoder_rel_l2_max_vs_fp32_oracle": rel(got, ref32),
+                              "encoder_rel_l2_max_vs_matched_precision_oracle": rel(got, ref16),
+                              "fp32_mode_rel_l2_max_vs_fp32_oracle": rel(got32, ref32),
+                              "fp32_mode_frames_per_sec": fps32,
+                              "fp32_mode_tflops_algorithmic": fps32 * VIT_B16_224_GEM.flops_per_frame() / 1e12,
+                              "frames": 32, "tolerance": 1e-3,
+                              "ok": bool(rel(got, ref32) <= 1e-3 and rel(got32, ref32) <= 1e-3)}
+            del enc32, xd
+            torch.cuda.empty_cache()
         if args.workload in ("both", "sim"):
             cb = cpu_baseline_sim()
             tgt = line["sim"] if "sim" in line else line

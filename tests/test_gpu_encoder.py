@@ -8,11 +8,12 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-# bf16 tensor-core operands with fp32 accumulation/residual/LN/softmax: per-descriptor relative L2
-# error vs the fp32 oracle.  (The reference itself ran these matmuls in TF32 on A100, torch 1.11
-# default; BASELINE config 2 names bf16.)  The north-star 1e-3 figure is met by the similarity path;
-# for the encoder the bf16 figure below is the contract, measured and reported by bench.py.
-BF16_REL_TOL = 2e-2
+# The tests of this file run the bf16 tensor-core mode (operands rounded to bf16; fp32 accumulation / residual / LN /
+# softmax) on SMALL configurations against the fp32 oracle / reference-class goldens: per-descriptor relative L2 error.
+# The 1e-3 contract itself is asserted at the full configurations in tests/test_gpu_parity_full.py (bf16 mode on
+# ViT-B/16, fp32-equivalent mode everywhere) and tests/test_gpu_exact.py; this bound only has to catch wiring errors
+# (which show up as O(1) differences) while staying within a small multiple of the bf16 rounding level.
+BF16_REL_TOL = 6e-3
 
 
 def _rel(out, ref):

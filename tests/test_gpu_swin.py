@@ -30,7 +30,7 @@ def test_swin_matches_reference_class_golden(torch, golden_dir):
     out = enc(torch.from_numpy(g["frames"]).cuda()).cpu().numpy()          # 3 frames, max_frames 2: two chunks
     rel = _rel_l2(out, g["desc"])
     print("swin small rel L2 vs reference class:", rel)
-    assert rel.max() < 2e-2
+    assert rel.max() < 8e-3          # bf16 mode: measured 4.6e-3 (the bf16-operand floor); fp32 mode: tests/test_gpu_exact.py
 
 
 def test_swin_b_256_matches_oracle(torch):
@@ -46,7 +46,7 @@ def test_swin_b_256_matches_oracle(torch):
     rel = _rel_l2(out, ref)
     cos = (out * ref).sum(1) / (np.linalg.norm(out, axis=1) * np.linalg.norm(ref, axis=1))
     print("swinv2-b rel L2 vs fp32 oracle:", rel, "cos", cos)
-    assert rel.max() < 3e-2 and cos.min() > 0.999
+    assert rel.max() < 8e-3 and cos.min() > 0.9999      # bf16 mode: measured 5.0e-3; the 1e-3 contract: test_gpu_parity_full.py
     # host API == device API, ragged batch
     out_h = enc.forward_host(x.numpy()[:1])
     assert np.abs(out_h - out[:1]).max() < 1e-5

@@ -64,6 +64,10 @@ class DeviceIndex:
     def ntotal(self) -> int:
         return int(_lib.lib().vscb200_index_ntotal(self._ptr))
 
+    def last_fallbacks(self) -> int:
+        """Diagnostic: queries of the last small-k batch search that needed the exhaustive fp32 fallback (-1: none ran)."""
+        return int(_lib.lib().vscb200_index_last_fallbacks(self._ptr))
+
     def set_id_offset(self, offset: int):
         """Global id of this shard's first row (bank sharding over ranks)."""
         _lib.check(_lib.lib().vscb200_index_set_id_offset(self._ptr, int(offset)), "index_set_id_offset")
