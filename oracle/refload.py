@@ -79,10 +79,40 @@ def swinv2_module():
     return mod
 
 
+def _backbones_package(path: str, pkg: str):
+    """Load one file of .../model_factory/backbones/ as `<pkg>.backbones.<name>` with the BACKBONES registry of its
+    `..utils` neutralised (the registry pulls in mmcv.Registry and every other backbone of the tree)."""
+    import types
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+
+    utils = types.ModuleType(pkg + ".utils")
+    utils.BACKBONES = _Reg()
+    top, sub = types.ModuleType(pkg), types.ModuleType(pkg + ".backbones")
+    top.__path__, sub.__path__ = [], [os.path.dirname(path)]
+    sys.modules[pkg], sys.modules[pkg + ".utils"], sys.modules[pkg + ".backbones"] = top, utils, sub
+    name = pkg + ".backbones." + os.path.splitext(os.path.basename(path))[0]
+    with _shimmed():
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    return mod
+
+
 def sscd_gem_module():
-    """D/train/train_v68/.../backbones/sscd.py would need timm itself (timm.create_model);
-    only its GlobalGeMPool2d head is file-loadable.  Returns None when that fails."""
-    return None
+    """D/train/train_v68/vsc/baseline/model_factory/backbones/sscd.py: GlobalGeMPool2d (:11-40), Model (:59-106) and
+    SSCDModel (:109-152), unmodified.  Its `timm.create_model` call resolves to the ViT restated in
+    oracle/refshim/timm (timm 0.6.12 itself is not in the tree); set `timm.TIMM_SHIM_VIT` for a toy size."""
+    return _backbones_package(os.path.join(D, "train/train_v68/vsc/baseline/model_factory/backbones/sscd.py"), "_ref_v68")
+
+
+def vit_hf_module():
+    """D/train/train_v106/vsc/baseline/model_factory/backbones/vit.py: backbone `VIT` (:10-58) = transformers.ViTModel +
+    gem + Linear, unmodified (transformers is installed here)."""
+    return _backbones_package(os.path.join(D, "train/train_v106/vsc/baseline/model_factory/backbones/vit.py"), "_ref_v106")
 
 
 def vsc_package(track: str = "D_infer"):

@@ -368,9 +368,10 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
       if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
       if ((rc = q_hi_norm(qb, ix->q_planes, ix->qnorm, ix->qnorm + nb, nb, ix->d, ix->dp, s))) return rc;
       VSCB_CUDA_OK(cudaMemsetAsync(ix->flags + nb, 0, sizeof(int), s));
-      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, pairs, slots,
+      const int depth = sim1_depth(k);
+      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, pairs, slots, depth,
                           ix->cand_d, ix->cand_i, s))) return rc;
-      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slots, k, ix->qnorm,
+      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slots, depth, k, ix->qnorm,
                              ix->qnorm + nb, ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->flags + nb, s))) return rc;
       ix->last_flag_count = ix->flags + nb;
     }

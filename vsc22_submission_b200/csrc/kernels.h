@@ -45,11 +45,13 @@ void sim1_plan(int64_t nq, int64_t nr, int* pairs_out, int* slots_out);
 int sim1_list_len();
 int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream);
 int bank_norm_max(const float* x, int64_t n, int d, unsigned int* max_bits, cudaStream_t stream);
+int sim1_depth(int k);
 int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn, int pairs,
-              int slots, float* cand_v, int32_t* cand_i, cudaStream_t stream);
+              int slots, int depth, float* cand_v, int32_t* cand_i, cudaStream_t stream);
 int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const float* cand_v,
-                 const int32_t* cand_i, int slots, int k, const float* qn, const float* qn_lo, const unsigned int* bank_max_bits,
-                 float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged, cudaStream_t stream);
+                 const int32_t* cand_i, int slots, int depth, int k, const float* qn, const float* qn_lo,
+                 const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged,
+                 cudaStream_t stream);
 int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
                  float* out, cudaStream_t stream, const int* drop_dim_dev = nullptr);
 // row r = S + r*ldS, element i of a row at [i*es] (es = 1: dense rows; es > 1: a column of a row-major matrix)

@@ -216,15 +216,22 @@ int col_sums(const float* x, int64_t n, int d, const double* sum_in, double inv_
   return VSCB200_OK;
 }
 
-// first minimum (numpy argmin) of the column variances; the common factor 1/n does not change it.  d is a few hundred.
+// first minimum (numpy argmin) of the column variances; the common factor 1/n does not change it.  One warp.
 __global__ void var_argmin_kernel(const double* __restrict__ ss, int d, int* __restrict__ out) {
-  int best = 0;
+  const int lane = threadIdx.x;
+  int best = -1;
   double best_var = 0;
-  for (int c = 0; c < d; ++c) {
+  for (int c = lane; c < d; c += 32) {
     const double var = ss[c];
-    if (c == 0 || var < best_var) { best = c; best_var = var; }
+    if (best < 0 || var < best_var) { best = c; best_var = var; }      // strict: keeps the first of equal values
   }
-  *out = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best_var, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (ob >= 0 && (best < 0 || ov < best_var || (ov == best_var && ob < best))) { best = ob; best_var = ov; }
+  }
+  if (lane == 0) *out = best < 0 ? 0 : best;
 }
 
 // both passes + argmin for a bank that lives on one device; scratch: 2 d doubles
@@ -232,7 +239,7 @@ int low_var_dim_local(const float* x, int64_t n, int d, double* scratch, int* di
   int rc = col_sums(x, n, d, nullptr, 0.0, scratch, stream);
   if (rc) return rc;
   if ((rc = col_sums(x, n, d, scratch, 1.0 / static_cast<double>(n), scratch + d, stream))) return rc;
-  var_argmin_kernel<<<1, 1, 0, stream>>>(scratch + d, d, dim_dev);
+  var_argmin_kernel<<<1, 32, 0, stream>>>(scratch + d, d, dim_dev);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -277,7 +284,7 @@ int vscb200_col_sums(const float* x_dev, int64_t n, int d, const double* sum_in_
 int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stream) {
   using namespace vscb200;
   VSCB_REQUIRE(ss_dev && d > 0 && dim_dev, "var_argmin_dev: bad argument");
-  var_argmin_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(ss_dev, d, dim_dev);
+  var_argmin_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ss_dev, d, dim_dev);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;

@@ -50,6 +50,7 @@ struct Sim1Params {
   const float* rn;       // squared bank norms
   int tiles_m2, tiles_n;            // pair tiles along M, 256-wide tiles along N
   int pairs, slots;                 // CTA pairs launched; candidate-list slots per query row (pairs that may meet a row)
+  int depth;                        // entries kept per list (<= kS1List): 8 / 16 / 32 by k
   float* cand_v;         // [nq, slots * 2 * kS1List] selection keys (larger = better; -distance for L2)
   int32_t* cand_i;       // bank rows (-1 = empty; the buffer is pre-filled with -1)
 };
@@ -146,6 +147,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int cur_pm = -1;
     int64_t row0 = 0;
     float qn_lane = 0.f;
+    const int tl = p.depth - 1;                        // lane holding a list's threshold (its last kept entry)
     auto flush = [&]() {
       if (cur_pm < 0) return;
       const int slot = static_cast<int>(pair - s1_pair_of(static_cast<int64_t>(cur_pm) * p.tiles_n, T, p.pairs));
@@ -154,7 +156,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (row0 + r < p.nq) {
           const int64_t base = (((row0 + r) * p.slots + slot) * 2 + half) * kS1List;
           p.cand_v[base + lane] = ls[r];
-          p.cand_i[base + lane] = li[r];
+          p.cand_i[base + lane] = lane <= tl ? li[r] : -1;
         }
       }
     };
@@ -194,20 +196,40 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
+        // Pass 1, branch-free and fully pipelined: which of the warp's 32 rows have a score above their list's threshold?
+        float val[32];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const float val = *reinterpret_cast<const float*>(tile + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-          uint32_t m = __ballot_sync(0xffffffffu, val > __shfl_sync(0xffffffffu, ls[r], 31));
-          while (m) {                                                 // warp-uniform; rare once the list has warmed up
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const float vb = __shfl_sync(0xffffffffu, val, b);
-            if (vb > __shfl_sync(0xffffffffu, ls[r], 31)) {
+        for (int r = 0; r < 32; ++r)
+          val[r] = *reinterpret_cast<const float*>(tile + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+        uint32_t lanehit = 0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) lanehit |= val[r] > __shfl_sync(0xffffffffu, ls[r], tl) ? (1u << r) : 0u;
+        const uint32_t rowmask = __reduce_or_sync(0xffffffffu, lanehit);
+        if (rowmask == 0u) continue;                                  // the common case once the lists have warmed up
+        // Pass 2: insert the hits, four rows at a time in straight-line predicated code -- an insertion is a chain of
+        // dependent warp shuffles / votes (~70 cycles); four independent chains issued back to back hide it
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          if (((rowmask >> (4 * g4)) & 0xFu) == 0u) continue;         // warp-uniform
+          uint32_t m[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            m[i] = __ballot_sync(0xffffffffu, val[4 * g4 + i] > __shfl_sync(0xffffffffu, ls[4 * g4 + i], tl));
+          while ((m[0] | m[1] | m[2] | m[3]) != 0u) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 4 * g4 + i;
+              const bool act = m[i] != 0u;
+              const int b = act ? __ffs(m[i]) - 1 : 0;
+              m[i] &= m[i] - 1u;
+              const float vb = __shfl_sync(0xffffffffu, val[r], b);
+              const bool ins = act && vb > __shfl_sync(0xffffffffu, ls[r], tl);
               const int pos = __popc(__ballot_sync(0xffffffffu, ls[r] >= vb));
               const float us = __shfl_up_sync(0xffffffffu, ls[r], 1);
               const int32_t ui = __shfl_up_sync(0xffffffffu, li[r], 1);
-              if (lane > pos) { ls[r] = us; li[r] = ui; }
-              else if (lane == pos) { ls[r] = vb; li[r] = static_cast<int32_t>(gcol + b); }
+              const bool shift = ins && lane > pos, put = ins && lane == pos;
+              ls[r] = shift ? us : (put ? vb : ls[r]);
+              li[r] = shift ? ui : (put ? static_cast<int32_t>(gcol + b) : li[r]);
             }
           }
         }
@@ -277,9 +299,9 @@ bank_norm_max_kernel(const float* __restrict__ x, int64_t n, int d, unsigned int
     s += __shfl_xor_sync(0xffffffffu, s, o);
     sl += __shfl_xor_sync(0xffffffffu, sl, o);
   }
-  if (lane == 0) {
-    atomicMax(max_bits, __float_as_uint(s));
-    atomicMax(max_bits + 1, __float_as_uint(sl));
+  if (lane == 0) {      // read first: after the first rows almost no row raises a maximum, and contended atomics serialise
+    if (__float_as_uint(s) > *reinterpret_cast<volatile unsigned int*>(max_bits)) atomicMax(max_bits, __float_as_uint(s));
+    if (__float_as_uint(sl) > *reinterpret_cast<volatile unsigned int*>(max_bits + 1)) atomicMax(max_bits + 1, __float_as_uint(sl));
   }
 }
 
@@ -327,7 +349,7 @@ __device__ __forceinline__ void warp_list_insert(unsigned long long& mine, unsig
 // bank_max_bits[0..1]: max |r|^2, max |r - bf16(r)|^2 over the bank (float bits).  k <= 32.
 __global__ void __launch_bounds__(kRrWarps * 32)
 row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2, int64_t nq,
-                   const float* __restrict__ cand_v, const int32_t* __restrict__ cand_i, int nlists, int k,
+                   const float* __restrict__ cand_v, const int32_t* __restrict__ cand_i, int nlists, int depth, int k,
                    const float* __restrict__ qn, const float* __restrict__ qn_lo, const unsigned int* __restrict__ bank_max_bits,
                    float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, int* __restrict__ flags,
                    int* __restrict__ n_flagged) {
@@ -373,7 +395,7 @@ row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, 
     const int c = c0 + lane;
     const int32_t id = c < ncand ? ci[c] : -1;
     const bool take = id >= 0 && cv[c < ncand ? c : 0] >= thr;
-    if (take && (c % kS1List) == kS1List - 1) overflow = true;
+    if (take && (c % kS1List) == depth - 1) overflow = true;
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     if (m == 0u) continue;
     const int ns = __popc(m);
@@ -492,8 +514,12 @@ void sim1_plan(int64_t nq, int64_t nr, int* pairs_out, int* slots_out) {
 int sim1_list_len() { return kS1List; }
 
 // Qh [nq, dp] / Rh [nr, dp]: bf16 hi planes.  cand_v / cand_i: [nq, slots * 2 * kS1List] (pairs / slots from sim1_plan).
+// Entries kept per candidate list: the cost of a running top-L is ~L (1 + ln(n / L)) insertions per list, and a list has to
+// hold its share of a query's survivors (~2 k on random data)
+int sim1_depth(int k) { return k <= 1 ? 8 : (k <= 3 ? 16 : kS1List); }
+
 int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn, int pairs,
-              int slots, float* cand_v, int32_t* cand_i, cudaStream_t stream) {
+              int slots, int depth, float* cand_v, int32_t* cand_i, cudaStream_t stream) {
   if (nq == 0 || nr == 0) return VSCB200_OK;
   VSCB_REQUIRE(dp % 8 == 0 && nr < (1ll << 31), "sim1_topk: dp must be a multiple of 8 and nr < 2^31");
   CUtensorMap tQ, tR;
@@ -506,7 +532,8 @@ int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bo
   VSCB_REQUIRE(tm2 < (1ll << 30) && tn < (1ll << 30), "sim1_topk: too many tiles");
   p.tiles_m2 = static_cast<int>(tm2);
   p.tiles_n = static_cast<int>(tn);
-  p.pairs = pairs; p.slots = slots; p.cand_v = cand_v; p.cand_i = cand_i;
+  VSCB_REQUIRE(depth >= 1 && depth <= kS1List, "sim1_topk: bad list depth");
+  p.pairs = pairs; p.slots = slots; p.depth = depth; p.cand_v = cand_v; p.cand_i = cand_i;
   // slots a pair never writes must read as empty
   VSCB_CUDA_OK(cudaMemsetAsync(cand_i, 0xFF, static_cast<size_t>(nq) * slots * 2 * kS1List * sizeof(int32_t), stream));
   VSCB_CUDA_OK(cudaFuncSetAttribute(sim1_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS1Smem));
@@ -519,17 +546,18 @@ int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bo
 
 // flags [nq] / n_flagged [1]: device scratch (n_flagged must be zero on entry; the fallback kernel reads it)
 int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const float* cand_v,
-                 const int32_t* cand_i, int slots, int k, const float* qn, const float* qn_lo, const unsigned int* bank_max_bits,
-                 float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged, cudaStream_t stream) {
+                 const int32_t* cand_i, int slots, int depth, int k, const float* qn, const float* qn_lo,
+                 const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged,
+                 cudaStream_t stream) {
   if (nq == 0) return VSCB200_OK;
-  VSCB_REQUIRE(k >= 1 && k <= kS1List, "sim1_rescore: k must be <= the candidate list length");
+  VSCB_REQUIRE(k >= 1 && k <= depth && depth <= kS1List, "sim1_rescore: k must be <= the candidate list depth");
   const size_t smem = static_cast<size_t>(kRrWarps) * d * 4 + static_cast<size_t>(kRrWarps) * 32 * 4;
   VSCB_REQUIRE(smem <= 200 * 1024 && d % 4 == 0, "sim1_rescore: dimension must be a multiple of 4 and <= 6144");
   VSCB_CUDA_OK(cudaFuncSetAttribute(row_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
     ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * slots * 2 * kS1List * 8);
     row_rescore_kernel<<<static_cast<unsigned>((nq + kRrWarps - 1) / kRrWarps), kRrWarps * 32, smem, stream>>>(
-        Q, bank, d, l2 ? 1 : 0, nq, cand_v, cand_i, slots * 2, k, qn, qn_lo, bank_max_bits, D, I, id_offset, flags, n_flagged);
+        Q, bank, d, l2 ? 1 : 0, nq, cand_v, cand_i, slots * 2, depth, k, qn, qn_lo, bank_max_bits, D, I, id_offset, flags, n_flagged);
     count_launch();
   }
   const size_t smem_ex = static_cast<size_t>(d) * 4 + static_cast<size_t>(kExWarps) * 32 * 8;

@@ -256,49 +256,150 @@ def weights_from_sscd_timm_state_dict(sd: Dict[str, torch.Tensor], layers: int) 
     return w
 
 
-def encoder_from_state_dict(sd: Dict[str, torch.Tensor], max_frames: int = 256) -> B200ViTEncoder:
-    """Recognise a reference checkpoint by its parameter names and build the matching encoder."""
+def weights_from_hf_vit_state_dict(sd: Dict[str, torch.Tensor], layers: int) -> Dict[str, torch.Tensor]:
+    """Backbone ``VIT`` = transformers.ViTModel + gem + Linear (D/train/train_v106/.../backbones/vit.py:10-58): names
+    ``vit.embeddings.* / vit.encoder.layer.N.* / vit.layernorm.* / output_proj.*``; q, k, v are separate Linears."""
+    e = "vit.embeddings."
+    w = {"patch_w": sd[e + "patch_embeddings.projection.weight"], "patch_b": sd[e + "patch_embeddings.projection.bias"],
+         "cls": sd[e + "cls_token"].reshape(-1), "pos": sd[e + "position_embeddings"][0],
+         "ln_post_w": sd["vit.layernorm.weight"], "ln_post_b": sd["vit.layernorm.bias"],
+         "head_w": sd["output_proj.weight"], "head_b": sd["output_proj.bias"]}
+    for l in range(layers):
+        s, p = f"vit.encoder.layer.{l}.", f"l{l}."
+        w[p + "ln1_w"], w[p + "ln1_b"] = sd[s + "layernorm_before.weight"], sd[s + "layernorm_before.bias"]
+        w[p + "qkv_w"] = torch.cat([sd[s + f"attention.attention.{n}.weight"] for n in ("query", "key", "value")])
+        w[p + "qkv_b"] = torch.cat([sd[s + f"attention.attention.{n}.bias"] for n in ("query", "key", "value")])
+        w[p + "proj_w"], w[p + "proj_b"] = sd[s + "attention.output.dense.weight"], sd[s + "attention.output.dense.bias"]
+        w[p + "ln2_w"], w[p + "ln2_b"] = sd[s + "layernorm_after.weight"], sd[s + "layernorm_after.bias"]
+        w[p + "fc1_w"], w[p + "fc1_b"] = sd[s + "intermediate.dense.weight"], sd[s + "intermediate.dense.bias"]
+        w[p + "fc2_w"], w[p + "fc2_b"] = sd[s + "output.dense.weight"], sd[s + "output.dense.bias"]
+    return w
+
+
+class _Tracked(dict):
+    """A state dict that remembers which entries a converter read."""
+
+    def __init__(self, sd):
+        super().__init__(sd)
+        self.read = set()
+
+    def __getitem__(self, k):
+        self.read.add(k)
+        return super().__getitem__(k)
+
+
+# entries of a reference checkpoint that carry no arithmetic of the inference path: registered index / mask / coordinate
+# buffers of Swin-V2 (recomputed from the spec), and the pooler of transformers.ViTModel (VIT.forward reads
+# last_hidden_state only, backbones/vit.py:44)
+_IGNORABLE = re.compile(r"(\.relative_position_index|\.relative_coords_table|\.attn_mask|^vit\.pooler\.)")
+
+
+def _precision_default() -> str:
+    import os
+    p = os.environ.get("VSCB200_ENCODER_PRECISION", "bf16")
+    if p not in ("bf16", "fp32"):
+        raise RuntimeError(f"VSCB200_ENCODER_PRECISION must be 'bf16' or 'fp32', got {p!r}")
+    return p
+
+
+def encoder_from_state_dict(sd: Dict[str, torch.Tensor], max_frames: int = 256, ln_eps: Optional[float] = None,
+                            precision: Optional[str] = None) -> nn.Module:
+    """Recognise a reference checkpoint by its parameter names and build the matching encoder.  EVERY entry of the state
+    dict must be accounted for (read by the converter, or a known arithmetic-free buffer): a checkpoint that is only
+    similar to a supported architecture (an extra ``proj``, a different head) raises instead of producing plausible but
+    wrong descriptors.  ``ln_eps``: LayerNorm epsilon when it is known from elsewhere (a TorchScript graph); ``precision``:
+    "bf16" | "fp32" (default: $VSCB200_ENCODER_PRECISION, else "bf16")."""
+    precision = precision or _precision_default()
+    sd = _Tracked(sd)
     keys = set(sd.keys())
+
+    def done(enc):
+        extra = sorted(k for k in keys - sd.read if not _IGNORABLE.search(k))
+        if extra:
+            raise RuntimeError(f"checkpoint has parameters this encoder does not use: {extra[:6]}{'...' if len(extra) > 6 else ''}")
+        return enc
+
     if "conv1.weight" in keys and "class_embedding" in keys:                    # CLIPModel
         width, _, patch, _ = sd["conv1.weight"].shape
         tokens = sd["positional_embedding"].shape[0]
         layers = 1 + max(int(m.group(1)) for k in keys if (m := re.match(r"transformer\.resblocks\.(\d+)\.", k)))
         img = int(round((tokens - 1) ** 0.5)) * patch
-        spec = VitSpec(img, patch, width, layers, width // 64, tail="tokens")
-        return B200ViTEncoder(spec, weights_from_clip_state_dict(sd, layers), max_frames)
+        spec = VitSpec(img, patch, width, layers, width // 64, tail="tokens", ln_eps=ln_eps or 1e-5, precision=precision)
+        return done(B200ViTEncoder(spec, weights_from_clip_state_dict(sd, layers), max_frames))
     if "model.backbone.patch_embed.proj.weight" in keys and "model.embeddings.0.conv.weight" in keys:   # vit_v68
         width, _, patch, _ = sd["model.backbone.patch_embed.proj.weight"].shape
         tokens = sd["model.backbone.pos_embed"].shape[1]
         layers = 1 + max(int(m.group(1)) for k in keys if (m := re.match(r"model\.backbone\.blocks\.(\d+)\.", k)))
         img = int(round((tokens - 1) ** 0.5)) * patch
         spec = VitSpec(img, patch, width, layers, width // 64, patch_bias=True, pre_norm=False, act="gelu",
-                       ln_eps=1e-6, tail="gem_conv_linear", out_dim=sd["model.embeddings.1.weight"].shape[0],
-                       gem_hidden=sd["model.embeddings.0.conv.weight"].shape[0])
-        return B200ViTEncoder(spec, weights_from_sscd_timm_state_dict(sd, layers), max_frames)
+                       ln_eps=ln_eps or 1e-6, tail="gem_conv_linear", out_dim=sd["model.embeddings.1.weight"].shape[0],
+                       gem_hidden=sd["model.embeddings.0.conv.weight"].shape[0], precision=precision)
+        return done(B200ViTEncoder(spec, weights_from_sscd_timm_state_dict(sd, layers), max_frames))
+    if "vit.embeddings.patch_embeddings.projection.weight" in keys and "output_proj.weight" in keys:   # backbone VIT (HF)
+        width, _, patch, _ = sd["vit.embeddings.patch_embeddings.projection.weight"].shape
+        tokens = sd["vit.embeddings.position_embeddings"].shape[1]
+        layers = 1 + max(int(m.group(1)) for k in keys if (m := re.match(r"vit\.encoder\.layer\.(\d+)\.", k)))
+        img = int(round((tokens - 1) ** 0.5)) * patch
+        spec = VitSpec(img, patch, width, layers, width // 64, patch_bias=True, pre_norm=False, act="gelu",
+                       ln_eps=ln_eps or 1e-12, tail="gem_linear", out_dim=sd["output_proj.weight"].shape[0], precision=precision)
+        return done(B200ViTEncoder(spec, weights_from_hf_vit_state_dict(sd, layers), max_frames))
     if "patch_embed.proj.weight" in keys and "layers.0.blocks.0.attn.logit_scale" in keys:             # swinv2_v1xx
-        from .swin_encoder import B200SwinEncoder, spec_from_state_dict
-        return B200SwinEncoder(spec_from_state_dict(sd), sd, max_frames)
+        import dataclasses as _dc
+
+        from .swin_encoder import B200SwinEncoder, param_names, spec_from_state_dict
+        spec = _dc.replace(spec_from_state_dict(sd), precision=precision, ln_eps=ln_eps or 1e-5)
+        for n in param_names(spec):
+            sd[n]
+        return done(B200SwinEncoder(spec, sd, max_frames))
     raise RuntimeError("encoder_from_state_dict: unrecognised checkpoint (implemented: CLIP ViT, timm ViT + GeM head, "
-                       "Swin-V2 -- the encoders on the reference's inference path)")
+                       "HF ViT + gem head, Swin-V2 -- the encoders on the reference's inference path)")
+
+
+def _jit_layer_norm_eps(module) -> Optional[float]:
+    """LayerNorm epsilon of a TorchScript module: a state dict does not carry it, the graph does (the constant fed to
+    the first aten::layer_norm node).  None when the graph cannot be read."""
+    try:
+        for node in module.inlined_graph.nodes():
+            if node.kind() == "aten::layer_norm":
+                v = list(node.inputs())[4].toIValue()
+                if v is not None:
+                    return float(v)
+    except Exception:
+        pass
+    return None
 
 
 _orig_jit_load = None
 
 
-def install_jit_load_hook(max_frames: int = 256):
-    """Make the reference's unmodified ``torch.jit.load(ckpt)`` calls return a B200ViTEncoder when the
-    checkpoint is a recognised ViT encoder (extract_ref_feats.py:24, extract_query_feats.py:77-92,
-    infer_matching.py:84-117).  Unrecognised TorchScript files are returned untouched."""
+def install_jit_load_hook(max_frames: int = 256, precision: Optional[str] = None):
+    """Make the reference's unmodified ``torch.jit.load(ckpt)`` calls return a B200 encoder when the checkpoint is a
+    recognised frame encoder (extract_ref_feats.py:24, extract_query_feats.py:77-92, infer_matching.py:84-117).
+    Anything else -- unrecognised modules, checkpoints with parameters the encoder would ignore -- is returned
+    untouched, with a log line either way."""
+    import logging
     global _orig_jit_load
     if _orig_jit_load is not None:
         return
     _orig_jit_load = torch.jit.load
+    log = logging.getLogger("vscb200")
 
     def _load(f, *a, **k):
         module = _orig_jit_load(f, *a, **k)
         try:
-            return encoder_from_state_dict(dict(module.state_dict()), max_frames)
-        except (RuntimeError, KeyError):
+            enc = encoder_from_state_dict(dict(module.state_dict()), max_frames, ln_eps=_jit_layer_norm_eps(module),
+                                          precision=precision)
+        except (RuntimeError, KeyError) as e:
+            log.warning("torch.jit.load(%s): kept the TorchScript module (%s)", f, e)
             return module
+        log.info("torch.jit.load(%s): replaced by %s %s", f, type(enc).__name__, enc.spec)
+        return enc
 
     torch.jit.load = _load
+
+
+def uninstall_jit_load_hook():
+    global _orig_jit_load
+    if _orig_jit_load is not None:
+        torch.jit.load = _orig_jit_load
+        _orig_jit_load = None
