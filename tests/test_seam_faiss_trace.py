@@ -30,8 +30,8 @@ def test_replay_against_faiss_compat(golden_dir):
     idx, checked = {}, {"search": 0, "range_search": 0}
     for o in ops:
         if o["op"] == "new":
-            idx[o["id"]] = faiss.index_factory(o["d"], "Flat", o["metric"]) if o["how"] == "index_factory" else \\
-                faiss.IndexFlat(o["d"], o["metric"])
+            idx[o["id"]] = (faiss.index_factory(o["d"], "Flat", o["metric"]) if o["how"] == "index_factory"
+                            else faiss.IndexFlat(o["d"], o["metric"]))
         elif o["op"] == "clone":
             co = faiss.GpuMultipleClonerOptions()
             co.shard = o["shard"]
