@@ -368,7 +368,8 @@ def test_near_duplicate_frame_filter_and_query_tail():
 def test_single_pass_search_equals_split_path_and_oracle(faiss, monkeypatch):
     """k <= 10 on a large bank: selection on ONE bf16 MMA per product + error margin + exact rescoring (sim_tc1.cu) must
     return exactly what the split-bf16 (3 MMAs) path and the fp32 oracle return -- also where the margin is crowded:
-    300 bank rows within 2e-3 of a query (survivor overflow -> exhaustive fp32 fallback for that query)."""
+    300 bank rows within 2e-3 of a query (the row buffers spill into the query's global list) and 700 such rows (the
+    list overflows -> exhaustive fp32 fallback for that query)."""
     from oracle import faiss_np
     rng = np.random.default_rng(31)
     d = 256
@@ -377,6 +378,8 @@ def test_single_pass_search_equals_split_path_and_oracle(faiss, monkeypatch):
     xq = unit(rng.standard_normal((700, d)))
     xb[20000:20300] = unit(xq[5] + 2e-3 * rng.standard_normal((300, d)))        # crowded margin for query 5
     xb[41000:41012] = unit(xq[9] + 1e-2 * rng.standard_normal((12, d)))         # a dozen close rows for query 9
+    xb[30000:30700] = unit(xq[7] + 2e-3 * rng.standard_normal((700, d)))        # more than a candidate list holds: query 7 is redone exhaustively
+    xb[45000:45700] = unit(xq[650] + 1e-3 * rng.standard_normal((700, d)))      # ... and one in the last query tile
     res = {}
     for passes in ("1", "3"):
         monkeypatch.setenv("VSCB200_SIM_PASSES", passes)
@@ -384,6 +387,9 @@ def test_single_pass_search_equals_split_path_and_oracle(faiss, monkeypatch):
             ix = faiss.IndexFlat(d, metric)
             ix.add(xb)
             res[passes, metric] = ix.search(xq, 10)
+            if passes == "1":       # queries 7 and 650 must have gone through the exhaustive kernel
+                from vsc22_submission_b200 import _lib
+                assert _lib.lib().vscb200_index_last_fallbacks(ix._h.ptr) >= 2
     for metric in (faiss.METRIC_INNER_PRODUCT, faiss.METRIC_L2):
         (D1, I1), (D3, I3) = res["1", metric], res["3", metric]
         np.testing.assert_array_equal(I1, I3)

@@ -15,7 +15,7 @@ SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attent
            "sort.cu", "global_topk.cu", "tn_align.cu", "resize.cu", "index.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--use_fast_math" if False else "-DVSCB200_NO_FAST_MATH", "-Xptxas", "-v"]
+         "-DVSCB200_NO_FAST_MATH", *os.environ.get("VSCB200_EXTRA_NVCC_FLAGS", "").split(), "-Xptxas", "-v"]
 
 
 def _stamp(src: str) -> str:

@@ -351,28 +351,25 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
   }
   // Small k on a large bank, single pass: approximate scores from ONE bf16 MMA per product select, per query, every
   // bank row within a proven error margin of the k-th best; the survivors are rescored in exact fp32 (sim_tc1.cu).
-  if (!ix->force_simt && !ix->no_fused && ix->sim_passes == 1 && k + 6 <= sim1_list_len() && ix->ntotal >= 2048 &&
+  if (!ix->force_simt && !ix->no_fused && ix->sim_passes == 1 && k <= sim1_max_k() && ix->ntotal >= 2048 &&
       ix->ntotal < (1ll << 31) && ix->d % 4 == 0) {
-    const int fk = sim1_list_len();
-    for (int64_t q0 = 0; q0 < nq; q0 += (1 << 20)) {
-      const int64_t nb = std::min<int64_t>(1 << 20, nq - q0);
-      int pairs = 0, slots = 0;
-      sim1_plan(nb, ix->ntotal, &pairs, &slots);
-      const size_t ncand = static_cast<size_t>(slots) * 2 * fk;
-      if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nb) * ncand * sizeof(float), s))) return rc;
-      if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nb) * ncand * sizeof(int32_t), s))) return rc;
+    const int64_t qblk = 1 << 18;
+    for (int64_t q0 = 0; q0 < nq; q0 += qblk) {
+      const int64_t nb = std::min<int64_t>(qblk, nq - q0);
+      if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nb) * sim1_list_cap() * 8, s))) return rc;
       if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(2 * nb) * sizeof(float), s))) return rc;
-      if ((rc = grow(&ix->flags, &ix->flags_bytes, static_cast<size_t>(nb + 1) * sizeof(int), s))) return rc;
+      const size_t scratch_bytes = static_cast<size_t>(sim1_scratch_ints(nb)) * sizeof(int);
+      if ((rc = grow(&ix->flags, &ix->flags_bytes, scratch_bytes, s))) return rc;
+      if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, sim1_partial_bytes(), s))) return rc;
       const float* qb = q + q0 * ix->d;
       const size_t plane = static_cast<size_t>(nb) * ix->dp;
       if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
       if ((rc = q_hi_norm(qb, ix->q_planes, ix->qnorm, ix->qnorm + nb, nb, ix->d, ix->dp, s))) return rc;
-      VSCB_CUDA_OK(cudaMemsetAsync(ix->flags + nb, 0, sizeof(int), s));
-      const int depth = sim1_depth(k);
-      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->dp, !keep_max, ix->qnorm, ix->rnorm, pairs, slots, depth,
-                          ix->cand_d, ix->cand_i, s))) return rc;
-      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, ix->cand_i, slots, depth, k, ix->qnorm,
-                             ix->qnorm + nb, ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->flags + nb, s))) return rc;
+      VSCB_CUDA_OK(cudaMemsetAsync(ix->flags, 0, scratch_bytes, s));
+      if ((rc = sim1_topk(ix->q_planes, ix->bank_hi, nb, ix->ntotal, ix->d, ix->dp, !keep_max, k, ix->qnorm, ix->qnorm + nb, ix->rnorm,
+                          ix->rmax2_bits, ix->cand_d, ix->flags, s))) return rc;
+      if ((rc = sim1_rescore(qb, ix->bank, ix->d, !keep_max, nb, ix->ntotal, ix->cand_d, k, ix->qnorm, ix->qnorm + nb,
+                             ix->rmax2_bits, D + q0 * k, I + q0 * k, ix->id_offset, ix->flags, ix->cand_i, s))) return rc;
       ix->last_flag_count = ix->flags + nb;
     }
     return VSCB200_OK;

@@ -39,7 +39,7 @@ struct vscb200_index {
   int sim_passes = 1;        // 1: single bf16 pass + margin + exact rescoring (sim_tc1.cu); 3: split-bf16 fused top-k (sim_tc.cu)
   unsigned int* rmax2_bits = nullptr;   // device [2]: max |r|^2 and max |r - bf16(r)|^2 as float bits (single-pass search margin)
   bool rmax2_reset = true;
-  int* flags = nullptr; size_t flags_bytes = 0;   // [nq + 1] survivor-overflow flags + their count
+  int* flags = nullptr; size_t flags_bytes = 0;   // sim_tc1.cu scratch: [nq] overflow flags + [1] their count + [nq] shared thresholds + [nq] list lengths
   int* last_flag_count = nullptr;                 // -> the count of the last single-pass search (diagnostics)
   float* gmax = nullptr; size_t gmax_bytes = 0;       // streaming search: per (32-row group, query) maxima
   // results of the last global (cross-query) candidate search, kept until the next one (global_topk.cu)

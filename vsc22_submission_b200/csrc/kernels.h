@@ -41,17 +41,19 @@ int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr
                 const float* qn, const float* rn, cudaStream_t stream);
 int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
 // sim_tc1.cu: single-pass (one bf16 MMA per product) top-k selection with an error margin + exact rescoring
-void sim1_plan(int64_t nq, int64_t nr, int* pairs_out, int* slots_out);
-int sim1_list_len();
+int sim1_pairs(int64_t nq, int64_t nr);
+int sim1_list_cap();
 int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream);
 int bank_norm_max(const float* x, int64_t n, int d, unsigned int* max_bits, cudaStream_t stream);
-int sim1_depth(int k);
-int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn, int pairs,
-              int slots, int depth, float* cand_v, int32_t* cand_i, cudaStream_t stream);
-int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const float* cand_v,
-                 const int32_t* cand_i, int slots, int depth, int k, const float* qn, const float* qn_lo,
-                 const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged,
-                 cudaStream_t stream);
+int sim1_max_k();
+int sim1_scratch_ints(int64_t nq);
+size_t sim1_partial_bytes();
+int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int d, int dp, bool l2, int k, const float* qn,
+              const float* qn_lo, const float* rn, const unsigned int* bank_max_bits, void* cand, int* scratch,
+              cudaStream_t stream);
+int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const void* cand, int k,
+                 const float* qn, const float* qn_lo, const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset,
+                 int* scratch, void* partial, cudaStream_t stream);
 int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
                  float* out, cudaStream_t stream, const int* drop_dim_dev = nullptr);
 // row r = S + r*ldS, element i of a row at [i*es] (es = 1: dense rows; es > 1: a column of a row-major matrix)

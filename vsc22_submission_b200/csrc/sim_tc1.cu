@@ -1,29 +1,32 @@
-// Batch top-k similarity search at ONE bf16 MMA per product (k <= 10): selection on approximate scores with a proven
+// Batch top-k similarity search at ONE bf16 MMA per product (k <= 12): selection on approximate scores with a proven
 // error margin, exact fp32 scores for the survivors.
 //
 //   sim1_topk_kernel     a ~ q.r from the hi planes only (bf16(q).bf16(r), fp32 accumulation) on tcgen05 with CTA pairs
 //                        (cta_group::2, 256 x 256 tiles, the skeleton of gemm.cu).  Every CTA pair walks ONE contiguous
 //                        range of the (query pair-tile, bank tile) sequence: perfectly balanced, and a query row meets as
-//                        few pairs as possible (<= 3 at config 3).  Epilogue: each warp transposes its 32 rows x 32
-//                        columns of scores through a 4 KB staging tile and then works ROW BY ROW -- lane = column for
-//                        the comparison against the row's threshold, lane = rank for the row's running top-32 list,
-//                        which lives in one register pair per row across the warp (insert = ballot + shuffle-up).  A
-//                        thread-per-row list would make the warp execute the union of 32 rows' insertions; here a chunk
-//                        without hits costs 5 instructions per row.  No score reaches HBM.
+//                        few pairs as possible (<= 3 at config 3).  Epilogue, THREAD = QUERY ROW (the layout tcgen05.ld
+//                        delivers, no transpose): per 32-column chunk a max tree and one comparison against the row's
+//                        threshold tau; hits are APPENDED to the row's 48-entry buffer in shared memory (count in a
+//                        register, no atomics).  When a buffer fills, the warp compacts that row together: k REDUX
+//                        rounds find the buffer's k-th best key, tau = that - 2 eps, entries below tau are dropped.  tau
+//                        is also published per query in global memory (atomicMax), so the lists of one query held by
+//                        different warps / CTA pairs tighten each other.  No score reaches HBM.
 //   row_rescore_kernel   one warp per query: A_k = k-th best approximate score over the row's lists; every bank row with
 //                        a >= A_k - 2 eps is rescored in exact fp32 (exact.cuh, the one summation order every search
 //                        path reports) and streamed into a warp-wide top-k by (score, lower id).
-//   exact_row_topk_kernel  brute-force fp32 search of the flagged rows (a full list inside the margin), normally none.
+//   exact_row_topk_kernel  brute-force fp32 search of the flagged rows (a buffer saturated by entries inside the margin),
+//                        normally none.
 //
 // Why this is exact.  Write q = qh + ql, r = rh + rl (h = bf16 rounding, l = its residual).  The kernel computes
 // a = fl(qh.rh); s = q.r = qh.rh + ql.r + qh.rl, so by Cauchy-Schwarz |a - s| <= |ql| |r| + |qh| |rl| + d 2^-23 |q| |r|
 // (last term: fp32 accumulation of the exact bf16 products).  |ql| and |qh| are measured per query, max |r| and
 // max |rl| per bank at add(): eps(q) = |ql| Rmax + |qh| RLmax + d 2^-23 |q| Rmax -- about 0.0026 |q| Rmax in practice, below
 // the worst case 2^-8.  The k rows with the best a have s >= A_k - eps, so the k-th best exact score s_k >= A_k - eps, and
-// a row of the exact top-k has a >= s_k - eps >= A_k - 2 eps: it is a survivor.  A list that is full with its last entry
-// inside the margin may have dropped a survivor: such queries are flagged and searched exhaustively in fp32.  Reference
-// semantics: faiss IndexFlat.search behind vsc/index.py:174 and vsc/baseline/score_normalization.py:93-98 (exact scores,
-// best first, ties to the lower id).
+// a row of the exact top-k has a >= s_k - eps >= A_k - 2 eps: it is a survivor.  A list only drops entries below
+// (k-th best key of a SUBSET of the row's columns) - 2 eps <= A_k - 2 eps, so every survivor reaches the rescoring pass
+// unless its buffer saturates (more than 40 entries inside the margin of one list): such queries are flagged and searched
+// exhaustively in fp32.  Reference semantics: faiss IndexFlat.search behind vsc/index.py:174 and
+// vsc/baseline/score_normalization.py:93-98 (exact scores, best first, ties to the lower id).
 #include <float.h>
 
 #include "exact.cuh"
@@ -34,31 +37,57 @@
 namespace vscb200 {
 
 constexpr int kS1BM = 128, kS1BN = 256, kS1BK = 64;     // per-CTA rows, pair-tile columns, K block
-constexpr int kS1Stages = 5;
+constexpr int kS1Stages = 4;
 constexpr int kS1EpiWarps = 8;
 constexpr int kS1Threads = 128 + 32 * kS1EpiWarps;
 constexpr int kS1ATile = kS1BM * kS1BK * 2;              // 16 KB
 constexpr int kS1BTile = (kS1BN / 2) * kS1BK * 2;        // 16 KB: each CTA stages half of the bank tile
-constexpr int kS1Smem = kS1Stages * (kS1ATile + kS1BTile) + kS1EpiWarps * 4096 + 256 + 1024;
-constexpr int kS1List = 32;                              // candidate list per (query row, column half, pair): one entry per lane
+constexpr int kS1Cap = 48;                               // entries per candidate list = per (query row, column half, pair)
+constexpr int kS1Keep = kS1Cap - 8;                      // a compaction that leaves more than this saturates the list
+constexpr int kS1BufBytes = kS1Cap * 32 * 8;             // one epilogue warp's 32 row buffers
+constexpr int kS1Smem = kS1Stages * (kS1ATile + kS1BTile) + kS1EpiWarps * kS1BufBytes + 256 + 1024;
+constexpr int kS1MaxK = 12;
+constexpr int kS1ListCap = 384;                          // entries of a query's global candidate list
+static_assert(kS1Smem <= 232448, "sim1: shared memory");
 
 struct Sim1Params {
   int64_t nq, nr;
   int K;                 // padded feature dim
+  int d;                 // feature dim (error bound)
   int l2;
-  const float* qn;       // squared query norms (L2 keys)
-  const float* rn;       // squared bank norms
+  int k;                 // neighbours wanted
+  const float* qn;       // squared query norms
+  const float* qn_lo;    // squared norms of q - bf16(q)
+  const float* rn;       // squared bank norms (L2 keys)
+  const unsigned int* bank_max_bits;    // max |r|^2, max |r - bf16(r)|^2 (float bits)
   int tiles_m2, tiles_n;            // pair tiles along M, 256-wide tiles along N
-  int pairs, slots;                 // CTA pairs launched; candidate-list slots per query row (pairs that may meet a row)
-  int depth;                        // entries kept per list (<= kS1List): 8 / 16 / 32 by k
-  float* cand_v;         // [nq, slots * 2 * kS1List] selection keys (larger = better; -distance for L2)
-  int32_t* cand_i;       // bank rows (-1 = empty; the buffer is pre-filled with -1)
+  int pairs;                        // CTA pairs launched
+  uint2* cand;           // [nq, cand_cap] (selection key bits: larger = better, -distance for L2; bank row)
+  int* cand_n;           // [nq] entries appended per query (zero on entry; may exceed cand_cap: the excess was dropped)
+  int cand_cap;
+  int* flags;            // [nq] set to 1 when a query's list overflowed cand_cap (zero on entry)
+  unsigned int* tau_g;   // [nq] shared threshold per query as an ordered key (zero on entry = none)
 };
 
 // Work split: pair p owns tiles [tile_start(p), tile_start(p + 1)) of the sequence t = pm * tiles_n + n_blk.
 __host__ __device__ inline int64_t s1_tile_start(int64_t p, int64_t T, int64_t P) { return p * T / P; }
-// the pair whose range holds tile t
-__host__ __device__ inline int64_t s1_pair_of(int64_t t, int64_t T, int64_t P) { return ((t + 1) * P - 1) / T; }
+
+__device__ __forceinline__ uint32_t okey32(float f) {          // order-preserving float -> uint (larger float = larger key)
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float okey32_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+// the scoring-error bound of the header, in key units (L2 keys are -(|q|^2 + |r|^2 - 2 q.r): twice the product's error)
+__device__ __forceinline__ float sim1_eps(float qn2, float qlo2, const unsigned int* __restrict__ bank_max_bits, int d, int l2) {
+  const float qnorm = sqrtf(qn2), qlo = sqrtf(qlo2);
+  const float rmax2 = __uint_as_float(bank_max_bits[0]);
+  const float rmax = sqrtf(rmax2), rlmax = sqrtf(__uint_as_float(bank_max_bits[1]));
+  float eps = (qlo * rmax + (qnorm + qlo) * rlmax + static_cast<float>(d) * 1.1920929e-7f * qnorm * rmax) * 1.001f;
+  if (l2) eps = 2.0f * eps + 1e-6f * (qn2 + rmax2);
+  return eps;
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kS1Threads, 1)
 sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR, Sim1Params p) {
@@ -67,8 +96,8 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kS1Stages * kS1ATile;
-  uint8_t* stage_all = sB + kS1Stages * kS1BTile;          // per-warp 4 KB staging rows of the epilogue
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_all + kS1EpiWarps * 4096);
+  uint8_t* buf_all = sB + kS1Stages * kS1BTile;            // per-warp candidate buffers of the epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_all + kS1EpiWarps * kS1BufBytes);
   uint64_t* empty_bar = full_bar + kS1Stages;
   uint64_t* tfull_bar = empty_bar + kS1Stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -137,28 +166,112 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int ew = warp - 4, quad = warp & 3, half = ew >> 2;
-    uint8_t* tile = stage_all + ew * 4096;             // 32 rows x 128 B, 16-byte chunk q of row r at q ^ (r & 7)
+    // buf[e][row]: entry e of the thread's row at slot (row ^ e) & 31 of line e -- conflict-free for the owner's appends
+    // (lanes = rows, equal e) and for the warp's cooperative reads of one row (lanes = entries)
+    uint2* buf = reinterpret_cast<uint2*>(buf_all + ew * kS1BufBytes);
+    auto slot_of = [&](int e, int row) { return e * 32 + ((row ^ e) & 31); };
     int acc = 0;
     uint32_t acc_phase = 0;
-    // ls[r] / li[r]: the running top-32 (key, bank row) of the warp's r-th query row over this warp's columns of the
-    // pair's range -- lane = rank, best first; strict comparisons keep the earlier (lower) bank row among equal keys
-    float ls[32];
-    int32_t li[32];
+    float tau = INFINITY, eps2 = 0.f, qn_lane = 0.f;   // tau: keys <= tau cannot be survivors of this row
+    int cnt = 0, trig = kS1Keep;                        // entries appended (may exceed kS1Cap: the excess was not stored)
     int cur_pm = -1;
     int64_t row0 = 0;
-    float qn_lane = 0.f;
-    const int tl = p.depth - 1;                        // lane holding a list's threshold (its last kept entry)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // The warp compacts row r's buffer: the k-th best key of the buffer minus the margin becomes the row's threshold.
+    auto compact = [&](int r) {
+      __syncwarp();
+      const int n = min(__shfl_sync(0xffffffffu, cnt, r), kS1Cap);
+      const float e2 = __shfl_sync(0xffffffffu, eps2, r);
+      const uint2 e0 = lane < n ? buf[slot_of(lane, r)] : make_uint2(0u, 0u);
+      const uint2 e1 = lane + 32 < n ? buf[slot_of(lane + 32, r)] : make_uint2(0u, 0u);
+      uint32_t a = lane < n ? okey32(__uint_as_float(e0.x)) : 0u;
+      uint32_t b = lane + 32 < n ? okey32(__uint_as_float(e1.x)) : 0u;
+      uint32_t kth = 0u;
+      if (p.k <= 2) {                                   // k rounds of "largest remaining key"
+        for (int i = 0; i < p.k; ++i) {
+          kth = __reduce_max_sync(0xffffffffu, max(a, b));
+          if (kth == 0u) break;
+          const uint32_t ba = __ballot_sync(0xffffffffu, a == kth);
+          if (ba != 0u) {
+            if (lane == __ffs(ba) - 1) a = 0u;
+          } else {
+            const uint32_t bb = __ballot_sync(0xffffffffu, b == kth);
+            if (lane == __ffs(bb) - 1) b = 0u;
+          }
+        }
+      } else {
+        // rank counting (no dependent chain): g = entries with a larger key; the k-th best key is the smallest key
+        // among the entries with g < k (equal keys share their g)
+        const float fa = lane < n ? __uint_as_float(e0.x) : -INFINITY, fb = lane + 32 < n ? __uint_as_float(e1.x) : -INFINITY;
+        int ga = 0, gb = 0;
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) {
+          const float fj = __uint_as_float(buf[slot_of(j, r)].x);      // same address in every lane: broadcast
+          ga += fj > fa ? 1 : 0;
+          gb += fj > fb ? 1 : 0;
+        }
+        const uint32_t ka = (lane < n && ga < p.k) ? a : 0xFFFFFFFFu, kb = (lane + 32 < n && gb < p.k) ? b : 0xFFFFFFFFu;
+        kth = __reduce_min_sync(0xffffffffu, min(ka, kb));
+        if (kth == 0xFFFFFFFFu) kth = 0u;
+      }
+      // threshold of the row: this buffer's k-th best minus the margin, or what the query's other lists have reached
+      float tnew = fmaxf(kth != 0u ? okey32_inv(kth) - e2 : -INFINITY, __shfl_sync(0xffffffffu, tau, r));
+      {
+        const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.tau_g + row0 + r);
+        if (g != 0u) tnew = fmaxf(tnew, okey32_inv(g));
+      }
+      const bool keep0 = lane < n && __uint_as_float(e0.x) > tnew, keep1 = lane + 32 < n && __uint_as_float(e1.x) > tnew;
+      const uint32_t m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
+      const int n0 = __popc(m0), nn = n0 + __popc(m1);
+      const bool spill = nn > kS1Keep;     // saturated by entries inside the margin: move them to the query's global list
+      int64_t dst = 0;
+      if (spill) {
+        if (lane == 0) dst = atomicAdd(p.cand_n + row0 + r, nn);
+        dst = __shfl_sync(0xffffffffu, dst, 0);
+        uint2* out = p.cand + (row0 + r) * p.cand_cap;
+        const int64_t i0 = dst + __popc(m0 & lt_mask), i1 = dst + n0 + __popc(m1 & lt_mask);
+        if (keep0 && i0 < p.cand_cap) out[i0] = e0;
+        if (keep1 && i1 < p.cand_cap) out[i1] = e1;
+      } else {
+        __syncwarp();
+        if (keep0) buf[slot_of(__popc(m0 & lt_mask), r)] = e0;
+        if (keep1) buf[slot_of(n0 + __popc(m1 & lt_mask), r)] = e1;
+        __syncwarp();
+      }
+      if (lane == r) {
+        const int64_t row = row0 + r;
+        if (spill && dst + nn > p.cand_cap) p.flags[row] = 1;
+        if (tnew > -INFINITY) {
+          const uint32_t old = atomicMax(p.tau_g + row, okey32(tnew));
+          if (old != 0u) tnew = fmaxf(tnew, okey32_inv(old));
+        }
+        tau = tnew;
+        cnt = spill ? 0 : nn;
+        trig = spill ? kS1Keep : max(kS1Keep, nn + 6);
+      }
+    };
+    // every row's buffer is appended to its query's global list (end of the pair's range over these rows)
     auto flush = [&]() {
       if (cur_pm < 0) return;
-      const int slot = static_cast<int>(pair - s1_pair_of(static_cast<int64_t>(cur_pm) * p.tiles_n, T, p.pairs));
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        if (row0 + r < p.nq) {
-          const int64_t base = (((row0 + r) * p.slots + slot) * 2 + half) * kS1List;
-          p.cand_v[base + lane] = ls[r];
-          p.cand_i[base + lane] = lane <= tl ? li[r] : -1;
-        }
+      __syncwarp();
+      const int nmine = min(cnt, kS1Cap);
+      int64_t dst_mine = 0;
+      if (row0 + lane < p.nq && nmine > 0) {
+        dst_mine = atomicAdd(p.cand_n + row0 + lane, nmine);
+        if (dst_mine + nmine > p.cand_cap) p.flags[row0 + lane] = 1;
       }
+#pragma unroll 1
+      for (int r = 0; r < 32; ++r) {
+        const int64_t row = row0 + r;
+        if (row >= p.nq) break;
+        const int n = __shfl_sync(0xffffffffu, nmine, r);
+        const int64_t dst = __shfl_sync(0xffffffffu, dst_mine, r);
+        uint2* out = p.cand + row * p.cand_cap;
+        if (lane < n && dst + lane < p.cand_cap) out[dst + lane] = buf[slot_of(lane, r)];
+        if (lane + 32 < n && dst + lane + 32 < p.cand_cap) out[dst + lane + 32] = buf[slot_of(lane + 32, r)];
+      }
+      __syncwarp();
     };
     for (int64_t t = t_begin; t < t_end; ++t) {
       const int pm = static_cast<int>(t / p.tiles_n), n_blk = static_cast<int>(t % p.tiles_n);
@@ -166,22 +279,27 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         flush();
         cur_pm = pm;
         row0 = static_cast<int64_t>(pm * 2 + static_cast<int>(crank)) * kS1BM + quad * 32;
-        qn_lane = (p.l2 && row0 + lane < p.nq) ? p.qn[row0 + lane] : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) { ls[r] = -INFINITY; li[r] = -1; }
+        const bool live = row0 + lane < p.nq;
+        qn_lane = live ? p.qn[row0 + lane] : 0.f;
+        eps2 = live ? 2.0002f * sim1_eps(qn_lane, p.qn_lo[row0 + lane], p.bank_max_bits, p.d, p.l2) : 0.f;
+        tau = live ? -INFINITY : INFINITY;
+        cnt = 0;
+        trig = kS1Keep;
       }
+      uint32_t g = 0u;                                                 // thresholds other warps / pairs have reached
+      if (tau < INFINITY) g = *reinterpret_cast<volatile unsigned int*>(p.tau_g + row0 + lane);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (g != 0u) tau = fmaxf(tau, okey32_inv(g));
 #pragma unroll 1
       for (int c = 0; c < kS1BN / 2 / 32; ++c) {
         const int col0 = half * (kS1BN / 2) + c * 32;
         const int64_t gcol = static_cast<int64_t>(n_blk) * kS1BN + col0;
         uint32_t v[32];
-        __syncwarp();
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kS1BN + col0, v);
         tmem_ld_wait();
         if (gcol >= p.nr) continue;                                   // warp-uniform
-        if (p.l2) {                                                   // key = -(|q|^2 + |r|^2 - 2 q.r); lane = query row here
+        if (p.l2) {                                                   // key = -(|q|^2 + |r|^2 - 2 q.r)
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             v[j] = __float_as_uint(2.0f * __uint_as_float(v[j]) - __ldg(p.rn + min(gcol + j, p.nr - 1)) - qn_lane);
@@ -191,47 +309,37 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int j = 0; j < 32; ++j)
             if (gcol + j >= p.nr) v[j] = 0xFF800000u;                 // -inf
         }
-        // transpose through the staging tile: written lane = row, read lane = column
+        float m8[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(tile + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        __syncwarp();
-        // Pass 1, branch-free and fully pipelined: which of the warp's 32 rows have a score above their list's threshold?
-        float val[32];
+        for (int j = 0; j < 8; ++j)
+          m8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                        fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+        const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        int jstart = 0;
+        for (;;) {
+          int jo = 32;                                                // first column of this chunk that found the buffer full
+          if (m > tau && jstart < 32) {
 #pragma unroll
-        for (int r = 0; r < 32; ++r)
-          val[r] = *reinterpret_cast<const float*>(tile + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-        uint32_t lanehit = 0;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) lanehit |= val[r] > __shfl_sync(0xffffffffu, ls[r], tl) ? (1u << r) : 0u;
-        const uint32_t rowmask = __reduce_or_sync(0xffffffffu, lanehit);
-        if (rowmask == 0u) continue;                                  // the common case once the lists have warmed up
-        // Pass 2: insert the hits, four rows at a time in straight-line predicated code -- an insertion is a chain of
-        // dependent warp shuffles / votes (~70 cycles); four independent chains issued back to back hide it
-#pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          if (((rowmask >> (4 * g4)) & 0xFu) == 0u) continue;         // warp-uniform
-          uint32_t m[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            m[i] = __ballot_sync(0xffffffffu, val[4 * g4 + i] > __shfl_sync(0xffffffffu, ls[4 * g4 + i], tl));
-          while ((m[0] | m[1] | m[2] | m[3]) != 0u) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = 4 * g4 + i;
-              const bool act = m[i] != 0u;
-              const int b = act ? __ffs(m[i]) - 1 : 0;
-              m[i] &= m[i] - 1u;
-              const float vb = __shfl_sync(0xffffffffu, val[r], b);
-              const bool ins = act && vb > __shfl_sync(0xffffffffu, ls[r], tl);
-              const int pos = __popc(__ballot_sync(0xffffffffu, ls[r] >= vb));
-              const float us = __shfl_up_sync(0xffffffffu, ls[r], 1);
-              const int32_t ui = __shfl_up_sync(0xffffffffu, li[r], 1);
-              const bool shift = ins && lane > pos, put = ins && lane == pos;
-              ls[r] = shift ? us : (put ? vb : ls[r]);
-              li[r] = shift ? ui : (put ? static_cast<int32_t>(gcol + b) : li[r]);
+            for (int j = 0; j < 32; ++j) {
+              if (j >= jstart && __uint_as_float(v[j]) > tau) {
+                if (cnt < kS1Cap) {
+                  buf[slot_of(cnt, lane)] = make_uint2(v[j], static_cast<uint32_t>(gcol + j));
+                  ++cnt;
+                } else {
+                  jo = min(jo, j);
+                }
+              }
             }
           }
+          uint32_t need = __ballot_sync(0xffffffffu, cnt >= trig || jo < 32);
+          if (need == 0u) break;
+          while (need != 0u) {
+            const int r = __ffs(need) - 1;
+            need &= need - 1u;
+            compact(r);
+          }
+          if (!__any_sync(0xffffffffu, jo < 32)) break;
+          jstart = jo;                                                // rescan the rest of the chunk against the new threshold
         }
       }
       tc_fence_before();
@@ -314,13 +422,6 @@ int bank_norm_max(const float* x, int64_t n, int d, unsigned int* max_bits, cuda
 }
 
 // ------------------------------------------------------------------ survivors -> exact scores -> top-k
-__device__ __forceinline__ uint32_t okey32(float f) {          // order-preserving float -> uint (larger float = larger key)
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float okey32_inv(uint32_t k) {
-  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
-}
 // composite key: (score key, ~id): larger = better, equal scores -> the lower id wins; 0 = empty
 __device__ __forceinline__ unsigned long long ckey(float key, uint32_t id) {
   return (static_cast<unsigned long long>(okey32(key)) << 32) | static_cast<uint32_t>(~id);
@@ -345,14 +446,15 @@ __device__ __forceinline__ void warp_list_insert(unsigned long long& mine, unsig
   else if (lane > pos) mine = up;
 }
 
-// cand_v / cand_i: [nq, nlists * kS1List] (each list best first, -1 = empty).  qn / qn_lo: |q|^2, |q - bf16(q)|^2.
-// bank_max_bits[0..1]: max |r|^2, max |r - bf16(r)|^2 over the bank (float bits).  k <= 32.
+// cand [nq, cand_cap] / cand_n [nq]: the queries' candidate lists (unordered).  qn / qn_lo: |q|^2, |q - bf16(q)|^2.
+// bank_max_bits[0..1]: max |r|^2, max |r - bf16(r)|^2 over the bank (float bits).  flags[q] != 0: the query's list
+// overflowed in sim1_topk_kernel (the exhaustive kernel redoes the query).  k <= 32.
 __global__ void __launch_bounds__(kRrWarps * 32)
 row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2, int64_t nq,
-                   const float* __restrict__ cand_v, const int32_t* __restrict__ cand_i, int nlists, int depth, int k,
+                   const uint2* __restrict__ cand, const int* __restrict__ cand_n, int cand_cap, int k,
                    const float* __restrict__ qn, const float* __restrict__ qn_lo, const unsigned int* __restrict__ bank_max_bits,
-                   float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, int* __restrict__ flags,
-                   int* __restrict__ n_flagged) {
+                   float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, const int* __restrict__ flags,
+                   int* __restrict__ n_flagged, int* __restrict__ flagged) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sq = reinterpret_cast<float*>(rr_smem) + warp * d;                                   // this warp's query row
@@ -360,19 +462,17 @@ row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, 
   const int64_t qrow = static_cast<int64_t>(blockIdx.x) * kRrWarps + warp;
   if (qrow >= nq) return;
   const bool keep_max = !l2;
-  const int ncand = nlists * kS1List;
-  const float* cv = cand_v + qrow * ncand;
-  const int32_t* ci = cand_i + qrow * ncand;
+  const int ncand = min(cand_n[qrow], cand_cap);
+  const uint2* ce = cand + qrow * cand_cap;
   for (int c = lane; c < d; c += 32) sq[c] = Q[qrow * d + c];
-  // ---- A_k: k-th best approximate key over all lists (k rounds of "best key below the previous one")
+  // ---- A_k: k-th best approximate key over the list (k rounds of "best key below the previous one")
   unsigned long long prev = ~0ull;
   int found = 0;
   for (int r = 0; r < k; ++r) {
     unsigned long long best = 0ull;
     for (int c = lane; c < ncand; c += 32) {
-      const int32_t id = ci[c];
-      if (id < 0) continue;
-      const unsigned long long key = ckey(cv[c], static_cast<uint32_t>(id));
+      const uint2 e = ce[c];
+      const unsigned long long key = ckey(__uint_as_float(e.x), e.y);
       if (key < prev && key > best) best = key;
     }
     best = warp_max_u64(best);
@@ -380,26 +480,21 @@ row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, 
     prev = best;
     ++found;
   }
-  // ---- margin (see the header): eps = |ql| Rmax + |qh| RLmax + d 2^-23 |q| Rmax, |qh| <= |q| + |ql|
-  const float qnorm = sqrtf(qn[qrow]), qlo = sqrtf(qn_lo[qrow]);
-  const float rmax = sqrtf(__uint_as_float(bank_max_bits[0])), rlmax = sqrtf(__uint_as_float(bank_max_bits[1]));
-  float eps = (qlo * rmax + (qnorm + qlo) * rlmax + static_cast<float>(d) * 1.1920929e-7f * qnorm * rmax) * 1.001f;
-  if (l2) eps = 2.0f * eps + 1e-6f * (qn[qrow] + __uint_as_float(bank_max_bits[0]));
+  // ---- margin (see the header)
+  const float eps = sim1_eps(qn[qrow], qn_lo[qrow], bank_max_bits, d, l2);
   const float thr = found == k ? okey32_inv(static_cast<uint32_t>(prev >> 32)) - 2.0f * eps : -INFINITY;
   // ---- survivors, 32 candidates at a time: exact fp32 score, streamed into the warp's top-k (lane = rank).
-  //      A full list whose last entry is inside the margin may have dropped a survivor: flag the query.
-  bool overflow = false;
+  const bool overflow = flags[qrow] != 0;                             // warp-uniform
   unsigned long long mine = 0ull;
   __syncwarp();
   for (int c0 = 0; c0 < ncand; c0 += 32) {
     const int c = c0 + lane;
-    const int32_t id = c < ncand ? ci[c] : -1;
-    const bool take = id >= 0 && cv[c < ncand ? c : 0] >= thr;
-    if (take && (c % kS1List) == depth - 1) overflow = true;
+    const uint2 e = c < ncand ? ce[c] : make_uint2(0u, 0u);
+    const bool take = c < ncand && __uint_as_float(e.x) >= thr;
     const uint32_t m = __ballot_sync(0xffffffffu, take);
     if (m == 0u) continue;
     const int ns = __popc(m);
-    if (take) ids[__popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(id);
+    if (take) ids[__popc(m & ((1u << lane) - 1u))] = e.y;
     __syncwarp();
     for (int s0 = 0; s0 < ns; s0 += 4) {
       const float* rp[4];
@@ -417,7 +512,6 @@ row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, 
     }
     __syncwarp();
   }
-  overflow = __any_sync(0xffffffffu, overflow);
   if (lane < k) {
     if (mine != 0ull) {
       const float sc = okey32_inv(static_cast<uint32_t>(mine >> 32));
@@ -428,98 +522,139 @@ row_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ bank, 
       I[qrow * k + lane] = -1;
     }
   }
-  if (lane == 0) {
-    flags[qrow] = overflow ? 1 : 0;
-    if (overflow) atomicAdd(n_flagged, 1);
-  }
+  if (lane == 0 && overflow) flagged[atomicAdd(n_flagged, 1)] = static_cast<int>(qrow);
 }
 
 // ------------------------------------------------------------------ exhaustive fp32 search of the flagged queries
-// One CTA per flagged query at a time; every warp keeps its k best rows as a sorted list spread over its lanes
-// (lane j = rank j), the warp lists are merged through shared memory.  k <= 32.
+// Work unit = (flagged query, one of kExSlices slices of the bank): every warp keeps its k best rows of the slice as a
+// sorted list spread over its lanes (lane j = rank j), the warp lists are merged through shared memory into the unit's
+// k best keys; the CTA that completes a query's last slice merges the kExSlices partial lists.  Flagged queries beyond
+// the scratch capacity (f_max) are searched whole by one CTA each.  k <= 32.
 constexpr int kExWarps = 8;
+constexpr int kExSlices = 64;
+constexpr int kExMaxFlagged = 1024;
 
-__global__ void __launch_bounds__(kExWarps * 32)
-exact_row_topk_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2, int64_t nq, int64_t nr, int k,
-                      float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, const int* __restrict__ flags,
-                      const int* __restrict__ n_flagged) {
-  extern __shared__ __align__(16) uint8_t ex_smem[];
-  if (*n_flagged == 0) return;
-  float* sq = reinterpret_cast<float*>(ex_smem);                                              // [d]
-  unsigned long long* merged = reinterpret_cast<unsigned long long*>(ex_smem + static_cast<size_t>(d) * 4);   // [kExWarps * 32]
+// k best composite keys of bank rows [r_begin, r_end) for the query row in sq -> best[0..k) (shared memory), best first
+__device__ __forceinline__ void exact_slice_topk(const float* sq, const float* __restrict__ bank, int d, bool l2, int64_t r_begin,
+                                                 int64_t r_end, int k, unsigned long long* merged, unsigned long long* best) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool keep_max = !l2;
-  for (int64_t qrow = blockIdx.x; qrow < nq; qrow += gridDim.x) {
-    if (!flags[qrow]) continue;                                       // CTA-uniform
+  unsigned long long mine = 0ull;                                     // lane j: the warp's j-th best composite key
+  for (int64_t r0 = r_begin + static_cast<int64_t>(warp) * 4; r0 < r_end; r0 += kExWarps * 4) {
+    const float* rp[4];
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rp[u] = bank + (r0 + u < r_end ? r0 + u : r_end - 1) * d;
+    exact_rows_warp<4>(sq, rp, d, lane, l2, acc);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u >= r_end) continue;
+      warp_list_insert(mine, ckey(keep_max ? acc[u] : -acc[u], static_cast<uint32_t>(r0 + u)), k, lane);
+    }
+  }
+  merged[warp * 32 + lane] = lane < k ? mine : 0ull;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long prev = ~0ull;
+    for (int r = 0; r < k; ++r) {
+      unsigned long long b = 0ull;
+      for (int c = lane; c < kExWarps * 32; c += 32) {
+        const unsigned long long key = merged[c];
+        if (key < prev && key > b) b = key;
+      }
+      b = warp_max_u64(b);
+      if (lane == 0) best[r] = b;
+      prev = b;
+      if (b == 0ull) prev = 0ull;                                     // nothing left: the remaining entries stay empty
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void exact_write_result(unsigned long long key, bool keep_max, float* D, int64_t* I, int64_t at,
+                                                   int64_t id_offset) {
+  if (key != 0ull) {
+    const float sc = okey32_inv(static_cast<uint32_t>(key >> 32));
+    D[at] = keep_max ? sc : -sc;
+    I[at] = id_offset + static_cast<int64_t>(~static_cast<uint32_t>(key & 0xFFFFFFFFull));
+  } else {
+    D[at] = keep_max ? -FLT_MAX : FLT_MAX;
+    I[at] = -1;
+  }
+}
+
+// flagged [n_flagged]: query rows to redo.  partial [f_max, kExSlices, k] keys, done [f_max] (zero on entry).
+__global__ void __launch_bounds__(kExWarps * 32)
+exact_flagged_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2, int64_t nr, int k,
+                     float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset, const int* __restrict__ flagged,
+                     const int* __restrict__ n_flagged, unsigned long long* __restrict__ partial, int* __restrict__ done, int f_max) {
+  extern __shared__ __align__(16) uint8_t ex_smem[];
+  const int nf_all = *n_flagged;
+  if (nf_all == 0) return;
+  float* sq = reinterpret_cast<float*>(ex_smem);                                              // [d]
+  unsigned long long* merged = reinterpret_cast<unsigned long long*>(ex_smem + static_cast<size_t>(d) * 4);   // [kExWarps * 32]
+  unsigned long long* best = merged + kExWarps * 32;                                          // [32]
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool keep_max = !l2;
+  const int nf = min(nf_all, f_max);
+  for (int64_t u = blockIdx.x; u < static_cast<int64_t>(nf) * kExSlices; u += gridDim.x) {
+    const int f = static_cast<int>(u / kExSlices), sl = static_cast<int>(u % kExSlices);
+    const int64_t qrow = flagged[f];
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += kExWarps * 32) sq[c] = Q[qrow * d + c];
     __syncthreads();
-    unsigned long long mine = 0ull;                                   // lane j: the warp's j-th best composite key
-    for (int64_t r0 = static_cast<int64_t>(warp) * 4; r0 < nr; r0 += kExWarps * 4) {
-      const float* rp[4];
-      float acc[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rp[u] = bank + (r0 + u < nr ? r0 + u : nr - 1) * d;
-      exact_rows_warp<4>(sq, rp, d, lane, l2 != 0, acc);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (r0 + u >= nr) continue;
-        warp_list_insert(mine, ckey(keep_max ? acc[u] : -acc[u], static_cast<uint32_t>(r0 + u)), k, lane);
-      }
-    }
-    merged[warp * 32 + lane] = lane < k ? mine : 0ull;
+    exact_slice_topk(sq, bank, d, l2 != 0, nr * sl / kExSlices, nr * (sl + 1) / kExSlices, k, merged, best);
+    unsigned long long* mine = partial + (static_cast<int64_t>(f) * kExSlices + sl) * k;
+    if (threadIdx.x < k) mine[threadIdx.x] = best[threadIdx.x];
+    __threadfence();
     __syncthreads();
-    if (warp == 0) {
+    if (threadIdx.x == 0) s_last = atomicAdd(done + f, 1) == kExSlices - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_last && warp == 0) {                                        // this CTA completed the query: merge its slices
+      __threadfence();
+      const unsigned long long* all = partial + static_cast<int64_t>(f) * kExSlices * k;
       unsigned long long prev = ~0ull;
       for (int r = 0; r < k; ++r) {
-        unsigned long long best = 0ull;
-        for (int c = lane; c < kExWarps * 32; c += 32) {
-          const unsigned long long key = merged[c];
-          if (key < prev && key > best) best = key;
+        unsigned long long b = 0ull;
+        for (int c = lane; c < kExSlices * k; c += 32) {
+          const unsigned long long key = *reinterpret_cast<const volatile unsigned long long*>(all + c);
+          if (key < prev && key > b) b = key;
         }
-        best = warp_max_u64(best);
-        if (lane == 0) {
-          if (best != 0ull) {
-            const float sc = okey32_inv(static_cast<uint32_t>(best >> 32));
-            D[qrow * k + r] = keep_max ? sc : -sc;
-            I[qrow * k + r] = id_offset + static_cast<int64_t>(~static_cast<uint32_t>(best & 0xFFFFFFFFull));
-          } else {
-            D[qrow * k + r] = keep_max ? -FLT_MAX : FLT_MAX;
-            I[qrow * k + r] = -1;
-          }
-        }
-        prev = best;
+        b = warp_max_u64(b);
+        if (lane == 0) exact_write_result(b, keep_max, D, I, qrow * k + r, id_offset);
+        prev = b;
       }
     }
+  }
+  for (int f = f_max + blockIdx.x; f < nf_all; f += gridDim.x) {      // beyond the scratch capacity: one CTA per query
+    const int64_t qrow = flagged[f];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += kExWarps * 32) sq[c] = Q[qrow * d + c];
+    __syncthreads();
+    exact_slice_topk(sq, bank, d, l2 != 0, 0, nr, k, merged, best);
+    if (threadIdx.x < k) exact_write_result(best[threadIdx.x], keep_max, D, I, qrow * k + threadIdx.x, id_offset);
   }
 }
 
 // ------------------------------------------------------------------ host side
-// Work split of one search (see sim1_topk_kernel): CTA pairs launched and candidate-list slots per query row = the
-// largest number of pairs whose tile range touches one pair-tile row.
-void sim1_plan(int64_t nq, int64_t nr, int* pairs_out, int* slots_out) {
+// Work split of one search (see sim1_topk_kernel): CTA pairs launched.
+int sim1_pairs(int64_t nq, int64_t nr) {
   const int64_t tm2 = (nq + 2 * kS1BM - 1) / (2 * kS1BM), tn = (nr + kS1BN - 1) / kS1BN;
   const int64_t T = tm2 * tn;
   int64_t P = device_sm_count() / 2;
   if (P > T) P = T;
   if (P < 1) P = 1;
-  int64_t slots = 1;
-  for (int64_t pm = 0; pm < tm2; ++pm) {
-    const int64_t n = s1_pair_of(pm * tn + tn - 1, T, P) - s1_pair_of(pm * tn, T, P) + 1;
-    if (n > slots) slots = n;
-  }
-  *pairs_out = static_cast<int>(P);
-  *slots_out = static_cast<int>(slots);
+  return static_cast<int>(P);
 }
-int sim1_list_len() { return kS1List; }
+int sim1_list_cap() { return kS1ListCap; }
+int sim1_max_k() { return kS1MaxK; }
 
-// Qh [nq, dp] / Rh [nr, dp]: bf16 hi planes.  cand_v / cand_i: [nq, slots * 2 * kS1List] (pairs / slots from sim1_plan).
-// Entries kept per candidate list: the cost of a running top-L is ~L (1 + ln(n / L)) insertions per list, and a list has to
-// hold its share of a query's survivors (~2 k on random data)
-int sim1_depth(int k) { return k <= 1 ? 8 : (k <= 3 ? 16 : kS1List); }
-
-int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn, int pairs,
-              int slots, int depth, float* cand_v, int32_t* cand_i, cudaStream_t stream) {
+// Qh [nq, dp] / Rh [nr, dp]: bf16 hi planes.  cand: [nq, sim1_list_cap()] entries of 8 bytes.
+// qn / qn_lo [nq]: |q|^2, |q - bf16(q)|^2.  scratch: see sim1_rescore (zero on entry).
+int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int d, int dp, bool l2, int k, const float* qn,
+              const float* qn_lo, const float* rn, const unsigned int* bank_max_bits, void* cand, int* scratch,
+              cudaStream_t stream) {
   if (nq == 0 || nr == 0) return VSCB200_OK;
   VSCB_REQUIRE(dp % 8 == 0 && nr < (1ll << 31), "sim1_topk: dp must be a multiple of 8 and nr < 2^31");
   CUtensorMap tQ, tR;
@@ -527,46 +662,57 @@ int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bo
   if ((rc = make_tmap_2d(&tQ, Qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nq, dp, dp, kS1BM, kS1BK, true))) return rc;
   if ((rc = make_tmap_2d(&tR, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, nr, dp, dp, kS1BN / 2, kS1BK, true))) return rc;
   Sim1Params p = {};
-  p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0; p.qn = qn; p.rn = rn;
+  VSCB_REQUIRE(k >= 1 && k <= kS1MaxK, "sim1_topk: k out of range");
+  p.nq = nq; p.nr = nr; p.K = dp; p.d = d; p.l2 = l2 ? 1 : 0; p.k = k; p.qn = qn; p.qn_lo = qn_lo; p.rn = rn;
+  p.bank_max_bits = bank_max_bits; p.flags = scratch; p.tau_g = reinterpret_cast<unsigned int*>(scratch + nq + 1);
   const int64_t tm2 = (nq + 2 * kS1BM - 1) / (2 * kS1BM), tn = (nr + kS1BN - 1) / kS1BN;
   VSCB_REQUIRE(tm2 < (1ll << 30) && tn < (1ll << 30), "sim1_topk: too many tiles");
   p.tiles_m2 = static_cast<int>(tm2);
   p.tiles_n = static_cast<int>(tn);
-  VSCB_REQUIRE(depth >= 1 && depth <= kS1List, "sim1_topk: bad list depth");
-  p.pairs = pairs; p.slots = slots; p.depth = depth; p.cand_v = cand_v; p.cand_i = cand_i;
-  // slots a pair never writes must read as empty
-  VSCB_CUDA_OK(cudaMemsetAsync(cand_i, 0xFF, static_cast<size_t>(nq) * slots * 2 * kS1List * sizeof(int32_t), stream));
+  p.pairs = sim1_pairs(nq, nr);
+  p.cand = reinterpret_cast<uint2*>(cand); p.cand_n = scratch + 2 * nq + 1; p.cand_cap = kS1ListCap;
   VSCB_CUDA_OK(cudaFuncSetAttribute(sim1_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kS1Smem));
   ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * dp);
-  sim1_topk_kernel<<<2 * pairs, kS1Threads, kS1Smem, stream>>>(tQ, tR, p);
+  sim1_topk_kernel<<<2 * p.pairs, kS1Threads, kS1Smem, stream>>>(tQ, tR, p);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
 }
 
-// flags [nq] / n_flagged [1]: device scratch (n_flagged must be zero on entry; the fallback kernel reads it)
-int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const float* cand_v,
-                 const int32_t* cand_i, int slots, int depth, int k, const float* qn, const float* qn_lo,
-                 const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset, int* flags, int* n_flagged,
-                 cudaStream_t stream) {
+int sim1_scratch_ints(int64_t nq) { return static_cast<int>(4 * nq + 1 + kExMaxFlagged); }
+size_t sim1_partial_bytes() { return static_cast<size_t>(kExMaxFlagged) * kExSlices * kS1MaxK * sizeof(unsigned long long); }
+
+// scratch [sim1_scratch_ints(nq)] (zero on entry, shared with sim1_topk): flags [nq] | flagged count [1] | shared
+// thresholds [nq] | list lengths [nq] | flagged query rows [nq] | slice counters [kExMaxFlagged].
+// partial: sim1_partial_bytes() of device scratch for the exhaustive pass.
+int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const void* cand, int k,
+                 const float* qn, const float* qn_lo, const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset,
+                 int* scratch, void* partial, cudaStream_t stream) {
   if (nq == 0) return VSCB200_OK;
-  VSCB_REQUIRE(k >= 1 && k <= depth && depth <= kS1List, "sim1_rescore: k must be <= the candidate list depth");
+  VSCB_REQUIRE(k >= 1 && k <= kS1MaxK, "sim1_rescore: k out of range");
+  VSCB_REQUIRE(nq < (1ll << 29), "sim1_rescore: too many query rows in one block");
+  const int* flags = scratch;
+  int* n_flagged = scratch + nq;
+  const int* cand_n = scratch + 2 * nq + 1;
+  int* flagged = scratch + 3 * nq + 1;
+  int* done = scratch + 4 * nq + 1;
   const size_t smem = static_cast<size_t>(kRrWarps) * d * 4 + static_cast<size_t>(kRrWarps) * 32 * 4;
   VSCB_REQUIRE(smem <= 200 * 1024 && d % 4 == 0, "sim1_rescore: dimension must be a multiple of 4 and <= 6144");
   VSCB_CUDA_OK(cudaFuncSetAttribute(row_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
-    ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * slots * 2 * kS1List * 8);
+    ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * 128 * 8);
     row_rescore_kernel<<<static_cast<unsigned>((nq + kRrWarps - 1) / kRrWarps), kRrWarps * 32, smem, stream>>>(
-        Q, bank, d, l2 ? 1 : 0, nq, cand_v, cand_i, slots * 2, depth, k, qn, qn_lo, bank_max_bits, D, I, id_offset, flags, n_flagged);
+        Q, bank, d, l2 ? 1 : 0, nq, reinterpret_cast<const uint2*>(cand), cand_n, kS1ListCap, k, qn, qn_lo, bank_max_bits, D, I,
+        id_offset, flags, n_flagged, flagged);
     count_launch();
   }
-  const size_t smem_ex = static_cast<size_t>(d) * 4 + static_cast<size_t>(kExWarps) * 32 * 8;
-  VSCB_CUDA_OK(cudaFuncSetAttribute(exact_row_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ex)));
-  const int64_t grid_ex = nq < 8ll * device_sm_count() ? nq : 8ll * device_sm_count();
+  const size_t smem_ex = static_cast<size_t>(d) * 4 + static_cast<size_t>(kExWarps) * 32 * 8 + 32 * 8;
+  VSCB_CUDA_OK(cudaFuncSetAttribute(exact_flagged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ex)));
   {
     ProfScope prof(kProfSelect, stream, 0.0);
-    exact_row_topk_kernel<<<static_cast<unsigned>(grid_ex), kExWarps * 32, smem_ex, stream>>>(Q, bank, d, l2 ? 1 : 0, nq, nr, k, D, I,
-                                                                                             id_offset, flags, n_flagged);
+    exact_flagged_kernel<<<4 * device_sm_count(), kExWarps * 32, smem_ex, stream>>>(
+        Q, bank, d, l2 ? 1 : 0, nr, k, D, I, id_offset, flagged, n_flagged, reinterpret_cast<unsigned long long*>(partial), done,
+        kExMaxFlagged);
     count_launch();
   }
   VSCB_CUDA_OK(cudaGetLastError());
