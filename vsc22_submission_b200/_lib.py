@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvscb200.so")
+LIB_PATH = os.environ.get("VSCB200_LIB") or os.path.join(_HERE, "libvscb200.so")   # VSCB200_LIB: A/B builds (tools/variants.py)
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1

@@ -5,12 +5,18 @@
 //                        (cta_group::2, 256 x 256 tiles, the skeleton of gemm.cu).  Every CTA pair walks ONE contiguous
 //                        range of the (query pair-tile, bank tile) sequence: perfectly balanced, and a query row meets as
 //                        few pairs as possible (<= 3 at config 3).  Epilogue, THREAD = QUERY ROW (the layout tcgen05.ld
-//                        delivers, no transpose): per 32-column chunk a max tree and one comparison against the row's
-//                        threshold tau; hits are APPENDED to the row's 48-entry buffer in shared memory (count in a
-//                        register, no atomics).  When a buffer fills, the warp compacts that row together: k REDUX
-//                        rounds find the buffer's k-th best key, tau = that - 2 eps, entries below tau are dropped.  tau
-//                        is also published per query in global memory (atomicMax), so the lists of one query held by
-//                        different warps / CTA pairs tighten each other.  No score reaches HBM.
+//                        delivers, no transpose), 16 columns per step with the next step's TMEM load in flight: four
+//                        4-column maxima against the row's threshold tau, one warp-wide OR, one uniform branch; where
+//                        some lane hit, the owners APPEND (key, column) to their row's 48-entry buffer in shared memory
+//                        with predicated stores (count in a register, no atomics; a buffer below 40 entries cannot
+//                        overflow within 8 columns, so there is no capacity test per append).  A buffer that reaches 40
+//                        entries is compacted by the whole warp: a lower bound of its k-th best key by 7 bisection votes
+//                        over the lanes' maxima (k = 1, 2: REDUX rounds; k = 1 also tightens tau on every append),
+//                        tau = that - 2 eps, entries below tau dropped; a buffer still holding > 32 entries (a crowded
+//                        margin) is moved to the query's list in global memory.  tau is published per query in global
+//                        memory (atomicMax) and re-read once per tile, so the lists of one query held by different
+//                        warps / CTA pairs tighten each other.  The accumulator is handed back to the MMA as soon as its
+//                        last 16 columns are in registers.  No score reaches HBM.
 //   row_rescore_kernel   one warp per query: A_k = k-th best approximate score over the row's lists; every bank row with
 //                        a >= A_k - 2 eps is rescored in exact fp32 (exact.cuh, the one summation order every search
 //                        path reports) and streamed into a warp-wide top-k by (score, lower id).
@@ -24,8 +30,8 @@
 // the worst case 2^-8.  The k rows with the best a have s >= A_k - eps, so the k-th best exact score s_k >= A_k - eps, and
 // a row of the exact top-k has a >= s_k - eps >= A_k - 2 eps: it is a survivor.  A list only drops entries below
 // (k-th best key of a SUBSET of the row's columns) - 2 eps <= A_k - 2 eps, so every survivor reaches the rescoring pass
-// unless its buffer saturates (more than 40 entries inside the margin of one list): such queries are flagged and searched
-// exhaustively in fp32.  Reference semantics: faiss IndexFlat.search behind vsc/index.py:174 and
+// unless the query's global list overflows (several hundred entries inside the margin): such queries are flagged and
+// searched exhaustively in fp32.  Reference semantics: faiss IndexFlat.search behind vsc/index.py:174 and
 // vsc/baseline/score_normalization.py:93-98 (exact scores, best first, ties to the lower id).
 #include <float.h>
 
@@ -37,15 +43,22 @@
 namespace vscb200 {
 
 constexpr int kS1BM = 128, kS1BN = 256, kS1BK = 64;     // per-CTA rows, pair-tile columns, K block
-constexpr int kS1Stages = 4;
+#ifndef S1_STAGES
+#define S1_STAGES 4
+#endif
+#ifndef S1_CAP
+#define S1_CAP 48
+#endif
+constexpr int kS1Stages = S1_STAGES;
 constexpr int kS1EpiWarps = 8;
 constexpr int kS1Threads = 128 + 32 * kS1EpiWarps;
 constexpr int kS1ATile = kS1BM * kS1BK * 2;              // 16 KB
 constexpr int kS1BTile = (kS1BN / 2) * kS1BK * 2;        // 16 KB: each CTA stages half of the bank tile
-constexpr int kS1Cap = 48;                               // entries per candidate list = per (query row, column half, pair)
-constexpr int kS1Keep = kS1Cap - 8;                      // a compaction that leaves more than this saturates the list
+constexpr int kS1Cap = S1_CAP;                               // entries per candidate list = per (query row, column half, pair)
+constexpr int kS1Keep = kS1Cap - 16;                     // a compaction that leaves more than this saturates the list
+constexpr int kS1Trig = kS1Cap - 8;                      // a half-granule (8 columns) never overflows a buffer below this fill
 constexpr int kS1BufBytes = kS1Cap * 32 * 8;             // one epilogue warp's 32 row buffers
-constexpr int kS1Smem = kS1Stages * (kS1ATile + kS1BTile) + kS1EpiWarps * kS1BufBytes + 256 + 1024;
+constexpr int kS1Smem = kS1Stages * (kS1ATile + kS1BTile) + kS1EpiWarps * (kS1BufBytes + 128) + 256 + 1024;
 constexpr int kS1MaxK = 12;
 constexpr int kS1ListCap = 384;                          // entries of a query's global candidate list
 static_assert(kS1Smem <= 232448, "sim1: shared memory");
@@ -89,6 +102,12 @@ __device__ __forceinline__ float sim1_eps(float qn2, float qlo2, const unsigned 
   return eps;
 }
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const unsigned int* p) {      // asynchronous: the consumer waits, not the issue
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kS1Threads, 1)
 sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR, Sim1Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -97,7 +116,8 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + kS1Stages * kS1ATile;
   uint8_t* buf_all = sB + kS1Stages * kS1BTile;            // per-warp candidate buffers of the epilogue
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_all + kS1EpiWarps * kS1BufBytes);
+  float* lmax_all = reinterpret_cast<float*>(buf_all + kS1EpiWarps * kS1BufBytes);     // per-warp 32 floats (compaction)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(buf_all + kS1EpiWarps * (kS1BufBytes + 128));
   uint64_t* empty_bar = full_bar + kS1Stages;
   uint64_t* tfull_bar = empty_bar + kS1Stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -166,22 +186,25 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int ew = warp - 4, quad = warp & 3, half = ew >> 2;
-    // buf[e][row]: entry e of the thread's row at slot (row ^ e) & 31 of line e -- conflict-free for the owner's appends
-    // (lanes = rows, equal e) and for the warp's cooperative reads of one row (lanes = entries)
+    // buf[e][row]: entry e of the thread's row -- the owner's append address advances by one line (256 B) per entry; the
+    // warp's cooperative reads of one row (compaction, lanes = entries) take the bank conflicts instead
     uint2* buf = reinterpret_cast<uint2*>(buf_all + ew * kS1BufBytes);
-    auto slot_of = [&](int e, int row) { return e * 32 + ((row ^ e) & 31); };
+    float* lmax = lmax_all + ew * 32;
+    auto slot_of = [&](int e, int row) { return e * 32 + row; };
     int acc = 0;
     uint32_t acc_phase = 0;
     float tau = INFINITY, eps2 = 0.f, qn_lane = 0.f;   // tau: keys <= tau cannot be survivors of this row
-    int cnt = 0, trig = kS1Keep;                        // entries appended (may exceed kS1Cap: the excess was not stored)
+    int cnt = 0;                                        // entries in the buffer; compaction at kS1Trig
     int cur_pm = -1;
     int64_t row0 = 0;
+    uint32_t g_next = 0u;
+    float tau_pub = INFINITY;                          // the threshold this thread last published
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // The warp compacts row r's buffer: the k-th best key of the buffer minus the margin becomes the row's threshold.
     auto compact = [&](int r) {
       __syncwarp();
-      const int n = min(__shfl_sync(0xffffffffu, cnt, r), kS1Cap);
+      const int n = __shfl_sync(0xffffffffu, cnt, r);
       const float e2 = __shfl_sync(0xffffffffu, eps2, r);
       const uint2 e0 = lane < n ? buf[slot_of(lane, r)] : make_uint2(0u, 0u);
       const uint2 e1 = lane + 32 < n ? buf[slot_of(lane + 32, r)] : make_uint2(0u, 0u);
@@ -201,26 +224,27 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           }
         }
       } else {
-        // rank counting (no dependent chain): g = entries with a larger key; the k-th best key is the smallest key
-        // among the entries with g < k (equal keys share their g)
-        const float fa = lane < n ? __uint_as_float(e0.x) : -INFINITY, fb = lane + 32 < n ? __uint_as_float(e1.x) : -INFINITY;
-        int ga = 0, gb = 0;
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) {
-          const float fj = __uint_as_float(buf[slot_of(j, r)].x);      // same address in every lane: broadcast
-          ga += fj > fa ? 1 : 0;
-          gb += fj > fb ? 1 : 0;
+        // A sound lower bound of the buffer's k-th best key from 32 values: the lanes' maxima M = max(entry l, entry
+        // l + 32) -- k distinct entries are at least as large as the k-th best M.  Bisection between min M and max M with
+        // one vote per step keeps "at least k lanes above lo" invariant; 7 steps resolve 1/128 of the spread, far below
+        // the margin.  (n >= kS1Trig >= 32: every lane holds an entry.)
+        const float fm = fmaxf(__uint_as_float(e0.x), lane + 32 < n ? __uint_as_float(e1.x) : -INFINITY);
+        const uint32_t km = okey32(fm);
+        float lo = okey32_inv(__reduce_min_sync(0xffffffffu, km)), hi = okey32_inv(__reduce_max_sync(0xffffffffu, km));
+        bool any_ok = false;                                          // lo itself has 31 lanes above it unless ties: verify
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {
+          const float mid = 0.5f * (lo + hi);
+          const bool ok = __popc(__ballot_sync(0xffffffffu, fm > mid)) >= p.k;
+          lo = ok ? mid : lo;
+          hi = ok ? hi : mid;
+          any_ok |= ok;
         }
-        const uint32_t ka = (lane < n && ga < p.k) ? a : 0xFFFFFFFFu, kb = (lane + 32 < n && gb < p.k) ? b : 0xFFFFFFFFu;
-        kth = __reduce_min_sync(0xffffffffu, min(ka, kb));
-        if (kth == 0xFFFFFFFFu) kth = 0u;
+        // no step succeeded (many equal maxima): fall back to "everything at or above the minimum"
+        kth = any_ok ? okey32(lo) : (okey32(lo) - 1u);
       }
       // threshold of the row: this buffer's k-th best minus the margin, or what the query's other lists have reached
-      float tnew = fmaxf(kth != 0u ? okey32_inv(kth) - e2 : -INFINITY, __shfl_sync(0xffffffffu, tau, r));
-      {
-        const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.tau_g + row0 + r);
-        if (g != 0u) tnew = fmaxf(tnew, okey32_inv(g));
-      }
+      const float tnew = fmaxf(kth != 0u ? okey32_inv(kth) - e2 : -INFINITY, __shfl_sync(0xffffffffu, tau, r));
       const bool keep0 = lane < n && __uint_as_float(e0.x) > tnew, keep1 = lane + 32 < n && __uint_as_float(e1.x) > tnew;
       const uint32_t m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
       const int n0 = __popc(m0), nn = n0 + __popc(m1);
@@ -242,13 +266,10 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == r) {
         const int64_t row = row0 + r;
         if (spill && dst + nn > p.cand_cap) p.flags[row] = 1;
-        if (tnew > -INFINITY) {
-          const uint32_t old = atomicMax(p.tau_g + row, okey32(tnew));
-          if (old != 0u) tnew = fmaxf(tnew, okey32_inv(old));
-        }
+        if (tnew > -INFINITY) atomicMax(p.tau_g + row, okey32(tnew));     // fire and forget; read back at the next tile
         tau = tnew;
+        tau_pub = tnew;
         cnt = spill ? 0 : nn;
-        trig = spill ? kS1Keep : max(kS1Keep, nn + 6);
       }
     };
     // every row's buffer is appended to its query's global list (end of the pair's range over these rows)
@@ -273,6 +294,59 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       __syncwarp();
     };
+    // One granule = this thread's row x 16 columns.  Main path: four 4-column maxima against the row's threshold, one
+    // warp-wide OR, one uniform branch.  Hit path: per 8 columns a uniform test per group some lane hit, the owners
+    // append with predicated stores (a buffer below kS1Trig cannot overflow within 8 columns), then one vote.
+    const bool k1 = p.k == 1;
+    auto granule = [&](uint32_t (&v)[16], int64_t gcol, bool plain) {
+      if (!plain) {                                                   // warp-uniform: L2 keys and / or the bank's last tile
+        if (gcol >= p.nr) return;
+        if (p.l2) {                                                   // key = -(|q|^2 + |r|^2 - 2 q.r)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = __float_as_uint(2.0f * __uint_as_float(v[j]) - __ldg(p.rn + min(gcol + j, p.nr - 1)) - qn_lane);
+        }
+        if (gcol + 16 > p.nr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (gcol + j >= p.nr) v[j] = 0xFF800000u;                 // -inf
+        }
+      }
+      uint32_t gm = 0u;                                               // groups of 4 columns with a key above the threshold
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float m4 = fmaxf(fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), __uint_as_float(v[4 * g + 2])),
+                               __uint_as_float(v[4 * g + 3]));
+        gm |= m4 > tau ? (1u << g) : 0u;
+      }
+      const uint32_t um = __reduce_or_sync(0xffffffffu, gm);
+      if (um == 0u) return;                                           // warp-uniform
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (((um >> (2 * h)) & 3u) == 0u) continue;                   // warp-uniform
+#pragma unroll
+        for (int g = 2 * h; g < 2 * h + 2; ++g) {
+          if ((um >> g) & 1u) {                                       // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * g + i;
+              const float val = __uint_as_float(v[j]);
+              if (val > tau) {
+                buf[slot_of(cnt, lane)] = make_uint2(v[j], static_cast<uint32_t>(gcol + j));
+                ++cnt;
+                if (k1) tau = fmaxf(tau, val - eps2);                 // k = 1: the running threshold is exact
+              }
+            }
+          }
+        }
+        uint32_t need = __ballot_sync(0xffffffffu, cnt >= kS1Trig);
+        while (need != 0u) {
+          const int r = __ffs(need) - 1;
+          need &= need - 1u;
+          compact(r);
+        }
+      }
+    };
     for (int64_t t = t_begin; t < t_end; ++t) {
       const int pm = static_cast<int>(t / p.tiles_n), n_blk = static_cast<int>(t % p.tiles_n);
       if (pm != cur_pm) {
@@ -284,67 +358,40 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         eps2 = live ? 2.0002f * sim1_eps(qn_lane, p.qn_lo[row0 + lane], p.bank_max_bits, p.d, p.l2) : 0.f;
         tau = live ? -INFINITY : INFINITY;
         cnt = 0;
-        trig = kS1Keep;
+        g_next = 0u;
+        tau_pub = tau;
       }
-      uint32_t g = 0u;                                                 // thresholds other warps / pairs have reached
-      if (tau < INFINITY) g = *reinterpret_cast<volatile unsigned int*>(p.tau_g + row0 + lane);
+      // thresholds other warps / pairs have reached: the load was issued a tile ago (g_next), so its L2 latency is hidden
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      if (g != 0u) tau = fmaxf(tau, okey32_inv(g));
+      if (g_next != 0u && tau < INFINITY) tau = fmaxf(tau, okey32_inv(g_next));
+      g_next = 0u;
+      if (tau < INFINITY) g_next = ld_volatile_u32(p.tau_g + row0 + lane);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kS1BN + half * (kS1BN / 2);
+      const int64_t gcol_t = static_cast<int64_t>(n_blk) * kS1BN + half * (kS1BN / 2);
+      const bool plain = !p.l2 && gcol_t + kS1BN / 2 <= p.nr;
+      // the TMEM load of the next granule is in flight while this one is scanned
+      uint32_t v[16], w[16];
+      tmem_ld_32x16(t_addr, v);
+      tmem_ld_wait();
 #pragma unroll 1
-      for (int c = 0; c < kS1BN / 2 / 32; ++c) {
-        const int col0 = half * (kS1BN / 2) + c * 32;
-        const int64_t gcol = static_cast<int64_t>(n_blk) * kS1BN + col0;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kS1BN + col0, v);
+      for (int gi = 0; gi < kS1BN / 2 / 16; ++gi) {
+        if (gi + 1 < kS1BN / 2 / 16) {
+          tmem_ld_32x16(t_addr + (gi + 1) * 16, w);
+        } else {                                       // the whole tile is in registers: hand the accumulator back now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));
+        }
+        granule(v, gcol_t + gi * 16, plain);
         tmem_ld_wait();
-        if (gcol >= p.nr) continue;                                   // warp-uniform
-        if (p.l2) {                                                   // key = -(|q|^2 + |r|^2 - 2 q.r)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = __float_as_uint(2.0f * __uint_as_float(v[j]) - __ldg(p.rn + min(gcol + j, p.nr - 1)) - qn_lane);
-        }
-        if (gcol + 32 > p.nr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (gcol + j >= p.nr) v[j] = 0xFF800000u;                 // -inf
-        }
-        float m8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          m8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
-                        fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-        const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-        int jstart = 0;
-        for (;;) {
-          int jo = 32;                                                // first column of this chunk that found the buffer full
-          if (m > tau && jstart < 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j >= jstart && __uint_as_float(v[j]) > tau) {
-                if (cnt < kS1Cap) {
-                  buf[slot_of(cnt, lane)] = make_uint2(v[j], static_cast<uint32_t>(gcol + j));
-                  ++cnt;
-                } else {
-                  jo = min(jo, j);
-                }
-              }
-            }
-          }
-          uint32_t need = __ballot_sync(0xffffffffu, cnt >= trig || jo < 32);
-          if (need == 0u) break;
-          while (need != 0u) {
-            const int r = __ffs(need) - 1;
-            need &= need - 1u;
-            compact(r);
-          }
-          if (!__any_sync(0xffffffffu, jo < 32)) break;
-          jstart = jo;                                                // rescan the rest of the chunk against the new threshold
-        }
+        for (int j = 0; j < 16; ++j) v[j] = w[j];
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));
+      if (tau > tau_pub) {                                            // k = 1 tightens without compacting: publish per tile
+        atomicMax(p.tau_g + row0 + lane, okey32(tau));
+        tau_pub = tau;
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     flush();
