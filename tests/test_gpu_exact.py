@@ -114,16 +114,17 @@ def test_swin_fp32_mode_matches_reference_class_golden(torch, golden_dir):
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
 def test_swin_windows_that_are_not_powers_of_two(torch, precision):
-    """6 x 6 and 12 x 12 windows (the fp32 attention kernel in both modes): same code path as the 24 x 24 windows of
-    SwinV2-L@384 (BASELINE configs[3]); shifted blocks included."""
+    """6 x 6 windows (the fp32 attention kernel in both modes), 12 x 12 and 24 x 24 windows (bf16 mode: the K-blocked tcgen05
+    kernel, attention_kb.cu -- the windows of SwinV2-L@384, BASELINE configs[3]); shifted blocks included."""
     import dataclasses
     from oracle import swin_ref
     from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SwinSpec, random_weights
     for kw in (dict(img=96, patch=4, embed=64, depths=(2, 2), heads=(2, 4), window=6, pretrained_windows=(4, 4), out_dim=48),
-               dict(img=96, patch=4, embed=64, depths=(2, 1), heads=(2, 4), window=12, pretrained_windows=(6, 6), out_dim=48)):
+               dict(img=96, patch=4, embed=64, depths=(2, 1), heads=(2, 4), window=12, pretrained_windows=(6, 6), out_dim=48),
+               dict(img=192, patch=4, embed=64, depths=(2, 2), heads=(2, 4), window=24, pretrained_windows=(12, 12), out_dim=48)):
         spec = SwinSpec(**kw, precision=precision)
         w = random_weights(spec, seed=2)
-        x = torch.randn(3, 3, 96, 96, generator=torch.Generator().manual_seed(5)).clamp(-1, 1)
+        x = torch.randn(3, 3, kw["img"], kw["img"], generator=torch.Generator().manual_seed(5)).clamp(-1, 1)
         ref = swin_ref.forward(swin_ref.SwinSpec(**kw), w, x, precision=precision).numpy()
         out = B200SwinEncoder(spec, w, max_frames=2).cuda().eval()(x.cuda()).cpu().numpy()
         rel = _rel(out, ref)

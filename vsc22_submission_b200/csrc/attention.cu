@@ -8,6 +8,7 @@
 // neither S nor P ever touches HBM.  head_dim is fixed at 64 (every ViT on the reference's path:
 // 768/12, 1024/16).  Attention is 4 % of the encoder FLOPs; the tcgen05 projections carry the rest.
 #include "host_util.h"
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace vscb200 {
@@ -201,9 +202,13 @@ int attention(const void* qkv, void* out, int n_frames, int T, int heads, int he
               bool reverse) {
   VSCB_REQUIRE(head_dim == 64, "attention: head_dim must be 64");
   VSCB_REQUIRE(n_frames > 0 && T > 0 && heads > 0, "attention: empty problem");
-  // T <= 256: tcgen05 kernel (attention_tc.cu); longer sequences (ViT-L/14: T = 257) stay on the mma.sync kernel
+  // T <= 257: tcgen05 kernel with S resident in TMEM (attention_tc.cu)
   if (attention_tc_supported(T, head_dim) && static_cast<int64_t>(n_frames) * T < (1ll << 31))
     return attention_tc(qkv, out, n_frames, T, heads, stream, reverse);
+  // 257 < T <= 640 (ViT-L/16 @ 384: T = 577): K-blocked tcgen05 kernel with an online softmax (attention_kb.cu)
+  if (attention_kb_supported(T, head_dim) && static_cast<int64_t>(n_frames) * T < (1ll << 31))
+    return attention_kb(qkv, out, n_frames, T, heads, head_dim, 1.0f / sqrtf(static_cast<float>(head_dim)), nullptr, 0, 0, 0, 0,
+                        stream);
   const int Tpad = (T + 15) & ~15;
   const size_t smem = static_cast<size_t>(Tpad) * 128 * 2;
   VSCB_REQUIRE(smem <= 200 * 1024, "attention: sequence too long for the single-pass K/V staging");

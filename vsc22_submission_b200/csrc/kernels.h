@@ -29,6 +29,11 @@ int im2row(const float* frames, void* patches, int64_t n, int img, int patch, in
 int attention_fp32(const void* qkv, int64_t qkv_lo_off, void* out, int64_t out_lo_off, int64_t n_segs, int N, int heads,
                    int head_dim, float scale, const float* tables, int ws, int res, int shift, int nWx, int nW_per_frame,
                    cudaStream_t stream);
+// attention_kb.cu: K-blocked tcgen05 attention, segments of 129..640 tokens (ViT form: head_dim 64; Swin-V2 form: head_dim 32
+// with relative-position bias tables and the shifted-window mask)
+bool attention_kb_supported(int N, int head_dim);
+int attention_kb(const void* qkv, void* out, int64_t n_segs, int N, int heads, int head_dim, float scale, const float* tables,
+                 int ws, int shift, int nWx, int nW_per_frame, cudaStream_t stream);
 int cls_rows(const float* cls, const float* pos, float* x, int64_t n, int T, int W, cudaStream_t stream);
 int gem_head(const float* y, const float* gamma, const float* beta, const float* head_w, const float* head_b,
              float* out, int64_t n, int T, int C, int out_dim, float eps, float p, bool fuse_ln,

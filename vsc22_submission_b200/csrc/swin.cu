@@ -307,6 +307,7 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
     const int64_t M = static_cast<int64_t>(n) * res * res;
     const int nWx = res / ws, nW = nWx * nWx;
     const bool tc_attn = !m->exact && (ws == 4 || ws == 8 || ws == 16);
+    const bool kb_attn = !m->exact && !tc_attn && st.heads % 2 == 0 && attention_kb_supported(ws * ws, 32);   // 24 x 24, 12 x 12
     for (size_t j = 0; j < st.blocks.size(); ++j) {
       const SwinBlockW& b = st.blocks[j];
       const int shift = (res > sp.window && (j & 1)) ? sp.window / 2 : 0;     // swinv2.py:223-226, 411
@@ -317,6 +318,8 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
                   2 * C, b.qscale, lo(m->h, h_lo), wlo(b.qkv_w, 3 * C, C), lo(m->qkv, qkv_lo)));
       if (tc_attn) {
         R(swin_attention(m->qkv, m->ao, b.table, static_cast<int64_t>(n) * nW, nW, nWx, ws, shift, st.heads, s));
+      } else if (kb_attn) {
+        R(attention_kb(m->qkv, m->ao, static_cast<int64_t>(n) * nW, ws * ws, st.heads, 32, 1.0f, b.table, ws, shift, nWx, nW, s));
       } else {
         R(attention_fp32(m->qkv, qkv_lo, m->ao, h_lo, static_cast<int64_t>(n) * nW, ws * ws, st.heads, 32, 1.0f, b.table, ws, res,
                          shift, nWx, nW, s));
