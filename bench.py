@@ -811,6 +811,112 @@ def cpu_baseline_sim():
 
 
 # ------------------------------------------------------------------------------------------------ main
+# ------------------------------------------------------------------------------------------------ BASELINE configs[3]
+def bench_config4(args, world, rank, peaks):
+    """configs[3]: "Swin-L + ViT-L ensemble 384^2, 200k frames + 200k x 1M sim, sharded 8 x B200".  STRONG scaling: the job
+    is fixed (--c4-frames query frames through BOTH encoders -- SwinV2-L/w24 @ 384 and ViT-L/16 @ 384 -- then the ensemble
+    tail, then every query descriptor against a --c4-bank-row reference bank with score normalisation and top-10);
+    frames and bank rows are sharded over the ranks.  Data-path collectives: ONE all-gather of the query descriptors
+    (each rank needs all queries for its bank shard) and ONE all-gather of the packed partial top-k.  The frames come
+    from a pool of 1024 distinct synthetic frames per rank (1.8 GB, >> L2) that is walked repeatedly -- 200k frames
+    do not fit the HBM of one GPU at N = 1."""
+    import numpy as np
+    import torch
+
+    from vsc22_submission_b200 import _lib, encoder, search, sharding, swin_encoder
+    from vsc22_submission_b200.ensemble import B200PCA
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_frames, n_bank, n_noise, d_out, k = args.c4_frames, args.c4_bank_rows, 40_000, 512, 10
+    f0, f1 = sharding.shard_range(n_frames, world, rank)
+    b0, b1 = sharding.shard_range(n_bank, world, rank)
+    z0, z1 = sharding.shard_range(n_noise, world, rank)
+    sw_spec, vit_spec = swin_encoder.SWINV2_L_384, encoder.VIT_L16_384
+    sw = swin_encoder.B200SwinEncoder(sw_spec, swin_encoder.random_weights(sw_spec, seed=0), max_frames=64).to(dev).eval()
+    vit = encoder.B200ViTEncoder(vit_spec, encoder.random_weights(vit_spec, seed=0), max_frames=128).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    pool_n = 1024
+    pool = torch.randn((pool_n, 3, 384, 384), generator=g, device=dev).clamp_(-1, 1)
+    d_cat = sw_spec.out_dim + vit_spec.width
+    gp = torch.Generator().manual_seed(5)
+    comp = torch.linalg.qr(torch.randn((d_cat, d_out), generator=gp))[0].T.contiguous()
+    pca = B200PCA((torch.randn(d_cat, generator=gp) * 0.01).numpy(), comp.numpy(), device=dev)
+    unit = lambda n, seed: torch.nn.functional.normalize(
+        torch.randn((n, d_out), generator=torch.Generator(device=dev).manual_seed(seed), device=dev))
+    R_s, Z_s = unit(b1 - b0, 300 + rank), unit(z1 - z0, 400 + rank)
+    n_mine = f1 - f0
+    desc = torch.empty((n_mine, d_out), dtype=torch.float32, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step(n_local):
+        ev[0].record()
+        for c0 in range(0, n_local, pool_n):
+            nc = min(pool_n, n_local - c0)
+            a = sw(pool[:nc])
+            b = vit(pool[:nc])[:, 0]
+            desc[c0:c0 + nc] = pca.transform_parts([a, b])
+        ev[1].record()
+        # every rank needs all query descriptors for its bank shard: one all-gather (NVLink)
+        Q = sharding.gather_descriptors(desc[:n_local], n_local * world if n_local != n_mine else n_frames) if world > 1 else desc[:n_local]
+        ev[2].record()
+        lvd = search.low_var_dim_device(Z_s) if world == 1 else sharding.global_low_var_dim(Z_s, n_total=n_noise)
+        zi = search.DeviceIndex(d_out)
+        zi.add(search.sn_transform(Z_s, lvd, True, fill=0.0))
+        Dz, _ = zi.search(search.sn_transform(Q, lvd, True, fill=0.0), 1)
+        if world > 1:
+            Dz = sharding.merge_partial_topk(Dz, torch.zeros_like(Dz, dtype=torch.int64), 1)[0]
+        q_t = search.sn_transform(Q, lvd, True, bias=search.bias_from_topk(Dz, 1.2, 1))
+        ri = search.DeviceIndex(d_out)
+        ri.set_id_offset(b0)
+        ri.add(search.sn_transform(R_s, lvd, True, fill=1.0))
+        D, I = ri.search(q_t, k)
+        if world > 1:
+            D, I = sharding.merge_partial_topk(D, I, k)
+        ev[3].record()
+        return D, I
+
+    warm_n = min(n_mine, 2 * pool_n)
+    for _ in range(args.warmup):                   # warm-up steps walk 2 pool passes per rank, the timed steps the whole share
+        step(warm_n)
+    barrier_sync(world)
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    n0 = _lib.launch_count()
+    tot = [0.0, 0.0, 0.0, 0.0]
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        barrier_sync(world)
+        D, I = step(n_mine)
+        torch.cuda.synchronize()
+        for i in range(3):
+            tot[i] += ev[i].elapsed_time(ev[i + 1])
+        tot[3] += ev[0].elapsed_time(ev[3])
+    barrier_sync(world)
+    t_wall1 = time.time()
+    ck = clocks.stop(t_wall0, t_wall1)
+    ms = max_over_ranks(tot[3], world) / args.steps
+    enc_ms = max_over_ranks(tot[0], world) / args.steps
+    launches = _lib.launch_count() - n0
+    fl_frame = sw_spec.flops_per_frame() + vit_spec.flops_per_frame()
+    pairs = float(n_frames) * (n_bank + n_noise)
+    return {"metric": "frame-descriptors/sec", "unit": "frame-descriptors/sec", "value": n_frames / (ms / 1e3), "ms_per_step": ms,
+            "scaling": "strong", "gpu_launches": int(launches), "clocks": ck,
+            "breakdown_ms": {"encode_both_models_plus_pca": enc_ms, "query_all_gather": tot[1] / args.steps,
+                             "score_norm_and_search": tot[2] / args.steps},
+            "encode_frames_per_sec": n_frames / (enc_ms / 1e3), "sim_pairs_per_sec": pairs / (tot[2] / args.steps / 1e3),
+            "roofline": {"bound": "tensor", "kernel": "whole step (both encoders + similarity)",
+                         "achieved": (n_frames * fl_frame + 2.0 * d_out * pairs) / (ms / 1e3) / 1e12 / world,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s per GPU",
+                         "frac": (n_frames * fl_frame + 2.0 * d_out * pairs) / (ms / 1e3) / 1e12 / world / peaks["bf16_tflops_sustained"],
+                         "peak_source": f"{peaks['source']} bf16_tflops_sustained", "traffic": None},
+            "config": {"workload": "configs[3]: SwinV2-L/w24@384 + ViT-L/16@384 ensemble (concat, PCA to 512), "
+                                   f"{n_frames} frames + {n_frames} x {n_bank} similarity (score-norm, 40k noise rows, top-10)",
+                       "frames_total": n_frames, "bank_rows_total": n_bank, "flops_per_frame": fl_frame,
+                       "frame_pool": f"{pool_n} distinct 384x384 frames per rank walked repeatedly (1.8 GB >> L2)",
+                       "parallelism": f"frames and bank rows sharded over {world} ranks; collectives: all-gather of the query "
+                                      "descriptors, all-gather of the packed partial top-k, two all-reduces of the noise moments"}}
+
+
+
 def run_reference(args):
     """--impl reference: the CPU port of the reference's path on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -846,7 +952,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="both", choices=["both", "encoder", "sim"])
+    ap.add_argument("--workload", default="both", choices=["both", "encoder", "sim", "config4"])
+    ap.add_argument("--c4-frames", type=int, default=200_000, help="config4: query frames of the whole job")
+    ap.add_argument("--c4-bank-rows", type=int, default=1_000_000, help="config4: reference bank rows of the whole job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -859,6 +967,17 @@ def main():
     line = {"metric": "frame-descriptors/sec", "unit": "frame-descriptors/sec", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic"}
+    if args.workload == "config4":
+        res = bench_config4(args, world, rank, peaks)
+        if rank == 0:
+            line.update(res)
+            line["e2e"] = None
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     enc_res = None
     if args.workload in ("both", "encoder"):
         enc_res = bench_encoder(args, world, rank, peaks)
