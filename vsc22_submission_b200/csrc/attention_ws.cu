@@ -1,0 +1,481 @@
+// Streaming tcgen05 attention for the ViT encoders (head_dim 64, 129 .. 640 tokens per frame): the two softmax warpgroups
+// of a CTA run INDEPENDENT streams of (frame, head, 128-query tile) items, each with its own MMA-issuing thread, keys in
+// blocks of 64 with S double-buffered in TMEM, so a warpgroup never waits for an MMA round trip between blocks:
+//
+//   warps 0-3 / 4-7   softmax warpgroup w, thread = query row.  Per key block (64 keys = two chunks of 32 columns): wait
+//                     S(b); per chunk ONE pass over registers: chunk maximum (FMNMX3 tree), p = 2^(s * scale - m), P over
+//                     S in place as bf16 pairs (truncation: one PRMT per pair); arrive P(b).  The running shift m only
+//                     moves when a chunk maximum exceeds it by more than 2^8; then O, the row sum and the P chunks
+//                     already written are rescaled through tcgen05.ld / st -- after the first chunks of an item this is
+//                     rare.  The ROW SUM is accumulated by the tensor core from the very P the output uses (a second
+//                     B operand of ones, 16 extra accumulator columns), so normalisation cancels the truncation bias
+//                     and the softmax threads carry no adds.  The epilogue of an item (O * 1 / l -> bf16 rows) is
+//                     DEFERRED until after the softmax of the next item's first block: by then the last P.V of the
+//                     item has long completed.
+//   warp 8 / 9        lane 0: MMA issuer of warpgroup 0 / 1 (warp 8 also owns the TMEM allocation).  Rolling order
+//                     S(g), S(g+1), [P(g)] PV(g), S(g+2), [P(g+1)] PV(g+1), S(g+3) ... over the warpgroup's flattened block
+//                     sequence g (blocks of consecutive items follow each other without a drain): S is always two
+//                     blocks ahead of the softmax.  TMEM per warpgroup (256 columns): S0 [0, 64), S1 [64, 128), O [128, 192),
+//                     row sums [192, 208).
+//   warp 10           TMA producer: K / V of a (frame, head) unit into one of two shared-memory stages (one stage for
+//                     long frames), the Q tile of every item into its warpgroup's Q buffers.
+//
+// The tensor pipe executes one thread's MMAs in issue order, so S(g+2) -- issued right behind PV(g) -- cannot overwrite
+// the buffer P(g) is read from, and "S(g) complete" implies "PV(g-2) complete".  PV(g-1) may still be accumulating
+// into O when the softmax of block g wants to rescale O: that (rare) path first waits on a barrier committed behind
+// every PV.
+//
+// Reference: nn.MultiheadAttention at D/train/train_vid_score/video/clip.py:45 (unfused bmm + softmax + bmm in
+// torch 1.11); frames of 197 (ViT-B/16 @ 224, BASELINE configs[1]), 145, 257 and 577 tokens.
+#include <stdlib.h>
+
+#include "host_util.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vscb200 {
+
+#ifdef WS_PROF
+#define WS_T(x) const long long x = clock64()
+#else
+#define WS_T(x)
+#endif
+
+constexpr int kWsThreads = 352;
+constexpr int kWsKB = 64;                    // keys per block
+constexpr int kWsKTile = kWsKB * 128;        // one K or V block: 64 rows x 64 bf16, 128-byte swizzled (8 atoms)
+constexpr int kWsQTile = 128 * 128;
+constexpr int kWsOCol = 128;                 // O accumulator [128, 192), row sums [192, 208)
+constexpr int kWsLCol = 192;
+constexpr int kWsOnes = 2048;                // 16 keys x 128 B of bf16 ones: B operand of the row-sum MMA
+constexpr int kWsMaxBlocks = 10;             // 640 keys
+
+struct WsParams {
+  __nv_bfloat16* out;        // [M, W]
+  long long* prof;           // WS_PROF builds: per-CTA cycle counters (nullptr otherwise)
+  int T, heads, W;
+  int nb, ntiles;            // key blocks, 128-query tiles per frame
+  int n_units;               // frames * heads
+  int kv_stages, q_bufs;     // 2 / 2 when they fit the shared memory, else 1 / 1
+  int reverse;
+  float scale_log2e;
+};
+
+__device__ __forceinline__ uint32_t ws_pack(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+
+// Cursor over the CTA's flattened item sequence (units blockIdx.x, + gridDim.x, ...; inside a unit the query tiles in
+// order).  The single-thread roles (producer, issuers) advance it incrementally: no division per item.
+struct WsItem {
+  int k;        // CTA-local unit index
+  int tile;
+  int frame, head;
+  bool ok;
+};
+__device__ __forceinline__ void ws_unit(WsItem& it, const WsParams& p) {
+  const int unit = static_cast<int>(blockIdx.x) + it.k * static_cast<int>(gridDim.x);
+  it.ok = unit < p.n_units;
+  if (it.ok) {
+    const int f = unit / p.heads;
+    it.head = unit - f * p.heads;
+    it.frame = p.reverse ? (p.n_units / p.heads - 1 - f) : f;
+  }
+}
+__device__ __forceinline__ void ws_first(WsItem& it, int J0, const WsParams& p) {      // J0 < ntiles
+  it.k = 0;
+  it.tile = J0;
+  ws_unit(it, p);
+}
+__device__ __forceinline__ void ws_next(WsItem& it, int step, const WsParams& p) {     // step <= ntiles
+  it.tile += step;
+  if (it.tile >= p.ntiles) {
+    it.tile -= p.ntiles;
+    ++it.k;
+    ws_unit(it, p);
+  }
+}
+// x mod n and x div n for n in {1, 2} (stage / buffer counts)
+__device__ __forceinline__ int ws_mod(int x, int n) { return x & (n - 1); }
+__device__ __forceinline__ int ws_div(int x, int n) { return x >> (n - 1); }
+
+// One key block of this thread's row: S in TMEM columns [tS, tS + 64) -> P (bf16 pairs over [tS, tS + 32)); running shift
+// m (log2 domain); accumulators at [tO, tO + 80) (O | row sum) rescaled when the shift moves.  kt: first key of the
+// block.  Warp-collective.
+__device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int kt, bool first, float& m, int T,
+                                                 float scale_log2e, uint64_t* pv_done, uint32_t pv_parity) {
+  const int nchunks = min(2, (T - kt + 31) >> 5);                     // chunks with a valid key (warp-uniform, >= 1)
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pk[16];
+    if (c < nchunks) {
+      uint32_t v[32];
+      tmem_ld_32x32(tS + c * 32, v);
+      tmem_ld_wait();
+      const int lim = T - (kt + c * 32);
+      if (lim < 32) {                                                 // warp-uniform: the frame's last chunk
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j >= lim) v[j] = 0xFF800000u;                           // -inf: p = 0
+      }
+      // chunk maximum on registers
+      float m0 = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+      float m1 = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+#pragma unroll
+      for (int j = 6; j < 30; j += 4) {
+        m0 = fmaxf(fmaxf(m0, __uint_as_float(v[j])), __uint_as_float(v[j + 1]));
+        m1 = fmaxf(fmaxf(m1, __uint_as_float(v[j + 2])), __uint_as_float(v[j + 3]));
+      }
+      const float cmax = fmaxf(fmaxf(m0, m1), fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]))) * scale_log2e;
+      // the shift only moves when the chunk maximum exceeds it by more than 2^8 (p stays below 2^8 otherwise)
+      const bool move = cmax > m + 8.0f;                              // m = -inf at the start of an item
+      if (__any_sync(0xffffffffu, move)) {
+        const float alpha = move ? ex2_approx(m - cmax) : 1.0f;       // 0 for the first chunk of an item
+        if (!first) {                                                 // O and the row sum of the blocks before this one
+          mbar_wait(pv_done, pv_parity);                              // the previous block's P.V has left them alone
+          tc_fence_after();
+#pragma unroll 1
+          for (int h = 0; h < 5; ++h) {
+            uint32_t o[16];
+            tmem_ld_32x16(tO + h * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+            tmem_st_32x16(tO + h * 16, o);
+          }
+        }
+        if (c == 1) {                                                 // P of this block's first chunk
+          uint32_t q[16];
+          tmem_ld_32x16(tS, q);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            q[j] = ws_pack(__uint_as_float(q[j] << 16) * alpha, __uint_as_float(q[j] & 0xFFFF0000u) * alpha);
+          tmem_st_32x16(tS, q);
+        }
+        tmem_st_wait();
+        if (move) m = cmax;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float q0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -m));
+        const float q1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -m));
+        pk[j >> 1] = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);     // truncation to bf16 pairs
+      }
+    } else {                                                          // keys past the frame: P = 0 (the MMA reads all 64)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = 0u;
+    }
+    // P of chunk c lands on columns [16c, 16c + 16) of the buffer: inside S chunk 0, consumed
+    tmem_st_32x16(tS + c * 16, pk);
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, WsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int kv_bytes = p.nb * kWsKTile;                   // K (or V) of one unit
+  uint8_t* sKV = smem;                                    // [kv_stages][K | V]
+  uint8_t* sQ = sKV + p.kv_stages * 2 * kv_bytes;         // [2 warpgroups][q_bufs] tiles
+  uint8_t* sOnes = sQ + 2 * p.q_bufs * kWsQTile;          // bf16 ones: the row-sum operand
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kWsOnes);
+  uint64_t* kv_full = bars;            // [2] per stage
+  uint64_t* kv_empty = bars + 2;       // [2]       both issuers have issued their last MMA of the unit
+  uint64_t* q_full = bars + 4;         // [2][2] per warpgroup and buffer
+  uint64_t* q_empty = bars + 8;        // [2][2]
+  uint64_t* s_full = bars + 12;        // [2][2] per warpgroup and S buffer
+  uint64_t* p_full = bars + 16;        // [2][2]
+  uint64_t* o_full = bars + 20;        // [2]
+  uint64_t* o_empty = bars + 22;       // [2]
+  uint64_t* pv_done = bars + 24;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
+  if (warp == 8) {
+    if (lane == 0) {
+      prefetch_tmap(&tmQ);
+      prefetch_tmap(&tmKV);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2);
+        mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&pv_done[i], 1);
+      }
+      for (int i = 0; i < 4; ++i) {
+        mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  for (int i = threadIdx.x; i < kWsOnes / 4; i += kWsThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();                                // generic-proxy writes -> visible to the MMA's operand reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 10) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int cur_k = -1;
+      int n_q[2] = {0, 0};
+      WsItem it;
+      int w = 0;
+      for (ws_first(it, 0, p); it.ok; ws_next(it, 1, p), w ^= 1) {
+        const int row0 = it.frame * p.T;
+        if (it.k != cur_k) {                               // new unit: K and V into the next stage
+          cur_k = it.k;
+          const int st = ws_mod(it.k, p.kv_stages);
+          uint8_t* sK = sKV + st * 2 * kv_bytes;
+          mbar_wait(&kv_empty[st], (ws_div(it.k, p.kv_stages) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * kv_bytes);
+          for (int b = 0; b < p.nb; ++b)
+            tma_load_2d(sK + b * kWsKTile, &tmKV, &kv_full[st], p.W + it.head * 64, row0 + b * kWsKB, kEvictFirst);
+          for (int b = 0; b < p.nb; ++b)
+            tma_load_2d(sK + kv_bytes + b * kWsKTile, &tmKV, &kv_full[st], 2 * p.W + it.head * 64, row0 + b * kWsKB, kEvictFirst);
+        }
+        const int qb = ws_mod(n_q[w], p.q_bufs);
+        const int use = ws_div(n_q[w], p.q_bufs);
+        ++n_q[w];
+        mbar_wait(&q_empty[w * 2 + qb], (use & 1) ^ 1);
+        mbar_expect_tx(&q_full[w * 2 + qb], kWsQTile);
+        tma_load_2d(sQ + (w * p.q_bufs + qb) * kWsQTile, &tmQ, &q_full[w * 2 + qb], it.head * 64, row0 + it.tile * 128, kEvictFirst);
+      }
+    }
+  } else if (warp == 8 || warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer of warpgroup w: the WHOLE warp runs the
+    // loop on warp-uniform values (uniform registers), one elected lane issues inside the umma_*_warp wrappers
+    {
+      const int w = warp - 8;
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, kWsKB);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, 64);
+      constexpr uint32_t idesc_l = make_idesc_bf16_f32_bmn(128, 16);
+      const uint64_t ones_d = make_desc_mn_sw128(smem_u32(sOnes));
+      const uint32_t tw = tmem_base + w * 256;
+      const uint32_t sKV_u = smem_u32(sKV), sQ_u = smem_u32(sQ);
+      // two cursors over the warpgroup's flattened block sequence: S runs two blocks ahead of PV
+      int sb = 0, s_item = 0, s_k = -1;                    // next S: block, warpgroup-local item index, unit seen
+      int pb = 0, p_item = 0;
+      uint32_t sg = 0, pg = 0;                             // global block counters
+      WsItem si, pi;
+      ws_first(si, w, p);
+      ws_first(pi, w, p);
+#ifdef WS_PROF
+      long long i_kv = 0, i_q = 0, i_p = 0, i_oe = 0;
+      const long long i_begin = clock64();
+#endif
+      auto issue_s = [&]() {
+        WS_T(u0);
+        if (si.k != s_k) {                                 // first S of a unit: K / V landed
+          s_k = si.k;
+          mbar_wait(&kv_full[ws_mod(si.k, p.kv_stages)], ws_div(si.k, p.kv_stages) & 1);
+        }
+        WS_T(u1);
+        const int qb = ws_mod(s_item, p.q_bufs);
+        if (sb == 0) mbar_wait(&q_full[w * 2 + qb], ws_div(s_item, p.q_bufs) & 1);
+#ifdef WS_PROF
+        i_kv += u1 - u0; i_q += clock64() - u1;
+#endif
+        tc_fence_after();
+        const uint64_t qd = make_desc_k_sw128(sQ_u + (w * p.q_bufs + qb) * kWsQTile);
+        const uint64_t kd = make_desc_k_sw128(sKV_u + ws_mod(si.k, p.kv_stages) * 2 * kv_bytes + sb * kWsKTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss_warp(tw + (sg & 1) * kWsKB, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit_warp(&s_full[w * 2 + (sg & 1)]);
+        ++sg;
+        if (++sb == p.nb) {                                // last S of the item: its Q buffer is free once these retire
+          umma_commit_warp(&q_empty[w * 2 + qb]);
+          sb = 0;
+          ++s_item;
+          ws_next(si, 2, p);
+        }
+      };
+      // S runs up to two blocks ahead of PV, but never into a unit whose K / V stage is still held by a unit this
+      // warpgroup has not finished (the producer refills a stage only after BOTH issuers released it)
+      auto fill_s = [&]() {
+        while (si.ok && sg - pg < 2u && si.k < pi.k + p.kv_stages) issue_s();
+      };
+      while (pi.ok) {
+        fill_s();
+        WS_T(u2);
+        mbar_wait(&p_full[w * 2 + (pg & 1)], (pg >> 1) & 1);
+        WS_T(u3);
+        if (pb == 0 && p_item > 0) mbar_wait(&o_empty[w], (p_item - 1) & 1);   // the warpgroup has read the previous item's O
+#ifdef WS_PROF
+        i_p += u3 - u2; i_oe += clock64() - u3;
+#endif
+        tc_fence_after();
+        const uint64_t vd = make_desc_mn_sw128(sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile);
+#pragma unroll
+        for (int i = 0; i < kWsKB / 16; ++i) {
+          umma_bf16_ts_warp(tw + kWsOCol, tw + (pg & 1) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
+          umma_bf16_ts_warp(tw + kWsLCol, tw + (pg & 1) * kWsKB + i * 8, ones_d, idesc_l, (pb | i) ? 1u : 0u);      // row sums
+        }
+        umma_commit_warp(&pv_done[w]);
+        ++pg;
+        const int prev_k = pi.k;
+        if (++pb == p.nb) {
+          umma_commit_warp(&o_full[w]);
+          pb = 0;
+          ++p_item;
+          ws_next(pi, 2, p);
+          if (!pi.ok || pi.k != prev_k) umma_commit_warp(&kv_empty[ws_mod(prev_k, p.kv_stages)]);   // this warpgroup is done with the unit
+        }
+      }
+#ifdef WS_PROF
+      if (p.prof && lane == 0) {
+        long long* o = p.prof + (static_cast<long long>(blockIdx.x) * 8 + 3 + 4 * w) * 5;   // slots of the mostly idle warps 3 / 7
+        o[0] = i_kv; o[1] = i_q; o[2] = i_p; o[3] = i_oe; o[4] = clock64() - i_begin;
+      }
+#endif
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int w = warp >> 2, quad = warp & 3;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + w * 256;
+    uint32_t g = 0;
+    int n_item = 0;
+    // deferred epilogue of the previous item
+    bool pend = false, pend_valid = false;
+    __nv_bfloat16* pend_row = nullptr;
+    auto epilogue = [&]() {                                // O of the previous item -> registers, accumulator released
+      mbar_wait(&o_full[w], (n_item - 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32], ls[16];
+      tmem_ld_32x32(tlane + kWsOCol, o0);
+      tmem_ld_32x32(tlane + kWsOCol + 32, o1);
+      tmem_ld_32x16(tlane + kWsLCol, ls);
+      tmem_ld_wait();
+      const float pend_inv_l = 1.0f / __uint_as_float(ls[0]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[w]);
+      if (pend_valid) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t* o = q < 4 ? o0 : o1;
+          const int b8 = (q & 3) * 8;
+          uint4 u;
+          // cvt.rn.bf16x2 (one F2FP per pair): the XU pipe it issues on is idle during the epilogue
+          u.x = pack_bf16x2(__uint_as_float(o[b8]) * pend_inv_l, __uint_as_float(o[b8 + 1]) * pend_inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[b8 + 2]) * pend_inv_l, __uint_as_float(o[b8 + 3]) * pend_inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[b8 + 4]) * pend_inv_l, __uint_as_float(o[b8 + 5]) * pend_inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[b8 + 6]) * pend_inv_l, __uint_as_float(o[b8 + 7]) * pend_inv_l);
+          *reinterpret_cast<uint4*>(pend_row + q * 8) = u;
+        }
+      }
+      pend = false;
+    };
+    WsItem it;
+#ifdef WS_PROF
+    long long c_wait = 0, c_soft = 0, c_epi = 0, c_arr = 0;
+    const long long c_begin = clock64();
+#endif
+    for (ws_first(it, w, p); it.ok; ws_next(it, 2, p)) {
+      const int i_tok = it.tile * 128 + quad * 32 + lane;
+      const bool warp_valid = it.tile * 128 + quad * 32 < p.T;
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int b = 0; b < p.nb; ++b) {
+        WS_T(t0);
+        mbar_wait(&s_full[w * 2 + (g & 1)], (g >> 1) & 1);
+        tc_fence_after();
+        WS_T(t1);
+        // warps whose 32 rows all lie past the frame skip the block: the MMA reads stale TMEM for them, and whatever it
+        // computes stays in rows nobody stores
+        if (warp_valid)
+          ws_softmax_block(tlane + (g & 1) * kWsKB, tlane + kWsOCol, b * kWsKB, b == 0, m, p.T, p.scale_log2e, &pv_done[w],
+                           (g - 1) & 1);
+        WS_T(t2);
+        if (b == 0 && pend) epilogue();                    // before P.V of this item's first block may overwrite O
+        WS_T(t3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[w * 2 + (g & 1)]);
+        ++g;
+#ifdef WS_PROF
+        const long long t4 = clock64();
+        c_wait += t1 - t0; c_soft += t2 - t1; c_epi += t3 - t2; c_arr += t4 - t3;
+#endif
+      }
+      ++n_item;
+      pend = true;
+      pend_valid = i_tok < p.T;
+      pend_row = p.out + (static_cast<int64_t>(it.frame) * p.T + (pend_valid ? i_tok : 0)) * p.W + it.head * 64;
+    }
+    if (pend) epilogue();
+#ifdef WS_PROF
+    if (p.prof && lane == 0 && quad != 3) {
+      long long* o = p.prof + (static_cast<long long>(blockIdx.x) * 8 + warp) * 5;
+      o[0] = c_wait; o[1] = c_soft; o[2] = c_epi; o[3] = c_arr; o[4] = clock64() - c_begin;
+    }
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+bool attention_ws_supported(int T, int head_dim) {
+  static const int off = [] { const char* e = getenv("VSCB200_ATTN_NO_WS"); return e ? atoi(e) : 0; }();
+  return !off && head_dim == 64 && T > 128 && T <= kWsKB * kWsMaxBlocks;
+}
+
+// qkv: [n_frames * T, 3W] bf16 (q | k | v, heads 64-wide contiguous); out: [n_frames * T, W] bf16
+int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse) {
+  VSCB_REQUIRE(attention_ws_supported(T, 64), "attention_ws: unsupported frame length");
+  const int W = heads * 64;
+  const int64_t M = static_cast<int64_t>(n_frames) * T;
+  VSCB_REQUIRE(M < (1ll << 31) && static_cast<int64_t>(n_frames) * heads < (1ll << 30), "attention_ws: problem too large");
+  CUtensorMap tmQ, tmKV;
+  int rc = make_tmap_2d(&tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, 128, 64, true);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, kWsKB, 64, true))) return rc;
+  WsParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.T = T; p.heads = heads; p.W = W;
+  p.nb = (T + kWsKB - 1) / kWsKB;
+  p.ntiles = (T + 127) / 128;
+  p.n_units = n_frames * heads;
+  p.reverse = reverse ? 1 : 0;
+  p.scale_log2e = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
+  const int kv_bytes = p.nb * kWsKTile;
+  const int fixed = kWsOnes + 28 * 8 + 64 + 1024;
+  p.kv_stages = 2; p.q_bufs = 2;
+  if (2 * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.kv_stages = 1;
+  if (p.kv_stages * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.q_bufs = 1;
+  const int smem = p.kv_stages * 2 * kv_bytes + 2 * p.q_bufs * kWsQTile + fixed;
+  VSCB_REQUIRE(smem <= 232448, "attention_ws: shared memory");
+  VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = p.n_units < device_sm_count() ? p.n_units : device_sm_count();
+  ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * 64);
+  p.prof = nullptr;
+#ifdef WS_PROF
+  static long long* prof_buf = nullptr;
+  if (!prof_buf) cudaMalloc(&prof_buf, 148 * 8 * 5 * sizeof(long long));
+  p.prof = prof_buf;
+#endif
+  attention_ws_kernel<<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
+#ifdef WS_PROF
+  {
+    static long long h[148 * 8 * 5];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static int calls = 0;
+    if (++calls == 5)
+      for (int cta : {0, 77})
+        for (int wp = 0; wp < 8; ++wp) {
+          const long long* o = h + (cta * 8 + wp) * 5;
+          printf((wp & 3) == 3 ? "WS_PROF cta %d issuer %d: wait kv_full %lld q_full %lld p_full %lld o_empty %lld total %lld\n" : "WS_PROF cta %d warp %d: wait_s %lld softmax %lld epilogue %lld arrive %lld total %lld\n", cta, wp, o[0], o[1], o[2], o[3], o[4]);
+        }
+  }
+#endif
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+}  // namespace vscb200
