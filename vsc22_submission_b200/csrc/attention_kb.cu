@@ -188,7 +188,7 @@ attention_kb_kernel(const __grid_constant__ CUtensorMap tm, KbParams p, int n_un
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   float* tabs = reinterpret_cast<float*>(bars + 14);      // Swin: [2 heads][(2ws-1)^2]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   if (warp == 9) {
     if (lane == 0) {
       prefetch_tmap(&tm);
@@ -204,7 +204,7 @@ attention_kb_kernel(const __grid_constant__ CUtensorMap tm, KbParams p, int n_un
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int nqp = (p.ntiles + 1) >> 1;           // query tile pairs per segment
   // units are head-group major: a CTA keeps a head group's bias tables over consecutive units
   auto unit_seg_hg = [&](int unit, int& seg, int& hg) { hg = unit / p.n_segs; seg = unit - hg * p.n_segs; };
@@ -231,7 +231,7 @@ attention_kb_kernel(const __grid_constant__ CUtensorMap tm, KbParams p, int n_un
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {                                                      // whole warp, warp-uniform operands, one elected lane issues
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, 128);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, HD);
       uint32_t n_kv = 0, n_q = 0, n_p[2] = {0, 0}, n_oe[2] = {0, 0};
@@ -239,8 +239,8 @@ attention_kb_kernel(const __grid_constant__ CUtensorMap tm, KbParams p, int n_un
       auto issue_s = [&](int w, int hh, int b) {
         const uint64_t qd = make_desc_k_sw128(sQ_u + w * kKbTile + hh * 64), kd = make_desc_k_sw128(sK_u + b * kKbTile + hh * 64);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit(&s_full[w]);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss_warp(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit_warp(&s_full[w]);
       };
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         mbar_wait(kv_full, n_kv & 1);
@@ -264,16 +264,16 @@ attention_kb_kernel(const __grid_constant__ CUtensorMap tm, KbParams p, int n_un
                 const uint64_t vd = make_desc_mn_sw128(sV_u + b * kKbTile + hh * 64);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  umma_bf16_ts(tmem_base + w * 256 + kKbOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
+                  umma_bf16_ts_warp(tmem_base + w * 256 + kKbOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
                                idesc_o, (b | i) ? 1u : 0u);
                 if (b + 1 < p.nb) issue_s(w, hh, b + 1);
-                else umma_commit(&o_full[w]);
+                else umma_commit_warp(&o_full[w]);
               }
             }
           }
-          umma_commit(q_empty);                            // every S MMA of the tile pair has read Q
+          umma_commit_warp(q_empty);                            // every S MMA of the tile pair has read Q
         }
-        umma_commit(kv_empty);
+        umma_commit_warp(kv_empty);
       }
     }
   } else {

@@ -311,7 +311,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_empty = bars + 14;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   pdl_launch_dependents();
   if (warp == 9) {
     if (lane == 0) {
@@ -331,7 +331,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();
 
   auto unit_frame_head = [&](int unit, int& frame, int& head) {
@@ -423,7 +423,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     if (extra && prev_unit >= 0) extra_rows(prev_unit, it - 1);
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform operands, one elected lane issues (umma_*_warp)
       const uint32_t idesc_s = make_idesc_bf16_f32(128, p.Tpad);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, 64);
       const int ksteps = p.Tpad >> 4;
@@ -436,8 +436,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         const uint64_t qd = make_desc_k_sw128(sQ + w * 16384), kd = make_desc_k_sw128(sQ + 32768);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit(&s_full[w]);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss_warp(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit_warp(&s_full[w]);
       };
       auto issue_pv = [&](int w, int it) {
         const int st = it & 1;
@@ -446,9 +446,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&p_full[w], it & 1);
         tc_fence_after();
         for (int i = 0; i < ksteps; ++i)
-          umma_bf16_ts(tmem_base + w * 256 + kAtcOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
+          umma_bf16_ts_warp(tmem_base + w * 256 + kAtcOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
                        idesc_o, i ? 1u : 0u);
-        umma_commit(&o_full[w]);
+        umma_commit_warp(&o_full[w]);
       };
       // The two warpgroups run half a period apart: while one is in its exponentials (XU-bound) the other one's
       // MMAs and epilogue run, so they do not queue on the same XU pipe at the same time.
@@ -456,16 +456,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int it = 0; it < n_it; ++it) {
         if (it > 0) {
           issue_pv(1, it - 1);
-          umma_commit(&v_empty[(it - 1) & 1]);
+          umma_commit_warp(&v_empty[(it - 1) & 1]);
         }
         issue_s(1, it);
-        umma_commit(&qk_empty[it & 1]);
+        umma_commit_warp(&qk_empty[it & 1]);
         issue_pv(0, it);
         if (it + 1 < n_it) issue_s(0, it + 1);
       }
       if (n_it > 0) {
         issue_pv(1, n_it - 1);
-        umma_commit(&v_empty[(n_it - 1) & 1]);
+        umma_commit_warp(&v_empty[(n_it - 1) & 1]);
       }
     }
   } else {

@@ -116,7 +116,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);     // uniform for the compiler
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
 
@@ -145,7 +145,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();    // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();        // everything above overlapped the previous kernel's tail; its results are visible from here
 
   // Tile schedule.  kCluster == 1: tile = blockIdx.x + i*gridDim.x.  kCluster == 2: the pair walks
@@ -187,7 +187,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    // the WHOLE warp runs the issue loop on warp-uniform values (uniform registers); one elected lane issues inside the
+    // umma_*_warp wrappers -- no per-MMA R2UR broadcasts (isolated GEMMs +1..5 %)
+    if (__shfl_sync(0xffffffffu, crank, 0) == 0) {
       constexpr uint32_t idesc = make_idesc_bf16_f32(kBM * kCluster, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -205,20 +207,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128B swizzle row: +2 in the (addr>>4) field
-            if (kCluster > 1) umma_bf16_ss_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (kCluster > 1) umma_bf16_ss_cg2_warp(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss_warp(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             if (kSplit) {       // + lo.hi + hi.lo (the lo tiles follow their hi tiles inside the stage)
               const uint64_t a_lo = a_desc + (Cfg::kATile >> 4), b_lo = b_desc + (Cfg::kBTile >> 4);
-              umma_bf16_ss(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1u);
-              umma_bf16_ss(d_tmem, a_desc + 2 * k, b_lo + 2 * k, idesc, 1u);
+              umma_bf16_ss_warp(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1u);
+              umma_bf16_ss_warp(d_tmem, a_desc + 2 * k, b_lo + 2 * k, idesc, 1u);
             }
           }
-          if (kCluster > 1) umma_commit_cg2_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
-          else umma_commit(&empty_bar[stage]);
+          if (kCluster > 1) umma_commit_cg2_mcast_warp(&empty_bar[stage], static_cast<uint16_t>(0x3));
+          else umma_commit_warp(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (kCluster > 1) umma_commit_cg2_mcast(&tfull_bar[acc], static_cast<uint16_t>(0x3));
-        else umma_commit(&tfull_bar[acc]);
+        if (kCluster > 1) umma_commit_cg2_mcast_warp(&tfull_bar[acc], static_cast<uint16_t>(0x3));
+        else umma_commit_warp(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

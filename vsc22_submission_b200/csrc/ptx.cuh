@@ -263,6 +263,26 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
       : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_ss_cg2_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_mcast_warp(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- attention building blocks
 // MN-major B operand (e.g. V [keys][64 d] as the [N = d, K = keys] operand of O = P.V), 128-byte swizzle:
 // 64 N elements contiguous in a 128 B row, 8 K rows per 1024 B swizzle atom, atoms along K at SBO = 1024 B

@@ -123,7 +123,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQ); prefetch_tmap(&tmR); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kS1Stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -135,7 +135,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const uint32_t crank = cluster_ctarank();
   const int64_t T = static_cast<int64_t>(p.tiles_m2) * p.tiles_n;
@@ -161,7 +161,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {
+    if (__shfl_sync(0xffffffffu, crank, 0) == 0) {         // whole warp, warp-uniform operands, one elected lane issues
       constexpr uint32_t idesc = make_idesc_bf16_f32(2 * kS1BM, kS1BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -176,11 +176,11 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint64_t b_desc = make_desc_k_sw128(smem_u32(sB + stage * kS1BTile));
 #pragma unroll
           for (int k = 0; k < kS1BK / 16; ++k)
-            umma_bf16_ss_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_cg2_mcast(&empty_bar[stage], static_cast<uint16_t>(0x3));
+            umma_bf16_ss_cg2_warp(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg2_mcast_warp(&empty_bar[stage], static_cast<uint16_t>(0x3));
           if (++stage == kS1Stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_cg2_mcast(&tfull_bar[acc], static_cast<uint16_t>(0x3));
+        umma_commit_cg2_mcast_warp(&tfull_bar[acc], static_cast<uint16_t>(0x3));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

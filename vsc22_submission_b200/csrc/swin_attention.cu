@@ -134,7 +134,7 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* tabs = reinterpret_cast<float*>(bars + 18);    // [2 warpgroups][2 heads][TS*TS]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   if (warp == 9) {
     if (lane == 0) {
       prefetch_tmap(&tmQKV);
@@ -150,7 +150,7 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int hpairs = p.heads >> 1;
   const int n_it = (n_units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
@@ -172,7 +172,7 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform operands, one elected lane issues (umma_*_warp)
       // items = (unit, head of the pair); both warpgroups work on the same item sequence, half a period apart
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, N);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, 32);
@@ -185,8 +185,8 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
         tc_fence_after();
         const uint64_t qd = make_desc_k_sw128(sQ + w * 16384 + hh * 64), kd = make_desc_k_sw128(sQ + kTile + hh * 64);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_bf16_ss(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit(&s_full[w]);
+        for (int k = 0; k < 2; ++k) umma_bf16_ss_warp(tmem_base + w * 256, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit_warp(&s_full[w]);
       };
       auto issue_pv = [&](int w, int item) {
         const int it = item >> 1, hh = item & 1, st = it & 1;
@@ -196,32 +196,32 @@ swin_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, SwinAttnParams 
         tc_fence_after();
 #pragma unroll 1
         for (int i = 0; i < N / 16; ++i)
-          umma_bf16_ts(tmem_base + w * 256 + kSwOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
+          umma_bf16_ts_warp(tmem_base + w * 256 + kSwOCol, tmem_base + w * 256 + i * 8, vd + static_cast<uint64_t>(i) * 128,
                        idesc_o, i ? 1u : 0u);
-        umma_commit(&o_full[w]);
+        umma_commit_warp(&o_full[w]);
       };
       if (kMT == 2) {
         if (n_items > 0) issue_s(0, 0);
         for (int item = 0; item < n_items; ++item) {
           if (item > 0) {
             issue_pv(1, item - 1);
-            if ((item - 1) & 1) umma_commit(&v_empty[((item - 1) >> 1) & 1]);
+            if ((item - 1) & 1) umma_commit_warp(&v_empty[((item - 1) >> 1) & 1]);
           }
           issue_s(1, item);
-          if (item & 1) umma_commit(&qk_empty[(item >> 1) & 1]);
+          if (item & 1) umma_commit_warp(&qk_empty[(item >> 1) & 1]);
           issue_pv(0, item);
           if (item + 1 < n_items) issue_s(0, item + 1);
         }
         if (n_items > 0) {
           issue_pv(1, n_items - 1);
-          umma_commit(&v_empty[((n_items - 1) >> 1) & 1]);
+          umma_commit_warp(&v_empty[((n_items - 1) >> 1) & 1]);
         }
       } else {
         for (int item = 0; item < n_items; ++item) {
           issue_s(0, item);
-          if (item & 1) umma_commit(&qk_empty[(item >> 1) & 1]);
+          if (item & 1) umma_commit_warp(&qk_empty[(item >> 1) & 1]);
           issue_pv(0, item);
-          if (item & 1) umma_commit(&v_empty[(item >> 1) & 1]);
+          if (item & 1) umma_commit_warp(&v_empty[(item >> 1) & 1]);
         }
       }
     }
