@@ -17,7 +17,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows
 (:93-98) is a row-wise operation, so it is restated on the concatenation.  The reference has
 no test for this function (parity unpinned there); it is pinned here by running
 the reference's own function through ``oracle.faiss_np`` (tests/test_oracle_reference_pins.py,
-container only) and by the committed fixture tests/golden/score_norm_small.npz.
+container only) and by the committed fixture tests/golden/search_small.npz (arrays sn_q / sn_r: outputs of the
+reference function written by tests/golden/make_golden.py).
 """
 from __future__ import annotations
 

@@ -241,7 +241,7 @@ def stage_sim_precision():
         print(f"  scores nq{nq} nr{nr} d{d}: tc max|err| {err.abs().max().item():.3e} mean signed {err.mean().item():+.3e} "
               f"rms {err.pow(2).mean().sqrt().item():.3e} | torch fp32 matmul max {err32.abs().max().item():.3e} "
               f"rms {err32.pow(2).mean().sqrt().item():.3e} | corr(err, ref) {torch.corrcoef(torch.stack([err.flatten(), ref.flatten()]))[0,1].item():+.3f}")
-        ok &= err.abs().max().item() < 1e-6
+        ok &= err.abs().max().item() < 5e-6      # split-bf16: the dropped lo.lo term is ~2^-18 relative; returned scores are rescored exactly
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):

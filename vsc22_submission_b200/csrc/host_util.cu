@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace vscb200 {
@@ -29,8 +30,33 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// Encoded descriptors are cached per thread, keyed by every argument: an encoder plan launches the same few dozen
+// (buffer, shape, box) combinations thousands of times per step, and cuTensorMapEncodeTiled costs ~1 us a call.
+namespace {
+struct TmapKey {
+  const void* base; uint64_t rows, cols, ld; uint32_t box_rows, box_cols; int dtype, elem_bytes, swz;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+           dtype == o.dtype && elem_bytes == o.elem_bytes && swz == o.swz;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.rows, k.cols, k.ld, (static_cast<uint64_t>(k.box_rows) << 32) | k.box_cols,
+                       (static_cast<uint64_t>(k.dtype) << 16) ^ (static_cast<uint64_t>(k.elem_bytes) << 8) ^ static_cast<uint64_t>(k.swz)})
+      h = (h ^ v) * 0xBF58476D1CE4E5B9ull + (h >> 29);
+    return static_cast<size_t>(h);
+  }
+};
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> t_tmaps;
+}  // namespace
+
 int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, int elem_bytes, uint64_t rows,
                  uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128) {
+  const TmapKey key{base, rows, cols, ld, box_rows, box_cols, static_cast<int>(dtype), elem_bytes, swizzle128 ? 1 : 0};
+  auto hit = t_tmaps.find(key);
+  if (hit != t_tmaps.end()) { *out = hit->second; return VSCB200_OK; }
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -49,6 +75,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
                    " box=" + std::to_string(box_rows) + "x" + std::to_string(box_cols) + ")");
     return VSCB200_ERR_CUDA;
   }
+  if (t_tmaps.size() >= 8192) t_tmaps.clear();
+  t_tmaps.emplace(key, *out);
   return VSCB200_OK;
 }
 
