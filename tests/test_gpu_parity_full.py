@@ -115,3 +115,53 @@ def test_swinv2_b_256_fp32_mode_vs_fp32_oracle(torch):
     rel = _rel(out, refs["fp32"])
     print(f"SwinV2-B@256 fp32-equivalent mode: rel-L2 vs fp32 oracle max {rel.max():.3e} mean {rel.mean():.3e}")
     assert rel.max() <= TOL / 10, rel       # measured 1.0e-5
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs[3]
+# SwinV2-L / window 24 @ 384 (swinv2.py:72-185, 509-665 at the large hyper-parameters) and ViT-L/16 @ 384 (clip.py:85-163,
+# T = 577): the K-blocked / streaming tcgen05 attention kernels at the sizes they were written for.  4 frames each (the
+# fp32 oracle of one 384 x 384 frame is ~0.3 TFLOP on the host).
+C4_FRAMES = 4
+
+
+def _c4_vit(torch):
+    from oracle import vit_ref
+    w = vit_ref.init_weights(vit_ref.CLIP_L16_384, seed=0)
+    x = torch.randn(C4_FRAMES, 3, 384, 384, generator=torch.Generator().manual_seed(21)).clamp(-1, 1)
+    refs = {p: vit_ref.forward(vit_ref.CLIP_L16_384, w, x, precision=p)[:, 0].numpy() for p in ("fp32", "bf16")}
+    return w, x, refs
+
+
+def test_config4_vit_l16_384(torch):
+    import dataclasses
+    from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_L16_384
+    w, x, refs = _c4_vit(torch)
+    enc = B200ViTEncoder(dataclasses.replace(VIT_L16_384, precision="bf16"), w, max_frames=4).cuda().eval()
+    out = enc(x.cuda())[:, 0].cpu().numpy()
+    rel_m, rel_f = _rel(out, refs["bf16"]), _rel(out, refs["fp32"])
+    print(f"ViT-L/16@384 bf16 mode: rel-L2 vs matched-precision oracle max {rel_m.max():.3e}; vs fp32 oracle max {rel_f.max():.3e}")
+    assert rel_m.max() <= 6e-3, rel_m          # 24 blocks: same regime as CLIP ViT-L/14 above
+    del enc
+    enc = B200ViTEncoder(dataclasses.replace(VIT_L16_384, precision="fp32"), w, max_frames=4).cuda().eval()
+    rel = _rel(enc(x.cuda())[:, 0].cpu().numpy(), refs["fp32"])
+    print(f"ViT-L/16@384 fp32-equivalent mode: rel-L2 vs fp32 oracle max {rel.max():.3e}")
+    assert rel.max() <= TOL / 10, rel
+
+
+def test_config4_swinv2_l_384(torch):
+    import dataclasses
+    from oracle import swin_ref
+    from vsc22_submission_b200.swin_encoder import B200SwinEncoder, SWINV2_L_384, random_weights
+    w = random_weights(SWINV2_L_384, seed=1)
+    x = torch.randn(C4_FRAMES, 3, 384, 384, generator=torch.Generator().manual_seed(22)).clamp(-1, 1)
+    refs = {p: swin_ref.forward(swin_ref.SWINV2_L_384, w, x, precision=p).numpy() for p in ("fp32", "bf16")}
+    enc = B200SwinEncoder(dataclasses.replace(SWINV2_L_384, precision="bf16"), w, max_frames=4).cuda().eval()
+    out = enc(x.cuda()).cpu().numpy()
+    rel_m, rel_f = _rel(out, refs["bf16"]), _rel(out, refs["fp32"])
+    print(f"SwinV2-L/w24@384 bf16 mode: rel-L2 vs matched-precision oracle max {rel_m.max():.3e}; vs fp32 oracle max {rel_f.max():.3e}")
+    assert rel_m.max() <= 3.5e-3, rel_m        # same bound as SwinV2-B above
+    del enc
+    enc = B200SwinEncoder(dataclasses.replace(SWINV2_L_384, precision="fp32"), w, max_frames=4).cuda().eval()
+    rel = _rel(enc(x.cuda()).cpu().numpy(), refs["fp32"])
+    print(f"SwinV2-L/w24@384 fp32-equivalent mode: rel-L2 vs fp32 oracle max {rel.max():.3e}")
+    assert rel.max() <= TOL / 10, rel

@@ -51,59 +51,82 @@ constexpr int kWsOnes = 2048;                // 16 keys x 128 B of bf16 ones: B 
 constexpr int kWsMaxBlocks = 10;             // 640 keys
 
 struct WsParams {
-  __nv_bfloat16* out;        // [M, W]
+  __nv_bfloat16* out;        // [M, C]
   long long* prof;           // WS_PROF builds: per-CTA cycle counters (nullptr otherwise)
-  int T, heads, W;
-  int nb, ntiles;            // key blocks, 128-query tiles per frame
-  int n_units;               // frames * heads
+  const float* tables;       // Swin form: [heads][(2ws-1)^2]  16*sigmoid(cpb); nullptr for the ViT form
+  int T, C;                  // tokens per segment (frame / window), row width of out
+  int hgroups, n_segs;       // 64-column head groups per segment (heads, or head pairs for head_dim 32), segments
+  int nb, ntiles, ipu;       // key blocks, 128-query tiles per segment, items per unit (= tiles x heads per group)
+  int n_units;               // segments * head groups
   int kv_stages, q_bufs;     // 2 / 2 when they fit the shared memory, else 1 / 1
   int reverse;
-  float scale_log2e;
+  float scale_log2e;         // ViT: head_dim^-0.5 * log2 e; Swin: log2 e (q carries the logit scale)
+  int ws, shift, nWx, nW_per_frame;
 };
 
 __device__ __forceinline__ uint32_t ws_pack(float lo, float hi) {
   return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
 
-// Cursor over the CTA's flattened item sequence (units blockIdx.x, + gridDim.x, ...; inside a unit the query tiles in
-// order).  The single-thread roles (producer, issuers) advance it incrementally: no division per item.
+// Cursor over the CTA's flattened item sequence (units blockIdx.x, + gridDim.x, ...; inside a unit the items r =
+// tile * HH + head-of-the-group).  The single-thread roles (producer, issuers) advance it incrementally: no division
+// per item.  ViT form: unit = frame * heads + head; Swin form: unit = head pair * n_segs + window (a CTA keeps a pair's
+// bias tables over consecutive units).
 struct WsItem {
   int k;        // CTA-local unit index
-  int tile;
-  int frame, head;
+  int r;        // item inside the unit
+  int seg, hg;
   bool ok;
 };
+template <bool kSwin>
 __device__ __forceinline__ void ws_unit(WsItem& it, const WsParams& p) {
   const int unit = static_cast<int>(blockIdx.x) + it.k * static_cast<int>(gridDim.x);
   it.ok = unit < p.n_units;
   if (it.ok) {
-    const int f = unit / p.heads;
-    it.head = unit - f * p.heads;
-    it.frame = p.reverse ? (p.n_units / p.heads - 1 - f) : f;
+    if (kSwin) {
+      it.hg = unit / p.n_segs;
+      it.seg = unit - it.hg * p.n_segs;
+    } else {
+      const int f = unit / p.hgroups;
+      it.hg = unit - f * p.hgroups;
+      it.seg = p.reverse ? (p.n_segs - 1 - f) : f;
+    }
   }
 }
-__device__ __forceinline__ void ws_first(WsItem& it, int J0, const WsParams& p) {      // J0 < ntiles
+template <bool kSwin>
+__device__ __forceinline__ void ws_first(WsItem& it, int r0, const WsParams& p) {      // r0 < ipu
   it.k = 0;
-  it.tile = J0;
-  ws_unit(it, p);
+  it.r = r0;
+  ws_unit<kSwin>(it, p);
 }
-__device__ __forceinline__ void ws_next(WsItem& it, int step, const WsParams& p) {     // step <= ntiles
-  it.tile += step;
-  if (it.tile >= p.ntiles) {
-    it.tile -= p.ntiles;
+template <bool kSwin>
+__device__ __forceinline__ void ws_next(WsItem& it, int step, const WsParams& p) {     // step <= ipu
+  it.r += step;
+  if (it.r >= p.ipu) {
+    it.r -= p.ipu;
     ++it.k;
-    ws_unit(it, p);
+    ws_unit<kSwin>(it, p);
   }
 }
 // x mod n and x div n for n in {1, 2} (stage / buffer counts)
 __device__ __forceinline__ int ws_mod(int x, int n) { return x & (n - 1); }
 __device__ __forceinline__ int ws_div(int x, int n) { return x >> (n - 1); }
 
+// Swin form, per item: this row's position in the bias table and its penalties against the four mask regions
+struct WsSwinRow {
+  const float* tab;          // the head's (2ws-1)^2 table (shared memory)
+  int base_i;                // (yi + ws - 1) * (2ws - 1) + xi + ws - 1
+  float pen[2][2];           // [key y-region][key x-region]: -100 where it differs from the row's region
+  bool masked;               // the window mixes regions (warp-uniform)
+};
+
 // One key block of this thread's row: S in TMEM columns [tS, tS + 64) -> P (bf16 pairs over [tS, tS + 32)); running shift
-// m (log2 domain); accumulators at [tO, tO + 80) (O | row sum) rescaled when the shift moves.  kt: first key of the
-// block.  Warp-collective.
-__device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int kt, bool first, float& m, int T,
-                                                 float scale_log2e, uint64_t* pv_done, uint32_t pv_parity) {
+// m (log2 domain); accumulators O [tO, tO + HD) and row sum [tL, tL + 16) rescaled when the shift moves.  kt: first key
+// of the block.  Warp-collective.
+template <int HD, bool kSwin>
+__device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint32_t tL, int kt, bool first, float& m, int T,
+                                                 float scale_log2e, uint64_t* pv_done, uint32_t pv_parity, const WsSwinRow& sw,
+                                                 int ws, int shift) {
   const int nchunks = min(2, (T - kt + 31) >> 5);                     // chunks with a valid key (warp-uniform, >= 1)
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
@@ -113,7 +136,24 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int k
       tmem_ld_32x32(tS + c * 32, v);
       tmem_ld_wait();
       const int lim = T - (kt + c * 32);
-      if (lim < 32) {                                                 // warp-uniform: the frame's last chunk
+      if (kSwin) {
+        // z = s + bias + mask: table index base_i - (yk * TS + xk); along the chunk the key term grows by 1 per key and
+        // by another ws - 1 whenever xk wraps (warp-uniform integer bookkeeping)
+        const int TS = 2 * ws - 1, edge = ws - shift;
+        int yk = (kt + c * 32) / ws, xk = (kt + c * 32) - yk * ws;
+        const float* tp = sw.tab + sw.base_i - (yk * TS + xk);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float zz = __uint_as_float(v[j]) + tp[-j];
+          if (sw.masked) {                                            // selects, not indexing: pen stays in registers
+            const float pe0 = xk >= edge ? sw.pen[0][1] : sw.pen[0][0], pe1 = xk >= edge ? sw.pen[1][1] : sw.pen[1][0];
+            zz += yk >= edge ? pe1 : pe0;
+          }
+          v[j] = __float_as_uint(zz);
+          if (++xk == ws) { xk = 0; ++yk; tp -= ws - 1; }
+        }
+      }
+      if (lim < 32) {                                                 // warp-uniform: the segment's last chunk
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (j >= lim) v[j] = 0xFF800000u;                           // -inf: p = 0
@@ -135,13 +175,14 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int k
           mbar_wait(pv_done, pv_parity);                              // the previous block's P.V has left them alone
           tc_fence_after();
 #pragma unroll 1
-          for (int h = 0; h < 5; ++h) {
+          for (int h = 0; h < HD / 16 + 1; ++h) {
+            const uint32_t ta = h < HD / 16 ? tO + h * 16 : tL;
             uint32_t o[16];
-            tmem_ld_32x16(tO + h * 16, o);
+            tmem_ld_32x16(ta, o);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-            tmem_st_32x16(tO + h * 16, o);
+            tmem_st_32x16(ta, o);
           }
         }
         if (c == 1) {                                                 // P of this block's first chunk
@@ -162,7 +203,7 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int k
         const float q1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -m));
         pk[j >> 1] = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);     // truncation to bf16 pairs
       }
-    } else {                                                          // keys past the frame: P = 0 (the MMA reads all 64)
+    } else {                                                          // keys past the segment: P = 0 (the MMA reads all 64)
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = 0u;
     }
@@ -172,8 +213,10 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, int k
   tmem_st_wait();
 }
 
+template <int HD, bool kSwin>
 __global__ void __launch_bounds__(kWsThreads, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, WsParams p) {
+  constexpr int HH = 64 / HD;                             // heads per 64-column group
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -192,6 +235,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_empty = bars + 22;       // [2]
   uint64_t* pv_done = bars + 24;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* tabs = reinterpret_cast<float*>(bars + 28);      // Swin form: [2 heads][(2ws-1)^2]
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   if (warp == 8) {
@@ -224,8 +268,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int n_q[2] = {0, 0};
       WsItem it;
       int w = 0;
-      for (ws_first(it, 0, p); it.ok; ws_next(it, 1, p), w ^= 1) {
-        const int row0 = it.frame * p.T;
+      for (ws_first<kSwin>(it, 0, p); it.ok; ws_next<kSwin>(it, 1, p), w ^= 1) {
+        const int row0 = it.seg * p.T;
         if (it.k != cur_k) {                               // new unit: K and V into the next stage
           cur_k = it.k;
           const int st = ws_mod(it.k, p.kv_stages);
@@ -233,16 +277,16 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&kv_empty[st], (ws_div(it.k, p.kv_stages) & 1) ^ 1);
           mbar_expect_tx(&kv_full[st], 2 * kv_bytes);
           for (int b = 0; b < p.nb; ++b)
-            tma_load_2d(sK + b * kWsKTile, &tmKV, &kv_full[st], p.W + it.head * 64, row0 + b * kWsKB, kEvictFirst);
+            tma_load_2d(sK + b * kWsKTile, &tmKV, &kv_full[st], p.C + it.hg * 64, row0 + b * kWsKB, kEvictFirst);
           for (int b = 0; b < p.nb; ++b)
-            tma_load_2d(sK + kv_bytes + b * kWsKTile, &tmKV, &kv_full[st], 2 * p.W + it.head * 64, row0 + b * kWsKB, kEvictFirst);
+            tma_load_2d(sK + kv_bytes + b * kWsKTile, &tmKV, &kv_full[st], 2 * p.C + it.hg * 64, row0 + b * kWsKB, kEvictFirst);
         }
         const int qb = ws_mod(n_q[w], p.q_bufs);
         const int use = ws_div(n_q[w], p.q_bufs);
         ++n_q[w];
         mbar_wait(&q_empty[w * 2 + qb], (use & 1) ^ 1);
         mbar_expect_tx(&q_full[w * 2 + qb], kWsQTile);
-        tma_load_2d(sQ + (w * p.q_bufs + qb) * kWsQTile, &tmQ, &q_full[w * 2 + qb], it.head * 64, row0 + it.tile * 128, kEvictFirst);
+        tma_load_2d(sQ + (w * p.q_bufs + qb) * kWsQTile, &tmQ, &q_full[w * 2 + qb], it.hg * 64, row0 + (it.r / HH) * 128, kEvictFirst);
       }
     }
   } else if (warp == 8 || warp == 9) {
@@ -251,7 +295,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       const int w = warp - 8;
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, kWsKB);
-      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, 64);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, HD);
       constexpr uint32_t idesc_l = make_idesc_bf16_f32_bmn(128, 16);
       const uint64_t ones_d = make_desc_mn_sw128(smem_u32(sOnes));
       const uint32_t tw = tmem_base + w * 256;
@@ -261,8 +305,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int pb = 0, p_item = 0;
       uint32_t sg = 0, pg = 0;                             // global block counters
       WsItem si, pi;
-      ws_first(si, w, p);
-      ws_first(pi, w, p);
+      ws_first<kSwin>(si, w, p);
+      ws_first<kSwin>(pi, w, p);
 #ifdef WS_PROF
       long long i_kv = 0, i_q = 0, i_p = 0, i_oe = 0;
       const long long i_begin = clock64();
@@ -280,17 +324,18 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         i_kv += u1 - u0; i_q += clock64() - u1;
 #endif
         tc_fence_after();
-        const uint64_t qd = make_desc_k_sw128(sQ_u + (w * p.q_bufs + qb) * kWsQTile);
-        const uint64_t kd = make_desc_k_sw128(sKV_u + ws_mod(si.k, p.kv_stages) * 2 * kv_bytes + sb * kWsKTile);
+        const int s_hh = (si.r % HH) * 64;                 // byte offset of the head inside the 64-column box
+        const uint64_t qd = make_desc_k_sw128(sQ_u + (w * p.q_bufs + qb) * kWsQTile + s_hh);
+        const uint64_t kd = make_desc_k_sw128(sKV_u + ws_mod(si.k, p.kv_stages) * 2 * kv_bytes + sb * kWsKTile + s_hh);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss_warp(tw + (sg & 1) * kWsKB, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss_warp(tw + (sg & 1) * kWsKB, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
         umma_commit_warp(&s_full[w * 2 + (sg & 1)]);
         ++sg;
         if (++sb == p.nb) {                                // last S of the item: its Q buffer is free once these retire
           umma_commit_warp(&q_empty[w * 2 + qb]);
           sb = 0;
           ++s_item;
-          ws_next(si, 2, p);
+          ws_next<kSwin>(si, 2, p);
         }
       };
       // S runs up to two blocks ahead of PV, but never into a unit whose K / V stage is still held by a unit this
@@ -308,7 +353,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         i_p += u3 - u2; i_oe += clock64() - u3;
 #endif
         tc_fence_after();
-        const uint64_t vd = make_desc_mn_sw128(sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile);
+        const uint64_t vd = make_desc_mn_sw128(sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile + (pi.r % HH) * 64);
 #pragma unroll
         for (int i = 0; i < kWsKB / 16; ++i) {
           umma_bf16_ts_warp(tw + kWsOCol, tw + (pg & 1) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
@@ -321,7 +366,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_commit_warp(&o_full[w]);
           pb = 0;
           ++p_item;
-          ws_next(pi, 2, p);
+          ws_next<kSwin>(pi, 2, p);
           if (!pi.ok || pi.k != prev_k) umma_commit_warp(&kv_empty[ws_mod(prev_k, p.kv_stages)]);   // this warpgroup is done with the unit
         }
       }
@@ -344,9 +389,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto epilogue = [&]() {                                // O of the previous item -> registers, accumulator released
       mbar_wait(&o_full[w], (n_item - 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32], ls[16];
-      tmem_ld_32x32(tlane + kWsOCol, o0);
-      tmem_ld_32x32(tlane + kWsOCol + 32, o1);
+      uint32_t o[HD], ls[16];
+#pragma unroll
+      for (int h = 0; h < HD / 32; ++h) tmem_ld_32x32(tlane + kWsOCol + h * 32, reinterpret_cast<uint32_t(&)[32]>(o[h * 32]));
       tmem_ld_32x16(tlane + kWsLCol, ls);
       tmem_ld_wait();
       const float pend_inv_l = 1.0f / __uint_as_float(ls[0]);
@@ -355,15 +400,13 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(&o_empty[w]);
       if (pend_valid) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t* o = q < 4 ? o0 : o1;
-          const int b8 = (q & 3) * 8;
+        for (int q = 0; q < HD / 8; ++q) {
           uint4 u;
           // cvt.rn.bf16x2 (one F2FP per pair): the XU pipe it issues on is idle during the epilogue
-          u.x = pack_bf16x2(__uint_as_float(o[b8]) * pend_inv_l, __uint_as_float(o[b8 + 1]) * pend_inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[b8 + 2]) * pend_inv_l, __uint_as_float(o[b8 + 3]) * pend_inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[b8 + 4]) * pend_inv_l, __uint_as_float(o[b8 + 5]) * pend_inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[b8 + 6]) * pend_inv_l, __uint_as_float(o[b8 + 7]) * pend_inv_l);
+          u.x = pack_bf16x2(__uint_as_float(o[8 * q]) * pend_inv_l, __uint_as_float(o[8 * q + 1]) * pend_inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * q + 2]) * pend_inv_l, __uint_as_float(o[8 * q + 3]) * pend_inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * q + 4]) * pend_inv_l, __uint_as_float(o[8 * q + 5]) * pend_inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * q + 6]) * pend_inv_l, __uint_as_float(o[8 * q + 7]) * pend_inv_l);
           *reinterpret_cast<uint4*>(pend_row + q * 8) = u;
         }
       }
@@ -374,9 +417,40 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     long long c_wait = 0, c_soft = 0, c_epi = 0, c_arr = 0;
     const long long c_begin = clock64();
 #endif
-    for (ws_first(it, w, p); it.ok; ws_next(it, 2, p)) {
-      const int i_tok = it.tile * 128 + quad * 32 + lane;
-      const bool warp_valid = it.tile * 128 + quad * 32 < p.T;
+    int loaded_hg = -1;
+    const int TS = 2 * p.ws - 1;
+    for (ws_first<kSwin>(it, w, p); it.ok; ws_next<kSwin>(it, 2, p)) {
+      const int tile = it.r / HH, hh = it.r - tile * HH;
+      const int i_tok = tile * 128 + quad * 32 + lane;
+      const bool warp_valid = tile * 128 + quad * 32 < p.T;
+      WsSwinRow sw;
+      sw.tab = tabs + hh * TS * TS;
+      sw.base_i = 0;
+      sw.masked = false;
+      sw.pen[0][0] = sw.pen[0][1] = sw.pen[1][0] = sw.pen[1][1] = 0.f;
+      if (kSwin) {
+        if (it.hg != loaded_hg) {                          // bias tables of the head pair -> shared memory.  Both warpgroups
+          named_bar_sync(1, 256);                          // walk the units in the same order: whoever gets here first waits
+          for (int e = threadIdx.x; e < 2 * TS * TS; e += 256) tabs[e] = p.tables[static_cast<int64_t>(it.hg) * 2 * TS * TS + e];
+          named_bar_sync(1, 256);                          // until the other one has finished the previous pair's items
+          loaded_hg = it.hg;
+        }
+        bool edge_y = false, edge_x = false;
+        if (p.shift > 0) {                                 // shifted-window regions: only the last window row / column of a frame
+          const int wf = it.seg % p.nW_per_frame;
+          edge_y = (wf / p.nWx) == (p.nW_per_frame / p.nWx) - 1;
+          edge_x = (wf % p.nWx) == p.nWx - 1;
+        }
+        sw.masked = edge_y || edge_x;
+        const int tok = i_tok < p.T ? i_tok : 0;
+        const int yi = tok / p.ws, xi = tok - yi * p.ws;
+        sw.base_i = (yi + p.ws - 1) * TS + xi + p.ws - 1;
+        const int ry_i = (edge_y && yi >= p.ws - p.shift) ? 1 : 0, rx_i = (edge_x && xi >= p.ws - p.shift) ? 1 : 0;
+#pragma unroll
+        for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) sw.pen[a2][b2] = ((edge_y && a2 != ry_i) || (edge_x && b2 != rx_i)) ? -100.0f : 0.0f;
+      }
       float m = -INFINITY;
 #pragma unroll 1
       for (int b = 0; b < p.nb; ++b) {
@@ -387,8 +461,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // warps whose 32 rows all lie past the frame skip the block: the MMA reads stale TMEM for them, and whatever it
         // computes stays in rows nobody stores
         if (warp_valid)
-          ws_softmax_block(tlane + (g & 1) * kWsKB, tlane + kWsOCol, b * kWsKB, b == 0, m, p.T, p.scale_log2e, &pv_done[w],
-                           (g - 1) & 1);
+          ws_softmax_block<HD, kSwin>(tlane + (g & 1) * kWsKB, tlane + kWsOCol, tlane + kWsLCol, b * kWsKB, b == 0, m, p.T,
+                                      p.scale_log2e, &pv_done[w], (g - 1) & 1, sw, p.ws, p.shift);
         WS_T(t2);
         if (b == 0 && pend) epilogue();                    // before P.V of this item's first block may overwrite O
         WS_T(t3);
@@ -404,7 +478,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ++n_item;
       pend = true;
       pend_valid = i_tok < p.T;
-      pend_row = p.out + (static_cast<int64_t>(it.frame) * p.T + (pend_valid ? i_tok : 0)) * p.W + it.head * 64;
+      pend_row = p.out + (static_cast<int64_t>(it.seg) * p.T + (pend_valid ? i_tok : 0)) * p.C + it.hg * 64 + hh * HD;
     }
     if (pend) epilogue();
 #ifdef WS_PROF
@@ -421,44 +495,59 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 bool attention_ws_supported(int T, int head_dim) {
   static const int off = [] { const char* e = getenv("VSCB200_ATTN_NO_WS"); return e ? atoi(e) : 0; }();
-  return !off && head_dim == 64 && T > 128 && T <= kWsKB * kWsMaxBlocks;
+  return !off && ((head_dim == 64 && T > 128) || (head_dim == 32 && T >= 64)) && T <= kWsKB * kWsMaxBlocks;
 }
 
-// qkv: [n_frames * T, 3W] bf16 (q | k | v, heads 64-wide contiguous); out: [n_frames * T, W] bf16
-int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse) {
-  VSCB_REQUIRE(attention_ws_supported(T, 64), "attention_ws: unsupported frame length");
-  const int W = heads * 64;
-  const int64_t M = static_cast<int64_t>(n_frames) * T;
-  VSCB_REQUIRE(M < (1ll << 31) && static_cast<int64_t>(n_frames) * heads < (1ll << 30), "attention_ws: problem too large");
+// The two forms share one launcher.  qkv: [n_segs * T, 3C] bf16 (q | k | v, heads head_dim-wide contiguous); out: [n_segs * T, C].
+static int attention_ws_launch(const void* qkv, void* out, int64_t n_segs, int T, int heads, int head_dim, float scale,
+                               const float* tables, int ws, int shift, int nWx, int nW_per_frame, cudaStream_t stream, bool reverse) {
+  VSCB_REQUIRE(attention_ws_supported(T, head_dim), "attention_ws: unsupported segment length / head_dim");
+  const bool swin = head_dim == 32;
+  VSCB_REQUIRE(swin == (tables != nullptr), "attention_ws: head_dim 32 is the Swin-V2 form (bias tables), 64 the ViT form");
+  VSCB_REQUIRE(!swin || (heads % 2 == 0 && ws * ws == T), "attention_ws: Swin form needs an even head count and T = ws * ws");
+  const int C = heads * head_dim;
+  const int64_t M = n_segs * T;
+  const int hgroups = C / 64;
+  VSCB_REQUIRE(M < (1ll << 31) && n_segs * hgroups < (1ll << 30), "attention_ws: problem too large");
   CUtensorMap tmQ, tmKV;
-  int rc = make_tmap_2d(&tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, 128, 64, true);
+  int rc = make_tmap_2d(&tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * C, 3 * C, 128, 64, true);
   if (rc) return rc;
-  if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * W, 3 * W, kWsKB, 64, true))) return rc;
+  if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * C, 3 * C, kWsKB, 64, true))) return rc;
   WsParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  p.T = T; p.heads = heads; p.W = W;
+  p.tables = tables;
+  p.T = T; p.C = C; p.hgroups = hgroups; p.n_segs = static_cast<int>(n_segs);
   p.nb = (T + kWsKB - 1) / kWsKB;
   p.ntiles = (T + 127) / 128;
-  p.n_units = n_frames * heads;
+  p.ipu = p.ntiles * (64 / head_dim);
+  p.n_units = static_cast<int>(n_segs) * hgroups;
   p.reverse = reverse ? 1 : 0;
-  p.scale_log2e = (1.0f / sqrtf(64.0f)) * 1.4426950408889634f;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.ws = swin ? ws : 1; p.shift = shift; p.nWx = nWx > 0 ? nWx : 1; p.nW_per_frame = nW_per_frame > 0 ? nW_per_frame : 1;
+  VSCB_REQUIRE(p.ipu >= 2, "attention_ws: a unit needs at least two items (one per warpgroup)");
   const int kv_bytes = p.nb * kWsKTile;
-  const int fixed = kWsOnes + 28 * 8 + 64 + 1024;
+  const int TS = 2 * p.ws - 1;
+  const int fixed = kWsOnes + 28 * 8 + (swin ? 2 * TS * TS * 4 : 0) + 64 + 1024;
   p.kv_stages = 2; p.q_bufs = 2;
   if (2 * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.kv_stages = 1;
   if (p.kv_stages * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.q_bufs = 1;
   const int smem = p.kv_stages * 2 * kv_bytes + 2 * p.q_bufs * kWsQTile + fixed;
   VSCB_REQUIRE(smem <= 232448, "attention_ws: shared memory");
-  VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.n_units < device_sm_count() ? p.n_units : device_sm_count();
-  ProfScope prof(kProfAttention, stream, 4.0 * n_frames * heads * static_cast<double>(T) * T * 64);
+  ProfScope prof(kProfAttention, stream, 4.0 * static_cast<double>(M) * T * C);
   p.prof = nullptr;
 #ifdef WS_PROF
   static long long* prof_buf = nullptr;
   if (!prof_buf) cudaMalloc(&prof_buf, 148 * 8 * 5 * sizeof(long long));
   p.prof = prof_buf;
 #endif
-  attention_ws_kernel<<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
+  if (swin) {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_ws_kernel<32, true><<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
+  } else {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_ws_kernel<64, false><<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
+  }
 #ifdef WS_PROF
   {
     static long long h[148 * 8 * 5];
@@ -476,6 +565,17 @@ int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cud
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
+}
+
+// ViT form: softmax(q.k / sqrt(64)) v per (frame, head)
+int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse) {
+  return attention_ws_launch(qkv, out, n_frames, T, heads, 64, 1.0f / sqrtf(64.0f), nullptr, 0, 0, 0, 0, stream, reverse);
+}
+// Swin-V2 form (head_dim 32): q, k arrive cosine-normalised with the logit scale in q; tables [heads][(2ws-1)^2]; the rows
+// of a segment are the tokens of one ws x ws window in row-major order (swin_attention.cu's conventions)
+int attention_ws_swin(const void* qkv, void* out, int64_t n_windows_total, int ws, int heads, const float* tables, int shift,
+                      int nWx, int nW_per_frame, cudaStream_t stream) {
+  return attention_ws_launch(qkv, out, n_windows_total, ws * ws, heads, 32, 1.0f, tables, ws, shift, nWx, nW_per_frame, stream, false);
 }
 
 }  // namespace vscb200

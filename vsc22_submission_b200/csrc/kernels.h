@@ -32,6 +32,8 @@ int attention_fp32(const void* qkv, int64_t qkv_lo_off, void* out, int64_t out_l
 // attention_ws.cu: streaming tcgen05 attention of the ViT encoders (head_dim 64, 129..672 tokens)
 bool attention_ws_supported(int T, int head_dim);
 int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse);
+int attention_ws_swin(const void* qkv, void* out, int64_t n_windows_total, int ws, int heads, const float* tables, int shift,
+                      int nWx, int nW_per_frame, cudaStream_t stream);
 // attention_kb.cu: K-blocked tcgen05 attention, segments of 129..640 tokens (ViT form: head_dim 64; Swin-V2 form: head_dim 32
 // with relative-position bias tables and the shifted-window mask)
 bool attention_kb_supported(int N, int head_dim);

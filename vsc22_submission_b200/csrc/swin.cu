@@ -306,8 +306,13 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
     const int C = st.C, res = st.res, ws = st.ws;
     const int64_t M = static_cast<int64_t>(n) * res * res;
     const int nWx = res / ws, nW = nWx * nWx;
-    const bool tc_attn = !m->exact && (ws == 4 || ws == 8 || ws == 16);
-    const bool kb_attn = !m->exact && !tc_attn && st.heads % 2 == 0 && attention_kb_supported(ws * ws, 32);   // 24 x 24, 12 x 12
+    // window attention kernels of the bf16 mode: S-resident kernel (swin_attention.cu) for 4 x 4 / 8 x 8 / 16 x 16 windows
+    // (measured at 16 x 16: 25 ms vs 38 ms per 1024 SwinV2-B frames for the streaming kernel), streaming kernel
+    // (attention_ws.cu) for larger windows or odd sides (12 x 12, 24 x 24), K-blocked kernel as its fallback
+    const bool ws_attn = !m->exact && st.heads % 2 == 0 && ws != 4 && ws != 8 && ws != 16 && ws * ws >= 64 &&
+                         attention_ws_supported(ws * ws, 32);
+    const bool tc_attn = !m->exact && !ws_attn && (ws == 4 || ws == 8 || ws == 16);
+    const bool kb_attn = !m->exact && !tc_attn && !ws_attn && st.heads % 2 == 0 && attention_kb_supported(ws * ws, 32);   // 24 x 24, 12 x 12
     for (size_t j = 0; j < st.blocks.size(); ++j) {
       const SwinBlockW& b = st.blocks[j];
       const int shift = (res > sp.window && (j & 1)) ? sp.window / 2 : 0;     // swinv2.py:223-226, 411
@@ -316,7 +321,9 @@ static int swin_forward_chunk(vscb200_swin* m, const float* frames, int n, float
       if (j == 0) R(window_gather_bf16(m->x, m->h, n, res, ws, shift, C, s, h_lo));
       R(gemm_bf16(m->h, b.qkv_w, b.qkv_bias, m->qkv, M, 3 * C, C, C, C, 3 * C, VSCB200_EPI_BF16, -1, s, nullptr, 0, false,
                   2 * C, b.qscale, lo(m->h, h_lo), wlo(b.qkv_w, 3 * C, C), lo(m->qkv, qkv_lo)));
-      if (tc_attn) {
+      if (ws_attn) {
+        R(attention_ws_swin(m->qkv, m->ao, static_cast<int64_t>(n) * nW, ws, st.heads, b.table, shift, nWx, nW, s));
+      } else if (tc_attn) {
         R(swin_attention(m->qkv, m->ao, b.table, static_cast<int64_t>(n) * nW, nW, nWx, ws, shift, st.heads, s));
       } else if (kb_attn) {
         R(attention_kb(m->qkv, m->ao, static_cast<int64_t>(n) * nW, ws * ws, st.heads, 32, 1.0f, b.table, ws, shift, nWx, nW, s));
