@@ -11,9 +11,10 @@ from vsc22_submission_b200.encoder import B200ViTEncoder, VIT_B16_224_GEM, rando
 
 what = sys.argv[1] if len(sys.argv) > 1 else "encoder"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 256      # plan chunk (bench.py uses 512)
 if what == "encoder":
-    enc = B200ViTEncoder(VIT_B16_224_GEM, random_weights(VIT_B16_224_GEM), max_frames=256).cuda().eval()
-    x = torch.randn(256, 3, 224, 224, device="cuda").clamp_(-1, 1)
+    enc = B200ViTEncoder(VIT_B16_224_GEM, random_weights(VIT_B16_224_GEM), max_frames=chunk).cuda().eval()
+    x = torch.randn(chunk, 3, 224, 224, device="cuda").clamp_(-1, 1)
     for _ in range(iters):
         enc(x)
 else:

@@ -327,10 +327,10 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
     const int kg = static_cast<int>(std::min<int64_t>(k + kStreamSlack, G));
     if ((rc = grow(&ix->gmax, &ix->gmax_bytes, static_cast<size_t>(G) * Npad * sizeof(float), s))) return rc;
     if ((rc = grow(&ix->qnorm, &ix->qnorm_bytes, static_cast<size_t>(nq) * sizeof(float), s))) return rc;
-    if ((rc = row_sqnorm(q, nq, ix->d, ix->qnorm, s))) return rc;
     const size_t plane = static_cast<size_t>(nq) * ix->dp;
     if ((rc = grow(&ix->q_planes, &ix->q_planes_bytes, 2 * plane * sizeof(uint16_t), s))) return rc;
-    if ((rc = split_planes(q, ix->q_planes, ix->q_planes + plane, nq, ix->d, ix->dp, s))) return rc;
+    // norms and both operand planes of the few query rows in ONE launch (the call is launch-latency sensitive)
+    if ((rc = q_hi_norm(q, ix->q_planes, ix->qnorm, nullptr, nq, ix->d, ix->dp, s, ix->q_planes + plane))) return rc;
     if ((rc = sim_stream_groupmax(ix->q_planes, ix->q_planes + plane, ix->bank_hi, ix->bank_lo, nq, ix->ntotal, ix->dp,
                                   !keep_max, ix->qnorm, ix->rnorm, ix->gmax, Npad, s))) return rc;
     const int chunks = group_topk_chunks(G);

@@ -53,7 +53,7 @@ int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream
 // sim_tc1.cu: single-pass (one bf16 MMA per product) top-k selection with an error margin + exact rescoring
 int sim1_pairs(int64_t nq, int64_t nr);
 int sim1_list_cap();
-int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream);
+int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo = nullptr);
 int bank_norm_max(const float* x, int64_t n, int d, unsigned int* max_bits, cudaStream_t stream);
 int sim1_max_k();
 int sim1_scratch_ints(int64_t nq);

@@ -403,10 +403,10 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ query prologue: hi plane + norms in one pass
-// sq[row] = |q|^2 ; sq_lo[row] = |q - bf16(q)|^2
+// sq[row] = |q|^2 ; sq_lo[row] = |q - bf16(q)|^2 (optional) ; lo plane = bf16(q - hi) (optional: the split-bf16 kernels)
 __global__ void __launch_bounds__(256)
-q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, float* __restrict__ sq, float* __restrict__ sq_lo,
-                 int64_t n, int d, int dp) {
+q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ sq,
+                 float* __restrict__ sq_lo, int64_t n, int d, int dp) {
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -418,19 +418,24 @@ q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, fl
     s = fmaf(v, v, s);
     sl = fmaf(e, e, sl);
     hi[row * dp + c] = h;
+    if (lo) lo[row * dp + c] = __float2bfloat16_rn(e);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     sl += __shfl_xor_sync(0xffffffffu, sl, o);
   }
-  if (lane == 0) { sq[row] = s; sq_lo[row] = sl; }
+  if (lane == 0) {
+    sq[row] = s;
+    if (sq_lo) sq_lo[row] = sl;
+  }
 }
 
-int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream) {
+// one pass over the query rows: hi plane (+ lo plane), squared norms (+ squared norms of the bf16 residual)
+int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo) {
   if (n == 0) return VSCB200_OK;
-  q_hi_norm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(hi), sq, sq_lo,
-                                                                                   n, d, dp);
+  q_hi_norm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), sq, sq_lo, n, d, dp);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
