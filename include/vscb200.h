@@ -139,6 +139,11 @@ int vscb200_topk_pack(const float* D_dev, const int64_t* I_dev, int64_t nq, int 
                       void* stream);
 int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin, int kout, int keep_max, float* D_dev,
                        int64_t* I_dev, void* stream);
+/* score_normalizev2 of the matching track (VSC22-Matching-Track-1st/vsc/baseline/score_normalization.py:141-153):
+ * out[row] = l2_normalize(x[row] - beta * mean_k z[ids[row, k]]), ids = the nk nearest noise rows of normalize(x[row])
+ * (from vscb200_index_search over the normalised noise bank); z is the UN-normalised noise bank. */
+int vscb200_sn2_adapt(const float* x_dev, const float* z_dev, const int64_t* ids_dev, int64_t n, int d, int nk, float beta,
+                      int l2_normalize, float* out_dev, void* stream);
 /* bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96) */
 int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream);
 

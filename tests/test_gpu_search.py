@@ -416,3 +416,33 @@ def test_single_pass_search_ragged_shapes(faiss):
         ok, frac = tie_aware_equal(I, D, Io, Do)
         assert ok and frac > 0.999, (nb, nq, d, k, frac)
         assert np.abs(D - Do).max() <= 1e-3 * np.abs(Do).max()
+
+
+def test_score_normalize_v2_matches_oracle(faiss):
+    """Matching-track score_normalizev2 (M/vsc/baseline/score_normalization.py:115-156) on the device: noise search through
+    the single-pass top-k path (nk = 10), gather-mean-subtract-normalise kernel; against the numpy oracle (pinned to the
+    reference function in tests/test_oracle_reference_pins.py), array form and the list-of-videos mirror."""
+    import dataclasses
+    import torch
+    from oracle import score_norm_np
+    from vsc22_submission_b200 import search
+    rng = np.random.default_rng(41)
+    q = rng.standard_normal((300, 64)).astype(np.float32)
+    r = rng.standard_normal((500, 64)).astype(np.float32)
+    z = rng.standard_normal((3000, 64)).astype(np.float32)
+    oq, orr = score_norm_np.score_normalize_v2(q, r, z, beta=0.35, nk=10)
+    dq, dr = search.score_normalize_v2_tensors(torch.from_numpy(q).cuda(), torch.from_numpy(r).cuda(), torch.from_numpy(z).cuda(),
+                                               beta=0.35, nk=10)
+    assert np.abs(dq.cpu().numpy() - oq).max() <= 2e-6 and np.abs(dr.cpu().numpy() - orr).max() <= 2e-6
+
+    @dataclasses.dataclass
+    class VF:
+        video_id: str
+        feature: np.ndarray
+
+    vids = lambda pre, x, per: [VF(f"{pre}{i}", x[i:i + per].copy()) for i in range(0, x.shape[0], per)]
+    sq, sr = search.score_normalizev2(vids("Q", q, 50), vids("R", r, 100), vids("N", z, 500), beta=0.35, nk=10)
+    assert np.abs(np.concatenate([v.feature for v in sq]) - oq).max() <= 2e-6
+    assert [v.video_id for v in sr] == [f"R{i}" for i in range(0, 500, 100)]
+    with pytest.raises(Exception, match="against VSC rules"):
+        search.score_normalizev2(vids("Q", q, 50), vids("R", r, 100), vids("R", z, 500))

@@ -59,3 +59,28 @@ def test_score_normalize_restated_equals_reference_function():
         np.testing.assert_allclose(orr, cat(sr), atol=2e-7)
     finally:
         refload.unload_vsc()
+
+
+def test_score_normalize_v2_restated_equals_reference_function():
+    """The matching track's score_normalizev2 (M/vsc/baseline/score_normalization.py:115-156), run unmodified over the
+    oracle's faiss stand-in, against oracle/score_norm_np.score_normalize_v2."""
+    refload.vsc_package("M")
+    try:
+        from vsc.baseline.score_normalization import score_normalizev2
+        from vsc.index import VideoFeature
+        from oracle import score_norm_np
+        rng = np.random.default_rng(4)
+
+        def vids(prefix, lens):
+            return [VideoFeature(video_id=f"{prefix}{i}", timestamps=np.arange(n, dtype=np.float32),
+                                 feature=rng.standard_normal((n, 32)).astype(np.float32)) for i, n in enumerate(lens)]
+
+        q, r, z = vids("Q", [3, 5, 1]), vids("R", [4, 4, 6]), vids("N", [17, 19])
+        cat = lambda vs: np.concatenate([v.feature for v in vs])
+        q0, r0, z0 = cat(q).copy(), cat(r).copy(), cat(z).copy()      # the reference adapts query.feature in place
+        sq, sr = score_normalizev2(q, r, z, beta=0.35, nk=10)
+        oq, orr = score_norm_np.score_normalize_v2(q0, r0, z0, beta=0.35, nk=10)
+        np.testing.assert_allclose(oq, cat(sq), atol=3e-7)
+        np.testing.assert_allclose(orr, cat(sr), atol=3e-7)
+    finally:
+        refload.unload_vsc()

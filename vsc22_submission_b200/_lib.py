@@ -76,6 +76,7 @@ SIGNATURES = {
     "vscb200_low_var_dim_dev": (_i, [_p, _i64, _i, _p, _p]),
     "vscb200_low_var_dim": (_i, [_p, _i64, _i, C.POINTER(_i), _p]),
     "vscb200_sn_bias": (_i, [_p, _i64, _i, _i, _f, _p, _p]),
+    "vscb200_sn2_adapt": (_i, [_p, _p, _p, _i64, _i, _i, _f, _i, _p, _p]),
     "vscb200_col_sums": (_i, [_p, _i64, _i, _p, C.c_double, _p, _p]),
     "vscb200_var_argmin_dev": (_i, [_p, _i, _p, _p]),
     "vscb200_topk_pack": (_i, [_p, _p, _i64, _i, _i, _p, _p]),

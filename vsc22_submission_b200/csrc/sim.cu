@@ -290,6 +290,48 @@ int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stre
   return VSCB200_OK;
 }
 
+namespace vscb200 {
+// score_normalizev2 (M/vsc/baseline/score_normalization.py:141-153): out[row] = l2_normalize(x[row] - beta * mean_k z[ids[row, k]]).
+// One warp per row; the mean accumulates the nk rows in order in fp32 (numpy's reduction over the middle axis), the norm is
+// sklearn's normalize: x / max(||x||, eps -> the row is left as is when its norm is 0).
+__global__ void __launch_bounds__(256)
+sn2_adapt_kernel(const float* __restrict__ x, const float* __restrict__ z, const int64_t* __restrict__ ids, int64_t n, int d,
+                 int nk, float beta, int l2_normalize, float* __restrict__ out) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float acc = 0.f;
+    for (int k = 0; k < nk; ++k) {
+      const int64_t id = ids[row * nk + k];
+      acc += id >= 0 ? z[id * d + c] : 0.f;
+    }
+    const float v = x[row * d + c] - (acc / static_cast<float>(nk)) * beta;
+    out[row * d + c] = v;
+    ss = fmaf(v, v, ss);
+  }
+  if (!l2_normalize) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float nrm = sqrtf(ss);
+  if (nrm > 0.f)
+    for (int c = lane; c < d; c += 32) out[row * d + c] = out[row * d + c] / nrm;
+}
+}  // namespace vscb200
+
+int vscb200_sn2_adapt(const float* x_dev, const float* z_dev, const int64_t* ids_dev, int64_t n, int d, int nk, float beta,
+                      int l2_normalize, float* out_dev, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(d > 0 && nk >= 1 && (n == 0 || (x_dev && z_dev && ids_dev && out_dev)), "sn2_adapt: bad argument");
+  if (n == 0) return VSCB200_OK;
+  sn2_adapt_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, z_dev, ids_dev, n, d, nk, beta, l2_normalize, out_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
 int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream) {
   using namespace vscb200;
   VSCB_REQUIRE(nk >= 1 && nk <= k, "sn_bias: need 1 <= nk <= k");

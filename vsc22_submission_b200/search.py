@@ -275,6 +275,25 @@ def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch
     return q_t, r_t, lvd
 
 
+def score_normalize_v2_tensors(q: torch.Tensor, r: torch.Tensor, z: torch.Tensor, l2_normalize: bool = True,
+                               beta: float = 0.35, nk: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Array form of the matching track's ``score_normalizev2`` (M/vsc/baseline/score_normalization.py:115-156): every
+    query / reference row loses beta x the mean of its nk nearest (cosine) noise rows, then is L2-normalised."""
+    q, r, z = (_f32_cuda(t, n) for t, n in ((q, "queries"), (r, "refs"), (z, "noise")))
+    d = z.shape[1]
+    unit = (lambda t: sn_transform(t, -1, True)[:, :d].contiguous()) if l2_normalize else (lambda t: t)
+    ix = DeviceIndex(d, METRIC_INNER_PRODUCT, z.device)
+    ix.add(unit(z))
+    outs = []
+    for x in (q, r):
+        _, ids = ix.search(unit(x), nk)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().vscb200_sn2_adapt(_p(x), _p(z), _p(ids), x.shape[0], d, nk, float(beta), 1 if l2_normalize else 0,
+                                                _p(out), _stream(x.device)), "sn2_adapt")
+        outs.append(out)
+    return outs[0], outs[1]
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's function signatures (lists of VideoFeature-like objects, numpy features)
 # ------------------------------------------------------------------------------------------------
@@ -413,3 +432,14 @@ def ref_score_normalize(refs, score_norm_refs, l2_normalize: bool = True, replac
         lvd = low_var_dim(_cat(score_norm_refs, dev, "z"))
     r_t = sn_transform(_cat(refs, dev, "r"), lvd, l2_normalize, fill=1.0)
     return _split(refs, _to_host(r_t, "ro"))
+
+
+def score_normalizev2(queries, refs, score_norm_refs, l2_normalize: bool = True, replace_dim: bool = True,
+                      beta: float = 0.35, nk: int = 10, device="cuda"):
+    """VSC22-Matching-Track-1st/vsc/baseline/score_normalization.py:115-156 (same signature; ``replace_dim`` is accepted
+    and unused there too)."""
+    _check_disjoint(refs, score_norm_refs)
+    dev = torch.device(device)
+    q_t, r_t = score_normalize_v2_tensors(_cat(queries, dev, "q"), _cat(refs, dev, "r"), _cat(score_norm_refs, dev, "z"),
+                                          l2_normalize, beta, nk)
+    return _split(queries, _to_host(q_t, "qo")), _split(refs, _to_host(r_t, "ro"))
