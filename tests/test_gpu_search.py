@@ -237,8 +237,10 @@ def test_ensemble_pca_tail_matches_oracle():
     ref = pca_np.ensemble_pca(parts, mean, comp)
     pca = B200PCA(mean, comp)
     got = pca.transform_parts([torch.from_numpy(p).cuda() for p in parts]).cpu().numpy()
-    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())       # 1000 frames: split-bf16 tcgen05 projection
     assert np.abs(pca.transform_parts_host(parts) - got).max() == 0.0
+    few = pca.transform_parts([torch.from_numpy(p[:100]).cuda() for p in parts]).cpu().numpy()     # < 256 frames: fp32 FFMA kernel
+    assert np.abs(few - ref[:100]).max() <= 1e-5 * max(1.0, np.abs(ref).max())
     assert pca.transform_parts([torch.zeros((0, d), device="cuda") for d in dims]).shape == (0, 512)
 
 

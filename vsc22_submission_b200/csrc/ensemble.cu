@@ -2,8 +2,11 @@
 //   per-model sklearn `normalize` (row L2) -> concatenate -> PCA.transform = (X - mean_) @ components_.T
 // Reference: D/infer/concat_pca_sn.py:56-64 (reference bank), D/infer/extract_query_feats.py:169-204 and
 // M/infer/infer_matching.py:140-145 (queries) -- numpy/sklearn on the host, one call per video.  Here: one
-// gather kernel (normalise + concatenate + centre, warp per frame) and the exact-fp32 FFMA tile kernel of sim.cu
-// for the [n, D] x [out, D]^T projection; every descriptor of a batch in one call, nothing leaves the device.
+// gather kernel (normalise + concatenate + centre, warp per frame) writing split-bf16 operand planes and the fp32-equivalent
+// tcgen05 GEMM of gemm.cu for the [n, D] x [out, D]^T projection (batches under 256 frames: the exact-fp32 FFMA tile kernel
+// of sim.cu); every descriptor of a batch in one call, nothing leaves the device.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -36,6 +39,32 @@ ensemble_center_kernel(EnsParts parts, const float* __restrict__ mean, float* __
     float* dst = xc + row * D + parts.off[p];
     const float* mu = mean + parts.off[p];
     for (int c = lane; c < parts.dim[p]; c += 32) dst[c] = src[c] * inv - mu[c];
+  }
+}
+
+// the same, written as split-bf16 operand planes (hi = bf16(v), lo = bf16(v - hi)) for the tensor-core projection
+__global__ void __launch_bounds__(256)
+ensemble_center_planes_kernel(EnsParts parts, const float* __restrict__ mean, __nv_bfloat16* __restrict__ hi,
+                              __nv_bfloat16* __restrict__ lo, int64_t n, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= n) return;
+  for (int p = 0; p < parts.n_parts; ++p) {
+    const float* src = parts.ptr[p] + row * parts.dim[p];
+    float ss = 0.f;
+    for (int c = lane; c < parts.dim[p]; c += 32) { const float v = src[c]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(ss);
+    const float inv = nrm > 0.f ? 1.0f / nrm : 1.0f;
+    const int64_t base = row * D + parts.off[p];
+    const float* mu = mean + parts.off[p];
+    for (int c = lane; c < parts.dim[p]; c += 32) {
+      const float v = src[c] * inv - mu[c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[base + c] = h;
+      lo[base + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
   }
 }
 
@@ -146,6 +175,30 @@ extern "C" int vscb200_ensemble_pca(const float* const* parts_dev, const int* di
     parts.dim[p] = dims[p];
     parts.off[p] = D;
     D += dims[p];
+  }
+  // Batches of frames: the [n, D] x [out, D]^T projection on the tensor cores in the split-bf16 form (hi.hi + lo.hi + hi.lo,
+  // fp32 accumulation: fp32-equivalent to ~1e-6 relative, gemm.cu) -- 2 n D out FLOP leave the FFMA pipe.
+  static const int pca_simt = [] { const char* e = getenv("VSCB200_PCA_SIMT"); return e ? atoi(e) : 0; }();
+  if (!pca_simt && n >= 256 && D % 8 == 0 && out_dim % 8 == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 15) == 0) {
+    const size_t xe = static_cast<size_t>(n) * D, we = static_cast<size_t>(out_dim) * D;
+    uint16_t* planes = nullptr;
+    int rc = pool_alloc(reinterpret_cast<void**>(&planes), (2 * xe + 2 * we) * sizeof(uint16_t), s);
+    if (rc) return rc;
+    uint16_t *xh = planes, *xl = planes + xe, *wh = planes + 2 * xe, *wl = wh + we;
+    {
+      ProfScope prof(kProfVitOther, s, static_cast<double>(n) * D * 8);
+      ensemble_center_planes_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(
+          parts, mean_dev, reinterpret_cast<__nv_bfloat16*>(xh), reinterpret_cast<__nv_bfloat16*>(xl), n, D);
+      count_launch();
+    }
+    rc = split_planes(components_dev, wh, wl, out_dim, D, D, s);
+    if (rc == VSCB200_OK)
+      rc = gemm_bf16(xh, wh, nullptr, out_dev, n, out_dim, D, D, D, out_dim, VSCB200_EPI_F32, -1, s, nullptr, 0, false, 0, nullptr,
+                     xl, wl, nullptr);
+    pool_free(planes, s);
+    if (rc) return rc;
+    VSCB_CUDA_OK(cudaGetLastError());
+    return VSCB200_OK;
   }
   float* xc = nullptr;
   int rc = pool_alloc(reinterpret_cast<void**>(&xc), static_cast<size_t>(n) * D * sizeof(float), s);

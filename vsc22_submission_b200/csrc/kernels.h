@@ -50,6 +50,8 @@ namespace vscb200 {
 int scores_simt(const float* Q, const float* R, float* S, int64_t nq, int64_t nr, int d, int64_t ldS, bool l2,
                 const float* qn, const float* rn, cudaStream_t stream);
 int row_sqnorm(const float* x, int64_t n, int d, float* out, cudaStream_t stream);
+// x [n, d] fp32 -> hi, lo [n, dp] bf16 planes (sim_tc.cu)
+int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, cudaStream_t stream);
 // sim_tc1.cu: single-pass (one bf16 MMA per product) top-k selection with an error margin + exact rescoring
 int sim1_pairs(int64_t nq, int64_t nr);
 int sim1_list_cap();
