@@ -371,29 +371,43 @@ def make_sim_data(device, world=1, rank=0):
 
 
 def sim_step_device(Q, R_shard, Z_shard, world, rank, row0_r):
-    """score_normalize(beta=1.2, nk=1) + top-10 with Q, R, Z resident in HBM.  With world > 1 the noise
-    bank and the reference bank are sharded by rows; partial top-k are all-gathered and merged."""
+    """score_normalize(beta=1.2, nk=1) + top-10 with Q, R, Z resident in HBM.  With world > 1 the noise bank and the
+    reference bank are sharded by rows and the step has TWO collectives: one all-reduce of the noise bank's column
+    moments and ONE all-gather in which the partial top-nk of the noise search and the partial top-k of the reference
+    search travel together.  That is possible because the score-normalisation bias of a query is a constant added to all
+    of its scores (score_normalization.py:96-101: last feature column = bias on the query side, 1 on the reference
+    side): it does not change the ranking of the query's references, so the reference search runs on the un-biased
+    query features and the merge kernel adds the bias afterwards."""
     import torch
 
-    from vsc22_submission_b200 import search
-    lvd = search.low_var_dim_device(Z_shard) if world == 1 else _global_low_var_dim(Z_shard, world)
-    z_t = search.sn_transform(Z_shard, lvd, True, fill=0.0)
+    from vsc22_submission_b200 import search, sharding
+    if world == 1:
+        lvd = search.low_var_dim_device(Z_shard)
+        z_t = search.sn_transform(Z_shard, lvd, True, fill=0.0)
+        q_0 = search.sn_transform(Q, lvd, True, fill=0.0)
+        zi = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
+        zi.add(z_t)
+        Dz, _ = zi.search(q_0, 1)
+        bias = search.bias_from_topk(Dz, 1.2, 1)
+        q_t = search.sn_transform(Q, lvd, True, bias=bias)
+        r_t = search.sn_transform(R_shard, lvd, True, fill=1.0)
+        ri = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
+        ri.add(r_t)
+        return ri.search(q_t, SIM_K)
+    lvd = _global_low_var_dim(Z_shard, world)
     q_0 = search.sn_transform(Q, lvd, True, fill=0.0)
     zi = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
-    zi.add(z_t)
-    Dz, _ = zi.search(q_0, 1)
-    if world > 1:
-        Dz = _merge_topk(Dz, torch.zeros_like(Dz, dtype=torch.int64), 1)[0]
-    bias = search.bias_from_topk(Dz, 1.2, 1)
-    q_t = search.sn_transform(Q, lvd, True, bias=bias)
-    r_t = search.sn_transform(R_shard, lvd, True, fill=1.0)
+    zi.set_id_offset(rank * Z_shard.shape[0])          # global ids: the merged keys of a row stay distinct
+    zi.add(search.sn_transform(Z_shard, lvd, True, fill=0.0))
+    Dz, Iz = zi.search(q_0, 1)
     ri = search.DeviceIndex(SIM_D, search.METRIC_INNER_PRODUCT)
     ri.set_id_offset(row0_r)
-    ri.add(r_t)
-    D, I = ri.search(q_t, SIM_K)
-    if world > 1:
-        D, I = _merge_topk(D, I, SIM_K)
-    return D, I
+    ri.add(search.sn_transform(R_shard, lvd, True, fill=1.0))
+    D0, I0 = ri.search(q_0, SIM_K)                      # last query column 0: q.r without the bias
+    keys = sharding.gather_partial_topk_multi([(Dz, Iz), (D0, I0)])
+    Dz_g, _ = search.merge_packed_topk_cols(keys, 0, 1, 1)
+    bias = search.bias_from_topk(Dz_g, 1.2, 1)
+    return search.merge_packed_topk_cols(keys, 1, SIM_K, SIM_K, bias=bias)
 
 
 def _merge_topk(D, I, k):
@@ -1000,7 +1014,8 @@ def main():
                         e2e=sim["e2e"], gpu_launches=sim["gpu_launches"], roofline=sim["roofline"], dtype="f32",
                         config=sim["config"], stream=sim.get("stream"), dense=sim.get("dense"),
                         candidates=sim.get("candidates"), localization=sim.get("localization"),
-                        host_issue_ms_per_step=sim.get("host_issue_ms_per_step"))
+                        host_issue_ms_per_step=sim.get("host_issue_ms_per_step"), parity=sim.get("parity"),
+                        step_ms=sim.get("step_ms"))
         else:
             line["sim"] = sim
     if rank == 0 and world == 1 and args.workload == "both":

@@ -131,6 +131,12 @@ int vscb200_low_var_dim(const float* x_dev, int64_t n, int d, int* dim_host, voi
 int vscb200_col_sums(const float* x_dev, int64_t n, int d, const double* sum_in_dev, double inv_n, double* out_dev,
                      void* stream);
 int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stream);
+/* The same with ONE collective for a row-sharded bank: vscb200_col_moments_local writes out3_dev[0..3d) = per column
+ * (sum x | sum (x - local mean)^2 | (sum x)^2 / n) of the local shard; the caller all-reduces (sums) the 3d doubles over
+ * the shards; vscb200_var_argmin_moments combines them exactly (M2 = sum M2_r + sum S_r^2 / n_r - (sum S_r)^2 / N) and
+ * writes the first column of minimum variance. */
+int vscb200_col_moments_local(const float* x_dev, int64_t n, int d, double* out3_dev, void* stream);
+int vscb200_var_argmin_moments(const double* m3_dev, double n_total, int d, int* dim_dev, void* stream);
 /* Exchange format of partial top-k results between bank shards: one 64-bit key per entry,
  * (order-preserving score bits << 32) | ~id (0 = padding; ids < 2^32), so ONE all-gather moves scores and ids.
  * vscb200_topk_merge: keys_dev [parts][nq][kin] (the all-gather layout) -> the kout best per query, best first, ties to
@@ -144,6 +150,11 @@ int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin,
  * (from vscb200_index_search over the normalised noise bank); z is the UN-normalised noise bank. */
 int vscb200_sn2_adapt(const float* x_dev, const float* z_dev, const int64_t* ids_dev, int64_t n, int d, int nk, float beta,
                       int l2_normalize, float* out_dev, void* stream);
+/* The same over columns [col0, col0 + kin) of rows of ld keys (several partial results travelling in one all-gather), with
+ * an optional per-row bias added to the merged scores (the score-normalisation bias of the query, which does not change
+ * the ranking of a query's references and can therefore be applied after the exchange). */
+int vscb200_topk_merge_cols(const uint64_t* keys_dev, int parts, int64_t nq, int ld, int col0, int kin, int kout, int keep_max,
+                            const float* bias_dev, float* D_dev, int64_t* I_dev, void* stream);
 /* bias[row] = -beta * mean(D[row, :nk])  (score_normalization.py:96) */
 int vscb200_sn_bias(const float* D_dev, int64_t nq, int k, int nk, float beta, float* bias_dev, void* stream);
 

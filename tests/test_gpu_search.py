@@ -448,3 +448,37 @@ def test_score_normalize_v2_matches_oracle(faiss):
     assert [v.video_id for v in sr] == [f"R{i}" for i in range(0, 500, 100)]
     with pytest.raises(Exception, match="against VSC rules"):
         search.score_normalizev2(vids("Q", q, 50), vids("R", r, 100), vids("R", z, 500))
+
+
+def test_sharded_step_primitives_single_process(faiss):
+    """The two collectives of the sharded config-3 step, emulated in one process: (1) per-shard column moments summed over
+    the shards -> the same low-variance column as numpy on the whole bank, also for near-tied columns; (2) two partial
+    top-k results side by side in one key tensor, merged per column range, with the per-row bias added after the merge."""
+    import torch
+    from vsc22_submission_b200 import search
+    rng = np.random.default_rng(51)
+    z = rng.standard_normal((5000, 96)).astype(np.float32)
+    z[:, 17] *= 0.5
+    z[:, 63] = z[:, 17] * (1 + 1e-4) + 3.0                      # nearly tied variances, very different means
+    shards = [z[:1800], z[1800:1801], z[1801:]]
+    m3 = sum(search.col_moments_local(torch.from_numpy(s_).cuda()) for s_ in shards)
+    got = int(search.var_argmin_moments(m3, z.shape[0]).item())
+    assert got == int(z.astype(np.float64).var(axis=0).argmin()) == 17
+    # merge with column ranges and bias
+    nq, k = 700, 10
+    parts = 3
+    Dn = rng.standard_normal((parts, nq, 1)).astype(np.float32)
+    Dr = rng.standard_normal((parts, nq, k)).astype(np.float32)
+    Dr.sort(axis=2); Dr = Dr[:, :, ::-1].copy()
+    Ir = np.stack([rng.permutation(1000)[:k][None].repeat(nq, 0) + 1000 * p_ for p_ in range(parts)]).astype(np.int64)
+    keys = torch.stack([torch.cat([search.pack_topk(torch.from_numpy(Dn[p_]).cuda(), torch.full((nq, 1), 7 + p_, dtype=torch.int64, device="cuda")),
+                                   search.pack_topk(torch.from_numpy(Dr[p_]).cuda(), torch.from_numpy(Ir[p_]).cuda())], dim=1)
+                        for p_ in range(parts)]).contiguous()
+    Dz, _ = search.merge_packed_topk_cols(keys, 0, 1, 1)
+    np.testing.assert_array_equal(Dz.cpu().numpy()[:, 0], Dn.max(axis=0)[:, 0])
+    bias = torch.from_numpy(rng.standard_normal(nq).astype(np.float32)).cuda()
+    D, I = search.merge_packed_topk_cols(keys, 1, k, k, bias=bias)
+    allD = np.concatenate(list(Dr), axis=1); allI = np.concatenate(list(Ir), axis=1)
+    order = np.argsort(-allD, axis=1, kind="stable")[:, :k]
+    np.testing.assert_array_equal(I.cpu().numpy(), np.take_along_axis(allI, order, 1))
+    np.testing.assert_array_equal(D.cpu().numpy(), np.take_along_axis(allD, order, 1) + bias.cpu().numpy()[:, None])

@@ -41,9 +41,9 @@ __device__ __forceinline__ unsigned long long mg_warp_max(unsigned long long v) 
   return (static_cast<unsigned long long>(mh) << 32) | ml;
 }
 
-__device__ __forceinline__ void mg_emit(unsigned long long key, int keep_max, float* D, int64_t* I) {
+__device__ __forceinline__ void mg_emit(unsigned long long key, int keep_max, float* D, int64_t* I, float bias = 0.f) {
   if (key != 0ull) {
-    *D = mk_okey_inv(static_cast<uint32_t>(key >> 32), keep_max != 0);
+    *D = mk_okey_inv(static_cast<uint32_t>(key >> 32), keep_max != 0) + bias;
     *I = static_cast<int64_t>(~static_cast<uint32_t>(key & 0xFFFFFFFFull));
   } else {
     *D = keep_max ? -FLT_MAX : FLT_MAX;
@@ -51,11 +51,13 @@ __device__ __forceinline__ void mg_emit(unsigned long long key, int keep_max, fl
   }
 }
 
-// keys: [parts][nq][kin] (one block per rank, as the all-gather lays them out).  Small merges (parts * kin <= 1024):
-// one warp per query row, kout rounds of "best key below the previous one" (keys of a row are distinct: one per bank row).
+// keys: [parts][nq][ld] (one block per rank, as the all-gather lays them out); the merged result uses columns [col0,
+// col0 + kin) of every row (several results may travel in one gather); bias (optional): added to every emitted score of
+// the row.  Small merges (parts * kin <= 1024): one warp per query row, kout rounds of "best key below the previous one"
+// (keys of a row are distinct: one per bank row).
 __global__ void __launch_bounds__(256)
-topk_merge_warp_kernel(const unsigned long long* __restrict__ keys, int parts, int64_t nq, int kin, int kout, int keep_max,
-                       float* __restrict__ D, int64_t* __restrict__ I) {
+topk_merge_warp_kernel(const unsigned long long* __restrict__ keys, int parts, int64_t nq, int ld, int col0, int kin, int kout,
+                       int keep_max, float* __restrict__ D, int64_t* __restrict__ I, const float* __restrict__ bias) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= nq) return;
@@ -64,24 +66,24 @@ topk_merge_warp_kernel(const unsigned long long* __restrict__ keys, int parts, i
   for (int r = 0; r < kout; ++r) {
     unsigned long long best = 0ull;
     for (int c = lane; c < total; c += 32) {
-      const unsigned long long key = keys[(static_cast<int64_t>(c / kin) * nq + row) * kin + c % kin];
+      const unsigned long long key = keys[(static_cast<int64_t>(c / kin) * nq + row) * ld + col0 + c % kin];
       if (key < prev && key > best) best = key;
     }
     best = mg_warp_max(best);
-    if (lane == 0) mg_emit(best, keep_max, D + row * kout + r, I + row * kout + r);
+    if (lane == 0) mg_emit(best, keep_max, D + row * kout + r, I + row * kout + r, bias ? bias[row] : 0.f);
     prev = best;           // 0 once the row is exhausted: every later round emits padding
   }
 }
 
 // Large merges: one CTA per query row, bitonic sort (descending) of the padded key list in shared memory.
 __global__ void __launch_bounds__(512)
-topk_merge_sort_kernel(const unsigned long long* __restrict__ keys, int parts, int64_t nq, int kin, int kout, int npad,
-                       int keep_max, float* __restrict__ D, int64_t* __restrict__ I) {
+topk_merge_sort_kernel(const unsigned long long* __restrict__ keys, int parts, int64_t nq, int ld, int col0, int kin, int kout,
+                       int npad, int keep_max, float* __restrict__ D, int64_t* __restrict__ I, const float* __restrict__ bias) {
   extern __shared__ unsigned long long mg_smem[];
   const int64_t row = blockIdx.x;
   const int total = parts * kin;
   for (int c = threadIdx.x; c < npad; c += blockDim.x)
-    mg_smem[c] = c < total ? keys[(static_cast<int64_t>(c / kin) * nq + row) * kin + c % kin] : 0ull;
+    mg_smem[c] = c < total ? keys[(static_cast<int64_t>(c / kin) * nq + row) * ld + col0 + c % kin] : 0ull;
   __syncthreads();
   for (int size = 2; size <= npad; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -94,7 +96,8 @@ topk_merge_sort_kernel(const unsigned long long* __restrict__ keys, int parts, i
       __syncthreads();
     }
   }
-  for (int r = threadIdx.x; r < kout; r += blockDim.x) mg_emit(r < npad ? mg_smem[r] : 0ull, keep_max, D + row * kout + r, I + row * kout + r);
+  for (int r = threadIdx.x; r < kout; r += blockDim.x)
+    mg_emit(r < npad ? mg_smem[r] : 0ull, keep_max, D + row * kout + r, I + row * kout + r, bias ? bias[row] : 0.f);
 }
 
 }  // namespace vscb200
@@ -113,27 +116,35 @@ int vscb200_topk_pack(const float* D_dev, const int64_t* I_dev, int64_t nq, int 
   return VSCB200_OK;
 }
 
-int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin, int kout, int keep_max, float* D_dev,
-                       int64_t* I_dev, void* stream_v) {
+int vscb200_topk_merge_cols(const uint64_t* keys_dev, int parts, int64_t nq, int ld, int col0, int kin, int kout, int keep_max,
+                            const float* bias_dev, float* D_dev, int64_t* I_dev, void* stream_v) {
   using namespace vscb200;
-  VSCB_REQUIRE(parts >= 1 && nq >= 0 && kin >= 1 && kout >= 1 && (nq == 0 || (keys_dev && D_dev && I_dev)), "topk_merge: bad argument");
+  VSCB_REQUIRE(parts >= 1 && nq >= 0 && kin >= 1 && kout >= 1 && col0 >= 0 && col0 + kin <= ld &&
+                   (nq == 0 || (keys_dev && D_dev && I_dev)), "topk_merge: bad argument");
   if (nq == 0) return VSCB200_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(keys_dev);
   const int64_t total = static_cast<int64_t>(parts) * kin;
   if (total <= 1024 && kout <= 32) {
-    topk_merge_warp_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, stream>>>(keys, parts, nq, kin, kout, keep_max, D_dev, I_dev);
+    topk_merge_warp_kernel<<<static_cast<unsigned>((nq + 7) / 8), 256, 0, stream>>>(keys, parts, nq, ld, col0, kin, kout, keep_max,
+                                                                                   D_dev, I_dev, bias_dev);
   } else {
     int npad = 2;
     while (npad < total) npad <<= 1;
     VSCB_REQUIRE(npad <= 16384, "topk_merge: more than 16384 partial results per query");
     const size_t smem = static_cast<size_t>(npad) * sizeof(unsigned long long);
     VSCB_CUDA_OK(cudaFuncSetAttribute(topk_merge_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    topk_merge_sort_kernel<<<static_cast<unsigned>(nq), 512, smem, stream>>>(keys, parts, nq, kin, kout, npad, keep_max, D_dev, I_dev);
+    topk_merge_sort_kernel<<<static_cast<unsigned>(nq), 512, smem, stream>>>(keys, parts, nq, ld, col0, kin, kout, npad, keep_max,
+                                                                            D_dev, I_dev, bias_dev);
   }
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
+}
+
+int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin, int kout, int keep_max, float* D_dev,
+                       int64_t* I_dev, void* stream_v) {
+  return vscb200_topk_merge_cols(keys_dev, parts, nq, kin, 0, kin, kout, keep_max, nullptr, D_dev, I_dev, stream_v);
 }
 
 }  // extern "C"

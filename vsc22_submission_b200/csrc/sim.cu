@@ -291,6 +291,61 @@ int vscb200_var_argmin_dev(const double* ss_dev, int d, int* dim_dev, void* stre
 }
 
 namespace vscb200 {
+// Row-sharded banks, ONE collective: every shard contributes (S = sum x, M2 = sum (x - S / n)^2, Q = S^2 / n) per column;
+// the sums over the shards combine exactly (Chan et al.): M2_total = sum M2 + sum Q - (sum S)^2 / N.
+__global__ void col_moment_pack_kernel(const double* __restrict__ sums, double n, int d, double* __restrict__ out3) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  out3[c] = sums[c];
+  out3[2 * d + c] = n > 0 ? sums[c] * sums[c] / n : 0.0;
+}
+__global__ void var_argmin_moments_kernel(const double* __restrict__ m3, double n_total, int d, int* __restrict__ out) {
+  const int lane = threadIdx.x;
+  int best = -1;
+  double best_var = 0;
+  for (int c = lane; c < d; c += 32) {
+    const double var = m3[d + c] + m3[2 * d + c] - m3[c] * m3[c] / n_total;
+    if (best < 0 || var < best_var) { best = c; best_var = var; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best_var, o);
+    const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+    if (ob >= 0 && (best < 0 || ov < best_var || (ov == best_var && ob < best))) { best = ob; best_var = ov; }
+  }
+  if (lane == 0) *out = best < 0 ? 0 : best;
+}
+}  // namespace vscb200
+
+int vscb200_col_moments_local(const float* x_dev, int64_t n, int d, double* out3_dev, void* stream_v) {
+  using namespace vscb200;
+  VSCB_REQUIRE(n >= 0 && d > 0 && out3_dev && (n == 0 || x_dev), "col_moments_local: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream_v);
+  double* sums = nullptr;
+  int rc = pool_alloc(reinterpret_cast<void**>(&sums), sizeof(double) * d, s);
+  if (rc) return rc;
+  rc = col_sums(x_dev, n, d, nullptr, 0.0, sums, s);
+  if (rc == VSCB200_OK) rc = col_sums(x_dev, n, d, sums, n > 0 ? 1.0 / static_cast<double>(n) : 0.0, out3_dev + d, s);
+  if (rc == VSCB200_OK) {
+    col_moment_pack_kernel<<<(d + 127) / 128, 128, 0, s>>>(sums, static_cast<double>(n), d, out3_dev);
+    count_launch();
+  }
+  pool_free(sums, s);
+  if (rc) return rc;
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+int vscb200_var_argmin_moments(const double* m3_dev, double n_total, int d, int* dim_dev, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(m3_dev && d > 0 && n_total > 0 && dim_dev, "var_argmin_moments: bad argument");
+  var_argmin_moments_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(m3_dev, n_total, d, dim_dev);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+namespace vscb200 {
 // score_normalizev2 (M/vsc/baseline/score_normalization.py:141-153): out[row] = l2_normalize(x[row] - beta * mean_k z[ids[row, k]]).
 // One warp per row; the mean accumulates the nk rows in order in fp32 (numpy's reduction over the middle axis), the norm is
 // sklearn's normalize: x / max(||x||, eps -> the row is left as is when its norm is 0).

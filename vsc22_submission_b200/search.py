@@ -174,6 +174,21 @@ def merge_packed_topk(keys: torch.Tensor, k: int, keep_max: bool = True) -> Tupl
     return D, I
 
 
+def merge_packed_topk_cols(keys: torch.Tensor, col0: int, kin: int, k: int, keep_max: bool = True,
+                           bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``merge_packed_topk`` over columns [col0, col0 + kin) of keys [parts, nq, ld]; ``bias`` f32 [nq] (or [nq, 1]) is
+    added to every merged score of its row."""
+    assert keys.dim() == 3 and keys.dtype == torch.int64 and keys.is_cuda and keys.is_contiguous()
+    parts, nq, ld = keys.shape
+    D = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    if nq:
+        with torch.cuda.device(keys.device):
+            _lib.check(_lib.lib().vscb200_topk_merge_cols(_p(keys), parts, nq, ld, int(col0), int(kin), int(k), int(bool(keep_max)),
+                                                          _p(bias), _p(D), _p(I), _stream(keys.device)), "topk_merge_cols")
+    return D, I
+
+
 def col_sums(x: torch.Tensor, sum_in: Optional[torch.Tensor] = None, inv_n: float = 0.0) -> torch.Tensor:
     """float64 [d]: column sums of x, or (``sum_in`` given) sums of squared deviations from ``sum_in * inv_n``."""
     x = _f32_cuda(x, "col_sums")
@@ -189,6 +204,25 @@ def var_argmin_device(ss: torch.Tensor) -> torch.Tensor:
     out = torch.empty((1,), dtype=torch.int32, device=ss.device)
     with torch.cuda.device(ss.device):
         _lib.check(_lib.lib().vscb200_var_argmin_dev(_p(ss), ss.numel(), _p(out), _stream(ss.device)), "var_argmin_dev")
+    return out
+
+
+def col_moments_local(x: torch.Tensor) -> torch.Tensor:
+    """float64 [3d]: (sum x | sum (x - local mean)^2 | (sum x)^2 / n) per column of a bank shard -- all-reduce it over the
+    shards, then ``var_argmin_moments`` (one collective instead of two)."""
+    x = _f32_cuda(x, "col_moments_local")
+    out = torch.empty((3 * x.shape[1],), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vscb200_col_moments_local(_p(x), x.shape[0], x.shape[1], _p(out), _stream(x.device)), "col_moments_local")
+    return out
+
+
+def var_argmin_moments(m3: torch.Tensor, n_total: int) -> torch.Tensor:
+    """First column of minimum variance from the all-reduced moments, left on the device (int32 [1])."""
+    out = torch.empty((1,), dtype=torch.int32, device=m3.device)
+    with torch.cuda.device(m3.device):
+        _lib.check(_lib.lib().vscb200_var_argmin_moments(_p(m3), float(n_total), m3.numel() // 3, _p(out), _stream(m3.device)),
+                   "var_argmin_moments")
     return out
 
 

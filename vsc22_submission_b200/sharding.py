@@ -84,6 +84,27 @@ def merge_partial_topk(D: torch.Tensor, I: torch.Tensor, k: int, keep_max: bool 
     return _merge_cpu(keys, k, keep_max)
 
 
+def gather_partial_topk_multi(parts, keep_max: bool = True, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Several partial top-k results of the same query rows in ONE all-gather: ``parts`` = [(D, I), ...] with D / I
+    [nq, k_i]; the packed keys are laid side by side ([nq, sum k_i]) and gathered once -> int64 [world, nq, sum k_i].
+    Merge result i with ``search.merge_packed_topk_cols(keys, col0_i, k_i, k)`` (config 3's step: the noise search's
+    top-nk and the reference search's top-k travel together)."""
+    from . import search
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    nq = parts[0][0].shape[0]
+    ld = sum(D.shape[1] for D, _ in parts)
+    keys = torch.empty((nq, ld), dtype=torch.int64, device=parts[0][0].device)
+    c0 = 0
+    for D, I in parts:
+        keys[:, c0:c0 + D.shape[1]] = search.pack_topk(D, I, keep_max)
+        c0 += D.shape[1]
+    if world == 1:
+        return keys.unsqueeze(0)
+    gathered = torch.empty((world, nq, ld), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(gathered, keys, group=group)
+    return gathered
+
+
 def merge_partial_global_topk(scores: torch.Tensor, qrows: torch.Tensor, brows: torch.Tensor, global_k: int,
                               keep_max: bool = True, group: Optional[dist.ProcessGroup] = None
                               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -112,10 +133,10 @@ def merge_partial_global_topk(scores: torch.Tensor, qrows: torch.Tensor, brows: 
 
 
 def global_low_var_dim(z_shard: torch.Tensor, n_total: Optional[int] = None, group: Optional[dist.ProcessGroup] = None):
-    """argmin of the column variance of the row-sharded noise bank (score_normalization.py:72): two passes (column sums,
-    then squared deviations from the global mean) with one all-reduce of a float64 [d] vector after each.  CUDA shards:
-    device kernels with a fixed reduction order, the result stays on the device (int32 [1] tensor, no host sync) -- feed
-    it to ``search.sn_transform``.  ``n_total``: rows over all shards (default: all-reduced too).  CPU tensors (gloo
+    """argmin of the column variance of the row-sharded noise bank (score_normalization.py:72).  CUDA shards: every shard
+    computes (sum, sum of squared deviations from ITS mean, sum^2 / n) per column with fixed-order device kernels; ONE
+    all-reduce of the float64 [3d] vector; the shards' moments combine exactly (M2 = sum M2_r + sum S_r^2 / n_r - S^2 / N);
+    the result stays on the device (int32 [1] tensor, no host sync) -- feed it to ``search.sn_transform``.  ``n_total``: rows over all shards (default: all-reduced too).  CPU tensors (gloo
     tests): the same two passes in torch, returns an int."""
     sharded = dist.is_initialized() and dist.get_world_size(group) > 1
     if n_total is None:
@@ -124,14 +145,12 @@ def global_low_var_dim(z_shard: torch.Tensor, n_total: Optional[int] = None, gro
             dist.all_reduce(n, group=group)
         n_total = int(n.item())
     if z_shard.is_cuda:
+        # one collective: per-shard (sum, centred sum of squares, sum^2 / n) combine exactly over the shards
         from . import search
-        sums = search.col_sums(z_shard)
+        m3 = search.col_moments_local(z_shard)
         if sharded:
-            dist.all_reduce(sums, group=group)
-        ss = search.col_sums(z_shard, sums, 1.0 / n_total)
-        if sharded:
-            dist.all_reduce(ss, group=group)
-        return search.var_argmin_device(ss)
+            dist.all_reduce(m3, group=group)
+        return search.var_argmin_moments(m3, n_total)
     z = z_shard.double()
     sums = z.sum(0)
     if sharded:
