@@ -219,7 +219,7 @@ template <bool kLN, int kVec>
 __global__ void __launch_bounds__(kTailThreads)
 gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ pooled, int T, int C, float eps, float p) {
-  extern __shared__ float tail_smem[];   // [C] pooled sums / g
+  extern __shared__ float tail_smem[];   // [C] pooled sums / g, then (LN form) [nwarp][C] per-warp partial sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = kTailThreads >> 5;
   const int64_t f = blockIdx.x;
   const float* yf = y + f * T * C;
@@ -273,15 +273,18 @@ gem_head_kernel(const float* __restrict__ y, const float* __restrict__ gamma, co
         }
       }
     }
+    // per-warp partial sums, then a FIXED-order sum over the warps: the pooled descriptor is bit-reproducible
+    float* part = tail_smem + C + warp * C;
 #pragma unroll
     for (int i = 0; i < kVec; ++i) {
       const int c = lane + 32 * i;
-      if (c < nvec) {
-        atomicAdd(&tail_smem[4 * c + 0], acc[i].x);
-        atomicAdd(&tail_smem[4 * c + 1], acc[i].y);
-        atomicAdd(&tail_smem[4 * c + 2], acc[i].z);
-        atomicAdd(&tail_smem[4 * c + 3], acc[i].w);
-      }
+      if (c < nvec) *reinterpret_cast<float4*>(part + 4 * c) = acc[i];
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kTailThreads) {
+      float a = 0.f;
+      for (int w2 = 0; w2 < nwarp; ++w2) a += tail_smem[C + w2 * C + c];
+      tail_smem[c] = a;
     }
   } else {
     // thread per column, coalesced across the row
@@ -342,7 +345,12 @@ int gem_head(const float* y, const float* gamma, const float* beta, const float*
              cudaStream_t stream) {
   if (n == 0) return VSCB200_OK;
   VSCB_REQUIRE(!fuse_ln || (C % 4 == 0 && C <= 128 * kLnWideVec), "gem_head: fused LN needs width % 4 == 0 and <= 2048");
-  const size_t smem = static_cast<size_t>(C) * sizeof(float);
+  // pooled sums [C] (+ the per-warp partial sums of the fused-LN form: deterministic pooling, no atomics)
+  const size_t smem = static_cast<size_t>(C) * sizeof(float) * (fuse_ln ? 1 + kTailThreads / 32 : 1);
+  if (fuse_ln) {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(gem_head_kernel<true, kLnMaxVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    VSCB_CUDA_OK(cudaFuncSetAttribute(gem_head_kernel<true, kLnWideVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
   const size_t hl_smem_bytes = static_cast<size_t>(kHlFrames) * C * sizeof(float);
   VSCB_REQUIRE(hl_smem_bytes <= 200 * 1024, "gem_head: width too large for the head kernel");
   VSCB_CUDA_OK(cudaFuncSetAttribute(head_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hl_smem_bytes)));
