@@ -270,6 +270,15 @@ int vscb200_pair_topk(const float* sims_dev, int64_t n_pairs, const int32_t* q_l
 int vscb200_resize_normalize(const uint8_t* frames_dev, int64_t n, int H, int W, int out_h, int out_w, const float* mean3,
                              const float* std3, uint8_t* mid_scratch_dev, float* out_dev, void* stream);
 
+/* Frame decoding (the decode half): the baseline JPEG files of one video's frames -> RGB on the device,
+ * bit-identical to PIL.Image.open(...).convert("RGB") (libjpeg-turbo defaults: islow IDCT, fancy upsampling), which the
+ * reference calls frame by frame at D/infer/src/dataset.py:137-141.  jpeg_ptrs / jpeg_sizes: the n files in host memory
+ * (all of one size and chroma subsampling); rgb_dev: [n, H, W, 3] uint8 (device) -- the input of vscb200_resize_normalize.
+ * rgb_dev == NULL: only parse and return the frame size through h_out / w_out.  8-bit YCbCr 4:2:0 / 4:2:2 / 4:4:4 or
+ * grey, one interleaved scan, restart intervals; progressive / arithmetic / CMYK files return VSCB200_ERR_INVALID. */
+int vscb200_jpeg_decode(const uint8_t* const* jpeg_ptrs, const uint64_t* jpeg_sizes, int64_t n, uint8_t* rgb_dev, int* h_out,
+                        int* w_out, void* stream);
+
 /* Matching-track candidate features: M/infer/src/utils.py:18-47 / :50-73 + the zero-padded
  * similarity images of M/infer/src/dataset.py:103-144.  sims_dev: the blocks written by vscb200_pair_sims (whole query
  * video x reference).  seg_len[p] = query_video_len_map[qid]: when the query holds several seg_len-frame copies, the one

@@ -102,6 +102,7 @@ SIGNATURES = {
     "vscb200_pair_topk": (_i, [_p, _i64, _p, _p, _p, _p, _i, _p, _p, _p]),
     "vscb200_pair_segment_images": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "vscb200_resize_normalize": (_i, [_p, _i64, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
+    "vscb200_jpeg_decode": (_i, [_p, _p, _i64, _p, _p, _p, _p]),
     "vscb200_tn_align": (_i, [_p, _p, _i, _i64, _p, _p, _p, _i, _i, _i, C.c_double, C.c_double, C.c_double, _p, _p, _p]),
     "vscb200_tn_box_scores": (_i, [_p, _p, _p, _i64, _p, _p, _i, _f, _p, _p]),
     "vscb200_gemm_bf16": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i64, _i64, _i64, _i, _i, _p]),

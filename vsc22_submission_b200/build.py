@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvscb200.so")
 SOURCES = ["host_util.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_kb.cu", "attention_ws.cu", "attention_fp32.cu", "vit_kernels.cu", "vit.cu", "swin_attention.cu", "swin_kernels.cu", "swin.cu", "sim.cu", "sim_tc.cu", "sim_tc1.cu", "sim_stream.cu", "select.cu", "merge.cu", "ensemble.cu", "pair_sims.cu",
-           "sort.cu", "global_topk.cu", "tn_align.cu", "resize.cu", "index.cu"]
+           "sort.cu", "global_topk.cu", "tn_align.cu", "resize.cu", "jpeg.cu", "index.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-DVSCB200_NO_FAST_MATH", *os.environ.get("VSCB200_EXTRA_NVCC_FLAGS", "").split(), "-Xptxas", "-v"]

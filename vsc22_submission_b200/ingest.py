@@ -5,7 +5,12 @@ Mirrors the transform factories of VSC22-Descriptor-Track-1st/infer/src/transfor
 reference applies frame by frame on PIL images inside CPU DataLoader workers (infer/src/dataset.py:126-155,
 extract_query_feats.py:96-125).  Here the decoded uint8 frames of a video are uploaded once (1 byte per sample instead of
 the 4-byte float tensor the reference ships) and resized + normalised by csrc/resize.cu with Pillow's exact fixed-point
-arithmetic; the result is the ``[n, 3, h, w]`` float32 CUDA tensor the encoders take.  JPEG decoding stays on the host.
+arithmetic; the result is the ``[n, 3, h, w]`` float32 CUDA tensor the encoders take.
+
+The decode half runs on the device too: ``decode_jpeg_frames`` takes the JPEG files of a video's frames (the ``bytes`` the
+reference reads from the zip, dataset.py:137-139) and returns the RGB frames as a CUDA tensor, bit-identical to
+``PIL.Image.open(io.BytesIO(b)).convert("RGB")`` (csrc/jpeg.cu); ``FramePreprocessor`` accepts those ``bytes`` directly and
+``video_zip_frames`` mirrors ``D_vsc.__getitem__`` (dataset.py:126-148) without a PIL image in between.
 """
 from __future__ import annotations
 
@@ -18,6 +23,36 @@ import torch
 from . import _lib
 
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def decode_jpeg_frames(files: Sequence[bytes], device="cuda") -> torch.Tensor:
+    """The JPEG files of equally sized frames -> uint8 CUDA tensor ``[n, H, W, 3]`` (RGB), bit-identical to Pillow's decode.
+    Baseline YCbCr (4:2:0 / 4:2:2 / 4:4:4) or grey files, as ffmpeg writes them; anything else raises (no CPU fallback)."""
+    device = torch.device(device)
+    n = len(files)
+    if n == 0:
+        return torch.empty((0, 0, 0, 3), dtype=torch.uint8, device=device)
+    bufs = [bytes(f) if not isinstance(f, (bytes, bytearray)) else f for f in files]
+    keep = [(C.c_char * len(b)).from_buffer_copy(b) for b in bufs]
+    ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+    sizes = (C.c_uint64 * n)(*[len(b) for b in bufs])
+    h, w = C.c_int(0), C.c_int(0)
+    lib = _lib.lib()
+    with torch.cuda.device(device):
+        stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.vscb200_jpeg_decode(ptrs, sizes, n, None, C.byref(h), C.byref(w), stream), "jpeg_decode (headers)")
+        out = torch.empty((n, h.value, w.value, 3), dtype=torch.uint8, device=device)
+        _lib.check(lib.vscb200_jpeg_decode(ptrs, sizes, n, C.c_void_p(out.data_ptr()), C.byref(h), C.byref(w), stream), "jpeg_decode")
+    return out
+
+
+def video_zip_frames(zip_path: str, preprocess: "FramePreprocessor") -> torch.Tensor:
+    """``D_vsc.__getitem__`` (VSC22-Descriptor-Track-1st/infer/src/dataset.py:126-148) on the device: the frames of one video
+    -- the JPEG members of its zip in sorted name order -- decoded, resized and normalised -> ``[n, 3, h, w]`` float32."""
+    from zipfile import ZipFile
+    with ZipFile(zip_path, "r") as z:
+        files = [z.read(name) for name in sorted(z.namelist())]
+    return preprocess(files)
 
 
 class FramePreprocessor:
@@ -34,6 +69,8 @@ class FramePreprocessor:
     def _frames(self, frames) -> torch.Tensor:
         if isinstance(frames, torch.Tensor):
             t = frames
+        elif isinstance(frames, (list, tuple)) and len(frames) and isinstance(frames[0], (bytes, bytearray)):
+            return decode_jpeg_frames(frames, self.device)          # JPEG files: decoded on the device
         else:
             if not isinstance(frames, np.ndarray):
                 frames = np.stack([np.asarray(f) for f in frames])
