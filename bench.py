@@ -322,6 +322,67 @@ def bench_ingest(n=512, h=360, w=640, out=224):
             "parity": {"bit_identical_to_pillow": same}}
 
 
+def bench_jpeg(n=256, h=360, w=640, out=224):
+    """SURVEY.md 8f row f4, the decode half: the JPEG files of n 360 x 640 frames (quality 90, 4:2:0, as ffmpeg writes them)
+    -> RGB on the device (csrc/jpeg.cu) -> resize + normalise; host bytes in, [n, 3, 224, 224] float32 on the device out.
+    Beside it: Pillow (libjpeg-turbo) decode + resize on one host core -- what a DataLoader worker of the reference runs
+    (D/infer/src/dataset.py:137-141) -- on a bounded sample, and bit-identity of the decoded frames."""
+    import io
+
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    from vsc22_submission_b200 import ingest
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:h, 0:w]
+    files = []
+    for i in range(n):                              # smooth content + noise: ~60-80 KB per frame like real video frames
+        img = np.stack([128 + 90 * np.sin(xx / (17.0 + i % 7) + yy / 29.0), 128 + 90 * np.cos(xx / 23.0 - yy / (11.0 + i % 5)),
+                        (xx * 2 + yy * 3 + 5 * i) % 256], axis=-1) + rng.normal(0, 10, (h, w, 3))
+        buf = io.BytesIO()
+        Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(buf, format="JPEG", quality=90, subsampling=2)
+        files.append(buf.getvalue())
+    pre = ingest.sscd_transform(out, out)
+    pre(files[:8])
+    torch.cuda.synchronize()
+    t_dec, t_all = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        rgb = ingest.decode_jpeg_frames(files)
+        torch.cuda.synchronize()
+        t_dec.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter()
+        y = pre(files)
+        torch.cuda.synchronize()
+        t_all.append((time.perf_counter() - t0) * 1e3)
+    files4 = files * 4                               # a segment is a serial bit stream: throughput grows with frames per call
+    ingest.decode_jpeg_frames(files4[:8])
+    t_big = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        big = ingest.decode_jpeg_frames(files4)
+        torch.cuda.synchronize()
+        t_big.append((time.perf_counter() - t0) * 1e3)
+    del big
+    sample = 32
+    t0 = time.perf_counter()
+    for i in range(sample):
+        ref = np.asarray(Image.open(io.BytesIO(files[i])).convert("RGB"))
+        Image.fromarray(ref).resize((out, out), Image.BICUBIC)
+    cpu = sample / (time.perf_counter() - t0)
+    same = bool(np.array_equal(ref, rgb[sample - 1].cpu().numpy()))
+    nbytes = sum(len(f) for f in files)
+    return {"workload": f"{n} JPEG frames {h}x{w} (quality 90, 4:2:0, {nbytes // n} B each) -> RGB -> bicubic {out}x{out} + Normalize",
+            "decode_frames_per_sec": n / (min(t_dec) / 1e3), "decode_ms": min(t_dec),
+            "decode_resize_frames_per_sec": n / (min(t_all) / 1e3), "decode_resize_ms": min(t_all),
+            "decode_frames_per_sec_1024_per_call": 4 * n / (min(t_big) / 1e3), "decode_ms_1024_per_call": min(t_big),
+            "h2d_bytes": nbytes, "api": "ingest.sscd_transform(224, 224)(list of JPEG bytes)  [host bytes in, CUDA tensor out]",
+            "cpu_baseline": {"value": cpu, "unit": "frames/sec", "cores": 1, "kind": "reference",
+                             "sample": f"{sample} frames through Pillow Image.open + convert('RGB') + resize(BICUBIC)"},
+            "parity": {"decoded_bit_identical_to_pillow": same}}
+
+
 def h2d_bandwidth_gbs():
     """Pinned host -> device copy rate of this box (the ceiling of every e2e number that ships fp32 frames)."""
     import torch
@@ -1021,6 +1082,7 @@ def main():
     if rank == 0 and world == 1 and args.workload == "both":
         line["swin"] = bench_swin(args)
         line["ingest"] = bench_ingest()
+        line["ingest"]["jpeg"] = bench_jpeg()
         line["h2d_pinned_gbs"] = h2d_bandwidth_gbs()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         g = torch.Generator().manual_seed(1)

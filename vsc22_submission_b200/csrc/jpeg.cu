@@ -15,9 +15,13 @@
 // Host: marker parsing of every frame (tables, geometry, the entropy-coded segment; restart intervals are located by
 // scanning for RSTn), one descriptor per independent entropy segment, compressed bytes + descriptors staged and uploaded.
 // Device:
+//   jpeg_unstuff_kernel   one CTA per entropy segment: the zero byte behind every 0xFF is removed by a block-wide
+//                         compaction, so that the decoder reads plain aligned 32-bit words
 //   jpeg_huffman_kernel   one entropy segment (a whole frame, or one restart interval) per warp, decoded by lane 0 while
 //                         the other lanes have loaded the frame's Huffman tables into shared memory; quantised
-//                         coefficients (natural order, int16) into the zero-filled coefficient planes
+//                         coefficients (natural order, int16) into the zero-filled coefficient planes.  A segment is a
+//                         serial bit stream: the parallelism is over frames (and restart intervals), so throughput
+//                         grows with the number of frames per call until every SM holds a few dozen warps
 //   jpeg_idct_kernel      one thread per 8 x 8 block: dequantise, two-pass integer IDCT in registers, uint8 samples into the
 //                         component planes
 //   jpeg_color_kernel     one thread per pixel: Y + fancy-upsampled Cb / Cr -> RGB, [n, H, W, 3] uint8 -- the layout
@@ -59,7 +63,8 @@ struct JpGeom {                    // identical for every frame of a batch
 struct JpSegment {                 // one independently decodable entropy-coded segment
   int frame;
   int mcu0, n_mcu;
-  uint32_t byte0, byte1;           // [byte0, byte1) of the batch's byte buffer
+  uint32_t byte0, byte1;           // [byte0, byte1) of the batch's byte buffer (as in the file: byte-stuffed)
+  uint32_t clean0;                 // offset of the segment's unstuffed bytes in the clean buffer (16-byte aligned)
   int16_t tab_dc[3], tab_ac[3];    // Huffman table indices per component
 };
 
@@ -73,28 +78,18 @@ const uint8_t h_zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18
                               30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
 // ------------------------------------------------------------------------------------------------ entropy decoding
+// Reads the UNSTUFFED bytes of one segment (jpeg_unstuff_kernel: 0xFF00 -> 0xFF, zero padding behind the data) as aligned
+// 32-bit words: no per-byte loads and no marker tests on the decoder's critical path.
 struct BitReader {
-  const uint8_t* p;
-  const uint8_t* end;
+  const uint32_t* p;               // next word (the segment's clean bytes start 16-byte aligned)
   uint64_t acc;
   int n;
-  bool marker;
-  __device__ __forceinline__ void fill() {
-    while (n <= 48) {
-      uint32_t b = 0;
-      if (!marker && p < end) {
-        b = *p++;
-        if (b == 0xFF) {
-          const uint32_t nxt = p < end ? *p : 0xD9u;
-          if (nxt == 0) ++p;                         // stuffed zero
-          else { --p; marker = true; b = 0; }        // a marker: stop and feed zeros (jdhuff.c)
-        }
-      }
-      acc = (acc << 8) | b;
-      n += 8;
-    }
+  __device__ __forceinline__ void fill() {                 // n <= 32 on entry
+    const uint32_t w = __ldg(p++);
+    acc = (acc << 32) | __byte_perm(w, 0, 0x0123);         // big-endian bit order
+    n += 32;
   }
-  __device__ __forceinline__ uint32_t peek(int k) {
+  __device__ __forceinline__ uint32_t peek(int k) {        // k <= 16
     if (n < k) fill();
     return static_cast<uint32_t>(acc >> (n - k)) & ((1u << k) - 1u);
   }
@@ -129,10 +124,57 @@ __device__ __forceinline__ int jp_extend(uint32_t v, int t) {
   return t == 0 ? 0 : (v >= (1u << (t - 1)) ? static_cast<int>(v) : static_cast<int>(v) - (1 << t) + 1);
 }
 
+// One CTA per segment: drop the zero byte behind every 0xFF (T.81 B.1.1.5 byte stuffing) with a block-wide compaction, and
+// put 16 zero bytes behind the data (the decoder may read ahead; a truncated stream decodes zeros like jdhuff.c).
+constexpr int kJpUnThreads = 256, kJpUnPer = 16;
+__global__ void __launch_bounds__(kJpUnThreads)
+jpeg_unstuff_kernel(const uint8_t* __restrict__ bytes, const JpSegment* __restrict__ segs, uint8_t* __restrict__ clean) {
+  __shared__ int s_cnt[kJpUnThreads];
+  __shared__ int s_base;
+  const JpSegment sg = segs[blockIdx.x];
+  const uint8_t* src = bytes + sg.byte0;
+  const int len = static_cast<int>(sg.byte1 - sg.byte0);
+  uint8_t* dst = clean + sg.clean0;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < len; t0 += kJpUnThreads * kJpUnPer) {
+    const int i0 = t0 + threadIdx.x * kJpUnPer;
+    uint8_t v[kJpUnPer];
+    int keep = 0, cnt = 0;
+    uint8_t prev = i0 > 0 && i0 - 1 < len ? src[i0 - 1] : 0;
+#pragma unroll
+    for (int j = 0; j < kJpUnPer; ++j) {
+      const int i = i0 + j;
+      const uint8_t b = i < len ? src[i] : 0;
+      const bool k = i < len && !(b == 0x00 && prev == 0xFF);
+      if (k) { keep |= 1 << j; ++cnt; }
+      v[j] = b;
+      prev = b;
+    }
+    s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    // exclusive scan of the per-thread counts (Hillis-Steele over 256 entries)
+    for (int o = 1; o < kJpUnThreads; o <<= 1) {
+      const int add = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
+      __syncthreads();
+      s_cnt[threadIdx.x] += add;
+      __syncthreads();
+    }
+    int at = s_base + s_cnt[threadIdx.x] - cnt;
+#pragma unroll
+    for (int j = 0; j < kJpUnPer; ++j)
+      if (keep & (1 << j)) dst[at++] = v[j];
+    __syncthreads();
+    if (threadIdx.x == kJpUnThreads - 1) s_base += s_cnt[kJpUnThreads - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x < 16) dst[s_base + threadIdx.x] = 0;
+}
+
 constexpr int kJpTabsPerSeg = 6;          // DC / AC of up to three components, staged in shared memory per warp
 
 __global__ void __launch_bounds__(32)
-jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const JpSegment* __restrict__ segs, const JpHuff* __restrict__ tabs,
+jpeg_huffman_kernel(const uint8_t* __restrict__ clean, const JpSegment* __restrict__ segs, const JpHuff* __restrict__ tabs,
                     JpGeom g, int16_t* __restrict__ coef) {
   __shared__ JpHuff s_tab[kJpTabsPerSeg];
   const JpSegment sg = segs[blockIdx.x];
@@ -147,7 +189,7 @@ jpeg_huffman_kernel(const uint8_t* __restrict__ bytes, const JpSegment* __restri
   __syncwarp();
   if (lane != 0) return;
   BitReader br;
-  br.p = bytes + sg.byte0; br.end = bytes + sg.byte1; br.acc = 0; br.n = 0; br.marker = false;
+  br.p = reinterpret_cast<const uint32_t*>(clean + sg.clean0); br.acc = 0; br.n = 0;
   int pred[3] = {0, 0, 0};
   int16_t* fc = coef + static_cast<int64_t>(sg.frame) * g.coef_per_frame;
   for (int m = sg.mcu0; m < sg.mcu0 + sg.n_mcu; ++m) {
@@ -423,9 +465,16 @@ bool parse_jpeg(const uint8_t* d, size_t n, ParsedFrame* pf, std::string* err) {
         pf->ta[c] = s[2 + 2 * k] & 15;
         if (pf->td[c] > 3 || pf->ta[c] > 3) return fail("corrupt JPEG: bad Huffman table id");
       }
+      // end of the entropy-coded segment: the first 0xFF that is neither stuffed (0xFF00) nor a restart marker
       size_t j = i;
-      while (j + 1 < n && !(d[j] == 0xFF && d[j + 1] != 0x00 && !(d[j + 1] >= 0xD0 && d[j + 1] <= 0xD7))) ++j;
-      if (j + 1 >= n) j = n;
+      for (;;) {
+        const void* hit = j < n ? memchr(d + j, 0xFF, n - j) : nullptr;
+        if (!hit) { j = n; break; }
+        j = static_cast<size_t>(static_cast<const uint8_t*>(hit) - d);
+        if (j + 1 >= n) { j = n; break; }
+        if (d[j + 1] != 0x00 && !(d[j + 1] >= 0xD0 && d[j + 1] <= 0xD7)) break;
+        j += 2;
+      }
       pf->scan0 = i;
       pf->scan1 = j;
       have_sos = true;
@@ -560,8 +609,14 @@ extern "C" int vscb200_jpeg_decode(const uint8_t* const* jpeg_ptrs, const uint64
       int mcu = 0;
       while (mcu < total_mcu) {
         size_t p1 = p0;                              // the next RSTn (or the end of the scan)
-        while (p1 + 1 < f.scan1 && !(d[p1] == 0xFF && d[p1 + 1] >= 0xD0 && d[p1 + 1] <= 0xD7)) ++p1;
-        if (p1 + 1 >= f.scan1) p1 = f.scan1;
+        for (;;) {
+          const void* hit = p1 < f.scan1 ? memchr(d + p1, 0xFF, f.scan1 - p1) : nullptr;
+          if (!hit) { p1 = f.scan1; break; }
+          p1 = static_cast<size_t>(static_cast<const uint8_t*>(hit) - d);
+          if (p1 + 1 >= f.scan1) { p1 = f.scan1; break; }
+          if (d[p1 + 1] >= 0xD0 && d[p1 + 1] <= 0xD7) break;
+          p1 += 2;
+        }
         sg.mcu0 = mcu; sg.n_mcu = std::min(f.dri, total_mcu - mcu);
         sg.byte0 = static_cast<uint32_t>(off + (p0 - f.scan0)); sg.byte1 = static_cast<uint32_t>(off + (p1 - f.scan0));
         segs.push_back(sg);
@@ -571,6 +626,14 @@ extern "C" int vscb200_jpeg_decode(const uint8_t* const* jpeg_ptrs, const uint64
     }
     off += f.scan1 - f.scan0 + 8;
   }
+  // unstuffed copies of the segments: 16-byte aligned starts, room for the 16 zero bytes behind each
+  size_t clean_total = 0;
+  for (JpSegment& sg : segs) {
+    sg.clean0 = static_cast<uint32_t>(clean_total);
+    clean_total += ((static_cast<size_t>(sg.byte1 - sg.byte0) + 16 + 15) & ~static_cast<size_t>(15));
+  }
+  clean_total += 256;
+  VSCB_REQUIRE(clean_total < (1ull << 32), "jpeg_decode: more than 4 GiB of compressed data in one call");
   // one staging block: bytes | segments | tables | quant
   const size_t seg_bytes = segs.size() * sizeof(JpSegment), tab_bytes = tabs.size() * sizeof(JpHuff), q_bytes = quant.size() * sizeof(JpQuant);
   auto al = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
@@ -599,20 +662,22 @@ extern "C" int vscb200_jpeg_decode(const uint8_t* const* jpeg_ptrs, const uint64
   const size_t coef_bytes = static_cast<size_t>(n) * g.coef_per_frame * sizeof(int16_t);
   const size_t plane_bytes = static_cast<size_t>(n) * g.plane_per_frame;
   uint8_t* dev = nullptr;
-  int rc = pool_alloc(reinterpret_cast<void**>(&dev), stage_total + coef_bytes + plane_bytes + 512, s);
+  int rc = pool_alloc(reinterpret_cast<void**>(&dev), al(stage_total) + al(clean_total) + coef_bytes + plane_bytes + 512, s);
   if (rc) return rc;
-  int16_t* coef = reinterpret_cast<int16_t*>(dev + al(stage_total));
+  uint8_t* clean = dev + al(stage_total);
+  int16_t* coef = reinterpret_cast<int16_t*>(clean + al(clean_total));
   uint8_t* planes = reinterpret_cast<uint8_t*>(coef) + coef_bytes;
   cudaError_t e = cudaMemcpyAsync(dev, host, stage_total, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaMemsetAsync(coef, 0, coef_bytes, s);
   if (e == cudaSuccess) {
-    jpeg_huffman_kernel<<<static_cast<unsigned>(segs.size()), 32, 0, s>>>(dev, reinterpret_cast<const JpSegment*>(dev + o_seg),
+    jpeg_unstuff_kernel<<<static_cast<unsigned>(segs.size()), kJpUnThreads, 0, s>>>(dev, reinterpret_cast<const JpSegment*>(dev + o_seg), clean);
+    jpeg_huffman_kernel<<<static_cast<unsigned>(segs.size()), 32, 0, s>>>(clean, reinterpret_cast<const JpSegment*>(dev + o_seg),
                                                                          reinterpret_cast<const JpHuff*>(dev + o_tab), g, coef);
     const int64_t nblocks = n * (g.coef_per_frame / 64);
     jpeg_idct_kernel<<<static_cast<unsigned>((nblocks + 127) / 128), 128, 0, s>>>(coef, reinterpret_cast<const JpQuant*>(dev + o_q), g, n, planes);
     const int64_t npix = n * static_cast<int64_t>(g.H) * g.W;
     jpeg_color_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256, 0, s>>>(planes, g, n, rgb_dev);
-    count_launch(3);
+    count_launch(4);
     e = cudaGetLastError();
   }
   // the staging block is reused by the next call: the upload must have left it

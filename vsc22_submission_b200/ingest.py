@@ -33,14 +33,13 @@ def decode_jpeg_frames(files: Sequence[bytes], device="cuda") -> torch.Tensor:
     if n == 0:
         return torch.empty((0, 0, 0, 3), dtype=torch.uint8, device=device)
     bufs = [bytes(f) if not isinstance(f, (bytes, bytearray)) else f for f in files]
-    keep = [(C.c_char * len(b)).from_buffer_copy(b) for b in bufs]
-    ptrs = (C.c_void_p * n)(*[C.addressof(k) for k in keep])
+    ptrs = (C.c_char_p * n)(*bufs)                 # no copy: ctypes passes the bytes objects' own buffers
     sizes = (C.c_uint64 * n)(*[len(b) for b in bufs])
     h, w = C.c_int(0), C.c_int(0)
     lib = _lib.lib()
     with torch.cuda.device(device):
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(lib.vscb200_jpeg_decode(ptrs, sizes, n, None, C.byref(h), C.byref(w), stream), "jpeg_decode (headers)")
+        _lib.check(lib.vscb200_jpeg_decode(ptrs, sizes, 1, None, C.byref(h), C.byref(w), stream), "jpeg_decode (header)")
         out = torch.empty((n, h.value, w.value, 3), dtype=torch.uint8, device=device)
         _lib.check(lib.vscb200_jpeg_decode(ptrs, sizes, n, C.c_void_p(out.data_ptr()), C.byref(h), C.byref(w), stream), "jpeg_decode")
     return out
