@@ -41,14 +41,13 @@ namespace vscb200 {
 #define WS_T(x)
 #endif
 
-constexpr int kWsThreads = 352;
-constexpr int kWsKB = 64;                    // keys per block
-constexpr int kWsKTile = kWsKB * 128;        // one K or V block: 64 rows x 64 bf16, 128-byte swizzled (8 atoms)
+// Two shapes of the same kernel: NW = 2 softmax warpgroups with 64-key blocks (11 warps; TMEM per warpgroup S0 S1 O L =
+// 64 + 64 + 64 + 16 columns) and NW = 3 warpgroups with 32-key blocks (16 warps; 32 + 32 + 64 + 16 columns each): a third
+// warp per scheduler fills the issue slots the other two leave while they wait on TMEM loads and barriers.
 constexpr int kWsQTile = 128 * 128;
-constexpr int kWsOCol = 128;                 // O accumulator [128, 192), row sums [192, 208)
-constexpr int kWsLCol = 192;
 constexpr int kWsOnes = 2048;                // 16 keys x 128 B of bf16 ones: B operand of the row-sum MMA
-constexpr int kWsMaxBlocks = 10;             // 640 keys
+constexpr int kWsMaxKeys = 640;
+constexpr int kWsBars = 4 + 11 * 3;          // mbarriers of the widest shape
 
 struct WsParams {
   __nv_bfloat16* out;        // [M, C]
@@ -94,17 +93,17 @@ __device__ __forceinline__ void ws_unit(WsItem& it, const WsParams& p) {
   }
 }
 template <bool kSwin>
-__device__ __forceinline__ void ws_first(WsItem& it, int r0, const WsParams& p) {      // r0 < ipu
+__device__ __forceinline__ void ws_first(WsItem& it, int r0, const WsParams& p) {
   it.k = 0;
   it.r = r0;
+  while (it.r >= p.ipu) { it.r -= p.ipu; ++it.k; }
   ws_unit<kSwin>(it, p);
 }
 template <bool kSwin>
-__device__ __forceinline__ void ws_next(WsItem& it, int step, const WsParams& p) {     // step <= ipu
+__device__ __forceinline__ void ws_next(WsItem& it, int step, const WsParams& p) {
   it.r += step;
   if (it.r >= p.ipu) {
-    it.r -= p.ipu;
-    ++it.k;
+    do { it.r -= p.ipu; ++it.k; } while (it.r >= p.ipu);
     ws_unit<kSwin>(it, p);
   }
 }
@@ -120,16 +119,16 @@ struct WsSwinRow {
   bool masked;               // the window mixes regions (warp-uniform)
 };
 
-// One key block of this thread's row: S in TMEM columns [tS, tS + 64) -> P (bf16 pairs over [tS, tS + 32)); running shift
-// m (log2 domain); accumulators O [tO, tO + HD) and row sum [tL, tL + 16) rescaled when the shift moves.  kt: first key
-// of the block.  Warp-collective.
-template <int HD, bool kSwin>
+// One key block of this thread's row: S in TMEM columns [tS, tS + KB) -> P (bf16 pairs over [tS, tS + KB / 2)); running
+// shift m (log2 domain); accumulators O [tO, tO + HD) and row sum [tL, tL + 16) rescaled when the shift moves.  kt: first
+// key of the block.  Warp-collective.
+template <int HD, bool kSwin, int KB>
 __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint32_t tL, int kt, bool first, float& m, int T,
                                                  float scale_log2e, uint64_t* pv_done, uint32_t pv_parity, const WsSwinRow& sw,
                                                  int ws, int shift) {
-  const int nchunks = min(2, (T - kt + 31) >> 5);                     // chunks with a valid key (warp-uniform, >= 1)
+  const int nchunks = min(KB / 32, (T - kt + 31) >> 5);               // chunks with a valid key (warp-uniform, >= 1)
 #pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
+  for (int c = 0; c < KB / 32; ++c) {
     uint32_t pk[16];
     if (c < nchunks) {
       uint32_t v[32];
@@ -185,14 +184,14 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint3
             tmem_st_32x16(ta, o);
           }
         }
-        if (c == 1) {                                                 // P of this block's first chunk
+        for (int cc = 0; cc < c; ++cc) {                              // P chunks of this block already written
           uint32_t q[16];
-          tmem_ld_32x16(tS, q);
+          tmem_ld_32x16(tS + cc * 16, q);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             q[j] = ws_pack(__uint_as_float(q[j] << 16) * alpha, __uint_as_float(q[j] & 0xFFFF0000u) * alpha);
-          tmem_st_32x16(tS, q);
+          tmem_st_32x16(tS + cc * 16, q);
         }
         tmem_st_wait();
         if (move) m = cmax;
@@ -203,7 +202,7 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint3
         const float q1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -m));
         pk[j >> 1] = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);     // truncation to bf16 pairs
       }
-    } else {                                                          // keys past the segment: P = 0 (the MMA reads all 64)
+    } else {                                                          // keys past the segment: P = 0 (the MMA reads the whole block)
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = 0u;
     }
@@ -213,42 +212,47 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint3
   tmem_st_wait();
 }
 
-template <int HD, bool kSwin>
-__global__ void __launch_bounds__(kWsThreads, 1)
+template <int HD, bool kSwin, int NW, int KB, int D>
+__global__ void __launch_bounds__((5 * NW + 1) * 32, 1)
 attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, WsParams p) {
   constexpr int HH = 64 / HD;                             // heads per 64-column group
+  constexpr int kWsThreads = (5 * NW + 1) * 32;           // 4 NW softmax warps, NW issuer warps, one producer warp
+  constexpr int kWsKB = KB;                               // keys per block
+  constexpr int kWsKTile = KB * 128;                      // one K or V block: KB rows x 64 bf16, 128-byte swizzled
+  constexpr int kTStride = D * KB + 80;                   // TMEM columns of a warpgroup: D S buffers | O (64) | row sums (16)
+  constexpr int kWsOCol = D * KB, kWsLCol = D * KB + 64;
+  static_assert(4 + NW * (7 + 2 * D) <= kWsBars, "attention_ws: barrier block");
+  constexpr int kIssuer0 = 4 * NW, kProducer = 5 * NW;
+  static_assert(NW * kTStride <= 512, "attention_ws: TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int kv_bytes = p.nb * kWsKTile;                   // K (or V) of one unit
   uint8_t* sKV = smem;                                    // [kv_stages][K | V]
-  uint8_t* sQ = sKV + p.kv_stages * 2 * kv_bytes;         // [2 warpgroups][q_bufs] tiles
-  uint8_t* sOnes = sQ + 2 * p.q_bufs * kWsQTile;          // bf16 ones: the row-sum operand
+  uint8_t* sQ = sKV + p.kv_stages * 2 * kv_bytes;         // [NW warpgroups][q_bufs] tiles
+  uint8_t* sOnes = sQ + NW * p.q_bufs * kWsQTile;          // bf16 ones: the row-sum operand
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kWsOnes);
-  uint64_t* kv_full = bars;            // [2] per stage
-  uint64_t* kv_empty = bars + 2;       // [2]       both issuers have issued their last MMA of the unit
-  uint64_t* q_full = bars + 4;         // [2][2] per warpgroup and buffer
-  uint64_t* q_empty = bars + 8;        // [2][2]
-  uint64_t* s_full = bars + 12;        // [2][2] per warpgroup and S buffer
-  uint64_t* p_full = bars + 16;        // [2][2]
-  uint64_t* o_full = bars + 20;        // [2]
-  uint64_t* o_empty = bars + 22;       // [2]
-  uint64_t* pv_done = bars + 24;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-  float* tabs = reinterpret_cast<float*>(bars + 28);      // Swin form: [2 heads][(2ws-1)^2]
+  uint64_t* kv_full = bars;                 // [2] per stage
+  uint64_t* kv_empty = bars + 2;            // [2]       the issuers with items in the unit have issued their last MMA of it
+  uint64_t* q_full = bars + 4;              // [NW][2] per warpgroup and buffer
+  uint64_t* q_empty = q_full + 2 * NW;      // [NW][2]
+  uint64_t* s_full = q_empty + 2 * NW;      // [NW][D] per warpgroup and S buffer
+  uint64_t* p_full = s_full + D * NW;       // [NW][D]
+  uint64_t* o_full = p_full + D * NW;       // [NW]
+  uint64_t* o_empty = o_full + NW;          // [NW]
+  uint64_t* pv_done = o_empty + NW;         // [NW]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kWsBars);
+  float* tabs = reinterpret_cast<float*>(bars + kWsBars + 2);      // Swin form: [2 heads][(2ws-1)^2]
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
-  if (warp == 8) {
+  if (warp == kIssuer0) {
     if (lane == 0) {
       prefetch_tmap(&tmQ);
       prefetch_tmap(&tmKV);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2);
-        mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&pv_done[i], 1);
-      }
-      for (int i = 0; i < 4; ++i) {
-        mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
-      }
+      for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], min(p.ipu, NW)); }
+      for (int i = 0; i < NW; ++i) { mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4); mbar_init(&pv_done[i], 1); }
+      for (int i = 0; i < 2 * NW; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+      for (int i = 0; i < D * NW; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -261,14 +265,14 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 10) {
+  if (warp == kProducer) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int cur_k = -1;
-      int n_q[2] = {0, 0};
+      int n_q[NW] = {};
       WsItem it;
       int w = 0;
-      for (ws_first<kSwin>(it, 0, p); it.ok; ws_next<kSwin>(it, 1, p), w ^= 1) {
+      for (ws_first<kSwin>(it, 0, p); it.ok; ws_next<kSwin>(it, 1, p), w = (w + 1 == NW ? 0 : w + 1)) {
         const int row0 = it.seg * p.T;
         if (it.k != cur_k) {                               // new unit: K and V into the next stage
           cur_k = it.k;
@@ -289,18 +293,18 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_2d(sQ + (w * p.q_bufs + qb) * kWsQTile, &tmQ, &q_full[w * 2 + qb], it.hg * 64, row0 + (it.r / HH) * 128, kEvictFirst);
       }
     }
-  } else if (warp == 8 || warp == 9) {
+  } else if (warp >= kIssuer0 && warp < kProducer) {
     // ------------------------------------------------------------------ MMA issuer of warpgroup w: the WHOLE warp runs the
     // loop on warp-uniform values (uniform registers), one elected lane issues inside the umma_*_warp wrappers
     {
-      const int w = warp - 8;
+      const int w = warp - kIssuer0;
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, kWsKB);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, HD);
       constexpr uint32_t idesc_l = make_idesc_bf16_f32_bmn(128, 16);
       const uint64_t ones_d = make_desc_mn_sw128(smem_u32(sOnes));
-      const uint32_t tw = tmem_base + w * 256;
+      const uint32_t tw = tmem_base + w * kTStride;
       const uint32_t sKV_u = smem_u32(sKV), sQ_u = smem_u32(sQ);
-      // two cursors over the warpgroup's flattened block sequence: S runs two blocks ahead of PV
+      // two cursors over the warpgroup's flattened block sequence: S runs up to D blocks ahead of PV
       int sb = 0, s_item = 0, s_k = -1;                    // next S: block, warpgroup-local item index, unit seen
       int pb = 0, p_item = 0;
       uint32_t sg = 0, pg = 0;                             // global block counters
@@ -328,25 +332,25 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint64_t qd = make_desc_k_sw128(sQ_u + (w * p.q_bufs + qb) * kWsQTile + s_hh);
         const uint64_t kd = make_desc_k_sw128(sKV_u + ws_mod(si.k, p.kv_stages) * 2 * kv_bytes + sb * kWsKTile + s_hh);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss_warp(tw + (sg & 1) * kWsKB, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit_warp(&s_full[w * 2 + (sg & 1)]);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss_warp(tw + (sg % D) * kWsKB, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit_warp(&s_full[w * D + (sg % D)]);
         ++sg;
         if (++sb == p.nb) {                                // last S of the item: its Q buffer is free once these retire
           umma_commit_warp(&q_empty[w * 2 + qb]);
           sb = 0;
           ++s_item;
-          ws_next<kSwin>(si, 2, p);
+          ws_next<kSwin>(si, NW, p);
         }
       };
-      // S runs up to two blocks ahead of PV, but never into a unit whose K / V stage is still held by a unit this
+      // S runs up to D blocks ahead of PV, but never into a unit whose K / V stage is still held by a unit this
       // warpgroup has not finished (the producer refills a stage only after BOTH issuers released it)
       auto fill_s = [&]() {
-        while (si.ok && sg - pg < 2u && si.k < pi.k + p.kv_stages) issue_s();
+        while (si.ok && sg - pg < static_cast<uint32_t>(D) && si.k < pi.k + p.kv_stages) issue_s();
       };
       while (pi.ok) {
         fill_s();
         WS_T(u2);
-        mbar_wait(&p_full[w * 2 + (pg & 1)], (pg >> 1) & 1);
+        mbar_wait(&p_full[w * D + (pg % D)], (pg / D) & 1);
         WS_T(u3);
         if (pb == 0 && p_item > 0) mbar_wait(&o_empty[w], (p_item - 1) & 1);   // the warpgroup has read the previous item's O
 #ifdef WS_PROF
@@ -356,8 +360,8 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint64_t vd = make_desc_mn_sw128(sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile + (pi.r % HH) * 64);
 #pragma unroll
         for (int i = 0; i < kWsKB / 16; ++i) {
-          umma_bf16_ts_warp(tw + kWsOCol, tw + (pg & 1) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
-          umma_bf16_ts_warp(tw + kWsLCol, tw + (pg & 1) * kWsKB + i * 8, ones_d, idesc_l, (pb | i) ? 1u : 0u);      // row sums
+          umma_bf16_ts_warp(tw + kWsOCol, tw + (pg % D) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
+          umma_bf16_ts_warp(tw + kWsLCol, tw + (pg % D) * kWsKB + i * 8, ones_d, idesc_l, (pb | i) ? 1u : 0u);      // row sums
         }
         umma_commit_warp(&pv_done[w]);
         ++pg;
@@ -366,12 +370,12 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_commit_warp(&o_full[w]);
           pb = 0;
           ++p_item;
-          ws_next<kSwin>(pi, 2, p);
+          ws_next<kSwin>(pi, NW, p);
           if (!pi.ok || pi.k != prev_k) umma_commit_warp(&kv_empty[ws_mod(prev_k, p.kv_stages)]);   // this warpgroup is done with the unit
         }
       }
 #ifdef WS_PROF
-      if (p.prof && lane == 0) {
+      if (p.prof && lane == 0 && w < 2) {
         long long* o = p.prof + (static_cast<long long>(blockIdx.x) * 8 + 3 + 4 * w) * 5;   // slots of the mostly idle warps 3 / 7
         o[0] = i_kv; o[1] = i_q; o[2] = i_p; o[3] = i_oe; o[4] = clock64() - i_begin;
       }
@@ -380,7 +384,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ------------------------------------------------------------------ softmax warpgroups
     const int w = warp >> 2, quad = warp & 3;
-    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + w * 256;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + w * kTStride;
     uint32_t g = 0;
     int n_item = 0;
     // deferred epilogue of the previous item
@@ -419,7 +423,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
     int loaded_hg = -1;
     const int TS = 2 * p.ws - 1;
-    for (ws_first<kSwin>(it, w, p); it.ok; ws_next<kSwin>(it, 2, p)) {
+    for (ws_first<kSwin>(it, w, p); it.ok; ws_next<kSwin>(it, NW, p)) {
       const int tile = it.r / HH, hh = it.r - tile * HH;
       const int i_tok = tile * 128 + quad * 32 + lane;
       const bool warp_valid = tile * 128 + quad * 32 < p.T;
@@ -430,9 +434,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       sw.pen[0][0] = sw.pen[0][1] = sw.pen[1][0] = sw.pen[1][1] = 0.f;
       if (kSwin) {
         if (it.hg != loaded_hg) {                          // bias tables of the head pair -> shared memory.  Both warpgroups
-          named_bar_sync(1, 256);                          // walk the units in the same order: whoever gets here first waits
-          for (int e = threadIdx.x; e < 2 * TS * TS; e += 256) tabs[e] = p.tables[static_cast<int64_t>(it.hg) * 2 * TS * TS + e];
-          named_bar_sync(1, 256);                          // until the other one has finished the previous pair's items
+          named_bar_sync(1, 128 * NW);                     // walk the units in the same order: whoever gets here first waits
+          for (int e = threadIdx.x; e < 2 * TS * TS; e += 128 * NW) tabs[e] = p.tables[static_cast<int64_t>(it.hg) * 2 * TS * TS + e];
+          named_bar_sync(1, 128 * NW);                     // until the others have finished the previous pair's items
           loaded_hg = it.hg;
         }
         bool edge_y = false, edge_x = false;
@@ -455,20 +459,20 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll 1
       for (int b = 0; b < p.nb; ++b) {
         WS_T(t0);
-        mbar_wait(&s_full[w * 2 + (g & 1)], (g >> 1) & 1);
+        mbar_wait(&s_full[w * D + (g % D)], (g / D) & 1);
         tc_fence_after();
         WS_T(t1);
         // warps whose 32 rows all lie past the frame skip the block: the MMA reads stale TMEM for them, and whatever it
         // computes stays in rows nobody stores
         if (warp_valid)
-          ws_softmax_block<HD, kSwin>(tlane + (g & 1) * kWsKB, tlane + kWsOCol, tlane + kWsLCol, b * kWsKB, b == 0, m, p.T,
+          ws_softmax_block<HD, kSwin, KB>(tlane + (g % D) * kWsKB, tlane + kWsOCol, tlane + kWsLCol, b * kWsKB, b == 0, m, p.T,
                                       p.scale_log2e, &pv_done[w], (g - 1) & 1, sw, p.ws, p.shift);
         WS_T(t2);
         if (b == 0 && pend) epilogue();                    // before P.V of this item's first block may overwrite O
         WS_T(t3);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[w * 2 + (g & 1)]);
+        if (lane == 0) mbar_arrive(&p_full[w * D + (g % D)]);
         ++g;
 #ifdef WS_PROF
         const long long t4 = clock64();
@@ -482,7 +486,7 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     if (pend) epilogue();
 #ifdef WS_PROF
-    if (p.prof && lane == 0 && quad != 3) {
+    if (p.prof && lane == 0 && quad != 3 && warp < 8) {
       long long* o = p.prof + (static_cast<long long>(blockIdx.x) * 8 + warp) * 5;
       o[0] = c_wait; o[1] = c_soft; o[2] = c_epi; o[3] = c_arr; o[4] = clock64() - c_begin;
     }
@@ -490,48 +494,46 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc<512>(tmem_base);
+  if (warp == kIssuer0) tmem_dealloc<512>(tmem_base);
 }
 
 bool attention_ws_supported(int T, int head_dim) {
   static const int off = [] { const char* e = getenv("VSCB200_ATTN_NO_WS"); return e ? atoi(e) : 0; }();
-  return !off && ((head_dim == 64 && T > 128) || (head_dim == 32 && T >= 64)) && T <= kWsKB * kWsMaxBlocks;
+  return !off && ((head_dim == 64 && T > 128) || (head_dim == 32 && T >= 64)) && T <= kWsMaxKeys;
 }
 
 // The two forms share one launcher.  qkv: [n_segs * T, 3C] bf16 (q | k | v, heads head_dim-wide contiguous); out: [n_segs * T, C].
-static int attention_ws_launch(const void* qkv, void* out, int64_t n_segs, int T, int heads, int head_dim, float scale,
-                               const float* tables, int ws, int shift, int nWx, int nW_per_frame, cudaStream_t stream, bool reverse) {
-  VSCB_REQUIRE(attention_ws_supported(T, head_dim), "attention_ws: unsupported segment length / head_dim");
-  const bool swin = head_dim == 32;
-  VSCB_REQUIRE(swin == (tables != nullptr), "attention_ws: head_dim 32 is the Swin-V2 form (bias tables), 64 the ViT form");
-  VSCB_REQUIRE(!swin || (heads % 2 == 0 && ws * ws == T), "attention_ws: Swin form needs an even head count and T = ws * ws");
-  const int C = heads * head_dim;
+template <int HD, bool kSwin, int NW, int KB, int D>
+static int attention_ws_launch_shape(const void* qkv, void* out, int64_t n_segs, int T, int heads, float scale, const float* tables,
+                                     int ws, int shift, int nWx, int nW_per_frame, cudaStream_t stream, bool reverse) {
+  constexpr int kKTile = KB * 128;
+  constexpr int kThreads = (5 * NW + 1) * 32;
+  const int C = heads * HD;
   const int64_t M = n_segs * T;
   const int hgroups = C / 64;
-  VSCB_REQUIRE(M < (1ll << 31) && n_segs * hgroups < (1ll << 30), "attention_ws: problem too large");
   CUtensorMap tmQ, tmKV;
   int rc = make_tmap_2d(&tmQ, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * C, 3 * C, 128, 64, true);
   if (rc) return rc;
-  if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * C, 3 * C, kWsKB, 64, true))) return rc;
+  if ((rc = make_tmap_2d(&tmKV, qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, 3 * C, 3 * C, KB, 64, true))) return rc;
   WsParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.tables = tables;
   p.T = T; p.C = C; p.hgroups = hgroups; p.n_segs = static_cast<int>(n_segs);
-  p.nb = (T + kWsKB - 1) / kWsKB;
+  p.nb = (T + KB - 1) / KB;
   p.ntiles = (T + 127) / 128;
-  p.ipu = p.ntiles * (64 / head_dim);
+  p.ipu = p.ntiles * (64 / HD);
   p.n_units = static_cast<int>(n_segs) * hgroups;
   p.reverse = reverse ? 1 : 0;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.ws = swin ? ws : 1; p.shift = shift; p.nWx = nWx > 0 ? nWx : 1; p.nW_per_frame = nW_per_frame > 0 ? nW_per_frame : 1;
-  VSCB_REQUIRE(p.ipu >= 2, "attention_ws: a unit needs at least two items (one per warpgroup)");
-  const int kv_bytes = p.nb * kWsKTile;
+  p.ws = kSwin ? ws : 1; p.shift = shift; p.nWx = nWx > 0 ? nWx : 1; p.nW_per_frame = nW_per_frame > 0 ? nW_per_frame : 1;
+  const int kv_bytes = p.nb * kKTile;
   const int TS = 2 * p.ws - 1;
-  const int fixed = kWsOnes + 28 * 8 + (swin ? 2 * TS * TS * 4 : 0) + 64 + 1024;
+  const int fixed = kWsOnes + (kWsBars + 2) * 8 + (kSwin ? 2 * TS * TS * 4 : 0) + 64 + 1024;
   p.kv_stages = 2; p.q_bufs = 2;
-  if (2 * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.kv_stages = 1;
-  if (p.kv_stages * 2 * kv_bytes + 4 * kWsQTile + fixed > 232448) p.q_bufs = 1;
-  const int smem = p.kv_stages * 2 * kv_bytes + 2 * p.q_bufs * kWsQTile + fixed;
+  if (2 * 2 * kv_bytes + NW * 2 * kWsQTile + fixed > 232448) p.q_bufs = 1;
+  if (2 * 2 * kv_bytes + NW * p.q_bufs * kWsQTile + fixed > 232448) { p.kv_stages = 1; p.q_bufs = 2; }
+  if (p.kv_stages * 2 * kv_bytes + NW * p.q_bufs * kWsQTile + fixed > 232448) p.q_bufs = 1;
+  const int smem = p.kv_stages * 2 * kv_bytes + NW * p.q_bufs * kWsQTile + fixed;
   VSCB_REQUIRE(smem <= 232448, "attention_ws: shared memory");
   const int grid = p.n_units < device_sm_count() ? p.n_units : device_sm_count();
   ProfScope prof(kProfAttention, stream, 4.0 * static_cast<double>(M) * T * C);
@@ -541,13 +543,8 @@ static int attention_ws_launch(const void* qkv, void* out, int64_t n_segs, int T
   if (!prof_buf) cudaMalloc(&prof_buf, 148 * 8 * 5 * sizeof(long long));
   p.prof = prof_buf;
 #endif
-  if (swin) {
-    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attention_ws_kernel<32, true><<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
-  } else {
-    VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attention_ws_kernel<64, false><<<grid, kWsThreads, smem, stream>>>(tmQ, tmKV, p);
-  }
+  VSCB_CUDA_OK(cudaFuncSetAttribute(attention_ws_kernel<HD, kSwin, NW, KB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  attention_ws_kernel<HD, kSwin, NW, KB, D><<<grid, kThreads, smem, stream>>>(tmQ, tmKV, p);
 #ifdef WS_PROF
   {
     static long long h[148 * 8 * 5];
@@ -565,6 +562,36 @@ static int attention_ws_launch(const void* qkv, void* out, int64_t n_segs, int T
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
+}
+
+// VSCB200_ATTN_WS_SHAPE (A/B switch, read once): 2 = two warpgroups / 64-key blocks, 3 = three warpgroups / 32-key blocks,
+// 4..6 = two warpgroups / 32-key blocks with 4, 3, 2 S buffers.  Default: 3 for the ViT form (99 vs 103.5 us at 256 x 12 x 197,
+// 220 vs 223 us at 64 x 16 x 577 -- a third warp per scheduler; deeper S buffering measured no gain, profiles/README.md),
+// 2 for the Swin form.
+static int attention_ws_shape() {
+  static const int shape = [] { const char* e = getenv("VSCB200_ATTN_WS_SHAPE"); return e ? atoi(e) : 0; }();
+  return shape;
+}
+
+static int attention_ws_launch(const void* qkv, void* out, int64_t n_segs, int T, int heads, int head_dim, float scale,
+                               const float* tables, int ws, int shift, int nWx, int nW_per_frame, cudaStream_t stream, bool reverse) {
+  VSCB_REQUIRE(attention_ws_supported(T, head_dim), "attention_ws: unsupported segment length / head_dim");
+  const bool swin = head_dim == 32;
+  VSCB_REQUIRE(swin == (tables != nullptr), "attention_ws: head_dim 32 is the Swin-V2 form (bias tables), 64 the ViT form");
+  VSCB_REQUIRE(!swin || (heads % 2 == 0 && ws * ws == T), "attention_ws: Swin form needs an even head count and T = ws * ws");
+  const int C = heads * head_dim;
+  VSCB_REQUIRE(n_segs * T < (1ll << 31) && n_segs * (C / 64) < (1ll << 30), "attention_ws: problem too large");
+  const int shape = attention_ws_shape();
+  if (swin) {
+    if (shape == 3) return attention_ws_launch_shape<32, true, 3, 32, 2>(qkv, out, n_segs, T, heads, scale, tables, ws, shift, nWx, nW_per_frame, stream, reverse);
+    return attention_ws_launch_shape<32, true, 2, 64, 2>(qkv, out, n_segs, T, heads, scale, tables, ws, shift, nWx, nW_per_frame, stream, reverse);
+  }
+#define WS_ARGS qkv, out, n_segs, T, heads, scale, tables, ws, shift, nWx, nW_per_frame, stream, reverse
+  if (shape == 0 || shape == 3) return attention_ws_launch_shape<64, false, 3, 32, 2>(WS_ARGS);
+  if (shape == 4) return attention_ws_launch_shape<64, false, 2, 32, 4>(WS_ARGS);
+  if (shape == 5) return attention_ws_launch_shape<64, false, 2, 32, 3>(WS_ARGS);
+  if (shape == 6) return attention_ws_launch_shape<64, false, 2, 32, 2>(WS_ARGS);
+  return attention_ws_launch_shape<64, false, 2, 64, 2>(qkv, out, n_segs, T, heads, scale, tables, ws, shift, nWx, nW_per_frame, stream, reverse);
 }
 
 // ViT form: softmax(q.k / sqrt(64)) v per (frame, head)

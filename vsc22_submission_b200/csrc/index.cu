@@ -240,7 +240,7 @@ void vscb200_index_destroy(vscb200_index* ix) {
   // the blocks go back to the library pool, ordered after the last stream this index worked on
   cudaStream_t s = ix->last_stream;
   void* blocks[] = {ix->rmax2_bits, ix->flags, ix->bank, ix->rnorm, ix->ws, ix->q_stage, ix->D_stage, ix->I_stage, ix->qnorm, ix->counts,
-                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax,
+                    ix->bank_hi, ix->bank_lo, ix->q_planes, ix->Dtmp, ix->Itmp, ix->cand_d, ix->cand_i, ix->gmax, ix->gr_keys, ix->gr_count,
                     ix->g_score, ix->g_q, ix->g_r, ix->vp_score, ix->vp_q, ix->vp_r};
   if (ix->own_stream && s == ix->own_stream) {
     cudaStreamSynchronize(s);     // own stream is destroyed below: drain it, then free un-ordered
@@ -340,8 +340,13 @@ int vscb200_index_search(vscb200_index* ix, const float* q, int64_t nq, int k, f
       if ((rc = grow(&ix->cand_d, &ix->cand_d_bytes, static_cast<size_t>(nq) * ncg * sizeof(float), s))) return rc;
       if ((rc = grow(&ix->cand_i, &ix->cand_i_bytes, static_cast<size_t>(nq) * ncg * sizeof(int32_t), s))) return rc;
       if ((rc = group_topk(ix->gmax, G, Npad, static_cast<int>(nq), kg, chunks, ix->cand_d, ix->cand_i, s))) return rc;
-      return group_rescore(q, ix->bank, ix->d, !keep_max, ix->ntotal, nullptr, ix->cand_d, ix->cand_i, static_cast<int>(ncg),
-                           kg, nq, k, D, I, ix->id_offset, s);
+      if (!ix->gr_count) {
+        if ((rc = pool_alloc(reinterpret_cast<void**>(&ix->gr_count), 128 * sizeof(int), s))) return rc;
+        VSCB_CUDA_OK(cudaMemsetAsync(ix->gr_count, 0, 128 * sizeof(int), s));
+      }
+      if ((rc = grow(&ix->gr_keys, &ix->gr_keys_bytes, group_rescore_few_key_bytes(nq, kg, 32), s))) return rc;
+      return group_rescore_few(q, ix->bank, ix->d, !keep_max, ix->ntotal, ix->cand_d, ix->cand_i, static_cast<int>(ncg), kg, nq, k,
+                               D, I, ix->id_offset, ix->gr_keys, ix->gr_count, s);
     }
     if ((rc = grow(&ix->Dtmp, &ix->Dtmp_bytes, static_cast<size_t>(nq) * kg * sizeof(float), s))) return rc;
     if ((rc = grow(&ix->Itmp, &ix->Itmp_bytes, static_cast<size_t>(nq) * kg * sizeof(int64_t), s))) return rc;

@@ -42,6 +42,8 @@ struct vscb200_index {
   int* flags = nullptr; size_t flags_bytes = 0;   // sim_tc1.cu scratch: [nq] overflow flags + [1] their count + [nq] shared thresholds + [nq] list lengths
   int* last_flag_count = nullptr;                 // -> the count of the last single-pass search (diagnostics)
   float* gmax = nullptr; size_t gmax_bytes = 0;       // streaming search: per (32-row group, query) maxima
+  unsigned long long* gr_keys = nullptr; size_t gr_keys_bytes = 0;   // streaming search: rescored keys per (query, group, row)
+  int* gr_count = nullptr;                            // [128] arrival counters of group_rescore_few (zero between calls)
   // results of the last global (cross-query) candidate search, kept until the next one (global_topk.cu)
   float* g_score = nullptr; size_t g_score_bytes = 0;   // [g_n] exact scores, best first
   int64_t* g_q = nullptr; size_t g_q_bytes = 0;         // [g_n] query rows

@@ -80,6 +80,11 @@ int group_topk(const float* gmax, int64_t G, int Npad, int nq, int kg, int chunk
 int group_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nr, const int64_t* gsel, const float* cand_v,
                   const int32_t* cand_g, int ncg, int kg, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset,
                   cudaStream_t stream, int gs = 32);
+// few query rows: one CTA per (query, group); keys / counters: scratch (counters zero before the first call, left zero)
+size_t group_rescore_few_key_bytes(int64_t nq, int kg, int gs);
+int group_rescore_few(const float* Q, const float* bank, int d, bool l2, int64_t nr, const float* cand_v, const int32_t* cand_g,
+                      int ncg, int kg, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset, void* keys, int* counters,
+                      cudaStream_t stream, int gs = 32);
 int rescore_sort(const float* Q, const float* bank, int d, bool l2, const int64_t* Iin, int kin, int64_t nq, int k,
                  float* D, int64_t* I, int64_t id_offset, cudaStream_t stream);
 // Q != nullptr: S holds tensor-core scores; borderline pairs and reported distances are recomputed in fp32

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kSsThreads, 1)
 sim_stream_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                   const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl, StreamParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();                               // the selection kernel may be scheduled early; it waits for this grid
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int q_tile = p.Npad * 128;                       // Npad rows x 64 bf16
@@ -67,6 +68,7 @@ sim_stream_kernel(const __grid_constant__ CUtensorMap tmRh, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                            // the query planes and norms come from the kernel before this one
 
   const int kblocks = (p.K + 63) / 64;
   const int nseg = kblocks < 2 ? 1 : 2;
@@ -193,7 +195,7 @@ int sim_stream_groupmax(const void* Qh, const void* Ql, const void* Rh, const vo
   VSCB_CUDA_OK(cudaFuncSetAttribute(sim_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.tiles < device_sm_count() ? p.tiles : device_sm_count();
   ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * dp);
-  sim_stream_kernel<<<grid, kSsThreads, smem, stream>>>(tRh, tRl, tQh, tQl, p);
+  VSCB_CUDA_OK(launch_pdl(sim_stream_kernel, dim3(grid), dim3(kSsThreads), static_cast<size_t>(smem), stream, tRh, tRl, tQh, tQl, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -204,12 +206,14 @@ int sim_stream_groupmax(const void* Qh, const void* Ql, const void* Rh, const vo
 // the lower group id.  The chunk is staged through shared memory with coalesced loads; one warp per query holds
 // the query's 256 keys in registers (8 per lane) and extracts kg maxima with two REDUX per round.
 constexpr int kGtChunk = 256;
-constexpr int kGtThreads = 256;
+constexpr int kGtThreads = 1024;    // 32 warps: a query per warp, at most two rounds of queries at nq <= 64
 
 __global__ void __launch_bounds__(kGtThreads)
 group_topk_kernel(const float* __restrict__ gmax, int64_t G, int Npad, int nq, int kg, int chunks,
                   float* __restrict__ cand_v, int32_t* __restrict__ cand_g) {
   extern __shared__ float gt_tile[];                      // [kGtChunk][Npad + 1]
+  pdl_launch_dependents();
+  pdl_wait();                                             // gmax comes from the kernel before this one in the stream
   const int chunk = blockIdx.x;
   const int64_t g0 = static_cast<int64_t>(chunk) * kGtChunk;
   const int ng = static_cast<int>(G - g0 < kGtChunk ? G - g0 : kGtChunk);
@@ -258,7 +262,7 @@ int group_topk(const float* gmax, int64_t G, int Npad, int nq, int kg, int chunk
   const size_t smem = static_cast<size_t>(kGtChunk) * (Npad + 1) * sizeof(float);
   VSCB_CUDA_OK(cudaFuncSetAttribute(group_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   ProfScope prof(kProfSelect, stream, static_cast<double>(G) * Npad * 4);
-  group_topk_kernel<<<chunks, kGtThreads, smem, stream>>>(gmax, G, Npad, nq, kg, chunks, cand_v, cand_g);
+  VSCB_CUDA_OK(launch_pdl(group_topk_kernel, dim3(chunks), dim3(kGtThreads), smem, stream, gmax, G, Npad, nq, kg, chunks, cand_v, cand_g));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -388,6 +392,177 @@ int group_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nr,
   ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * kg * gs * d * 4);
   group_rescore_kernel<<<static_cast<unsigned>(nq), kGrThreads, smem, stream>>>(Q, bank, d, l2 ? 1 : 0, nr, gsel, cand_v, cand_g,
                                                                                 ncg, gpad, kg, gs, cpad, k, D, I, id_offset);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+// ------------------------------------------------------------------ the same for a few query rows: one CTA per (query, group)
+// With nq <= 128 the one-CTA-per-query kernel above leaves most SMs idle and serialises 16 groups' worth of HBM
+// latency.  Here every CTA (j, q) repeats the cheap selection of the query's kg best groups (two levels of warp
+// arg-max rounds over the composite keys in shared memory), rescores group j's rows, parks their keys in global
+// scratch, and the last CTA of the query to arrive sorts the kg * gs keys and writes the k results.  Same keys,
+// same tie rule (score, then lower id), same exact_rows_warp summation order: results are identical to the kernel above.
+constexpr int kGfThreads = 256;
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  const uint32_t hi = static_cast<uint32_t>(v >> 32);
+  const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? static_cast<uint32_t>(v) : 0u);
+  return (static_cast<unsigned long long>(mh) << 32) | ml;
+}
+
+// the `rounds` largest keys of a[0:n) (destroyed: winners are zeroed) -> out[0:rounds), best first; warp-collective
+__device__ __forceinline__ void warp_select_u64(unsigned long long* a, int n, int rounds, unsigned long long* out, int lane) {
+  for (int r = 0; r < rounds; ++r) {
+    unsigned long long lm = 0ull;
+    int li = -1;
+    for (int i = lane; i < n; i += 32) {
+      const unsigned long long c = a[i];
+      if (c > lm) { lm = c; li = i; }
+    }
+    const unsigned long long best = warp_max_u64(lm);
+    if (best != 0ull && lm == best) a[li] = 0ull;          // keys are unique (the id is part of them)
+    if (lane == 0) out[r] = best;
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kGfThreads)
+group_rescore_few_kernel(const float* __restrict__ Q, const float* __restrict__ bank, int d, int l2, int64_t nr,
+                         const float* __restrict__ cand_v, const int32_t* __restrict__ cand_g, int ncg, int kg, int gs,
+                         int cpad, int k, unsigned long long* __restrict__ keys, int* __restrict__ counters,
+                         float* __restrict__ D, int64_t* __restrict__ I, int64_t id_offset) {
+  extern __shared__ unsigned long long gf_smem[];        // [max(ncg, cpad)] composite keys | [8 * kg] warp winners | [d] floats
+  pdl_launch_dependents();
+  unsigned long long* cand = gf_smem;
+  const int csz = ncg > cpad ? ncg : cpad;
+  unsigned long long* wins = cand + csz;
+  float* sq = reinterpret_cast<float*>(wins + (kGfThreads / 32) * kg);
+  __shared__ int32_t my_group;
+  __shared__ int is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x;
+  const int64_t qrow = blockIdx.y;
+  const bool keep_max = !l2;
+  for (int c = tid; c < d; c += kGfThreads) sq[c] = Q[qrow * d + c];     // an input of the call: safe before the wait
+  pdl_wait();
+  // ---- the kg best groups of this query over all chunks; this CTA needs the j-th
+  for (int i = tid; i < ncg; i += kGfThreads) {
+    const int32_t g = cand_g[qrow * ncg + i];
+    cand[i] = g >= 0 ? (static_cast<unsigned long long>(okey_u(cand_v[qrow * ncg + i], true)) << 32) |
+                           static_cast<uint32_t>(~static_cast<uint32_t>(g))
+                     : 0ull;
+  }
+  __syncthreads();
+  {
+    const int per = (ncg + kGfThreads / 32 - 1) / (kGfThreads / 32);
+    const int a0 = warp * per;
+    const int n = a0 < ncg ? (ncg - a0 < per ? ncg - a0 : per) : 0;
+    warp_select_u64(cand + a0, n, j + 1, wins + warp * kg, lane);       // only the first j + 1 of each slice can matter
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // compact the warps' first j + 1 winners, then the j-th best of them
+    const int m = j + 1;
+    for (int i = lane; i < (kGfThreads / 32) * m; i += 32) cand[i] = wins[(i / m) * kg + (i % m)];
+    __syncwarp();
+    unsigned long long best = 0ull;
+    for (int r = 0; r <= j; ++r) {
+      unsigned long long lm = 0ull;
+      int li = -1;
+      for (int i = lane; i < (kGfThreads / 32) * m; i += 32) {
+        const unsigned long long c = cand[i];
+        if (c > lm) { lm = c; li = i; }
+      }
+      best = warp_max_u64(lm);
+      if (best != 0ull && lm == best) cand[li] = 0ull;
+      __syncwarp();
+    }
+    if (lane == 0) my_group = best != 0ull ? static_cast<int32_t>(~static_cast<uint32_t>(best & 0xFFFFFFFFull)) : -1;
+  }
+  __syncthreads();
+  // ---- exact scores of the group's rows: four rows per warp, all loads of the CTA in flight at once
+  const int64_t g = my_group;
+  unsigned long long* out = keys + (qrow * kg + j) * gs;
+  for (int r0 = warp * 4; r0 < gs; r0 += (kGfThreads / 32) * 4) {
+    const float* rp[4];
+    int64_t ids[4];
+    bool ok[4];
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ids[u] = g * gs + r0 + u;
+      ok[u] = g >= 0 && r0 + u < gs && ids[u] < nr;
+      rp[u] = bank + (ok[u] ? ids[u] : 0) * d;
+    }
+    exact_rows_warp<4>(sq, rp, d, lane, l2 != 0, acc);       // the shared summation order (exact.cuh)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (lane == 0 && r0 + u < gs)
+        out[r0 + u] = ok[u] ? (static_cast<unsigned long long>(okey_u(acc[u], keep_max)) << 32) |
+                                  static_cast<uint32_t>(~static_cast<uint32_t>(ids[u]))
+                            : 0ull;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&counters[qrow], 1);
+    is_last = prev == kg - 1;
+    if (is_last) counters[qrow] = 0;                          // every CTA of the query has arrived: ready for the next call
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last CTA of the query: sort the kg * gs keys, emit k
+  const int ncand = kg * gs;
+  for (int i = tid; i < cpad; i += kGfThreads) cand[i] = i < ncand ? __ldcg(keys + qrow * ncand + i) : 0ull;
+  __syncthreads();
+  for (int size = 2; size <= cpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (cpad >> 1); i += kGfThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = cand[lo], b = cand[hi];
+        if ((a < b) == desc) { cand[lo] = b; cand[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int jj = tid; jj < k; jj += kGfThreads) {
+    const unsigned long long c = cand[jj];
+    if (c != 0ull) {
+      const uint32_t key = static_cast<uint32_t>(c >> 32);
+      const uint32_t ok = keep_max ? key : ~key;
+      const uint32_t u = (ok & 0x80000000u) ? (ok ^ 0x80000000u) : ~ok;
+      D[qrow * k + jj] = __uint_as_float(u);
+      I[qrow * k + jj] = id_offset + static_cast<int64_t>(~static_cast<uint32_t>(c & 0xFFFFFFFFull));
+    } else {
+      D[qrow * k + jj] = keep_max ? -FLT_MAX : FLT_MAX;
+      I[qrow * k + jj] = -1;
+    }
+  }
+}
+
+size_t group_rescore_few_key_bytes(int64_t nq, int kg, int gs) { return static_cast<size_t>(nq) * kg * gs * sizeof(unsigned long long); }
+
+// keys: group_rescore_few_key_bytes of scratch; counters: [nq] ints, zero before the first call (the kernel leaves them zero)
+int group_rescore_few(const float* Q, const float* bank, int d, bool l2, int64_t nr, const float* cand_v, const int32_t* cand_g,
+                      int ncg, int kg, int64_t nq, int k, float* D, int64_t* I, int64_t id_offset, void* keys, int* counters,
+                      cudaStream_t stream, int gs) {
+  if (nq == 0) return VSCB200_OK;
+  VSCB_REQUIRE(cand_v && cand_g && keys && counters && nq <= 65535 && kg >= 1, "group_rescore_few: bad arguments");
+  int cpad = 2;
+  while (cpad < kg * gs) cpad <<= 1;
+  const size_t smem = static_cast<size_t>(ncg > cpad ? ncg : cpad) * 8 + static_cast<size_t>(kGfThreads / 32) * kg * 8 +
+                      static_cast<size_t>(d) * sizeof(float);
+  VSCB_REQUIRE(smem <= 200 * 1024, "group_rescore_few: too many groups / dimension too large");
+  VSCB_CUDA_OK(cudaFuncSetAttribute(group_rescore_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * kg * gs * d * 4);
+  VSCB_CUDA_OK(launch_pdl(group_rescore_few_kernel, dim3(kg, static_cast<unsigned>(nq)), dim3(kGfThreads), smem, stream, Q, bank, d,
+                          l2 ? 1 : 0, nr, cand_v, cand_g, ncg, kg, gs, cpad, k, reinterpret_cast<unsigned long long*>(keys),
+                          counters, D, I, id_offset));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;

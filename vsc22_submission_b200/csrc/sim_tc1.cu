@@ -407,6 +407,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 __global__ void __launch_bounds__(256)
 q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ sq,
                  float* __restrict__ sq_lo, int64_t n, int d, int dp) {
+  pdl_launch_dependents();                                // the streaming search launches its kernel behind this one early
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;

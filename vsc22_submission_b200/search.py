@@ -90,9 +90,13 @@ class DeviceIndex:
         D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
         I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         if nq:
-            with torch.cuda.device(self.device):
+            if torch.cuda.current_device() == self.device.index:      # the per-video call pattern is host-latency sensitive
                 _lib.check(_lib.lib().vscb200_index_search(self._ptr, _p(q), nq, int(k), _p(D), _p(I),
                                                            _stream(self.device)), "index.search")
+            else:
+                with torch.cuda.device(self.device):
+                    _lib.check(_lib.lib().vscb200_index_search(self._ptr, _p(q), nq, int(k), _p(D), _p(I),
+                                                               _stream(self.device)), "index.search")
         return D, I
 
     def global_search(self, q: torch.Tensor, global_k: int = 0, threshold: Optional[float] = None
