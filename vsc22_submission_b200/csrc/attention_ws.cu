@@ -198,8 +198,11 @@ __device__ __forceinline__ void ws_softmax_block(uint32_t tS, uint32_t tO, uint3
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float q0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -m));
-        const float q1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -m));
+        float q0 = 0.f, q1 = 0.f;
+        if (j < lim) {                                                // warp-uniform: no exponentials for the padding keys
+          q0 = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2e, -m));
+          q1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), scale_log2e, -m));
+        }
         pk[j >> 1] = __byte_perm(__float_as_uint(q0), __float_as_uint(q1), 0x7632);     // truncation to bf16 pairs
       }
     } else {                                                          // keys past the segment: P = 0 (the MMA reads the whole block)
@@ -223,6 +226,11 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr int kWsOCol = D * KB, kWsLCol = D * KB + 64;
   static_assert(4 + NW * (7 + 2 * D) <= kWsBars, "attention_ws: barrier block");
   constexpr int kIssuer0 = 4 * NW, kProducer = 5 * NW;
+#ifdef WS_NO_FUSE_L
+  constexpr bool kFuseL = false;
+#else
+  constexpr bool kFuseL = HD == 64;                       // the row sums ride in the P.V MMA (ViT form)
+#endif
   static_assert(NW * kTStride <= 512, "attention_ws: TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -301,7 +309,9 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_s = make_idesc_bf16_f32(128, kWsKB);
       constexpr uint32_t idesc_o = make_idesc_bf16_f32_bmn(128, HD);
       constexpr uint32_t idesc_l = make_idesc_bf16_f32_bmn(128, 16);
-      const uint64_t ones_d = make_desc_mn_sw128(smem_u32(sOnes));
+      constexpr uint32_t idesc_ol = make_idesc_bf16_f32_bmn(128, 80);
+      const uint32_t ones_u = smem_u32(sOnes);
+      const uint64_t ones_d = make_desc_mn_sw128(ones_u);
       const uint32_t tw = tmem_base + w * kTStride;
       const uint32_t sKV_u = smem_u32(sKV), sQ_u = smem_u32(sQ);
       // two cursors over the warpgroup's flattened block sequence: S runs up to D blocks ahead of PV
@@ -357,11 +367,22 @@ attention_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         i_p += u3 - u2; i_oe += clock64() - u3;
 #endif
         tc_fence_after();
-        const uint64_t vd = make_desc_mn_sw128(sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile + (pi.r % HH) * 64);
+        const uint32_t v_addr = sKV_u + ws_mod(pi.k, p.kv_stages) * 2 * kv_bytes + kv_bytes + pb * kWsKTile + (pi.r % HH) * 64;
+        if constexpr (kFuseL) {
+          // O and the row sums in ONE MMA per 16 keys: N = 80, whose second 64-column block (LBO) is the tile of ones
 #pragma unroll
-        for (int i = 0; i < kWsKB / 16; ++i) {
-          umma_bf16_ts_warp(tw + kWsOCol, tw + (pg % D) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
-          umma_bf16_ts_warp(tw + kWsLCol, tw + (pg % D) * kWsKB + i * 8, ones_d, idesc_l, (pb | i) ? 1u : 0u);      // row sums
+          for (int i = 0; i < kWsKB / 16; ++i) {
+            const uint32_t va = v_addr + i * 2048;
+            umma_bf16_ts_warp(tw + kWsOCol, tw + (pg % D) * kWsKB + i * 8, make_desc_mn_sw128_lbo(va, ones_u - va), idesc_ol,
+                              (pb | i) ? 1u : 0u);
+          }
+        } else {
+          const uint64_t vd = make_desc_mn_sw128(v_addr);
+#pragma unroll
+          for (int i = 0; i < kWsKB / 16; ++i) {
+            umma_bf16_ts_warp(tw + kWsOCol, tw + (pg % D) * kWsKB + i * 8, vd + static_cast<uint64_t>(i) * 128, idesc_o, (pb | i) ? 1u : 0u);
+            umma_bf16_ts_warp(tw + kWsLCol, tw + (pg % D) * kWsKB + i * 8, ones_d, idesc_l, (pb | i) ? 1u : 0u);      // row sums
+          }
         }
         umma_commit_warp(&pv_done[w]);
         ++pg;

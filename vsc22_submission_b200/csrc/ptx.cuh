@@ -283,6 +283,15 @@ __device__ __forceinline__ void umma_commit_cg2_mcast_warp(uint64_t* bar, uint16
       : "memory");
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- attention building blocks
 // MN-major B operand (e.g. V [keys][64 d] as the [N = d, K = keys] operand of O = P.V), 128-byte swizzle:
 // 64 N elements contiguous in a 128 B row, 8 K rows per 1024 B swizzle atom, atoms along K at SBO = 1024 B
@@ -292,6 +301,17 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1024 >> 4) << 16;                    // LBO: next 64-element N block (unused for N = 64)
   d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // SBO: next 8-row K group
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// the same with an explicit LBO: N blocks of 64 elements need not be adjacent (attention_ws.cu points the second block of
+// an N = 80 operand at a tile of ones: O = P.V and the row sums P.1 in one MMA)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
