@@ -16,6 +16,11 @@
 //   block emitted again.  At the end every survivor is rescored in exact fp32 (exact.cuh: the one summation order of
 //   all search paths), sorted by (score, query row, bank row) with a stable LSD radix sort (sort.cu) and cut to K.
 //   The result is therefore the exact fp32 global top-K, not an approximation of it.
+//   Single-pass form (default when the bank has operand planes): no dense block at all.  The radius of a block comes
+//   from a 1/64 COLUMN sample scored by a small one-pass GEMM; the block is then scored by ONE bf16 MMA per product
+//   with the emission in the GEMM epilogue (sim_tc.cu emit mode), under the proven one-pass margin of margin.cuh; the
+//   K-th best survivor verifies the estimate, and only when it fails (or no sample is possible) the dense block of
+//   the first form is built.  Margins only decide what is rescored; the scores and the order stay exact.
 #include <math.h>
 #include <string.h>
 
@@ -26,6 +31,7 @@
 #include "host_util.h"
 #include "index_internal.h"
 #include "kernels.h"
+#include "margin.cuh"
 
 namespace vscb200 {
 size_t radix_sort_scratch_bytes(int64_t n);
@@ -67,15 +73,14 @@ __host__ __device__ __forceinline__ float key_value(uint32_t key, bool keep_max)
 struct GtBlock {
   const float* S; int64_t ldS; int64_t nb; int64_t n;     // score block [nb, n]
   int64_t q0;                                             // global query row of block row 0
-  const float* qn;                                        // [nq_total] squared query norms
-  const float* rn_max;                                    // device scalar: max squared bank norm
+  const float* marg;                                      // [nq_total] two-sided scoring-error margin of a query row's scores
   float radius; int has_radius; int keep_max;
 };
 
 // a pair survives when it is better than the radius by more than the scoring error could hide
 __device__ __forceinline__ float row_threshold(const GtBlock& a, int64_t row) {
   if (!a.has_radius) return a.keep_max ? -INFINITY : INFINITY;
-  const float m = 2.f * kTcMargin * sqrtf(a.qn[a.q0 + row] * *a.rn_max) * (a.keep_max ? 1.f : 2.f);
+  const float m = a.marg[a.q0 + row];
   return a.keep_max ? a.radius - m : a.radius + m;
 }
 __device__ __forceinline__ bool better(float v, float thr, int keep_max) { return keep_max ? v > thr : v < thr; }
@@ -220,7 +225,7 @@ gt_sample_kernel(const float* __restrict__ S, int64_t ldS, int64_t nb, int64_t n
 // ---- compaction of the survivor buffer against a raised radius -----------------------------------------------
 __global__ void __launch_bounds__(kGtThreads)
 gt_compact_kernel(const float* __restrict__ inv, const uint64_t* __restrict__ inp, int64_t n, int64_t ntotal,
-                  const float* __restrict__ qn, const float* __restrict__ rn_max, float radius, int keep_max,
+                  const float* __restrict__ marg, float radius, int keep_max,
                   float* __restrict__ outv, uint64_t* __restrict__ outp, unsigned long long* __restrict__ counter) {
   const int lane = threadIdx.x & 31;
   for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kGtThreads; i0 < n; i0 += static_cast<int64_t>(gridDim.x) * kGtThreads) {
@@ -231,7 +236,7 @@ gt_compact_kernel(const float* __restrict__ inv, const uint64_t* __restrict__ in
     if (i < n) {
       v = inv[i];
       p = inp[i];
-      const float m = 2.f * kTcMargin * sqrtf(qn[p / static_cast<uint64_t>(ntotal)] * *rn_max) * (keep_max ? 1.f : 2.f);
+      const float m = marg[p / static_cast<uint64_t>(ntotal)];
       keep = keep_max ? v > radius - m : v < radius + m;
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, keep);
@@ -262,6 +267,21 @@ max_reduce_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ ou
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (threadIdx.x == 0) *out = m;
   }
+}
+
+// scoring-error bound per query row.  one_pass: margin.cuh; else the split-bf16 bound relative to |q||r|
+__global__ void __launch_bounds__(kGtThreads)
+gt_eps_kernel(const float* __restrict__ qn, const float* __restrict__ qn_lo, int64_t nq, const float* __restrict__ rn_max,
+              const unsigned int* __restrict__ bank_max_bits, int d, int keep_max, int one_pass, float* __restrict__ eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (i >= nq) return;
+  eps[i] = one_pass ? sim1_eps(qn[i], qn_lo[i], bank_max_bits, d, keep_max ? 0 : 1)
+                    : kTcMargin * sqrtf(qn[i] * *rn_max) * (keep_max ? 1.f : 2.f);
+}
+__global__ void __launch_bounds__(kGtThreads)
+gt_margin_kernel(float* __restrict__ eps_to_marg, int64_t nq, const float* __restrict__ eps_max) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kGtThreads + threadIdx.x;
+  if (i < nq) eps_to_marg[i] = (eps_to_marg[i] + *eps_max) * 1.0001f;
 }
 
 // ---- exact rescoring + sort keys ---------------------------------------------------------------------------
@@ -416,13 +436,34 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   const uint64_t K = limited ? std::min<uint64_t>(static_cast<uint64_t>(global_k), total_pairs) : total_pairs;
 
   Scratch sc(s);
-  // squared norms of ALL query rows (error margins) and the largest bank norm
-  float *qn_all = nullptr, *rn_max = nullptr;
+  // One-pass form: the bank has bf16 operand planes and their norm maxima (index.cu add()).  VSCB200_GT_DENSE=1 forces the
+  // dense-block form.
+  static const int force_dense = [] { const char* e = getenv("VSCB200_GT_DENSE"); return e ? atoi(e) : 0; }();
+  const bool one_pass = !force_dense && !ix->force_simt && ix->bank_hi != nullptr && ix->rmax2_bits != nullptr;
+  static const int trace = [] { const char* e = getenv("VSCB200_GT_TRACE"); return e ? atoi(e) : 0; }();
+#define GT_TRACE(...) do { if (trace) fprintf(stderr, __VA_ARGS__); } while (0)
+  GT_TRACE("[gt] nq=%lld n=%lld K=%llu one_pass=%d\n", (long long)nq, (long long)n, (unsigned long long)K, one_pass ? 1 : 0);
+  // squared norms of ALL query rows, the largest bank norm, and the scoring-error margin of every query row.  A true
+  // top-K pair of row i scores >= (approximate K-th best) - eps_max - eps_i: the K-th best may sit in the row with the
+  // largest error.
+  float *qn_all = nullptr, *qlo_all = nullptr, *rn_max = nullptr, *marg = nullptr, *eps_max = nullptr;
+  uint16_t* qh_all = nullptr;          // one-pass form: bf16 plane of all query rows
   if ((rc = sc.get(&qn_all, static_cast<size_t>(nq) * sizeof(float)))) return rc;
-  if ((rc = sc.get(&rn_max, sizeof(float)))) return rc;
-  if ((rc = row_sqnorm(q, nq, ix->d, qn_all, s))) return rc;
+  if ((rc = sc.get(&marg, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+  if ((rc = sc.get(&rn_max, sizeof(float))) || (rc = sc.get(&eps_max, sizeof(float)))) return rc;
+  if (one_pass) {
+    if ((rc = sc.get(&qlo_all, static_cast<size_t>(nq) * sizeof(float)))) return rc;
+    if ((rc = sc.get(&qh_all, static_cast<size_t>(nq) * ix->dp * sizeof(uint16_t)))) return rc;
+    if ((rc = q_hi_norm(q, qh_all, qn_all, qlo_all, nq, ix->d, ix->dp, s))) return rc;
+  } else {
+    if ((rc = row_sqnorm(q, nq, ix->d, qn_all, s))) return rc;
+  }
   max_reduce_kernel<<<1, 1024, 0, s>>>(ix->rnorm, n, rn_max);
-  count_launch();
+  gt_eps_kernel<<<static_cast<unsigned>((nq + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
+      qn_all, qlo_all, nq, rn_max, ix->rmax2_bits, ix->d, keep_max ? 1 : 0, one_pass ? 1 : 0, marg);
+  max_reduce_kernel<<<1, 1024, 0, s>>>(marg, nq, eps_max);
+  gt_margin_kernel<<<static_cast<unsigned>((nq + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(marg, nq, eps_max);
+  count_launch(4);
 
   // survivor buffers (ping-pong for compaction).  Logical bound 2K like the reference's max_results: above it the
   // radius is raised to the K-th best survivor; the physical capacity is larger so that a block emitted under a loose
@@ -445,7 +486,6 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
 
   const int64_t blk = block_rows(ix, nq);
   const int64_t ldS = (n + 3) & ~3ll;
-  if ((rc = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s))) return rc;
   const int64_t per_row = ((n + kGtSampleStride * kGtSampleRun - 1) / (kGtSampleStride * kGtSampleRun)) * kGtSampleRun;
   float* sample = nullptr;
 
@@ -495,7 +535,7 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     if (r) return r;
     if (count) {
       gt_compact_kernel<<<grid_for((static_cast<int64_t>(count) + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(
-          bufv[0], bufp[0], static_cast<int64_t>(count), n, qn_all, rn_max, radius, keep_max ? 1 : 0, bufv[1], bufp[1], counter);
+          bufv[0], bufp[0], static_cast<int64_t>(count), n, marg, radius, keep_max ? 1 : 0, bufv[1], bufp[1], counter);
       count_launch();
       std::swap(bufv[0], bufv[1]);
       std::swap(bufp[0], bufp[1]);
@@ -506,14 +546,35 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     if (!has_radius || (keep_max ? kth > radius : kth < radius)) radius = kth;
     has_radius = true;
   };
-  const GtBlock no_block{nullptr, 0, 0, n, 0, qn_all, rn_max, 0.f, 0, keep_max ? 1 : 0};
+  const GtBlock no_block{nullptr, 0, 0, n, 0, marg, 0.f, 0, keep_max ? 1 : 0};
 
   for (int64_t q0 = 0; q0 < nq; q0 += blk) {
     const int64_t nb = std::min(blk, nq - q0);
-    if ((rc = score_block(ix, q + q0 * ix->d, nb, ix->ws, ldS, s))) return rc;
-    GtBlock a{ix->ws, ldS, nb, n, q0, qn_all, rn_max, radius, has_radius ? 1 : 0, keep_max ? 1 : 0};
+    GtBlock a{nullptr, ldS, nb, n, q0, marg, radius, has_radius ? 1 : 0, keep_max ? 1 : 0};
+    // the dense score block (split-bf16, fp32-equivalent): always in the dense form, on demand in the one-pass form
+    auto ensure_dense = [&]() -> int {
+      if (a.S) return VSCB200_OK;
+      GT_TRACE("[gt]   block q0=%lld: dense score block\n", (long long)q0);
+      int r = grow(&ix->ws, &ix->ws_bytes, static_cast<size_t>(blk) * std::max<int64_t>(ldS, 4) * sizeof(float), s);
+      if (r) return r;
+      if ((r = score_block(ix, q + q0 * ix->d, nb, ix->ws, ldS, s))) return r;
+      a.S = ix->ws;
+      return VSCB200_OK;
+    };
+    if (!one_pass && (rc = ensure_dense())) return rc;
     const int64_t work = nb * ((n + kGtChunk - 1) / kGtChunk);
     const int grid = grid_for(work);
+    // append the block's survivors under a.radius: from the dense block when there is one, else in the epilogue of a
+    // one-pass GEMM
+    auto emit = [&]() -> int {
+      if (a.S) {
+        gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
+        count_launch();
+        return VSCB200_OK;
+      }
+      return scores_tc_emit(qh_all + static_cast<size_t>(q0) * ix->dp, ix->bank_hi, nb, n, ix->dp, !keep_max, qn_all + q0, ix->rnorm,
+                            marg + q0, a.radius, a.has_radius != 0, q0, bufv[0], bufp[0], counter, cap, s);
+    };
     const uint64_t blk_pairs = static_cast<uint64_t>(nb) * static_cast<uint64_t>(n);
     unsigned long long after = 0;
     bool emitted = false, tentative = false;
@@ -522,28 +583,45 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
       // No radius yet and the block does not fit: estimate one from a 1/64 sample of the block -- the value that about
       // 4K entries of the block should exceed -- emit under it, then VERIFY below (the K-th best survivor must not be
       // worse than the estimate, otherwise pairs between the two were never emitted and the exact select runs instead).
-      const int64_t ns = nb * per_row;
       const uint64_t want_s = std::max<uint64_t>((4 * K) / kGtSampleStride, 16);     // >= ~1000 pairs even for a tiny K
-      if (static_cast<uint64_t>(ns) > 4 * want_s) {
-        if (!sample && (rc = sc.get(&sample, static_cast<size_t>(blk) * per_row * sizeof(float)))) return rc;
-        gt_sample_kernel<<<grid_for((ns + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(ix->ws, ldS, nb, n, per_row,
-                                                                                          keep_max ? 1 : 0, sample);
-        count_launch();
+      const int64_t ncs = (n / kGtSampleStride) & ~3ll;                                // one-pass form: sampled bank rows
+      if (one_pass && keep_max && ncs >= 4 && static_cast<uint64_t>(nb * ncs) > 4 * want_s) {
+        // every 64th bank row against the block's queries: a [nb, ncs] one-pass GEMM (the strided rows come from the
+        // tensor map, nothing is gathered)
+        const int64_t ns = nb * ncs;
+        if (!sample && (rc = sc.get(&sample, static_cast<size_t>(blk) * std::max(per_row, ncs) * sizeof(float)))) return rc;
+        if ((rc = scores_tc_planes(qh_all + static_cast<size_t>(q0) * ix->dp, nullptr, ix->bank_hi, nullptr, sample, nb, ncs, ix->dp, ncs,
+                                   false, nullptr, nullptr, s, 1, kGtSampleStride))) return rc;
         if ((rc = select_kth(no_block, sample, ns, want_s, &r_hat))) return rc;
         a.radius = r_hat;
         a.has_radius = 1;
         tentative = true;
+      } else {
+        if ((rc = ensure_dense())) return rc;
+        const int64_t ns = nb * per_row;
+        if (static_cast<uint64_t>(ns) > 4 * want_s) {
+          if (!sample && (rc = sc.get(&sample, static_cast<size_t>(blk) * std::max(per_row, ncs) * sizeof(float)))) return rc;
+          gt_sample_kernel<<<grid_for((ns + kGtThreads - 1) / kGtThreads), kGtThreads, 0, s>>>(ix->ws, ldS, nb, n, per_row,
+                                                                                            keep_max ? 1 : 0, sample);
+          count_launch();
+          if ((rc = select_kth(no_block, sample, ns, want_s, &r_hat))) return rc;
+          a.radius = r_hat;
+          a.has_radius = 1;
+          tentative = true;
+        }
       }
     }
     if (a.has_radius || count + blk_pairs <= cap) {
-      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
-      count_launch();
+      if (!a.has_radius && (rc = ensure_dense())) return rc;      // everything is emitted: no point in a threshold epilogue
+      if ((rc = emit())) return rc;
       if ((rc = read_counter(&after))) return rc;
       emitted = after <= cap;
       if (emitted && tentative) {
         float kth = 0.f;
         const bool enough = after >= K;
         if (enough && (rc = select_kth(no_block, bufv[0], static_cast<int64_t>(after), K, &kth))) return rc;
+        GT_TRACE("[gt]   block q0=%lld: bootstrap radius %.6f emitted %llu, K-th %.6f -> %s\n", (long long)q0, r_hat, after, kth,
+                 (enough && (keep_max ? kth >= r_hat : kth <= r_hat)) ? "verified" : "rejected");
         if (enough && (keep_max ? kth >= r_hat : kth <= r_hat)) {
           count = after;                     // every pair at least as good as kth was emitted: kth is exact
           raise_radius(kth);
@@ -563,13 +641,13 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     if (!emitted && limited) {
       // raise the radius: exact K-th best value over {buffer, block entries better than the radius}
       float kth = 0.f;
+      if ((rc = ensure_dense())) return rc;  // the select below walks the block's scores
       if ((rc = select_kth(a, bufv[0], static_cast<int64_t>(count), K, &kth))) return rc;
       raise_radius(kth);
       a.radius = radius;
       a.has_radius = 1;
       if ((rc = compact())) return rc;       // what the buffer held before this block
-      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
-      count_launch();
+      if ((rc = emit())) return rc;
       if ((rc = read_counter(&after))) return rc;
       emitted = after <= cap;
     }
@@ -587,8 +665,7 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
       bufv[0] = nv; bufp[0] = np; bufv[1] = nullptr; bufp[1] = nullptr;
       cap = ncap;
       if ((rc = set_counter(count))) return rc;
-      gt_emit_kernel<<<grid, kGtThreads, 0, s>>>(a, n, bufv[0], bufp[0], counter, cap);
-      count_launch();
+      if ((rc = emit())) return rc;
       if ((rc = read_counter(&after))) return rc;
       emitted = after <= cap;
     }

@@ -18,8 +18,6 @@ using namespace vscb200;
 namespace vscb200 {
 // sim_tc.cu: fp32-equivalent tensor-core scoring (split-bf16 tcgen05) on pre-split operand planes
 int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, cudaStream_t stream);
-int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
-                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream);
 int fused_topk_slabs(int64_t nq, int64_t nr);
 int fused_topk_list_len();
 int fused_topk_group_rows();

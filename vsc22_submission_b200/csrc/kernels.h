@@ -71,6 +71,14 @@ int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normaliz
 // row r = S + r*ldS, element i of a row at [i*es] (es = 1: dense rows; es > 1: a column of a row-major matrix)
 int topk_rows(const float* S, int64_t ldS, int64_t nq, int64_t n, int k, bool keep_max, float* D, int64_t* I,
               int64_t id_offset, cudaStream_t stream, int64_t es = 1);
+// sim_tc.cu: scores on pre-split operand planes.  passes = 3: fp32-equivalent (hi.hi + lo.hi + hi.lo), 1: Qh.Rh only;
+// r_stride > 1: bank row j of the call is row j * r_stride of the planes (column sample of the score block)
+int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
+                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream, int passes = 3,
+                     int64_t r_stride = 1);
+int scores_tc_emit(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn,
+                   const float* marg, float radius, bool has_radius, int64_t q0, float* bufv, uint64_t* bufp,
+                   unsigned long long* counter, unsigned long long cap, cudaStream_t stream);
 // sim_stream.cu: streaming search for a few query rows (group maxima + exact rescoring of the best groups)
 int sim_stream_groupmax(const void* Qh, const void* Ql, const void* Rh, const void* Rl, int64_t nq, int64_t nr, int dp,
                         bool l2, const float* qn, const float* rn, float* gmax, int Npad, cudaStream_t stream);

@@ -44,7 +44,24 @@ struct SimParams {
   int slabs;
   float* cand_d;
   int32_t* cand_i;
+  // passes = 3: the split above; passes = 1: Qh.Rh only (bf16-rounded operands, error bounded by margin.cuh) -- the lo
+  // planes are neither loaded nor multiplied
+  int passes;
+  // emit mode (kMode == 2, global_topk.cu): nothing dense is written; every score better than its row's threshold
+  // radius -/+ marg[row] is appended as (value, pair id = (q0 + row) * ntotal + column) to bufv / bufp through a
+  // per-CTA shared-memory buffer flushed once per tile (one atomicAdd on `counter` per tile instead of one per hit).
+  // `counter` keeps counting past `cap` so the host sees by how much a pass overflowed.
+  const float* marg;
+  float radius;
+  int has_radius;
+  int64_t q0, ntotal;
+  float* bufv;
+  uint64_t* bufp;
+  unsigned long long* counter;
+  unsigned long long cap;
 };
+
+constexpr int kEmitCap = 2048;    // entries of the per-CTA emit buffer (8 KB values + 16 KB pair ids of the 32 KB epilogue staging)
 
 constexpr int kFK = 16;     // per-thread list length of the fused top-k epilogue (k + rescoring slack <= kFK)
 constexpr int kFG = 8;      // rows per candidate group of the fused epilogue
@@ -66,30 +83,42 @@ struct ItemIter {
   __device__ int n1(bool fused) const { return fused ? static_cast<int>(static_cast<int64_t>(slab() + 1) * tiles_n / slabs) : slab() + 1; }
 };
 
-template <bool kFused>
+template <int kMode>      // 0: dense score block, 1: fused per-row top-k lists, 2: threshold emission
 __global__ void __launch_bounds__(kTThreads, 1)
 sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
             const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl, SimParams p) {
+  constexpr bool kFused = kMode == 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  // the ring holds 3 stages of {Qh, Ql, Rh, Rl} or, with one pass, 6 stages of {Qh, Rh}: the mainloop is bound by TMA
+  // round trips per k-block, not by bytes, so the one-pass form needs the deeper ring to go faster at all
+  const int nstages = p.passes == 3 ? kTStages : 2 * kTStages;
+  const int stage_bytes = p.passes == 3 ? kTStageBytes : kTStageBytes / 2;
+  const int r_off = p.passes == 3 ? 2 * kTTile : kTTile;      // Rh inside a stage
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTStages * kTStageBytes);
-  uint64_t* empty_bar = full_bar + kTStages;
-  uint64_t* tfull_bar = empty_bar + kTStages;
+  uint64_t* empty_bar = full_bar + 2 * kTStages;
+  uint64_t* tfull_bar = empty_bar + 2 * kTStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float4* stage_all = reinterpret_cast<float4*>(smem + kTStages * kTStageBytes + 256);
+  // emit mode reuses the staging area: [kEmitCap] values | [kEmitCap] pair ids | fill count | reserved base
+  float* emit_val = reinterpret_cast<float*>(stage_all);
+  uint64_t* emit_pid = reinterpret_cast<uint64_t*>(emit_val + kEmitCap);
+  unsigned long long* emit_base = reinterpret_cast<unsigned long long*>(emit_pid + kEmitCap);
+  uint32_t* emit_cnt = reinterpret_cast<uint32_t*>(emit_base + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQh); prefetch_tmap(&tmQl); prefetch_tmap(&tmRh); prefetch_tmap(&tmRl);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kTStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kTEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<kTTmemCols>(tmem_slot);
+  if (kMode == 2 && threadIdx.x == 0) *emit_cnt = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,13 +135,15 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       for (int n_blk = it.n0(kFused), n_end = it.n1(kFused), m_blk = it.m_blk(); n_blk < n_end; ++n_blk) {
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kTStageBytes);
-          uint8_t* st = smem + stage * kTStageBytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          uint8_t* st = smem + stage * stage_bytes;
           tma_load_2d(st, &tmQh, &full_bar[stage], kb * kTK, m_blk * kTM, kEvictLast);
-          tma_load_2d(st + kTTile, &tmQl, &full_bar[stage], kb * kTK, m_blk * kTM, kEvictLast);
-          tma_load_2d(st + 2 * kTTile, &tmRh, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
-          tma_load_2d(st + 3 * kTTile, &tmRl, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
-          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+          tma_load_2d(st + r_off, &tmRh, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
+          if (p.passes == 3) {
+            tma_load_2d(st + kTTile, &tmQl, &full_bar[stage], kb * kTK, m_blk * kTM, kEvictLast);
+            tma_load_2d(st + 3 * kTTile, &tmRl, &full_bar[stage], kb * kTK, n_blk * kTN, kEvictNormal);
+          }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -138,18 +169,20 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           const uint32_t d_tmem = tmem_base + (acc * kTSeg + seg) * kTN;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * kTStageBytes);
+          const uint32_t st = smem_u32(smem + stage * stage_bytes);
           const uint64_t qh = make_desc_k_sw128(st), ql = make_desc_k_sw128(st + kTTile);
-          const uint64_t rh = make_desc_k_sw128(st + 2 * kTTile), rl = make_desc_k_sw128(st + 3 * kTTile);
+          const uint64_t rh = make_desc_k_sw128(st + r_off), rl = make_desc_k_sw128(st + 3 * kTTile);
 #pragma unroll
           for (int k = 0; k < kTK / 16; ++k) {
             umma_bf16_ss(d_tmem, qh + 2 * k, rh + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
-            umma_bf16_ss(d_tmem, ql + 2 * k, rh + 2 * k, idesc, 1u);
-            umma_bf16_ss(d_tmem, qh + 2 * k, rl + 2 * k, idesc, 1u);
+            if (p.passes == 3) {
+              umma_bf16_ss(d_tmem, ql + 2 * k, rh + 2 * k, idesc, 1u);
+              umma_bf16_ss(d_tmem, qh + 2 * k, rl + 2 * k, idesc, 1u);
+            }
           }
           fresh = false;
           umma_commit(&empty_bar[stage]);
-          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -168,6 +201,15 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       float ls[kFK];
       int32_t li[kFK];
       float qn_row = 0.f;
+      float thr_row = 0.f;
+      if (kMode == 2) {
+        const int64_t grow = row_base + lane;
+        const bool live = grow < p.nq;
+        if (p.l2 && live) qn_row = p.qn[grow];
+        const float m = live ? p.marg[grow] : 0.f;
+        thr_row = !p.has_radius ? (p.l2 ? INFINITY : -INFINITY) : (p.l2 ? p.radius + m : p.radius - m);
+        if (!live) thr_row = p.l2 ? -INFINITY : INFINITY;      // rows past the block never emit
+      }
       if (kFused) {
 #pragma unroll
         for (int j = 0; j < kFK; ++j) { ls[j] = -INFINITY; li[j] = -1; }
@@ -195,6 +237,44 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           for (int j = 0; j < 32; ++j) f[j] += __uint_as_float(v[j]);
         }
         if (gcol >= p.nr) continue;   // warp-uniform
+        if (kMode == 2) {
+          uint32_t hits = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = f[j];
+            const bool in = gcol + j < p.nr;
+            if (p.l2) v = fmaxf(qn_row + (in ? p.rn[gcol + j] : 0.f) - 2.0f * v, 0.f);
+            f[j] = v;
+            if (in && (p.l2 ? v < thr_row : v > thr_row)) hits |= 1u << j;
+          }
+          // survivors are rare (a fraction of a percent): ONE copy of the append code, run per set bit, with the value
+          // picked out of the register array by a 31-select tree (an unrolled copy per column thrashed the
+          // instruction cache: 1.66 ms -> see profiles/README.md)
+          const uint64_t pid0 = static_cast<uint64_t>(p.q0 + row_base + lane) * static_cast<uint64_t>(p.ntotal) + static_cast<uint64_t>(gcol);
+#pragma unroll 1
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            float t16[16], t8[8], t4[4];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? f[2 * i + 1] : f[2 * i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
+            const float u0 = (j & 8) ? t4[1] : t4[0], u1 = (j & 8) ? t4[3] : t4[2];
+            const float v = (j & 16) ? u1 : u0;
+            const uint32_t slot = atomicAdd(emit_cnt, 1u);
+            if (slot < static_cast<uint32_t>(kEmitCap)) {
+              emit_val[slot] = v;
+              emit_pid[slot] = pid0 + j;
+            } else {                                     // buffer full before the tile ended: straight to the global list
+              const unsigned long long pos = atomicAdd(p.counter, 1ull);
+              if (pos < p.cap) { p.bufv[pos] = v; p.bufp[pos] = pid0 + j; }
+            }
+          }
+          continue;
+        }
         if (kFused) {
           // Candidates are GROUPS of kFG = 8 consecutive bank rows, keyed by the group's best selection key
           // (larger is better; negated squared distance for L2): 8x fewer list updates than per-pair
@@ -267,6 +347,19 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (kMode == 2) {                                    // flush the tile's survivors: one reservation for the CTA
+        const int et = threadIdx.x - 128;
+        named_bar_sync(2, 32 * kTEpiWarps);
+        const uint32_t filled = *emit_cnt;
+        const uint32_t nflush = filled < static_cast<uint32_t>(kEmitCap) ? filled : static_cast<uint32_t>(kEmitCap);
+        if (et == 0) *emit_base = nflush ? atomicAdd(p.counter, static_cast<unsigned long long>(nflush)) : 0ull;
+        named_bar_sync(2, 32 * kTEpiWarps);
+        const unsigned long long base = *emit_base;
+        for (uint32_t i = et; i < nflush; i += 32 * kTEpiWarps)
+          if (base + i < p.cap) { p.bufv[base + i] = emit_val[i]; p.bufp[base + i] = emit_pid[i]; }
+        if (et == 0) *emit_cnt = 0u;
+        named_bar_sync(2, 32 * kTEpiWarps);
+      }
       }   // tiles of the item
       if (kFused) {
         const int64_t grow = row_base + lane;
@@ -310,14 +403,17 @@ int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, c
   return VSCB200_OK;
 }
 
-static int launch_sim3(const void* Qh, const void* Ql, const void* Rh, const void* Rl, SimParams p, int dp, bool fused,
-                       cudaStream_t stream) {
+static int launch_sim3(const void* Qh, const void* Ql, const void* Rh, const void* Rl, SimParams p, int dp, int mode,
+                       cudaStream_t stream, int64_t r_stride = 1) {
   CUtensorMap tQh, tQl, tRh, tRl;
   int rc;
+  if (p.passes != 3) { p.passes = 1; Ql = Qh; Rl = Rh; }      // the lo maps are never dereferenced
+  // r_stride > 1: bank row j of this launch is row j * r_stride of the planes (a column sample of the score block)
   if ((rc = make_tmap_2d(&tQh, Qh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nq, dp, dp, kTM, kTK, true))) return rc;
   if ((rc = make_tmap_2d(&tQl, Ql, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nq, dp, dp, kTM, kTK, true))) return rc;
-  if ((rc = make_tmap_2d(&tRh, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp, kTN, kTK, true))) return rc;
-  if ((rc = make_tmap_2d(&tRl, Rl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp, kTN, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRh, Rh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp * r_stride, kTN, kTK, true))) return rc;
+  if ((rc = make_tmap_2d(&tRl, Rl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.nr, dp, dp * r_stride, kTN, kTK, true))) return rc;
+  const bool fused = mode == 1;
   p.tiles_m = static_cast<int>((p.nq + kTM - 1) / kTM);
   const int64_t tn = (p.nr + kTN - 1) / kTN;
   VSCB_REQUIRE(static_cast<int64_t>(p.tiles_m) * tn < (1ll << 31), "scores_tc: too many tiles");
@@ -325,12 +421,15 @@ static int launch_sim3(const void* Qh, const void* Ql, const void* Rh, const voi
   const int64_t items = fused ? static_cast<int64_t>(p.tiles_m) * p.slabs : static_cast<int64_t>(p.tiles_m) * p.tiles_n;
   const int grid = static_cast<int>(items < device_sm_count() ? items : device_sm_count());
   ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(p.nq) * p.nr * dp);
-  if (fused) {
-    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
-    sim3_kernel<true><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+  if (mode == 1) {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    sim3_kernel<1><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+  } else if (mode == 2) {
+    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    sim3_kernel<2><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
   } else {
-    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
-    sim3_kernel<false><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
+    VSCB_CUDA_OK(cudaFuncSetAttribute(sim3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmem));
+    sim3_kernel<0><<<grid, kTThreads, kTSmem, stream>>>(tQh, tQl, tRh, tRl, p);
   }
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
@@ -338,14 +437,33 @@ static int launch_sim3(const void* Qh, const void* Ql, const void* Rh, const voi
 }
 
 int scores_tc_planes(const void* Qh, const void* Ql, const void* Rh, const void* Rl, float* S, int64_t nq, int64_t nr,
-                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream) {
+                     int dp, int64_t ldS, bool l2, const float* qn, const float* rn, cudaStream_t stream, int passes,
+                     int64_t r_stride) {
   if (nq == 0 || nr == 0) return VSCB200_OK;
   VSCB_REQUIRE(dp % 8 == 0, "scores_tc: dp must be a multiple of 8");
   SimParams p = {};
   p.S = S; p.ldS = ldS; p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0;
   p.vec4 = (ldS % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) ? 1 : 0;
   p.qn = qn; p.rn = rn;
-  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, false, stream);
+  p.passes = passes;
+  VSCB_REQUIRE(r_stride == 1 || !l2, "scores_tc: a strided bank sample is inner-product only (rn is not strided)");
+  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, 0, stream, r_stride);
+}
+
+// Threshold emission for the global candidate search (global_topk.cu): one bf16 pass over the [nq, nr] block, survivors
+// (value better than radius -/+ marg[row]; everything when !has_radius) appended to bufv / bufp, `counter` advanced.
+// qn: squared norms of the block's rows (L2), marg: their margins, q0: global row of block row 0.
+int scores_tc_emit(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int dp, bool l2, const float* qn, const float* rn,
+                   const float* marg, float radius, bool has_radius, int64_t q0, float* bufv, uint64_t* bufp,
+                   unsigned long long* counter, unsigned long long cap, cudaStream_t stream) {
+  if (nq == 0 || nr == 0) return VSCB200_OK;
+  VSCB_REQUIRE(dp % 8 == 0, "scores_tc_emit: dp must be a multiple of 8");
+  SimParams p = {};
+  p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0; p.qn = qn; p.rn = rn;
+  p.passes = 1;
+  p.marg = marg; p.radius = radius; p.has_radius = has_radius ? 1 : 0; p.q0 = q0; p.ntotal = nr;
+  p.bufv = bufv; p.bufp = bufp; p.counter = counter; p.cap = cap;
+  return launch_sim3(Qh, nullptr, Rh, nullptr, p, dp, 2, stream);
 }
 
 // Number of bank slabs per query block for the fused top-k mode: enough work items to fill the GPU
@@ -370,7 +488,8 @@ int topk_tc_fused(const void* Qh, const void* Ql, const void* Rh, const void* Rl
   SimParams p = {};
   p.nq = nq; p.nr = nr; p.K = dp; p.l2 = l2 ? 1 : 0; p.qn = qn; p.rn = rn;
   p.slabs = slabs; p.cand_d = cand_d; p.cand_i = cand_i;
-  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, true, stream);
+  p.passes = 3;
+  return launch_sim3(Qh, Ql, Rh, Rl, p, dp, 1, stream);
 }
 
 }  // namespace vscb200

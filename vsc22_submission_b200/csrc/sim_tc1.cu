@@ -39,6 +39,7 @@
 #include "host_util.h"
 #include "kernels.h"
 #include "ptx.cuh"
+#include "margin.cuh"
 
 namespace vscb200 {
 
@@ -92,16 +93,6 @@ __device__ __forceinline__ uint32_t okey32(float f) {          // order-preservi
 __device__ __forceinline__ float okey32_inv(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
-// the scoring-error bound of the header, in key units (L2 keys are -(|q|^2 + |r|^2 - 2 q.r): twice the product's error)
-__device__ __forceinline__ float sim1_eps(float qn2, float qlo2, const unsigned int* __restrict__ bank_max_bits, int d, int l2) {
-  const float qnorm = sqrtf(qn2), qlo = sqrtf(qlo2);
-  const float rmax2 = __uint_as_float(bank_max_bits[0]);
-  const float rmax = sqrtf(rmax2), rlmax = sqrtf(__uint_as_float(bank_max_bits[1]));
-  float eps = (qlo * rmax + (qnorm + qlo) * rlmax + static_cast<float>(d) * 1.1920929e-7f * qnorm * rmax) * 1.001f;
-  if (l2) eps = 2.0f * eps + 1e-6f * (qn2 + rmax2);
-  return eps;
-}
-
 __device__ __forceinline__ uint32_t ld_volatile_u32(const unsigned int* p) {      // asynchronous: the consumer waits, not the issue
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
