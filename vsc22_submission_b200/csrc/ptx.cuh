@@ -364,6 +364,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// named barrier with an OR reduction: every participant gets the same answer
+__device__ __forceinline__ bool named_bar_or(uint32_t id, uint32_t nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"(static_cast<uint32_t>(pred)), "r"(id), "r"(nthreads)
+      : "memory");
+  return out != 0u;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

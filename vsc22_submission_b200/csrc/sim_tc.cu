@@ -108,7 +108,7 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
   unsigned long long* emit_base = reinterpret_cast<unsigned long long*>(emit_pid + kEmitCap);
   uint32_t* emit_cnt = reinterpret_cast<uint32_t*>(emit_base + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform for the compiler
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQh); prefetch_tmap(&tmQl); prefetch_tmap(&tmRh); prefetch_tmap(&tmRl);
   }
@@ -122,7 +122,7 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int kblocks = (p.K + kTK - 1) / kTK;
   const int nseg = kblocks < kTSeg ? kblocks : kTSeg;
@@ -148,7 +148,9 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the WHOLE warp runs the loop on warp-uniform values (uniform registers), one elected lane issues inside
+    // the umma_*_warp wrappers -- no per-MMA election loop, no register -> uniform-register moves
+    {
       constexpr uint32_t idesc = make_idesc_bf16_f32(kTM, kTN);
       int stage = 0;
       uint32_t phase = 0;
@@ -170,27 +172,44 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * stage_bytes);
-          const uint64_t qh = make_desc_k_sw128(st), ql = make_desc_k_sw128(st + kTTile);
-          const uint64_t rh = make_desc_k_sw128(st + r_off), rl = make_desc_k_sw128(st + 3 * kTTile);
+          const uint64_t qh = make_desc_k_sw128(st), rh = make_desc_k_sw128(st + r_off);
+          if (p.passes == 3) {
+            const uint64_t ql = make_desc_k_sw128(st + kTTile), rl = make_desc_k_sw128(st + 3 * kTTile);
 #pragma unroll
-          for (int k = 0; k < kTK / 16; ++k) {
-            umma_bf16_ss(d_tmem, qh + 2 * k, rh + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
-            if (p.passes == 3) {
-              umma_bf16_ss(d_tmem, ql + 2 * k, rh + 2 * k, idesc, 1u);
-              umma_bf16_ss(d_tmem, qh + 2 * k, rl + 2 * k, idesc, 1u);
+            for (int k = 0; k < kTK / 16; ++k) {
+              umma_bf16_ss_warp(d_tmem, qh + 2 * k, rh + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
+              umma_bf16_ss_warp(d_tmem, ql + 2 * k, rh + 2 * k, idesc, 1u);
+              umma_bf16_ss_warp(d_tmem, qh + 2 * k, rl + 2 * k, idesc, 1u);
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kTK / 16; ++k)
+              umma_bf16_ss_warp(d_tmem, qh + 2 * k, rh + 2 * k, idesc, (fresh && k == 0) ? 0u : 1u);
           }
           fresh = false;
-          umma_commit(&empty_bar[stage]);
+          umma_commit_warp(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_warp(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4, quad = warp & 3, half = ew >> 2;
     float4* stage = stage_all + ew * 256;
+    // emit mode: all epilogue threads have passed a barrier since the last append and agree that a flush is due
+    auto emit_flush = [&]() {
+      const int et = threadIdx.x - 128;
+      const uint32_t filled = *emit_cnt;
+      const uint32_t nflush = filled < static_cast<uint32_t>(kEmitCap) ? filled : static_cast<uint32_t>(kEmitCap);
+      if (et == 0) *emit_base = nflush ? atomicAdd(p.counter, static_cast<unsigned long long>(nflush)) : 0ull;
+      named_bar_sync(2, 32 * kTEpiWarps);
+      const unsigned long long base = *emit_base;
+      for (uint32_t i = et; i < nflush; i += 32 * kTEpiWarps)
+        if (base + i < p.cap) { p.bufv[base + i] = emit_val[i]; p.bufp[base + i] = emit_pid[i]; }
+      if (et == 0) *emit_cnt = 0u;
+      named_bar_sync(2, 32 * kTEpiWarps);
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
     for (ItemIter it(p, kFused); it.valid(); it.advance()) {
@@ -347,18 +366,11 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (kMode == 2) {                                    // flush the tile's survivors: one reservation for the CTA
-        const int et = threadIdx.x - 128;
-        named_bar_sync(2, 32 * kTEpiWarps);
-        const uint32_t filled = *emit_cnt;
-        const uint32_t nflush = filled < static_cast<uint32_t>(kEmitCap) ? filled : static_cast<uint32_t>(kEmitCap);
-        if (et == 0) *emit_base = nflush ? atomicAdd(p.counter, static_cast<unsigned long long>(nflush)) : 0ull;
-        named_bar_sync(2, 32 * kTEpiWarps);
-        const unsigned long long base = *emit_base;
-        for (uint32_t i = et; i < nflush; i += 32 * kTEpiWarps)
-          if (base + i < p.cap) { p.bufv[base + i] = emit_val[i]; p.bufp[base + i] = emit_pid[i]; }
-        if (et == 0) *emit_cnt = 0u;
-        named_bar_sync(2, 32 * kTEpiWarps);
+      if (kMode == 2) {
+        // flush the survivors once the buffer is half full (a tile adds a few dozen): one barrier per tile, whose OR
+        // reduction makes the decision the same for every thread (a fast warp may already be appending the next
+        // tile's survivors when a slow one looks); three more and one global reservation per flush
+        if (named_bar_or(2, 32 * kTEpiWarps, *emit_cnt > static_cast<uint32_t>(kEmitCap / 2))) emit_flush();
       }
       }   // tiles of the item
       if (kFused) {
@@ -372,6 +384,10 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
           }
         }
       }
+    }
+    if (kMode == 2) {                                      // what the last tiles left in the buffer
+      named_bar_sync(2, 32 * kTEpiWarps);
+      emit_flush();
     }
   }
   tc_fence_before();
