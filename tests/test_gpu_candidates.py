@@ -67,6 +67,8 @@ def _global(ix, q, k=0, thr=None):
     (257, 4099, 20, 1, 0, 1),           # K = 1, ragged sizes, d not a multiple of 8
     (2000, 20000, 64, 7, 0, None),      # tiny K on one 40 M-pair block: radius bootstrapped from the 1/64 sample
     (2000, 20000, 64, 7, 1, None),
+    (3000, 30000, 512, 50000, 0, None),  # 90 M pairs, one block: column-sample radius, one-pass emission in the GEMM epilogue
+    (3000, 30000, 512, 50000, 0, 64),    # the same over 6 blocks: later blocks emit under the radius the first one found
 ])
 def test_global_topk_matches_oracle(monkeypatch, nq, nr, d, k, metric, ws_mb):
     import torch

@@ -80,6 +80,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
   return VSCB200_OK;
 }
 
+bool stream_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("VSCB200_STREAM_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("VSCB200_PDL"); return e ? atoi(e) != 0 : false; }();
   return on;

@@ -58,7 +58,7 @@ bool pdl_enabled();     // VSCB200_PDL=1: launch with programmatic stream serial
 // <<<>>> with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in the
 // stream drains; it must execute griddepcontrol.wait (ptx.cuh pdl_wait) before touching global memory.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -66,10 +66,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// the encoder's launches: measured no gain, behind VSCB200_PDL=1
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  return launch_pdl_if(pdl_enabled(), kernel, grid, block, smem, stream, args...);
+}
+// the streaming search's chain of small launches: on unless VSCB200_STREAM_PDL=0
+bool stream_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  return launch_pdl_if(stream_pdl_enabled(), kernel, grid, block, smem, stream, args...);
 }
 
 // Caching device allocator for the index's transient buffers (score workspace, staging, operand

@@ -195,7 +195,7 @@ int sim_stream_groupmax(const void* Qh, const void* Ql, const void* Rh, const vo
   VSCB_CUDA_OK(cudaFuncSetAttribute(sim_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = p.tiles < device_sm_count() ? p.tiles : device_sm_count();
   ProfScope prof(kProfScores, stream, 2.0 * static_cast<double>(nq) * nr * dp);
-  VSCB_CUDA_OK(launch_pdl(sim_stream_kernel, dim3(grid), dim3(kSsThreads), static_cast<size_t>(smem), stream, tRh, tRl, tQh, tQl, p));
+  VSCB_CUDA_OK(launch_pdl_chain(sim_stream_kernel, dim3(grid), dim3(kSsThreads), static_cast<size_t>(smem), stream, tRh, tRl, tQh, tQl, p));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -262,7 +262,7 @@ int group_topk(const float* gmax, int64_t G, int Npad, int nq, int kg, int chunk
   const size_t smem = static_cast<size_t>(kGtChunk) * (Npad + 1) * sizeof(float);
   VSCB_CUDA_OK(cudaFuncSetAttribute(group_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   ProfScope prof(kProfSelect, stream, static_cast<double>(G) * Npad * 4);
-  VSCB_CUDA_OK(launch_pdl(group_topk_kernel, dim3(chunks), dim3(kGtThreads), smem, stream, gmax, G, Npad, nq, kg, chunks, cand_v, cand_g));
+  VSCB_CUDA_OK(launch_pdl_chain(group_topk_kernel, dim3(chunks), dim3(kGtThreads), smem, stream, gmax, G, Npad, nq, kg, chunks, cand_v, cand_g));
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;
@@ -560,7 +560,7 @@ int group_rescore_few(const float* Q, const float* bank, int d, bool l2, int64_t
   VSCB_REQUIRE(smem <= 200 * 1024, "group_rescore_few: too many groups / dimension too large");
   VSCB_CUDA_OK(cudaFuncSetAttribute(group_rescore_few_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   ProfScope prof(kProfSelect, stream, static_cast<double>(nq) * kg * gs * d * 4);
-  VSCB_CUDA_OK(launch_pdl(group_rescore_few_kernel, dim3(kg, static_cast<unsigned>(nq)), dim3(kGfThreads), smem, stream, Q, bank, d,
+  VSCB_CUDA_OK(launch_pdl_chain(group_rescore_few_kernel, dim3(kg, static_cast<unsigned>(nq)), dim3(kGfThreads), smem, stream, Q, bank, d,
                           l2 ? 1 : 0, nr, cand_v, cand_g, ncg, kg, gs, cpad, k, reinterpret_cast<unsigned long long*>(keys),
                           counters, D, I, id_offset));
   count_launch();
