@@ -785,8 +785,9 @@ def bench_candidates(peaks, nq=SIM_NQ_C, nr=SIM_NR_C, rows_q=40, rows_r=50, iter
                     "api": "candidates.CandidateGeneration(refs, MaxScoreAggregation()).query(queries, global_k) on "
                            "per-video host arrays (index build included)"},
             "roofline": {"bound": "tensor", "tensor_frac": 2.0 * nq * nr * SIM_D / (ms / 1e3) / 1e12 / peaks["bf16_tflops"],
-                         "note": "score block by the split-bf16 kernel (ceiling 1/3) + one HBM pass of the block per "
-                                 "radix-select level / emit"}}
+                         "note": "one bf16 MMA per product with the threshold emission in the GEMM epilogue (no dense "
+                                 "block); radius from a 1/64 column-sample GEMM, verified by the K-th best survivor; "
+                                 "survivors rescored in exact fp32 and radix-sorted"}}
 
 
 def bench_localization(n_q=2000, n_r=8000, per_q=5):

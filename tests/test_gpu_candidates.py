@@ -49,7 +49,7 @@ def _pairs_equal(got, ora, gap=1e-6):
     near[:-1] |= close
     near[-1] = True
     assert (same | near).all(), f"{(~(same | near)).sum()} pair ids differ outside near-ties"
-    assert same.mean() > (0.99 if len(d) < 100000 else 0.9)      # 1 M scores in [0, 0.75] sit < 1e-6 apart
+    assert same.mean() > (0.99 if len(d) < 20000 else 0.9)       # 50 k+ scores in [0.1, 0.75] sit a few 1e-6 apart: near-ties swap
 
 
 def _global(ix, q, k=0, thr=None):

@@ -258,13 +258,18 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
         if (gcol >= p.nr) continue;   // warp-uniform
         if (kMode == 2) {
           uint32_t hits = 0;
+          if (!p.l2 && gcol + 32 <= p.nr) {                // (warp-uniform) interior chunk, inner product: compare only
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = f[j];
-            const bool in = gcol + j < p.nr;
-            if (p.l2) v = fmaxf(qn_row + (in ? p.rn[gcol + j] : 0.f) - 2.0f * v, 0.f);
-            f[j] = v;
-            if (in && (p.l2 ? v < thr_row : v > thr_row)) hits |= 1u << j;
+            for (int j = 0; j < 32; ++j) hits |= (f[j] > thr_row ? 1u : 0u) << j;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = f[j];
+              const bool in = gcol + j < p.nr;
+              if (p.l2) v = fmaxf(qn_row + (in ? p.rn[gcol + j] : 0.f) - 2.0f * v, 0.f);
+              f[j] = v;
+              if (in && (p.l2 ? v < thr_row : v > thr_row)) hits |= 1u << j;
+            }
           }
           // survivors are rare (a fraction of a percent): ONE copy of the append code, run per set bit, with the value
           // picked out of the register array by a 31-select tree (an unrolled copy per column thrashed the
