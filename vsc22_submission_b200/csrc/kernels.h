@@ -63,6 +63,9 @@ size_t sim1_partial_bytes();
 int sim1_topk(const void* Qh, const void* Rh, int64_t nq, int64_t nr, int d, int dp, bool l2, int k, const float* qn,
               const float* qn_lo, const float* rn, const unsigned int* bank_max_bits, void* cand, int* scratch,
               cudaStream_t stream);
+// thresholds of the query rows from one-pass scores S [nq, ncs] against a column sample of the bank (ncs <= 1024)
+int sim1_boot_tau(const float* S, int64_t nq, int ncs, int k, const float* qn, const float* qn_lo,
+                  const unsigned int* bank_max_bits, int d, int* scratch, cudaStream_t stream);
 int sim1_rescore(const float* Q, const float* bank, int d, bool l2, int64_t nq, int64_t nr, const void* cand, int k,
                  const float* qn, const float* qn_lo, const unsigned int* bank_max_bits, float* D, int64_t* I, int64_t id_offset,
                  int* scratch, void* partial, cudaStream_t stream);

@@ -125,7 +125,9 @@ sim3_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CU
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int kblocks = (p.K + kTK - 1) / kTK;
-  const int nseg = kblocks < kTSeg ? kblocks : kTSeg;
+  // accumulator segments shorten the rounding chains of the fp32-equivalent form; the one-pass form (an approximate score
+  // with a proven margin) accumulates in one
+  const int nseg = p.passes != 3 ? 1 : (kblocks < kTSeg ? kblocks : kTSeg);
 
   if (warp == 0) {
     if (lane == 0) {

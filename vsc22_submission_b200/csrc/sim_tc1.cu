@@ -347,7 +347,9 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const bool live = row0 + lane < p.nq;
         qn_lane = live ? p.qn[row0 + lane] : 0.f;
         eps2 = live ? 2.0002f * sim1_eps(qn_lane, p.qn_lo[row0 + lane], p.bank_max_bits, p.d, p.l2) : 0.f;
-        tau = live ? -INFINITY : INFINITY;
+        // the query's shared threshold: what sim1_boot_tau derived from a column sample (or other pairs have reached)
+        const uint32_t g0 = live ? ld_volatile_u32(p.tau_g + row0 + lane) : 0u;
+        tau = live ? (g0 != 0u ? okey32_inv(g0) : -INFINITY) : INFINITY;
         cnt = 0;
         g_next = 0u;
         tau_pub = tau;
@@ -693,6 +695,55 @@ int sim1_pairs(int64_t nq, int64_t nr) {
 }
 int sim1_list_cap() { return kS1ListCap; }
 int sim1_max_k() { return kS1MaxK; }
+
+// ------------------------------------------------------------------ threshold bootstrap from a column sample
+// S [nq, ncs]: one-pass scores of every query against a sample of ncs <= 1024 bank rows (sim_tc.cu, strided tensor map).
+// The k-th best of a SUBSET of the bank cannot exceed the k-th best of the bank, so tau0 = (k-th best of the sample) - 2 eps
+// is a valid initial threshold for the query: sim1_topk_kernel starts every list of the row from it instead of from
+// -infinity (without it ~20 appends per 1024 scores while the thresholds warm up, per (row, pair) list).
+// One warp per query row: the row in registers (32 per lane), k rounds of warp arg-max.
+__global__ void __launch_bounds__(256)
+sim1_boot_tau_kernel(const float* __restrict__ S, int64_t nq, int ncs, int k, const float* __restrict__ qn,
+                     const float* __restrict__ qn_lo, const unsigned int* __restrict__ bank_max_bits, int d,
+                     unsigned int* __restrict__ tau_g) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i * 32 + lane < ncs ? S[row * ncs + i * 32 + lane] : -INFINITY;
+  float kth = -INFINITY;
+  for (int r = 0; r < k; ++r) {
+    float lm = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) lm = fmaxf(lm, v[i]);
+    const uint32_t best = __reduce_max_sync(0xffffffffu, okey32(lm));
+    const uint32_t owners = __ballot_sync(0xffffffffu, okey32(lm) == best);
+    if (lane == __ffs(owners) - 1) {                      // one instance leaves the row
+      bool done = false;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (!done && okey32(v[i]) == best) { v[i] = -INFINITY; done = true; }
+    }
+    kth = okey32_inv(best);
+  }
+  if (lane == 0 && kth > -INFINITY) {
+    const float tau0 = kth - 2.0002f * sim1_eps(qn[row], qn_lo[row], bank_max_bits, d, 0);
+    tau_g[row] = okey32(tau0);
+  }
+}
+
+// scratch: the zeroed scratch of sim1_topk (the thresholds live at scratch + nq + 1).  Inner-product metric only.
+int sim1_boot_tau(const float* S, int64_t nq, int ncs, int k, const float* qn, const float* qn_lo,
+                  const unsigned int* bank_max_bits, int d, int* scratch, cudaStream_t stream) {
+  if (nq == 0) return VSCB200_OK;
+  VSCB_REQUIRE(ncs >= k && ncs <= 1024 && k >= 1, "sim1_boot_tau: need k <= ncs <= 1024");
+  sim1_boot_tau_kernel<<<static_cast<unsigned>((nq * 32 + 255) / 256), 256, 0, stream>>>(
+      S, nq, ncs, k, qn, qn_lo, bank_max_bits, d, reinterpret_cast<unsigned int*>(scratch + nq + 1));
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
 
 // Qh [nq, dp] / Rh [nr, dp]: bf16 hi planes.  cand: [nq, sim1_list_cap()] entries of 8 bytes.
 // qn / qn_lo [nq]: |q|^2, |q - bf16(q)|^2.  scratch: see sim1_rescore (zero on entry).
