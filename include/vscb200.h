@@ -60,6 +60,12 @@ int vscb200_index_create(int d, int metric, vscb200_index** out);
 void vscb200_index_destroy(vscb200_index* ix);
 /* index.add(x) -- vsc/index.py:94.  x: [n, d] float32, C-contiguous. Rows get ids ntotal..ntotal+n-1. */
 int vscb200_index_add(vscb200_index* ix, const float* x_dev, int64_t n, void* stream);
+/* index.add(rows transformed by score normalisation) in one pass over the raw rows -- replaces the pair
+ * `sn_features = normalize(np.delete(x, low_var_dim, 1)); np.concatenate([.., fill])` (score_normalization.py:73-83,
+ * 96-101) + index.add (vsc/index.py:94) without materialising the transformed array.  See vscb200_sn_transform for the
+ * arguments; the index dimension is d_in when a column is dropped, else d_in + 1. */
+int vscb200_index_add_sn(vscb200_index* ix, const float* x_dev, int64_t n, int d_in, int drop_dim, const int* drop_dim_dev,
+                         int l2_normalize, float fill, const float* bias_dev, void* stream);
 int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n);
 /* index.reset() -- exhaustive_search.py:39 */
 int vscb200_index_reset(vscb200_index* ix);

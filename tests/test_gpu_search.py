@@ -482,3 +482,44 @@ def test_sharded_step_primitives_single_process(faiss):
     order = np.argsort(-allD, axis=1, kind="stable")[:, :k]
     np.testing.assert_array_equal(I.cpu().numpy(), np.take_along_axis(allI, order, 1))
     np.testing.assert_array_equal(D.cpu().numpy(), np.take_along_axis(allD, order, 1) + bias.cpu().numpy()[:, None])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,drop,fill,use_bias", [(512, "dev", 0.0, False), (512, 7, 1.0, False), (64, -1, 0.0, True),
+                                                  (20, 0, 1.0, True)])
+def test_add_sn_stores_what_sn_transform_plus_add_stores(faiss, d, drop, fill, use_bias):
+    """DeviceIndex.add_sn (one pass over the raw rows) vs sn_transform + add: identical stored rows, identical search
+    results (scores bit for bit: same planes, same norms, same margins)."""
+    import torch
+    from vsc22_submission_b200 import search
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = torch.randn((5000, d), generator=g, device="cuda")
+    x[17] = 0.0                                             # sklearn.normalize leaves zero rows zero
+    q = torch.nn.functional.normalize(torch.randn((300, d), generator=g, device="cuda"))
+    bias = torch.randn((5000,), generator=g, device="cuda") if use_bias else None
+    dd = search.low_var_dim_device(x) if drop == "dev" else drop
+    t = search.sn_transform(x, dd, True, fill=fill, bias=bias)
+    a = search.DeviceIndex(t.shape[1]); a.add(t[:2000]); a.add(t[2000:])
+    b = search.DeviceIndex(t.shape[1])
+    b.add_sn(x[:2000], dd, True, fill=fill, bias=None if bias is None else bias[:2000])
+    b.add_sn(x[2000:], dd, True, fill=fill, bias=None if bias is None else bias[2000:])
+    assert torch.equal(a.reconstruct_n(0, 5000), b.reconstruct_n(0, 5000))
+    qq = torch.nn.functional.normalize(torch.randn((300, t.shape[1]), generator=g, device="cuda"))
+    for k in (1, 10, 64):
+        Da, Ia = a.search(qq, k)
+        Db, Ib = b.search(qq, k)
+        assert torch.equal(Ia, Ib) and torch.equal(Da, Db)
+
+
+@pytest.mark.gpu
+def test_score_normalized_search_equals_the_two_step_form(faiss):
+    import torch
+    from vsc22_submission_b200 import search
+    g = torch.Generator(device="cuda").manual_seed(3)
+    unit = lambda n: torch.nn.functional.normalize(torch.randn((n, 512), generator=g, device="cuda"))
+    q, r, z = unit(700), unit(9000), unit(6000)
+    D, I = search.score_normalized_search(q, r, z, 10, beta=1.2, nk=1)
+    q_t, r_t, _ = search.score_normalize_tensors(q, r, z, beta=1.2, nk=1)
+    ix = search.DeviceIndex(r_t.shape[1]); ix.add(r_t)
+    D2, I2 = ix.search(q_t, 10)
+    assert torch.equal(I, I2) and torch.equal(D, D2)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "vscb200_index_create": (_i, [_i, _i, C.POINTER(_p)]),
     "vscb200_index_destroy": (None, [_p]),
     "vscb200_index_add": (_i, [_p, _p, _i64, _p]),
+    "vscb200_index_add_sn": (_i, [_p, _p, _i64, _i, _i, _p, _i, _f, _p, _p]),
     "vscb200_index_add_host": (_i, [_p, _p, _i64]),
     "vscb200_index_reset": (_i, [_p]),
     "vscb200_index_ntotal": (_i64, [_p]),

@@ -75,25 +75,33 @@ int ensure_capacity(vscb200_index* ix, int64_t rows, cudaStream_t s) {
   return VSCB200_OK;
 }
 
+// the bank's running norm maxima (margins of the one-pass searches): allocated at the first add, zeroed after a reset
+int norm_maxima_ready(vscb200_index* ix, cudaStream_t s) {
+  int rc;
+  if (!ix->rmax2_bits && (rc = pool_alloc(reinterpret_cast<void**>(&ix->rmax2_bits), 2 * sizeof(unsigned int), s))) return rc;
+  if (ix->rmax2_reset) {
+    VSCB_CUDA_OK(cudaMemsetAsync(ix->rmax2_bits, 0, 2 * sizeof(unsigned int), s));
+    ix->rmax2_reset = false;
+  }
+  return VSCB200_OK;
+}
+
 int append_rows(vscb200_index* ix, const float* x, int64_t n, cudaMemcpyKind kind, cudaStream_t s) {
   if (n == 0) return VSCB200_OK;
   int rc = ensure_capacity(ix, ix->ntotal + n, s);
   if (rc) return rc;
   float* dst = ix->bank + ix->ntotal * ix->d;
   VSCB_CUDA_OK(cudaMemcpyAsync(dst, x, static_cast<size_t>(n) * ix->d * sizeof(float), kind, s));
-  if (!ix->rmax2_bits && (rc = pool_alloc(reinterpret_cast<void**>(&ix->rmax2_bits), 2 * sizeof(unsigned int), s))) return rc;
-  if (ix->rmax2_reset) {
-    VSCB_CUDA_OK(cudaMemsetAsync(ix->rmax2_bits, 0, 2 * sizeof(unsigned int), s));
-    ix->rmax2_reset = false;
+  if ((rc = norm_maxima_ready(ix, s))) return rc;
+  if (ix->force_simt) {
+    rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);   // L2 transform + range-search error margins
+  } else {
+    // one pass over the new rows: squared norms (the same summation order as row_sqnorm), both bf16 operand planes, and
+    // the running maxima of |r|^2 and |r - bf16(r)|^2 (margin of the one-pass searches)
+    rc = q_hi_norm(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->rnorm + ix->ntotal, nullptr, n, ix->d, ix->dp, s,
+                   ix->bank_lo + ix->ntotal * ix->dp, ix->rmax2_bits);
   }
-  rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);   // L2 transform + range-search error margins
   if (rc) return rc;
-  if (!ix->force_simt) rc = bank_norm_max(dst, n, ix->d, ix->rmax2_bits, s);   // margin of the single-pass search
-  if (rc) return rc;
-  if (!ix->force_simt) {
-    rc = split_planes(dst, ix->bank_hi + ix->ntotal * ix->dp, ix->bank_lo + ix->ntotal * ix->dp, n, ix->d, ix->dp, s);
-    if (rc) return rc;
-  }
   ix->ntotal += n;
   return VSCB200_OK;
 }
@@ -257,6 +265,34 @@ int vscb200_index_add(vscb200_index* ix, const float* x_dev, int64_t n, void* st
   int rc = flush_pending(ix, s);
   if (rc) return rc;
   return append_rows(ix, x_dev, n, cudaMemcpyDeviceToDevice, s);
+}
+
+/* index.add(sn_transform(x)) in one pass: the score-normalisation transform of raw rows (score_normalization.py:73-83,
+ * 96-101: drop a column, L2-normalise, append `fill` or bias[row]) written straight into the index's storage.  Stored values
+ * are bit-identical to vscb200_sn_transform followed by vscb200_index_add.  d_in: columns of x; the index dimension must be
+ * d_in when a column is dropped (drop_dim_dev != NULL, or 0 <= drop_dim < d_in), else d_in + 1. */
+int vscb200_index_add_sn(vscb200_index* ix, const float* x_dev, int64_t n, int d_in, int drop_dim, const int* drop_dim_dev,
+                         int l2_normalize, float fill, const float* bias_dev, void* stream) {
+  VSCB_REQUIRE(ix && (n == 0 || x_dev), "index_add_sn: null argument");
+  VSCB_REQUIRE(n >= 0 && d_in > 0 && drop_dim < d_in, "index_add_sn: bad shape");
+  const bool drops = drop_dim_dev != nullptr || drop_dim >= 0;
+  VSCB_REQUIRE(ix->d == (drops ? d_in : d_in + 1), "index_add_sn: index dimension does not match the transformed rows");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = flush_pending(ix, s);
+  if (rc || n == 0) return rc;
+  if ((rc = ensure_capacity(ix, ix->ntotal + n, s))) return rc;
+  float* dst = ix->bank + ix->ntotal * ix->d;
+  if (ix->force_simt) {
+    if ((rc = sn_transform(x_dev, n, d_in, drop_dim, l2_normalize, fill, bias_dev, dst, s, drop_dim_dev))) return rc;
+    rc = row_sqnorm(dst, n, ix->d, ix->rnorm + ix->ntotal, s);
+  } else {
+    if ((rc = norm_maxima_ready(ix, s))) return rc;
+    rc = sn_add_rows(x_dev, n, d_in, drop_dim, l2_normalize, fill, bias_dev, drop_dim_dev, dst, ix->bank_hi + ix->ntotal * ix->dp,
+                     ix->bank_lo + ix->ntotal * ix->dp, ix->rnorm + ix->ntotal, ix->rmax2_bits, ix->d, ix->dp, s);
+  }
+  if (rc) return rc;
+  ix->ntotal += n;
+  return VSCB200_OK;
 }
 
 int vscb200_index_add_host(vscb200_index* ix, const float* x_host, int64_t n) {

@@ -55,7 +55,12 @@ int split_planes(const float* x, void* hi, void* lo, int64_t n, int d, int dp, c
 // sim_tc1.cu: single-pass (one bf16 MMA per product) top-k selection with an error margin + exact rescoring
 int sim1_pairs(int64_t nq, int64_t nr);
 int sim1_list_cap();
-int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo = nullptr);
+// sim.cu: score-normalisation transform of raw rows written straight into an index's storage (bank, planes, norms, maxima)
+int sn_add_rows(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
+                const int* drop_dim_dev, float* bank, void* hi, void* lo, float* rnorm, unsigned int* max_bits, int dout, int dp,
+                cudaStream_t stream);
+int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo = nullptr,
+              unsigned int* max_bits = nullptr);
 int bank_norm_max(const float* x, int64_t n, int d, unsigned int* max_bits, cudaStream_t stream);
 int sim1_max_k();
 int sim1_scratch_ints(int64_t nq);

@@ -152,6 +152,73 @@ int sn_transform(const float* x, int64_t n, int d, int drop_dim, int l2_normaliz
   return VSCB200_OK;
 }
 
+// The same transform written STRAIGHT into an index's storage (index.cu vscb200_index_add_sn): the fp32 bank row, both
+// bf16 operand planes, the squared norm of the transformed row and the bank's running norm maxima in one kernel -- what
+// sn_transform + the device copy of add() + the plane pass did in three (107 -> 45 us per 40k x 512 rows).  Arithmetic
+// and summation orders are those of sn_transform_kernel and q_hi_norm_kernel, so every stored value is bit-identical to
+// the unfused path.
+__global__ void __launch_bounds__(256)
+sn_add_rows_kernel(const float* __restrict__ x, int64_t n, int d, int drop_dim, int l2_normalize, float fill,
+                   const float* __restrict__ bias, const int* __restrict__ drop_dim_dev, float* __restrict__ bank,
+                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ rnorm,
+                   unsigned int* __restrict__ max_bits, int dout, int dp) {
+  const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  if (drop_dim_dev) drop_dim = *drop_dim_dev;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    if (c == drop_dim) continue;
+    const float v = xr[c];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float denom = 1.0f;
+  if (l2_normalize) {
+    denom = sqrtf(s);
+    if (denom == 0.f) denom = 1.0f;
+  }
+  const float last = bias ? bias[row] : fill;
+  float s2 = 0.f, sl = 0.f;
+  for (int oc = lane; oc < dp; oc += 32) {                 // output columns, in q_hi_norm_kernel's order
+    float v = 0.f;
+    if (oc < dout - 1) v = xr[(drop_dim >= 0 && oc >= drop_dim) ? oc + 1 : oc] / denom;
+    else if (oc == dout - 1) v = last;
+    if (oc < dout) bank[row * dout + oc] = v;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float e = v - __bfloat162float(h);
+    s2 = fmaf(v, v, s2);
+    sl = fmaf(e, e, sl);
+    hi[row * dp + oc] = h;
+    lo[row * dp + oc] = __float2bfloat16_rn(e);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    sl += __shfl_xor_sync(0xffffffffu, sl, o);
+  }
+  if (lane == 0) {
+    rnorm[row] = s2;
+    if (__float_as_uint(s2) > *reinterpret_cast<volatile unsigned int*>(max_bits)) atomicMax(max_bits, __float_as_uint(s2));
+    if (__float_as_uint(sl) > *reinterpret_cast<volatile unsigned int*>(max_bits + 1)) atomicMax(max_bits + 1, __float_as_uint(sl));
+  }
+}
+
+int sn_add_rows(const float* x, int64_t n, int d, int drop_dim, int l2_normalize, float fill, const float* bias,
+                const int* drop_dim_dev, float* bank, void* hi, void* lo, float* rnorm, unsigned int* max_bits, int dout, int dp,
+                cudaStream_t stream) {
+  if (n == 0) return VSCB200_OK;
+  VSCB_REQUIRE(drop_dim < d, "sn_add_rows: drop_dim out of range");
+  sn_add_rows_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(
+      x, n, d, drop_dim, l2_normalize, fill, bias, drop_dim_dev, bank, reinterpret_cast<__nv_bfloat16*>(hi),
+      reinterpret_cast<__nv_bfloat16*>(lo), rnorm, max_bits, dout, dp);
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
 // bias[row] = -beta * mean(D[row, :nk])
 __global__ void sn_bias_kernel(const float* __restrict__ D, int64_t nq, int k, int nk, float beta,
                                float* __restrict__ bias) {
@@ -200,7 +267,8 @@ __global__ void col_finish_kernel(const double* __restrict__ partial, int slabs,
 // out[c] = sum_r x[r, c]                         (sum_in == nullptr)
 //        = sum_r (x[r, c] - sum_in[c] * inv_n)^2 (sum_in != nullptr)
 int col_sums(const float* x, int64_t n, int d, const double* sum_in, double inv_n, double* out, cudaStream_t stream) {
-  const int slabs = static_cast<int>(n < 4096 ? 1 : (n / 2048 > 1024 ? 1024 : n / 2048));
+  // row slabs of ~256 rows: enough CTAs to keep the HBM pipes full (2048-row slabs: 304 CTAs, 73 us per pass over 40k x 512)
+  const int slabs = static_cast<int>(n < 4096 ? 1 : (n / 256 > 1024 ? 1024 : n / 256));
   double* partial = nullptr;
   int rc = pool_alloc(reinterpret_cast<void**>(&partial), sizeof(double) * static_cast<size_t>(slabs) * d, stream);
   if (rc) return rc;

@@ -399,7 +399,7 @@ sim1_topk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // sq[row] = |q|^2 ; sq_lo[row] = |q - bf16(q)|^2 (optional) ; lo plane = bf16(q - hi) (optional: the split-bf16 kernels)
 __global__ void __launch_bounds__(256)
 q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ sq,
-                 float* __restrict__ sq_lo, int64_t n, int d, int dp) {
+                 float* __restrict__ sq_lo, int64_t n, int d, int dp, unsigned int* __restrict__ max_bits) {
   pdl_launch_dependents();                                // the streaming search launches its kernel behind this one early
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -422,14 +422,22 @@ q_hi_norm_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __
   if (lane == 0) {
     sq[row] = s;
     if (sq_lo) sq_lo[row] = sl;
+    if (max_bits) {     // bank rows: running maxima of |r|^2 and |r - bf16(r)|^2 (float bits; the values are >= 0).  Read
+                        // first: after the first rows almost no row raises a maximum, and contended atomics serialise
+      if (__float_as_uint(s) > *reinterpret_cast<volatile unsigned int*>(max_bits)) atomicMax(max_bits, __float_as_uint(s));
+      if (__float_as_uint(sl) > *reinterpret_cast<volatile unsigned int*>(max_bits + 1)) atomicMax(max_bits + 1, __float_as_uint(sl));
+    }
   }
 }
 
-// one pass over the query rows: hi plane (+ lo plane), squared norms (+ squared norms of the bf16 residual)
-int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo) {
+// one pass over query (or bank) rows: hi plane (+ lo plane), squared norms (+ squared norms of the bf16 residual; + their
+// running maxima for bank rows: everything add() needs in ONE read of the rows -- three kernels before: 126 us per
+// 40k x 512 rows -> one)
+int q_hi_norm(const float* x, void* hi, float* sq, float* sq_lo, int64_t n, int d, int dp, cudaStream_t stream, void* lo,
+              unsigned int* max_bits) {
   if (n == 0) return VSCB200_OK;
   q_hi_norm_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, stream>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), sq, sq_lo, n, d, dp);
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), sq, sq_lo, n, d, dp, max_bits);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;

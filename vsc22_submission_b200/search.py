@@ -79,6 +79,27 @@ class DeviceIndex:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().vscb200_index_add(self._ptr, _p(x), x.shape[0], _stream(self.device)), "index.add")
 
+    def add_sn(self, x: torch.Tensor, drop_dim, l2_normalize: bool, fill: float = 0.0, bias: Optional[torch.Tensor] = None):
+        """``add(sn_transform(x, drop_dim, l2_normalize, fill, bias))`` in one pass over the raw rows: the transformed array
+        is never materialised (score_normalization.py:73-83, 96-101 + vsc/index.py:94); the stored rows are bit-identical to
+        the two-step form.  ``drop_dim``: int, or the device tensor of ``low_var_dim_device``."""
+        x = _f32_cuda(x, "DeviceIndex.add_sn")
+        dev_dim = isinstance(drop_dim, torch.Tensor)
+        drops = dev_dim or 0 <= int(drop_dim) < x.shape[1]
+        if x.dim() != 2 or x.shape[1] + (0 if drops else 1) != self.d:
+            raise AssertionError(f"add_sn: rows of {tuple(x.shape)} do not transform to dimension {self.d}")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().vscb200_index_add_sn(self._ptr, _p(x), x.shape[0], x.shape[1], -1 if dev_dim else int(drop_dim),
+                                                       _p(drop_dim) if dev_dim else None, int(bool(l2_normalize)), float(fill),
+                                                       _p(bias), _stream(self.device)), "index.add_sn")
+
+    def reconstruct_n(self, i0: int, n: int) -> torch.Tensor:
+        """Rows [i0, i0 + n) of the bank as stored (index.reconstruct_n)."""
+        out = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+        if n:
+            _lib.check(_lib.lib().vscb200_index_reconstruct_n(self._ptr, int(i0), int(n), _p(out)), "index.reconstruct_n")
+        return out
+
     def reset(self):
         _lib.check(_lib.lib().vscb200_index_reset(self._ptr), "index.reset")
 
@@ -295,6 +316,28 @@ def noise_bias(q_t: torch.Tensor, z_t: torch.Tensor, beta: float, nk: int) -> to
     return bias_from_topk(D, beta, nk)
 
 
+def sn_index(x: torch.Tensor, drop_dim, l2_normalize: bool, fill: float) -> "DeviceIndex":
+    """Inner-product index over ``sn_transform(x, drop_dim, l2_normalize, fill)`` built in one pass over ``x``."""
+    x = _f32_cuda(x, "sn_index")
+    drops = isinstance(drop_dim, torch.Tensor) or 0 <= int(drop_dim) < x.shape[1]
+    ix = DeviceIndex(x.shape[1] + (0 if drops else 1), METRIC_INNER_PRODUCT, x.device)
+    ix.add_sn(x, drop_dim, l2_normalize, fill=fill)
+    return ix
+
+
+def score_normalized_search(q: torch.Tensor, r: torch.Tensor, z: torch.Tensor, k: int, l2_normalize=True, replace_dim=True,
+                            beta=1.0, nk=1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``score_normalize`` followed by the top-k search of the normalised queries against the normalised references
+    (score_normalization.py:33-104 + vsc/index.py:174), everything resident on the device: the two banks go through
+    ``DeviceIndex.add_sn`` (no transformed copy), the queries through ``sn_transform``.  Same D, I as
+    ``score_normalize_tensors`` + ``DeviceIndex.add`` + ``search``."""
+    lvd = low_var_dim_device(z) if replace_dim else -1
+    q_0 = sn_transform(q, lvd, l2_normalize, fill=0.0)
+    Dz, _ = sn_index(z, lvd, l2_normalize, 0.0).search(q_0, nk)
+    q_t = sn_transform(q, lvd, l2_normalize, bias=bias_from_topk(Dz, beta, nk))
+    return sn_index(r, lvd, l2_normalize, 1.0).search(q_t, k)
+
+
 def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch.Tensor, l2_normalize=True,
                             replace_dim=True, beta=1.0, nk=1, low_var_dim_: Optional[int] = None,
                             gated_rows: Optional[torch.Tensor] = None):
@@ -302,10 +345,10 @@ def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch
     lvd = -1
     if replace_dim:
         lvd = low_var_dim_device(z) if low_var_dim_ is None else int(low_var_dim_)    # stays on the device: no sync
-    # the noise search ignores the appended column (0 on both sides)
-    z_t = sn_transform(z, lvd, l2_normalize, fill=0.0)
+    # the noise search ignores the appended column (0 on both sides); the noise bank goes straight into its index
     q_0 = sn_transform(q, lvd, l2_normalize, fill=0.0)
-    bias = noise_bias(q_0, z_t, beta, nk)
+    Dz, _ = sn_index(z, lvd, l2_normalize, 0.0).search(q_0, nk)
+    bias = bias_from_topk(Dz, beta, nk)
     if gated_rows is not None:
         bias = torch.where(gated_rows.to(bias.device), torch.full_like(bias, -100.0), bias)
     q_t = sn_transform(q, lvd, l2_normalize, bias=bias)
