@@ -334,8 +334,8 @@ def score_normalized_search(q: torch.Tensor, r: torch.Tensor, z: torch.Tensor, k
     lvd = low_var_dim_device(z) if replace_dim else -1
     q_0 = sn_transform(q, lvd, l2_normalize, fill=0.0)
     Dz, _ = sn_index(z, lvd, l2_normalize, 0.0).search(q_0, nk)
-    q_t = sn_transform(q, lvd, l2_normalize, bias=bias_from_topk(Dz, beta, nk))
-    return sn_index(r, lvd, l2_normalize, 1.0).search(q_t, k)
+    q_0[:, -1] = bias_from_topk(Dz, beta, nk)      # = sn_transform(q, lvd, l2_normalize, bias=...): only the last column differs
+    return sn_index(r, lvd, l2_normalize, 1.0).search(q_0, k)
 
 
 def score_normalize_tensors(q: torch.Tensor, r: Optional[torch.Tensor], z: torch.Tensor, l2_normalize=True,
