@@ -151,6 +151,9 @@ int vscb200_topk_pack(const float* D_dev, const int64_t* I_dev, int64_t nq, int 
                       void* stream);
 int vscb200_topk_merge(const uint64_t* keys_dev, int parts, int64_t nq, int kin, int kout, int keep_max, float* D_dev,
                        int64_t* I_dev, void* stream);
+/* vscb200_topk_pack into columns [col0, col0 + k) of rows of ld keys: the layout vscb200_topk_merge_cols reads. */
+int vscb200_topk_pack_cols(const float* D_dev, const int64_t* I_dev, int64_t nq, int k, int keep_max, uint64_t* keys_dev, int ld,
+                           int col0, void* stream);
 /* score_normalizev2 of the matching track (VSC22-Matching-Track-1st/vsc/baseline/score_normalization.py:141-153):
  * out[row] = l2_normalize(x[row] - beta * mean_k z[ids[row, k]]), ids = the nk nearest noise rows of normalize(x[row])
  * (from vscb200_index_search over the normalised noise bank); z is the UN-normalised noise bank. */

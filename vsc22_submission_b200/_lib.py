@@ -83,6 +83,7 @@ SIGNATURES = {
     "vscb200_col_moments_local": (_i, [_p, _i64, _i, _p, _p]),
     "vscb200_var_argmin_moments": (_i, [_p, C.c_double, _i, _p, _p]),
     "vscb200_topk_pack": (_i, [_p, _p, _i64, _i, _i, _p, _p]),
+    "vscb200_topk_pack_cols": (_i, [_p, _p, _i64, _i, _i, _p, _i, _i, _p]),
     "vscb200_topk_merge": (_i, [_p, _i, _i64, _i, _i, _i, _p, _p, _p]),
     "vscb200_topk_merge_cols": (_i, [_p, _i, _i64, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "vscb200_vit_create": (_i, [C.POINTER(VitSpecC), _i, C.POINTER(_p)]),

@@ -33,6 +33,19 @@ __global__ void topk_pack_kernel(const float* __restrict__ D, const int64_t* __r
                          static_cast<uint32_t>(~static_cast<uint32_t>(id));
 }
 
+// the same into columns [col0, col0 + k) of rows of ld keys (several partial results side by side: no copy afterwards)
+__global__ void topk_pack_cols_kernel(const float* __restrict__ D, const int64_t* __restrict__ I, int64_t nq, int k, int keep_max,
+                                      unsigned long long* __restrict__ keys, int ld, int col0) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nq * k) return;
+  const int64_t row = i / k;
+  const int c = static_cast<int>(i - row * k);
+  const int64_t id = I[i];
+  keys[row * ld + col0 + c] = id < 0 ? 0ull
+                                     : (static_cast<unsigned long long>(mk_okey(D[i], keep_max != 0)) << 32) |
+                                           static_cast<uint32_t>(~static_cast<uint32_t>(id));
+}
+
 __device__ __forceinline__ unsigned long long mg_warp_max(unsigned long long v) {
   const uint32_t hi = static_cast<uint32_t>(v >> 32);
   const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
@@ -111,6 +124,20 @@ int vscb200_topk_pack(const float* D_dev, const int64_t* I_dev, int64_t nq, int 
   if (n == 0) return VSCB200_OK;
   topk_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       D_dev, I_dev, n, keep_max, reinterpret_cast<unsigned long long*>(keys_dev));
+  count_launch();
+  VSCB_CUDA_OK(cudaGetLastError());
+  return VSCB200_OK;
+}
+
+int vscb200_topk_pack_cols(const float* D_dev, const int64_t* I_dev, int64_t nq, int k, int keep_max, uint64_t* keys_dev, int ld,
+                           int col0, void* stream) {
+  using namespace vscb200;
+  VSCB_REQUIRE(nq >= 0 && k >= 1 && col0 >= 0 && col0 + k <= ld && (nq == 0 || (D_dev && I_dev && keys_dev)),
+               "topk_pack_cols: bad argument");
+  const int64_t n = nq * k;
+  if (n == 0) return VSCB200_OK;
+  topk_pack_cols_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      D_dev, I_dev, nq, k, keep_max, reinterpret_cast<unsigned long long*>(keys_dev), ld, col0);
   count_launch();
   VSCB_CUDA_OK(cudaGetLastError());
   return VSCB200_OK;

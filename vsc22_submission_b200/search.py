@@ -185,6 +185,16 @@ def pack_topk(D: torch.Tensor, I: torch.Tensor, keep_max: bool = True) -> torch.
     return keys
 
 
+def pack_topk_into(keys: torch.Tensor, col0: int, D: torch.Tensor, I: torch.Tensor, keep_max: bool = True) -> None:
+    """``keys[:, col0:col0 + k] = pack_topk(D, I)`` in one kernel (keys int64 [nq, ld], contiguous)."""
+    D, I = _f32_cuda(D, "pack_topk_into"), I.contiguous()
+    assert keys.dim() == 2 and keys.dtype == torch.int64 and keys.is_contiguous() and keys.shape[0] == D.shape[0]
+    if D.numel():
+        with torch.cuda.device(D.device):
+            _lib.check(_lib.lib().vscb200_topk_pack_cols(_p(D), _p(I), D.shape[0], D.shape[1], int(bool(keep_max)), _p(keys),
+                                                         keys.shape[1], int(col0), _stream(D.device)), "topk_pack_cols")
+
+
 def merge_packed_topk(keys: torch.Tensor, k: int, keep_max: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """keys int64 [parts, nq, kin] (the all-gather layout) -> the k best per query (D f32 [nq,k], I i64 [nq,k])."""
     assert keys.dim() == 3 and keys.dtype == torch.int64 and keys.is_cuda

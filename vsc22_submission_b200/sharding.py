@@ -96,7 +96,7 @@ def gather_partial_topk_multi(parts, keep_max: bool = True, group: Optional[dist
     keys = torch.empty((nq, ld), dtype=torch.int64, device=parts[0][0].device)
     c0 = 0
     for D, I in parts:
-        keys[:, c0:c0 + D.shape[1]] = search.pack_topk(D, I, keep_max)
+        search.pack_topk_into(keys, c0, D, I, keep_max)      # straight into its columns: no strided copy afterwards
         c0 += D.shape[1]
     if world == 1:
         return keys.unsqueeze(0)
