@@ -523,3 +523,26 @@ def test_score_normalized_search_equals_the_two_step_form(faiss):
     ix = search.DeviceIndex(r_t.shape[1]); ix.add(r_t)
     D2, I2 = ix.search(q_t, 10)
     assert torch.equal(I, I2) and torch.equal(D, D2)
+
+
+@pytest.mark.gpu
+def test_pack_topk_into_columns_equals_pack_topk(faiss):
+    """The exchange layout of the sharded similarity step: several partial results side by side, each packed straight into its
+    columns (vscb200_topk_pack_cols) -- the same keys as pack_topk + a strided copy, -1 ids as padding."""
+    import torch
+    from vsc22_submission_b200 import search, sharding
+    g = torch.Generator(device="cuda").manual_seed(9)
+    nq = 1000
+    parts = []
+    for k in (1, 10, 3):
+        D = torch.randn((nq, k), generator=g, device="cuda")
+        I = torch.randint(0, 1 << 31, (nq, k), generator=g, device="cuda", dtype=torch.int64)
+        I[::7, -1] = -1
+        parts.append((D, I))
+    keys = sharding.gather_partial_topk_multi(parts)          # world size 1: [1, nq, 14]
+    assert keys.shape == (1, nq, 14) and keys.dtype == torch.int64
+    want = torch.cat([search.pack_topk(D, I) for D, I in parts], dim=1)
+    assert torch.equal(keys[0], want)
+    D10, I10 = search.merge_packed_topk_cols(keys, 1, 10, 10)
+    order = torch.argsort(parts[1][0].masked_fill(parts[1][1] < 0, float("-inf")), dim=1, descending=True, stable=True)
+    assert torch.equal(I10, torch.gather(parts[1][1], 1, order))
