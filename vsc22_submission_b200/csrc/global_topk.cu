@@ -101,8 +101,9 @@ __device__ __forceinline__ void hist_add(uint32_t* h, uint32_t key, int level, u
 }
 
 __global__ void __launch_bounds__(kGtThreads)
-gt_hist_kernel(GtBlock a, const float* __restrict__ bufv, int64_t nbuf, int level, uint32_t prefix,
+gt_hist_kernel(GtBlock a, const float* __restrict__ bufv, int64_t nbuf, int level, const unsigned long long* __restrict__ sel,
                unsigned long long* __restrict__ hist) {
+  const uint32_t prefix = level ? static_cast<uint32_t>(sel[0]) : 0u;      // key bits fixed by the levels before (gt_pick_kernel)
   __shared__ uint32_t h[2048];
   for (int i = threadIdx.x; i < 2048; i += kGtThreads) h[i] = 0;
   __syncthreads();
@@ -138,6 +139,39 @@ gt_hist_kernel(GtBlock a, const float* __restrict__ bufv, int64_t nbuf, int leve
   __syncthreads();
   for (int i = threadIdx.x; i < 2048; i += kGtThreads)
     if (h[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(h[i]));
+}
+
+// One level of the radix select on the device: the digit in which the `want`-th best key falls (scanning the histogram
+// from the best digit down), appended to the prefix; `want` becomes the rank inside that digit.  sel = {prefix, want}.
+// One warp: lane L owns nd / 32 consecutive digits, best first.  (The host used to fetch every histogram: three round
+// trips per select.)
+__global__ void gt_pick_kernel(const unsigned long long* __restrict__ hist, int level, unsigned long long* __restrict__ sel) {
+  const int lane = threadIdx.x;
+  const int nd = level == 2 ? 1024 : 2048, per = nd / 32;
+  const unsigned long long want = sel[1];
+  const int top = nd - 1 - lane * per;                       // this lane's best digit
+  unsigned long long mine = 0ull;
+  for (int i = 0; i < per; ++i) mine += hist[top - i];
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t cross = __ballot_sync(0xffffffffu, incl >= want);
+  const int owner = cross ? __ffs(cross) - 1 : 31;           // no digit reaches the rank: the scan ends at digit 0
+  if (lane == owner) {
+    unsigned long long cum = incl - mine;
+    int dgt = top;
+    for (; dgt > 0 && dgt > top - per; --dgt) {
+      if (cum + hist[dgt] >= want) break;
+      cum += hist[dgt];
+    }
+    if (dgt == top - per) dgt = top - per + 1;               // (only lane 31 without a crossing: stop at its last digit, 0)
+    const unsigned long long prefix = sel[0];
+    sel[0] = level == 2 ? ((prefix << 10) | static_cast<unsigned long long>(dgt)) : ((prefix << 11) | static_cast<unsigned long long>(dgt));
+    sel[1] = want - cum;
+  }
 }
 
 // ---- emit: append the survivors of one score block -----------------------------------------------------------
@@ -479,7 +513,9 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     return sc.get(p, c * sizeof(uint64_t));
   };
   if ((rc = alloc_bufs(cap, &bufv[0], &bufp[0]))) return rc;
-  unsigned long long *counter = nullptr, *hist = nullptr;
+  unsigned long long *counter = nullptr, *hist = nullptr, *sel = nullptr;
+  unsigned long long sel_host[2] = {0ull, 0ull};        // outlives every copy: each select ends with a synchronise
+  if ((rc = sc.get(&sel, 2 * sizeof(unsigned long long)))) return rc;
   if ((rc = sc.get(&counter, sizeof(unsigned long long)))) return rc;
   if ((rc = sc.get(&hist, 2048 * sizeof(unsigned long long)))) return rc;
   VSCB_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
@@ -492,7 +528,6 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   unsigned long long count = 0;     // host mirror of the buffer fill
   float radius = use_thresh ? thresh : 0.f;
   bool has_radius = use_thresh != 0;
-  std::vector<unsigned long long> hh(2048);
 
   auto read_counter = [&](unsigned long long* out) {
     VSCB_CUDA_OK(cudaMemcpyAsync(out, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -508,24 +543,20 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
   auto select_kth = [&](const GtBlock& a, const float* vals, int64_t nvals, uint64_t want, float* kth) {
     const int64_t work = a.nb * ((a.n + kGtChunk - 1) / kGtChunk);
     const int grid = grid_for(std::max<int64_t>(work, (nvals + kGtThreads - 1) / kGtThreads));
-    uint32_t prefix = 0;
+    // {prefix, want} live on the device; every level's digit is picked there (gt_pick_kernel): one host round trip per
+    // select instead of three histogram downloads
+    sel_host[0] = 0ull;
+    sel_host[1] = want;
+    VSCB_CUDA_OK(cudaMemcpyAsync(sel, sel_host, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
     for (int level = 0; level < 3; ++level) {
       VSCB_CUDA_OK(cudaMemsetAsync(hist, 0, 2048 * sizeof(unsigned long long), s));
-      gt_hist_kernel<<<grid, kGtThreads, 0, s>>>(a, vals, nvals, level, prefix, hist);
-      count_launch();
-      VSCB_CUDA_OK(cudaMemcpyAsync(hh.data(), hist, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-      VSCB_CUDA_OK(cudaStreamSynchronize(s));
-      const int nd = level == 2 ? 1024 : 2048;
-      int dgt = nd - 1;
-      uint64_t cum = 0;
-      for (; dgt > 0; --dgt) {
-        if (cum + hh[dgt] >= want) break;
-        cum += hh[dgt];
-      }
-      want -= cum;
-      prefix = level == 2 ? ((prefix << 10) | static_cast<uint32_t>(dgt)) : ((prefix << 11) | static_cast<uint32_t>(dgt));
+      gt_hist_kernel<<<grid, kGtThreads, 0, s>>>(a, vals, nvals, level, sel, hist);
+      gt_pick_kernel<<<1, 32, 0, s>>>(hist, level, sel);
+      count_launch(2);
     }
-    *kth = key_value(prefix, keep_max);
+    VSCB_CUDA_OK(cudaMemcpyAsync(sel_host, sel, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    VSCB_CUDA_OK(cudaStreamSynchronize(s));
+    *kth = key_value(static_cast<uint32_t>(sel_host[0]), keep_max);
     return static_cast<int>(VSCB200_OK);
   };
   // keep the buffer entries that can still be among the K best under `radius`; updates count
