@@ -535,6 +535,10 @@ int vscb200_index_global_search(vscb200_index* ix, const float* q, int64_t nq, i
     return static_cast<int>(VSCB200_OK);
   };
   auto set_counter = [&](unsigned long long v) {
+    if (v == 0) {                                  // the common case (compaction, rescoring): no host value, no round trip
+      VSCB_CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+      return static_cast<int>(VSCB200_OK);
+    }
     VSCB_CUDA_OK(cudaMemcpyAsync(counter, &v, sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
     VSCB_CUDA_OK(cudaStreamSynchronize(s));      // v lives on this frame
     return static_cast<int>(VSCB200_OK);
