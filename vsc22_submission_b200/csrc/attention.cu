@@ -202,7 +202,7 @@ int attention(const void* qkv, void* out, int n_frames, int T, int heads, int he
               bool reverse) {
   VSCB_REQUIRE(head_dim == 64, "attention: head_dim must be 64");
   VSCB_REQUIRE(n_frames > 0 && T > 0 && heads > 0, "attention: empty problem");
-  // 128 < T <= 672: streaming tcgen05 kernel (attention_ws.cu): decoupled warpgroups, keys in blocks of 96, S double-buffered
+  // 128 < T <= 640: streaming tcgen05 kernel (attention_ws.cu): decoupled warpgroups, keys in blocks of 32, S double-buffered
   if (attention_ws_supported(T, head_dim) && T != 257 && static_cast<int64_t>(n_frames) * T < (1ll << 31))   // 257 = 256 + 1: attention_tc.cu folds the odd token in
     return attention_ws(qkv, out, n_frames, T, heads, stream, reverse);
   // T <= 257: tcgen05 kernel with S resident in TMEM (attention_tc.cu)

@@ -1,32 +1,37 @@
-// Streaming tcgen05 attention for the ViT encoders (head_dim 64, 129 .. 640 tokens per frame): the two softmax warpgroups
-// of a CTA run INDEPENDENT streams of (frame, head, 128-query tile) items, each with its own MMA-issuing thread, keys in
-// blocks of 64 with S double-buffered in TMEM, so a warpgroup never waits for an MMA round trip between blocks:
+// Streaming tcgen05 attention for the ViT encoders (head_dim 64, 129 .. 640 tokens per frame) and the large Swin-V2 windows
+// (head_dim 32, 144 / 576 tokens): the NW softmax warpgroups of a CTA run INDEPENDENT streams of (segment, head, 128-query
+// tile) items, each with its own MMA-issuing warp, keys in blocks of KB with D S buffers per warpgroup in TMEM, so a
+// warpgroup never waits for an MMA round trip between blocks.  Shapes (template <HD, kSwin, NW, KB, D>): ViT 3 warpgroups x
+// 32-key blocks x 2 buffers (16 warps), Swin 2 x 64 x 2 (11 warps); VSCB200_ATTN_WS_SHAPE selects the others.
 //
-//   warps 0-3 / 4-7   softmax warpgroup w, thread = query row.  Per key block (64 keys = two chunks of 32 columns): wait
-//                     S(b); per chunk ONE pass over registers: chunk maximum (FMNMX3 tree), p = 2^(s * scale - m), P over
-//                     S in place as bf16 pairs (truncation: one PRMT per pair); arrive P(b).  The running shift m only
-//                     moves when a chunk maximum exceeds it by more than 2^8; then O, the row sum and the P chunks
-//                     already written are rescaled through tcgen05.ld / st -- after the first chunks of an item this is
-//                     rare.  The ROW SUM is accumulated by the tensor core from the very P the output uses (a second
-//                     B operand of ones, 16 extra accumulator columns), so normalisation cancels the truncation bias
-//                     and the softmax threads carry no adds.  The epilogue of an item (O * 1 / l -> bf16 rows) is
-//                     DEFERRED until after the softmax of the next item's first block: by then the last P.V of the
-//                     item has long completed.
-//   warp 8 / 9        lane 0: MMA issuer of warpgroup 0 / 1 (warp 8 also owns the TMEM allocation).  Rolling order
-//                     S(g), S(g+1), [P(g)] PV(g), S(g+2), [P(g+1)] PV(g+1), S(g+3) ... over the warpgroup's flattened block
-//                     sequence g (blocks of consecutive items follow each other without a drain): S is always two
-//                     blocks ahead of the softmax.  TMEM per warpgroup (256 columns): S0 [0, 64), S1 [64, 128), O [128, 192),
-//                     row sums [192, 208).
-//   warp 10           TMA producer: K / V of a (frame, head) unit into one of two shared-memory stages (one stage for
-//                     long frames), the Q tile of every item into its warpgroup's Q buffers.
+//   warps 0 .. 4 NW-1     softmax warpgroup w = warp / 4, thread = query row.  Per key block (KB / 32 chunks of 32 columns):
+//                     wait S(b); per chunk ONE pass over registers: chunk maximum (FMNMX3 tree), p = 2^(s * scale - m)
+//                     (predicated off for the padding keys of a segment's last chunk), P over S in place as bf16 pairs
+//                     (truncation: one PRMT per pair); arrive P(b).  The running shift m only moves when a chunk maximum
+//                     exceeds it by more than 2^8; then O, the row sum and the P chunks already written are rescaled
+//                     through tcgen05.ld / st -- after the first chunks of an item this is rare.  The ROW SUM is
+//                     accumulated by the tensor core from the very P the output uses, so normalisation cancels the
+//                     truncation bias and the softmax threads carry no adds: in the ViT form by the SAME MMA as O (an
+//                     N = 80 MN-major operand whose second 64-column block -- the descriptor's LBO -- is a tile of bf16
+//                     ones: O | l land in 80 adjacent TMEM columns), in the Swin form by a second N = 16 MMA.  The
+//                     epilogue of an item (O * 1 / l -> bf16 rows) is DEFERRED until after the softmax of the next item's
+//                     first block: by then the last P.V of the item has long completed.
+//   warps 4 NW .. 5 NW-1  MMA issuer of warpgroup w: the whole warp runs the loop on warp-uniform values, one elected lane
+//                     issues (the first issuer warp also owns the TMEM allocation).  Rolling order S(g), S(g+1), [P(g)]
+//                     PV(g), S(g+2), [P(g+1)] PV(g+1), S(g+3) ... over the warpgroup's flattened block sequence g (blocks
+//                     of consecutive items follow each other without a drain): S runs D blocks ahead of the softmax.
+//                     TMEM per warpgroup: D x KB columns of S, 64 of O, 16 of row sums.
+//   warp 5 NW             TMA producer: K / V of a (segment, head group) unit into one of two shared-memory stages (one
+//                     stage for long segments), the Q tile of every item into its warpgroup's Q buffers.
 //
-// The tensor pipe executes one thread's MMAs in issue order, so S(g+2) -- issued right behind PV(g) -- cannot overwrite
-// the buffer P(g) is read from, and "S(g) complete" implies "PV(g-2) complete".  PV(g-1) may still be accumulating
-// into O when the softmax of block g wants to rescale O: that (rare) path first waits on a barrier committed behind
-// every PV.
+// The tensor pipe executes one thread's MMAs in issue order, so S(g+D) -- issued right behind PV(g) -- cannot overwrite
+// the buffer P(g) is read from.  PV(g-1) may still be accumulating into O when the softmax of block g wants to rescale
+// O: that (rare) path first waits on a barrier committed behind every PV.  What bounds the kernel (exponentials and the
+// per-block barrier chain, about equally) is measured in profiles/r02_attention_ws_experiments.txt.
 //
 // Reference: nn.MultiheadAttention at D/train/train_vid_score/video/clip.py:45 (unfused bmm + softmax + bmm in
-// torch 1.11); frames of 197 (ViT-B/16 @ 224, BASELINE configs[1]), 145, 257 and 577 tokens.
+// torch 1.11); frames of 197 (ViT-B/16 @ 224, BASELINE configs[1]), 145 and 577 tokens; window attention of
+// D/train/train_v106/vsc/baseline/model_factory/backbones/swinv2.py:72-185.
 #include <stdlib.h>
 
 #include "host_util.h"

@@ -29,7 +29,7 @@ int im2row(const float* frames, void* patches, int64_t n, int img, int patch, in
 int attention_fp32(const void* qkv, int64_t qkv_lo_off, void* out, int64_t out_lo_off, int64_t n_segs, int N, int heads,
                    int head_dim, float scale, const float* tables, int ws, int res, int shift, int nWx, int nW_per_frame,
                    cudaStream_t stream);
-// attention_ws.cu: streaming tcgen05 attention of the ViT encoders (head_dim 64, 129..672 tokens)
+// attention_ws.cu: streaming tcgen05 attention of the ViT encoders (head_dim 64, 129..640 tokens) and large Swin-V2 windows
 bool attention_ws_supported(int T, int head_dim);
 int attention_ws(const void* qkv, void* out, int n_frames, int T, int heads, cudaStream_t stream, bool reverse);
 int attention_ws_swin(const void* qkv, void* out, int64_t n_windows_total, int ws, int heads, const float* tables, int shift,
