@@ -13,8 +13,10 @@
 //     gmax[group][q] = max over the group's rows of the selection key (score, or -squared distance)
 // 1/32 of a float per pair.  The top-k rows of a query lie in the <= k groups with the largest maxima
 // (each such group holds at least one of the k best rows), so search() selects k + slack groups per
-// query and rescores their 32 rows each exactly in fp32 (group_rescore_kernel) -- bit-exact ids, fp32
-// scores, no dense score block.
+// query and rescores their 32 rows each exactly in fp32 -- bit-exact ids, fp32 scores, no dense score block.
+// The selection and rescoring run as one CTA per 256-group chunk (group_topk_kernel) and one CTA per (query, group)
+// (group_rescore_few_kernel, last arriver of a query sorts); group_rescore_kernel (one CTA per query) serves the
+// many-query callers.  The launches of a call are chained by programmatic dependent launch (griddepcontrol).
 #include <float.h>
 
 #include "exact.cuh"

@@ -11,6 +11,11 @@
 // over 128x128 output tiles.  Epilogue: segment sum -> optional squared-L2 transform -> coalesced fp32
 // stores of the dense score block (consumed by select.cu: top-k, range search, dense sim matrices).
 //
+// Round 2: the same skeleton also runs ONE pass (Qh.Rh only; `passes = 1`, six-stage ring of {Qh, Rh} tiles, one accumulator
+// segment) where an approximate score with a proven margin is enough (margin.cuh): the column-sample GEMM of the candidate
+// search / the top-k threshold bootstrap, and mode 2, whose epilogue emits the pairs better than a per-row threshold
+// instead of storing anything dense (global_topk.cu).  The MMA-issuing warp runs on warp-uniform values.
+//
 // Reference: faiss IndexFlat scoring (cuBLAS SGEMM on GPU / sgemm on CPU) behind vsc/index.py:174,
 // vsc/exhaustive_search.py:62,74, vsc/baseline/score_normalization.py:95.
 #include "host_util.h"
